@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- shape-loss fwd+bwd throughput (Mpix/s) on B200, next to the reference's CPU path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one forward + backward of the whitening/MMD shape-regularization loss
+(WT_PSE.compute_whitening_loss, algorithms.py:1277-1309) over one synthetic batch.  At N=1 the workload is
+BASELINE.json configs[1] mapped onto what the reference's entry point accepts:
+z = 32 x 16 x 512 x 512 fp32 feature maps, 3 domains x 10 samples.  1 pix = one (b,h,w) site, all 16 channels.
+
+  value   device-resident throughput (inputs already in HBM), whole job over all ranks
+  e2e     same metric through the host-buffer C-ABI entry point (wtpse_host_plan_run): pinned host z in,
+          H2D, forward, backward, D2H of dz and of the losses, every step
+  roofline  the dominant kernel (apply_tma_kernel, backward) -- algorithmic bytes / its CUDA-event duration
+            measured inside the timed region, against MEASURED_PEAKS.json
+  cpu_baseline  the oracle's PyTorch-CPU port of the reference path on this box's host cores (bounded sample)
+
+N > 1 (torchrun, one rank per GPU): the path shards over whole [K domains x n] batches with no data-path
+collective; every rank processes its own batch -> "scaling": "weak".
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(B=32, C=16, H=512, W=512, n_per_domain=10, n_domains=3, margin=0.0, eps=1e-5)
+ALGO_BYTES_PER_PIX = {"gram_tma_kernel": 64, "apply_tma_kernel": 128}   # fwd read z; bwd read z + write dz
+FALLBACK_PEAK_GBS = 6650.0                                               # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10, help="steps of the host-buffer (PCIe-bound) loop")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
+    ap.add_argument("--batch", type=int, default=WORKLOAD["B"])
+    ap.add_argument("--size", type=int, default=WORKLOAD["H"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def synth_batch(B, H, W, seed, device=None, pin=False):
+    """SURVEY.md 8(d) synthetic input: 0.3*randn + per-sample-per-channel offset 0.2*randn (domains differ)."""
+    import torch
+
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    off = 0.2 * torch.randn(B, 16, 1, 1, generator=g)
+    if device is not None:
+        gd = torch.Generator(device=device).manual_seed(seed)
+        z = 0.3 * torch.randn(B, 16, H, W, generator=gd, device=device) + off.to(device)
+        return z
+    z = torch.empty(B, 16, H, W, pin_memory=pin)
+    torch.randn(B, 16, H, W, generator=g, out=z)
+    z.mul_(0.3).add_(off)
+    return z
+
+
+# -------------------------------------------------------------------------------------------------
+# clocks sampler (NVML, background thread)
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU legs (oracle port, or the real reference when its tree is on this box)
+# -------------------------------------------------------------------------------------------------
+def cpu_step_fn(n, K):
+    """Returns (callable(z) -> None doing one fwd+bwd, kind)."""
+    import torch
+    from oracle import ref_shim
+
+    if ref_shim.available() and not torch.cuda.is_available():
+        # build container: the unmodified reference through the import shim
+        alg, _, _ = ref_shim.load()
+        hp = dict(ref_shim.DEFAULT_HPARAMS)
+        torch.manual_seed(0)
+        model = alg.WT_PSE(3, 1, hp, "cpu", False, per_domain_batch=n, source_domain_num=K)
+
+        def step(z):
+            z = z.detach().requires_grad_(True)
+            ins, dom = model.compute_whitening_loss(z)
+            (ins + dom).backward()
+        return step, "reference"
+    from oracle import whitening_torch as wt
+
+    def step(z):
+        wt.fwd_bwd(z, n, K)
+    return step, "port"
+
+
+def time_cpu(B, H, W, n, K, budget_s, max_iters):
+    import torch
+
+    step, kind = cpu_step_fn(n, K)
+    z = synth_batch(B, H, W, seed=7)
+    step(z)                                     # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s:
+        t0 = time.perf_counter()
+        step(z)
+        times.append(time.perf_counter() - t0)
+    pix = B * H * W
+    return {"value": pix / min(times) / 1e6, "mean_value": pix / (sum(times) / len(times)) / 1e6, "unit": "Mpix/s",
+            "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind, "iters": len(times),
+            "sample": "%dx16x%dx%d fp32 (n=%d,K=%d) fwd+bwd, best of %d after 1 warm-up" % (B, H, W, n, K, len(times))}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    H = args.size
+    n, K = 2, 3
+    B = n * K                                   # bounded sample: 6 of the workload's samples per step
+    step, kind = cpu_step_fn(n, K)
+    z = synth_batch(B, H, H, seed=7)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step(z)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(z)
+    dt = time.perf_counter() - t0
+    pix = B * H * H
+    val = pix * args.steps / dt / 1e6
+    line = {
+        "impl": "reference", "metric": "shape-loss fwd+bwd Mpix/s", "value": val, "unit": "Mpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "whitening+MMD shape loss fwd+bwd, %dx16x%dx%d fp32, n=%d K=%d (bounded sample of the "
+                               "32x16x512x512 workload, CPU)" % (B, H, H, n, K)},
+        "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": "%dx16x%dx%d per step, %d steps" % (B, H, H, args.steps)},
+        "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import wtpse_b200 as wb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, H, W = args.batch, args.size, args.size
+    n = max(1, B // 3) if B != WORKLOAD["B"] else WORKLOAD["n_per_domain"]
+    K = WORKLOAD["n_domains"]
+    margin, eps = WORKLOAD["margin"], WORKLOAD["eps"]
+    pix = B * H * W
+    lib = wb._lib.load()
+
+    # two resident input batches, alternated, each 4x the 126 MB L2 -> no timed step finds its input in L2
+    zs = [synth_batch(B, H, W, seed=1234 + 17 * rank + i, device=dev).requires_grad_(True) for i in range(2)]
+
+    def step(i):
+        z = zs[i & 1]
+        z.grad = None
+        ins, dom = wb.whitening_folded(z, n, K, margin, eps)
+        torch.autograd.backward([ins, dom], [torch.ones_like(ins), torch.ones_like(dom)])
+        return ins, dom
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    lib.wtpse_profile_reset()
+    lib.wtpse_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        ins, dom = step(i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    lib.wtpse_profile_enable(0)
+    ms_total = ev0.elapsed_time(ev1)
+    losses = (float(ins), float(dom))
+
+    launches = int(lib.wtpse_profile_launches(-1))
+    import ctypes
+    kern = {}
+    for kid in range(lib.wtpse_profile_kernel_count()):
+        cnt, ms = ctypes.c_longlong(0), ctypes.c_double(0.0)
+        wb._lib.check(lib.wtpse_profile_read(kid, ctypes.byref(cnt), ctypes.byref(ms)))
+        if cnt.value:
+            kern[lib.wtpse_profile_kernel_name(kid).decode()] = {"launches": cnt.value, "avg_us": ms.value / cnt.value * 1e3}
+
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * pix / (ms_step * 1e-3) / 1e6
+
+    # ---- end to end through the host-buffer C-ABI entry point ------------------------------------------------
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    z_host = [synth_batch(B, H, W, seed=99 + rank + i, pin=True) for i in range(2)]
+    dz_host = torch.empty(B, 16, H, W, pin_memory=True)
+    plan = wb.HostPlan(B, H, W)
+    plan.run(z_host[0], n, K, margin, eps, (1.0, 1.0, 1.0), dz_host)       # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        plan.run(z_host[i & 1], n, K, margin, eps, (1.0, 1.0, 1.0), dz_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    plan.close()
+    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    nbytes = B * 16 * H * W * 4
+    e2e = {"value": world * pix * e2e_steps / e2e_s / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": nbytes + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+           "api": "wtpse_host_plan_run (pinned host z -> H2D -> fwd -> bwd -> D2H dz + losses)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline for the dominant kernel --------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_PEAK_GBS, "fallback (B200_PROFILING.md)"
+    dom_name = max((k for k in kern if k in ALGO_BYTES_PER_PIX), key=lambda k: kern[k]["avg_us"], default=None)
+    roofline = None
+    if dom_name:
+        achieved = ALGO_BYTES_PER_PIX[dom_name] * pix / (kern[dom_name]["avg_us"] * 1e-6) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom_name)
+        roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIX[dom_name] * pix,
+                    "kernel_avg_us": kern[dom_name]["avg_us"]}
+        other = "gram_tma_kernel" if dom_name == "apply_tma_kernel" else "apply_tma_kernel"
+        if other in kern:
+            a2 = ALGO_BYTES_PER_PIX[other] * pix / (kern[other]["avg_us"] * 1e-6) / 1e9
+            roofline["also"] = {"kernel": other, "achieved": a2, "frac": a2 / peak, "kernel_avg_us": kern[other]["avg_us"]}
+        roofline["step_frac"] = 192.0 * pix / (ms_step * 1e-3) / 1e9 / peak    # whole fwd+bwd step vs 192 B/pix
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        cpu = time_cpu(6, H, W, 2, 3, args.cpu_seconds, 40)
+
+    line = {
+        "metric": "shape-loss fwd+bwd Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "whitening+MMD shape loss fwd+bwd (WT_PSE.compute_whitening_loss), z=%dx16x%dx%d fp32, "
+                               "n=%d K=%d per GPU [BASELINE configs[1] mapped per SURVEY 8(d)]" % (B, H, W, n, K),
+                   "per_gpu_batch": B, "l2": "inputs (%.0f MB, two alternating buffers) larger than L2" % (nbytes / 1e6),
+                   "sharding": "independent [K x n] batches per rank, no data-path collective"},
+        "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "losses": losses,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,134 @@
+/*
+ * wtpse_b200.h -- C ABI of the B200-native shape-regularization hot path of WT-PSE.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes (no torch / C++ types) and
+ * returns an int status (WTPSE_OK == 0).  Nothing throws across the boundary;
+ * wtpse_last_error() returns the message of the last failing call on the calling thread.
+ * Device-pointer entry points are asynchronous on `stream` (a cudaStream_t passed as void*),
+ * never synchronise the host, never copy host<->device and never allocate.  The *_host entry
+ * points take HOST buffers and do the copies themselves (the plugin-facing path bench.py times
+ * as "e2e").
+ *
+ * The reference (tonyckc/WT-PSE-code) has no FFI: its boundary for this path is the Python
+ * method surface that Trainer.py calls.  Each function below names the reference statement(s)
+ * it replaces; INTEGRATION.md shows the ctypes binding and the method rebinding a maintainer
+ * would add to the reference.
+ *
+ * Layouts: all tensors fp32, NCHW contiguous, C == 16 (self.dim, algorithms.py:1157).
+ *   z       [B][16][P]      P = H*W
+ *   gram    [B][16][16]     f_cor of algorithms.py:1283 (symmetric, eps on the diagonal)
+ *   rowstat [B][2]          off_b (algorithms.py:1289) and diag_b (algorithms.py:1297), margin subtracted
+ *   losses  [4]             L_off, L_diag, L_dom, L_off + L_diag
+ */
+#ifndef WTPSE_B200_H
+#define WTPSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WTPSE_OK              0
+#define WTPSE_ERR_INVALID     1   /* bad argument (shape, null pointer, C != 16, ...) */
+#define WTPSE_ERR_CUDA        2   /* a CUDA runtime call or launch failed            */
+#define WTPSE_ERR_WORKSPACE   3   /* workspace too small                             */
+
+#define WTPSE_CHANNELS        16
+#define WTPSE_ABI_VERSION     1
+
+typedef void* wtpse_stream_t;     /* cudaStream_t */
+
+int         wtpse_abi_version(void);
+const char* wtpse_last_error(void);
+/* Number of SMs the persistent kernels size their grids for on the current device. */
+int         wtpse_sm_count(void);
+
+/* ---- whitening (Gram) loss: algorithms.py:1277-1309, shape_networks.py:561-594 ------------- */
+
+/* Bytes of scratch the forward/backward need for a [B][16][P] input (max of both). */
+size_t wtpse_whitening_workspace_bytes(int B, int64_t P);
+
+/*
+ * Forward.  Replaces the body of WT_PSE.compute_whitening_loss (algorithms.py:1280-1307) and of
+ * ShapeVariationalDist_x.compute_whitening_loss (shape_networks.py:564-592) including
+ * compute_MMD.forward (algorithms.py:102-121):
+ *   gram    = bmm(z, z^T)/(P-1) + eps*I
+ *   L_off   = mean_b clamp((sum_{i<j}|gram_ij| - margin)/120, 0)
+ *   L_diag  = mean_b clamp((sum_i |gram_ii - 1| - margin)/16, 0)
+ *   L_dom   = gaussian-kernel MMD over the n_domains chunks [k*n : (k+1)*n] of the 120-d
+ *             upper-triangle vectors (python slice semantics: chunks are truncated at B; an empty
+ *             chunk yields NaN exactly like the reference's mean over an empty tensor);
+ *             0 when n_domains <= 1.
+ * NaN/Inf in z propagate to the losses (the caller's NaN guard is Trainer.py:799-800).
+ */
+int wtpse_whitening_forward(const float* z, int B, int C, int64_t P,
+                            int n_per_domain, int n_domains, float margin, float eps,
+                            float* losses, float* gram, float* rowstat,
+                            void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
+/*
+ * Backward (what autograd derives from the statements above):
+ *   dz_b = (S_b + S_b^T) z_b / (P-1)
+ * g_off / g_diag / g_dom are DEVICE pointers to the upstream gradients of L_off / L_diag / L_dom
+ * (NULL == 0), so no host synchronisation is needed between forward and backward.
+ */
+int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat,
+                             const float* g_off, const float* g_diag, const float* g_dom,
+                             int B, int C, int64_t P, int n_per_domain, int n_domains,
+                             float margin, float* dz,
+                             void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
+/* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
+
+size_t wtpse_mmd_workspace_bytes(int B);
+/* v is [B][D] with D == 120; loss[0] = mean over domain pairs of (Kxx + Kyy - 2Kxy), gamma = [1]. */
+int wtpse_mmd_forward(const float* v, int B, int D, int n_per_domain, int n_domains, float* loss,
+                      void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+/* dv[B][D] = gout * dloss/dv (rows beyond n_domains*n_per_domain get 0); gout DEVICE scalar, NULL == 1. */
+int wtpse_mmd_backward(const float* v, const float* gout, int B, int D, int n_per_domain, int n_domains,
+                       float* dv, void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
+/* ---- KD loss: ShapeVariationalDist_x.wasser_distance, shape_networks.py:596-597 ----------- */
+
+size_t wtpse_mse_workspace_bytes(int64_t N);
+/* loss[0] = mean((a-b)^2) over N elements. */
+int wtpse_mse_forward(const float* a, const float* b, int64_t N, float* loss,
+                      void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+/* da = 2*gout*(a-b)/N, db = -da; gout is a DEVICE scalar; da or db may be NULL. */
+int wtpse_mse_backward(const float* a, const float* b, const float* gout, int64_t N,
+                       float* da, float* db, wtpse_stream_t stream);
+
+/* ---- host-buffer entry point (plugin-facing, used for the end-to-end number) --------------- */
+
+typedef struct wtpse_host_plan wtpse_host_plan;
+
+/* Allocates device buffers for one [B][16][P] batch on the current device. */
+int  wtpse_host_plan_create(int B, int64_t P, wtpse_host_plan** plan);
+void wtpse_host_plan_destroy(wtpse_host_plan* plan);
+/*
+ * z_host -> device, forward, backward with upstream weights grad_w[3] = (g_off, g_diag, g_dom),
+ * dz -> dz_host (may be NULL to skip backward), losses_host[4] as in `losses`.
+ * Synchronous: returns when the host buffers are complete.
+ */
+int  wtpse_host_plan_run(wtpse_host_plan* plan, const float* z_host,
+                         int n_per_domain, int n_domains, float margin, float eps,
+                         const float grad_w[3], float losses_host[4], float* dz_host);
+
+/* ---- launch accounting / in-step kernel timing (used by bench.py, not by the reference path) - */
+
+/* Every kernel launch made by this library is counted; with profiling enabled each launch is also
+ * bracketed by CUDA events on its own stream.  Kernel ids: 0 .. wtpse_profile_kernel_count()-1. */
+void        wtpse_profile_enable(int on);
+void        wtpse_profile_reset(void);
+int         wtpse_profile_kernel_count(void);
+const char* wtpse_profile_kernel_name(int id);
+long long   wtpse_profile_launches(int id);            /* id < 0: all kernels */
+/* Sum of event-timed durations (ms) of kernel `id` since the last reset; synchronises those events. */
+int         wtpse_profile_read(int id, long long* timed_launches, double* total_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTPSE_B200_H */

@@ -1,0 +1,77 @@
+"""CPU-side checks of the boundary: the C-ABI library builds for sm_100a, loads, and exports every
+symbol include/wtpse_b200.h declares; the host layer refuses CPU tensors instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "wtpse_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wtpse_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import wtpse_b200
+
+    path = wtpse_b200._build.build()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), "header declares %s but the library does not export it" % name
+    # and the ctypes binding covers exactly the header
+    assert sorted(wtpse_b200._lib.EXPORTS) == declared
+
+
+def test_library_is_sm100a_native():
+    import subprocess
+    import wtpse_b200
+
+    out = subprocess.run(["cuobjdump", "-lelf", wtpse_b200._build.build()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_abi_version_and_sizes_without_gpu():
+    import wtpse_b200
+
+    lib = wtpse_b200._lib.load()
+    assert lib.wtpse_abi_version() == 1
+    assert lib.wtpse_whitening_workspace_bytes(0, 100) == 0
+    assert lib.wtpse_mse_workspace_bytes(0) == 0
+
+
+def test_no_cpu_fallback():
+    import wtpse_b200
+
+    z = torch.randn(6, 16, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        wtpse_b200.whitening_terms(z, 2, 3)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        wtpse_b200.kd_mse(torch.randn(4), torch.randn(4))
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        wtpse_b200.mmd_penalty(torch.randn(6, 120), 2, 3)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    import wtpse_b200
+
+    monkeypatch.setattr(wtpse_b200._lib, "_LIB", None)
+    monkeypatch.setattr(wtpse_b200._build, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(wtpse_b200._lib.WtpseError, match="not found"):
+        wtpse_b200._lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "wt-pse-code_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, "%s mentions the oracle" % f

@@ -1,0 +1,12 @@
+"""wt-pse-code_b200: B200-native (sm_100a CUDA) shape-regularization hot path of WT-PSE.
+
+Import as ``wtpse_b200`` (alias package at the repo root).  The arithmetic lives in
+``libwtpse_b200.so`` (C ABI: include/wtpse_b200.h); this package is the thin PyTorch-facing host
+side.  There is no CPU or eager-PyTorch fallback: calls raise if the library is missing.
+"""
+from . import _build, _lib  # noqa: F401
+from .functional import HostPlan, gram_matrix, kd_mse, whitening_folded, whitening_terms  # noqa: F401
+from .mmd import mmd_penalty  # noqa: F401
+from . import dropin  # noqa: F401
+
+__all__ = ["whitening_terms", "whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin"]

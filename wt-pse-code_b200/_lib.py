@@ -1,0 +1,83 @@
+"""ctypes binding of the C ABI declared in include/wtpse_b200.h.
+
+There is NO fallback: if ``libwtpse_b200.so`` is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+from . import _build
+
+_c = ctypes
+_LIB = None
+
+WTPSE_OK = 0
+ABI_VERSION = 1
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "wtpse_abi_version": (_c.c_int, []),
+    "wtpse_last_error": (_c.c_char_p, []),
+    "wtpse_sm_count": (_c.c_int, []),
+    "wtpse_whitening_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64]),
+    "wtpse_whitening_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_float,
+                                           _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
+                                           _c.c_void_p]),
+    "wtpse_whitening_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                            _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p,
+                                            _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
+    "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                     _c.c_size_t, _c.c_void_p]),
+    "wtpse_mmd_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                      _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_mse_workspace_bytes": (_c.c_size_t, [_c.c_int64]),
+    "wtpse_mse_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_size_t,
+                                     _c.c_void_p]),
+    "wtpse_mse_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p,
+                                      _c.c_void_p]),
+    "wtpse_profile_enable": (None, [_c.c_int]),
+    "wtpse_profile_reset": (None, []),
+    "wtpse_profile_kernel_count": (_c.c_int, []),
+    "wtpse_profile_kernel_name": (_c.c_char_p, [_c.c_int]),
+    "wtpse_profile_launches": (_c.c_longlong, [_c.c_int]),
+    "wtpse_profile_read": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_double)]),
+    "wtpse_host_plan_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
+    "wtpse_host_plan_destroy": (None, [_c.c_void_p]),
+    "wtpse_host_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
+                                       _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.c_void_p]),
+}
+
+
+class WtpseError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library is absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise WtpseError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)" % path)
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)       # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.wtpse_abi_version() != ABI_VERSION:
+        raise WtpseError("ABI mismatch: library %d, binding %d" % (lib.wtpse_abi_version(), ABI_VERSION))
+    _LIB = lib
+    return lib
+
+
+def check(rc):
+    if rc != WTPSE_OK:
+        msg = load().wtpse_last_error()
+        raise WtpseError("wtpse call failed (code %d): %s" % (rc, msg.decode() if msg else "?"))

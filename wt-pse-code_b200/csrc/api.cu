@@ -1,0 +1,264 @@
+// C ABI (include/wtpse_b200.h) over the kernels.  No exceptions, no torch types, no host syncs on
+// the device-pointer entry points.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/wtpse_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "profile.cuh"
+
+using namespace wtpse;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(WTPSE_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+int sm_count_cached() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct WhitenWorkspace {
+    float* partial;
+    float* mmat;
+    double* scratch;
+    size_t total;
+};
+
+// K is not known when the workspace is sized; K*K <= B*B + 1 always holds for the domains that can be
+// non-empty, and the MMD never reads blk beyond K*K, so reserve B*B + 64 doubles for it.
+WhitenWorkspace carve(void* base, int B, long long P, int sms) {
+    WhitenWorkspace w;
+    size_t off = 0;
+    const size_t partial_bytes = align_up(gram_partial_floats(B, P, sms) * sizeof(float), 256);
+    const size_t mmat_bytes = align_up(size_t(B) * 256 * sizeof(float), 256);
+    const size_t scratch_bytes = align_up((epilogue_scratch_doubles(B, 1) + size_t(B) * B + 64) * sizeof(double), 256);
+    char* p = static_cast<char*>(base);
+    w.partial = reinterpret_cast<float*>(p + off); off += partial_bytes;
+    w.mmat = reinterpret_cast<float*>(p + off); off += mmat_bytes;
+    w.scratch = reinterpret_cast<double*>(p + off); off += scratch_bytes;
+    w.total = off;
+    return w;
+}
+
+int check_common(const void* z, int B, int C, long long P, int n, int K) {
+    if (!z) return fail(WTPSE_ERR_INVALID, "null input pointer");
+    if (C != WTPSE_CHANNELS) return fail(WTPSE_ERR_INVALID, "whitening loss is defined for C == 16 channels, got %d", C);
+    if (B <= 0 || P <= 1) return fail(WTPSE_ERR_INVALID, "need B >= 1 and H*W >= 2 (got B=%d, P=%lld)", B, P);
+    if (n < 0 || K < 0) return fail(WTPSE_ERR_INVALID, "negative domain configuration (n=%d, K=%d)", n, K);
+    if ((long long)K * K > (long long)B * B + 64) return fail(WTPSE_ERR_INVALID, "n_domains=%d too large for B=%d", K, B);
+    return WTPSE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wtpse_abi_version(void) { return WTPSE_ABI_VERSION; }
+const char* wtpse_last_error(void) { return g_err; }
+int wtpse_sm_count(void) { return sm_count_cached(); }
+
+size_t wtpse_whitening_workspace_bytes(int B, int64_t P) {
+    if (B <= 0 || P <= 0) return 0;
+    return carve(nullptr, B, P, sm_count_cached()).total;
+}
+
+int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_domain, int n_domains, float margin,
+                            float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                            size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
+    if (!losses || !gram || !rowstat || !workspace) return fail(WTPSE_ERR_INVALID, "null output/workspace pointer");
+    const int sms = sm_count_cached();
+    const WhitenWorkspace w = carve(workspace, B, P, sms);
+    if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const GramPlan g = plan_gram(z, B, P, sms);
+    cudaError_t e;
+    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, B, P, g, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "gram launch");
+    const EpilogueScratch sc = carve_epilogue_scratch(w.scratch, B, n_domains);
+    { LaunchScope scope(kKernEpilogueFwd, s); e = launch_whiten_epilogue_fwd(w.partial, g, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, sc, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "forward epilogue launch");
+    return WTPSE_OK;
+}
+
+int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* g_off,
+                             const float* g_diag, const float* g_dom, int B, int C, int64_t P, int n_per_domain,
+                             int n_domains, float margin, float* dz, void* workspace, size_t workspace_bytes,
+                             wtpse_stream_t stream) {
+    (void)margin;  // already folded into rowstat by the forward
+    if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
+    if (!gram || !rowstat || !dz || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    const int sms = sm_count_cached();
+    const WhitenWorkspace w = carve(workspace, B, P, sms);
+    if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const EpilogueScratch sc = carve_epilogue_scratch(w.scratch, B, n_domains);
+    cudaError_t e;
+    { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, sc, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
+    { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "apply launch");
+    return WTPSE_OK;
+}
+
+size_t wtpse_mmd_workspace_bytes(int B) {
+    if (B <= 0) return 0;
+    return align_up((epilogue_scratch_doubles(B, 1) + size_t(B) * B + 64) * sizeof(double), 256);
+}
+
+static int check_mmd(const void* v, int B, int D, int n, int K) {
+    if (!v) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (D != 120) return fail(WTPSE_ERR_INVALID, "MMD input must be B x 120 (upper triangle of a 16x16 Gram), got D=%d", D);
+    if (B <= 0 || n < 0 || K < 0 || (long long)K * K > (long long)B * B + 64)
+        return fail(WTPSE_ERR_INVALID, "bad MMD configuration (B=%d, n=%d, K=%d)", B, n, K);
+    return WTPSE_OK;
+}
+
+int wtpse_mmd_forward(const float* v, int B, int D, int n_per_domain, int n_domains, float* loss, void* workspace,
+                      size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_mmd(v, B, D, n_per_domain, n_domains)) return rc;
+    if (!loss || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    const EpilogueScratch sc = carve_epilogue_scratch(static_cast<double*>(workspace), B, n_domains);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernMmdFwd, s); e = launch_mmd(v, nullptr, B, n_per_domain, n_domains, loss, nullptr, sc, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "mmd forward launch");
+    return WTPSE_OK;
+}
+
+int wtpse_mmd_backward(const float* v, const float* gout, int B, int D, int n_per_domain, int n_domains, float* dv,
+                       void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_mmd(v, B, D, n_per_domain, n_domains)) return rc;
+    if (!dv || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    const EpilogueScratch sc = carve_epilogue_scratch(static_cast<double*>(workspace), B, n_domains);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernMmdBwd, s); e = launch_mmd(v, gout, B, n_per_domain, n_domains, nullptr, dv, sc, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "mmd backward launch");
+    return WTPSE_OK;
+}
+
+size_t wtpse_mse_workspace_bytes(int64_t N) {
+    if (N <= 0) return 0;
+    return align_up(mse_partial_doubles(N, sm_count_cached()) * sizeof(double), 256);
+}
+
+int wtpse_mse_forward(const float* a, const float* b, int64_t N, float* loss, void* workspace, size_t workspace_bytes,
+                      wtpse_stream_t stream) {
+    if (!a || !b || !loss || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (N <= 0) return fail(WTPSE_ERR_INVALID, "empty input (N=%lld)", (long long)N);
+    if (workspace_bytes < wtpse_mse_workspace_bytes(N)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernMseFwd, s); e = launch_mse_fwd(a, b, N, loss, static_cast<double*>(workspace), sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "mse forward launch");
+    return WTPSE_OK;
+}
+
+int wtpse_mse_backward(const float* a, const float* b, const float* gout, int64_t N, float* da, float* db,
+                       wtpse_stream_t stream) {
+    if (!a || !b) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (N <= 0) return fail(WTPSE_ERR_INVALID, "empty input (N=%lld)", (long long)N);
+    if (!da && !db) return WTPSE_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernMseBwd, s); e = launch_mse_bwd(a, b, gout, N, da, db, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "mse backward launch");
+    return WTPSE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer plan
+// ---------------------------------------------------------------------------------------------
+struct wtpse_host_plan {
+    int B;
+    long long P;
+    float *z, *dz, *gram, *rowstat, *losses, *gvec;
+    void* ws;
+    size_t ws_bytes;
+    cudaStream_t stream;
+};
+
+void wtpse_host_plan_destroy(wtpse_host_plan* p) {
+    if (!p) return;
+    cudaFree(p->z); cudaFree(p->dz); cudaFree(p->gram); cudaFree(p->rowstat); cudaFree(p->losses); cudaFree(p->gvec);
+    cudaFree(p->ws);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+int wtpse_host_plan_create(int B, int64_t P, wtpse_host_plan** out) {
+    if (!out) return fail(WTPSE_ERR_INVALID, "null plan pointer");
+    if (B <= 0 || P <= 1) return fail(WTPSE_ERR_INVALID, "need B >= 1 and P >= 2");
+    wtpse_host_plan* p = new wtpse_host_plan();
+    memset(p, 0, sizeof(*p));
+    p->B = B; p->P = P;
+    const size_t nz = size_t(B) * WTPSE_CHANNELS * size_t(P) * sizeof(float);
+    p->ws_bytes = wtpse_whitening_workspace_bytes(B, P);
+    cudaError_t e = cudaSuccess;
+    if ((e = cudaMalloc(&p->z, nz)) != cudaSuccess || (e = cudaMalloc(&p->dz, nz)) != cudaSuccess ||
+        (e = cudaMalloc(&p->gram, size_t(B) * 256 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->rowstat, size_t(B) * 2 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->losses, 4 * sizeof(float))) != cudaSuccess ||
+        (e = cudaMalloc(&p->gvec, 4 * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&p->ws, p->ws_bytes)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        wtpse_host_plan_destroy(p);
+        return cuda_fail(e, "host plan allocation");
+    }
+    *out = p;
+    return WTPSE_OK;
+}
+
+int wtpse_host_plan_run(wtpse_host_plan* p, const float* z_host, int n_per_domain, int n_domains, float margin, float eps,
+                        const float grad_w[3], float losses_host[4], float* dz_host) {
+    if (!p || !z_host || !losses_host) return fail(WTPSE_ERR_INVALID, "null pointer");
+    const size_t nz = size_t(p->B) * WTPSE_CHANNELS * size_t(p->P) * sizeof(float);
+    cudaError_t e = cudaMemcpyAsync(p->z, z_host, nz, cudaMemcpyHostToDevice, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "H2D copy");
+    int rc = wtpse_whitening_forward(p->z, p->B, WTPSE_CHANNELS, p->P, n_per_domain, n_domains, margin, eps, p->losses,
+                                     p->gram, p->rowstat, p->ws, p->ws_bytes, p->stream);
+    if (rc) return rc;
+    e = cudaMemcpyAsync(losses_host, p->losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "D2H losses");
+    if (dz_host) {
+        const float g[4] = {grad_w ? grad_w[0] : 1.f, grad_w ? grad_w[1] : 1.f, grad_w ? grad_w[2] : 1.f, 0.f};
+        e = cudaMemcpyAsync(p->gvec, g, sizeof(g), cudaMemcpyHostToDevice, p->stream);   // pageable source: staged at call time
+        if (e != cudaSuccess) return cuda_fail(e, "H2D grads");
+        rc = wtpse_whitening_backward(p->z, p->gram, p->rowstat, p->gvec, p->gvec + 1, p->gvec + 2, p->B, WTPSE_CHANNELS,
+                                      p->P, n_per_domain, n_domains, margin, p->dz, p->ws, p->ws_bytes, p->stream);
+        if (rc) return rc;
+        e = cudaMemcpyAsync(dz_host, p->dz, nz, cudaMemcpyDeviceToHost, p->stream);
+        if (e != cudaSuccess) return cuda_fail(e, "D2H dz");
+    }
+    e = cudaStreamSynchronize(p->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
+    return WTPSE_OK;
+}
+
+}  // extern "C"

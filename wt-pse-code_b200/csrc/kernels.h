@@ -1,0 +1,56 @@
+// Internal launch interface between the C-ABI layer (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace wtpse {
+
+struct GramPlan {
+    bool tma;                    // 1-D TMA pipeline (P % 4 == 0, 16B-aligned base) or generic fallback
+    long long tiles_per_sample;  // persistent path only
+    long long T;                 // total tiles
+    long long G;                 // grid (CTAs)
+    int nslots;                  // partial slots per sample
+};
+
+GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
+size_t gram_partial_floats(int B, long long P, int sm_count);
+cudaError_t launch_gram(const float* z, float* partial, int B, long long P, const GramPlan& g, cudaStream_t stream);
+
+// forward epilogue: partials -> gram, rowstat, losses
+struct EpilogueScratch {
+    double* gd;     // [B][136] scaled Gram (double)
+    double* stat;   // [B][4]   off_b, diag_b, |v_b|^2, unused
+    double* E;      // [B][B]   exp(-D)
+    double* coef;   // [B][B]   backward: dL/dD_ac + dL/dD_ca
+    double* blk;    // [K*K]    per-domain-pair sums of E
+    double* vd;     // [B][120] upper-triangle vectors (double)
+};
+size_t epilogue_scratch_doubles(int B, int K);
+EpilogueScratch carve_epilogue_scratch(double* base, int B, int K);
+
+cudaError_t launch_whiten_epilogue_fwd(const float* partial, const GramPlan& g, int B, long long P, int n_per_domain,
+                                       int n_domains, float margin, float eps, float* losses, float* gram,
+                                       float* rowstat, const EpilogueScratch& s, cudaStream_t stream);
+
+// backward epilogue: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
+cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
+                                       const float* g_dom, int B, long long P, int n_per_domain, int n_domains,
+                                       float* mmat, const EpilogueScratch& s, cudaStream_t stream);
+
+// standalone compute_MMD.forward / backward on v[B][120]; dv == nullptr selects the forward
+cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,
+                       const EpilogueScratch& s, cudaStream_t stream);
+
+// backward apply: dz_b = M_b z_b
+cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
+                         cudaStream_t stream);
+
+// KD MSE
+size_t mse_partial_doubles(long long N, int sm_count);
+cudaError_t launch_mse_fwd(const float* a, const float* b, long long N, float* loss, double* partial, int sm_count,
+                           cudaStream_t stream);
+cudaError_t launch_mse_bwd(const float* a, const float* b, const float* gout, long long N, float* da, float* db,
+                           int sm_count, cudaStream_t stream);
+
+}  // namespace wtpse

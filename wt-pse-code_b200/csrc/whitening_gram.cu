@@ -1,0 +1,246 @@
+// Forward pass, stage 1: per-sample 16x16 Gram  z_b z_b^T  (the one pass over z).
+//
+// Replaces the torch.bmm of algorithms.py:1283 / shape_networks.py:567.  HBM-bound: 64 B per pixel
+// are read once; 136 FMAs per pixel (symmetric half) run on the FP32 pipes underneath.
+//
+// Design (B200, 148 SMs, one persistent CTA per SM):
+//   * the B * ceil(P/896) pixel tiles are split into contiguous ranges, one per CTA;
+//   * a producer warp streams each tile -- 16 channel rows of 896 pixels, 56 KB -- into a 3-stage
+//     shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
+//   * 7 consumer warps read one float4 (4 pixels) per channel from shared memory (conflict-free
+//     LDS.128) and keep the 136 running sums in registers;
+//   * at a sample boundary the 136 sums are reduced across the warp with a halving butterfly
+//     (153 shuffles instead of 680), across warps through shared memory, and written to a
+//     per-(sample, slot) partial.  No float atomics: the epilogue sums slots in a fixed order.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wtpse {
+
+namespace {
+
+// 7 consumer warps + 1 producer warp = 256 threads: ptxas sizes the register budget for the block
+// rounded up to 128 threads, and the 136 accumulators + 64 staged inputs need > 168 registers.
+constexpr int kConsumers = 224;
+constexpr int kConsumerWarps = kConsumers / 32;
+constexpr int kThreads = kConsumers + 32;       // + producer warp
+constexpr int kTilePx = kConsumers * 4;         // 896 pixels per tile
+constexpr int kStages = 3;
+constexpr int kStageFloats = kC * kTilePx;      // 56 KB per stage
+
+constexpr size_t kSmemBytes =
+    size_t(kStages) * kStageFloats * sizeof(float) + size_t(kConsumerWarps) * kTri * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+
+template <int HALF>
+__device__ __forceinline__ void halve(float (&a)[kTri], int lane, int mask) {
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int k = 0; k < HALF; ++k) {
+        const float keep = up ? a[k + HALF] : a[k];
+        const float send = up ? a[k] : a[k + HALF];
+        a[k] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+}
+
+// Reduce the 136 per-thread sums over the consumer threads and store them to `out[136]`.
+__device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int warp, int lane, int tid, float* out) {
+    halve<68>(acc, lane, 16);
+    halve<34>(acc, lane, 8);
+    halve<17>(acc, lane, 4);
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 2);
+        acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], 1);
+    }
+    if ((lane & 3) == 0) {
+        const int base = ((lane >> 4) & 1) * 68 + ((lane >> 3) & 1) * 34 + ((lane >> 2) & 1) * 17;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) red[warp * kTri + base + k] = acc[k];
+    }
+    named_bar_sync(1, kConsumers);
+    if (tid < kTri) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) s += red[w * kTri + tid];
+        out[tid] = s;
+    }
+    named_bar_sync(1, kConsumers);
+}
+
+__device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4 (&x)[kC]) {
+#pragma unroll
+    for (int i = 0; i < kC; ++i) {
+#pragma unroll
+        for (int j = i; j < kC; ++j) {
+            float a = acc[tri_idx(i, j)];
+            a = fmaf(x[i].x, x[j].x, a);
+            a = fmaf(x[i].y, x[j].y, a);
+            a = fmaf(x[i].z, x[j].z, a);
+            a = fmaf(x[i].w, x[j].w, a);
+            acc[tri_idx(i, j)] = a;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, long long P, long long tiles_per_sample,
+                long long T, int nslots) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_buf = reinterpret_cast<float*>(smem_raw);
+    float* red = stage_buf + size_t(kStages) * kStageFloats;
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + kConsumerWarps * kTri);
+    uint64_t* empty = full + kStages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long G = gridDim.x, k = blockIdx.x;
+    const long long t0 = part_begin(k, T, G), t1 = part_begin(k + 1, T, G);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ---------------- producer: one lane issues the bulk copies ----------------
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = t0; t < t1; ++t) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                const long long b = t / tiles_per_sample;
+                const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+                const long long rem = P - px0;
+                const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
+                const uint32_t bytes = npx * 4u;
+                mbar_arrive_expect_tx(&full[stage], bytes * kC);
+                const float* src = z + (b * kC) * P + px0;
+                float* dst = stage_buf + size_t(stage) * kStageFloats;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    float acc[kTri];
+#pragma unroll
+    for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+
+    int stage = 0;
+    uint32_t phase = 0;
+    for (long long t = t0; t < t1; ++t) {
+        const long long b = t / tiles_per_sample;
+        const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+        const long long rem = P - px0;
+        mbar_wait(&full[stage], phase);
+        if (4LL * tid < rem) {
+            const float* src = stage_buf + size_t(stage) * kStageFloats + 4 * tid;
+            float4 x[kC];
+#pragma unroll
+            for (int c = 0; c < kC; ++c) x[c] = *reinterpret_cast<const float4*>(src + c * kTilePx);
+            gram_accumulate(acc, x);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+
+        const bool segment_end = (t + 1 == t1) || ((t + 1) / tiles_per_sample != b);
+        if (segment_end) {
+            const long long slot = k - part_owner(b * tiles_per_sample, T, G);
+            flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+#pragma unroll
+            for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+        }
+    }
+}
+
+// Fallback for inputs the bulk copies cannot take (P % 4 != 0 or a base pointer that is not 16-byte
+// aligned): same arithmetic, plain coalesced scalar loads, one pixel per thread per step.
+// grid = (nslots, B); block = 256.
+__global__ void __launch_bounds__(kConsumers)
+gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, long long P, int nslots) {
+    __shared__ float red[kConsumerWarps * kTri];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long b = blockIdx.y;
+    const int slot = blockIdx.x;
+    const long long chunk = (P + nslots - 1) / nslots;
+    const long long p0 = slot * chunk;
+    const long long p1 = (p0 + chunk < P) ? p0 + chunk : P;
+    const float* zb = z + b * kC * P;
+
+    float acc[kTri];
+#pragma unroll
+    for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+    for (long long p = p0 + tid; p < p1; p += kConsumers) {
+        float x[kC];
+#pragma unroll
+        for (int c = 0; c < kC; ++c) x[c] = __ldg(zb + c * P + p);
+#pragma unroll
+        for (int i = 0; i < kC; ++i)
+#pragma unroll
+            for (int j = i; j < kC; ++j) acc[tri_idx(i, j)] = fmaf(x[i], x[j], acc[tri_idx(i, j)]);
+    }
+    flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+}
+
+}  // namespace
+
+GramPlan plan_gram(const float* z, int B, long long P, int sm_count) {
+    GramPlan g;
+    g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
+    if (g.tma) {
+        g.tiles_per_sample = (P + kTilePx - 1) / kTilePx;
+        g.T = g.tiles_per_sample * B;
+        g.G = g.T < sm_count ? g.T : sm_count;
+        int nslots = 1;
+        for (int b = 0; b < B; ++b) {
+            const long long first = part_owner((long long)b * g.tiles_per_sample, g.T, g.G);
+            const long long last = part_owner((long long)(b + 1) * g.tiles_per_sample - 1, g.T, g.G);
+            if (last - first + 1 > nslots) nslots = int(last - first + 1);
+        }
+        g.nslots = nslots;
+    } else {
+        long long want = (2LL * sm_count + B - 1) / B;           // ~2 CTAs per SM in total
+        const long long max_useful = (P + 4 * kConsumers - 1) / (4 * kConsumers);
+        if (want > max_useful) want = max_useful;
+        if (want < 1) want = 1;
+        g.nslots = int(want);
+        g.tiles_per_sample = 0;
+        g.T = 0;
+        g.G = 0;
+    }
+    return g;
+}
+
+size_t gram_partial_floats(int B, long long P, int sm_count) {
+    // upper bound over both paths: nslots <= sm_count + 1 for the persistent path and <= 2*sm_count for the generic one
+    const long long tps = (P + kTilePx - 1) / kTilePx;
+    long long T = tps * B;
+    long long G = T < sm_count ? T : sm_count;
+    long long per_cta = (T + G - 1) / G;
+    long long slots_tma = (tps + per_cta - 1) / per_cta + 1;
+    long long slots_gen = (2LL * sm_count + B - 1) / B;
+    if (slots_gen < 1) slots_gen = 1;
+    long long slots = slots_tma > slots_gen ? slots_tma : slots_gen;
+    return size_t(B) * size_t(slots) * kTri;
+}
+
+cudaError_t launch_gram(const float* z, float* partial, int B, long long P, const GramPlan& g, cudaStream_t stream) {
+    if (g.tma) {
+        cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+        if (e != cudaSuccess) return e;
+        gram_tma_kernel<<<dim3(unsigned(g.G)), kThreads, kSmemBytes, stream>>>(z, partial, P, g.tiles_per_sample, g.T, g.nslots);
+    } else {
+        gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, P, g.nslots);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace wtpse

@@ -1,0 +1,213 @@
+"""Autograd-facing host side of the C ABI: the whitening (Gram) loss and the KD MSE.
+
+PyTorch is plumbing here (device memory, current stream, autograd graph); all arithmetic runs in
+``libwtpse_b200.so``.  Tensors must be CUDA float32; anything else raises -- there is no CPU path.
+
+Reference statements replaced:
+  whitening_terms        algorithms.py:1277-1309 / shape_networks.py:561-594 (+ compute_MMD.forward)
+  kd_mse                 shape_networks.py:596-597
+"""
+import ctypes
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+
+CHANNELS = 16
+
+
+def _require_cuda_f32(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %r" % (name, type(t)))
+    if not t.is_cuda:
+        raise RuntimeError("%s must live on a CUDA device: the shape-loss path has no CPU implementation" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _scalar_alias(buf, index):
+    """0-dim tensor aliasing buf[index] without being an autograd view of it."""
+    return torch.empty(0, dtype=buf.dtype, device=buf.device).set_(buf.untyped_storage(), buf.storage_offset() + index, ())
+
+
+def _grad_ptr(g, like):
+    if g is None:
+        return None, None
+    if g.dtype != torch.float32 or not g.is_cuda:
+        g = g.to(device=like.device, dtype=torch.float32)
+    g = g.contiguous()
+    return ctypes.c_void_p(g.data_ptr()), g      # keep the tensor alive until the launch is enqueued
+
+
+class _WhiteningLoss(torch.autograd.Function):
+    """(L_off, L_diag, L_dom) or, with fold=True, (L_off + L_diag, L_dom)."""
+
+    @staticmethod
+    def forward(ctx, z, n_per_domain, n_domains, margin, eps, fold):
+        _require_cuda_f32(z, "z")
+        if z.dim() != 4:
+            raise ValueError("z must be B x C x H x W, got shape %s" % (tuple(z.shape),))
+        B, C, H, W = z.shape
+        if C != CHANNELS:
+            raise ValueError("whitening loss is defined for C == 16 feature maps (self.dim), got C == %d" % C)
+        z = z.contiguous()
+        P = H * W
+        lib = _lib.load()
+        with torch.cuda.device(z.device):
+            ws_bytes = lib.wtpse_whitening_workspace_bytes(B, P)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+            losses = torch.empty(4, dtype=torch.float32, device=z.device)
+            gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
+            rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+            _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, P, int(n_per_domain), int(n_domains), float(margin),
+                                                   float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
+                                                   _stream_ptr(z.device)))
+        ctx.save_for_backward(z, gram, rowstat)
+        ctx.cfg = (int(n_per_domain), int(n_domains), float(margin), bool(fold), ws_bytes)
+        if fold:
+            return _scalar_alias(losses, 3), _scalar_alias(losses, 2)
+        return _scalar_alias(losses, 0), _scalar_alias(losses, 1), _scalar_alias(losses, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *grads):
+        z, gram, rowstat = ctx.saved_tensors
+        n, K, margin, fold, ws_bytes = ctx.cfg
+        if fold:
+            g_ins, g_dom = grads
+            g_off, g_diag = g_ins, g_ins
+        else:
+            g_off, g_diag, g_dom = grads
+        if not ctx.needs_input_grad[0] or (g_off is None and g_diag is None and g_dom is None):
+            return None, None, None, None, None, None
+        B, C, H, W = z.shape
+        lib = _lib.load()
+        with torch.cuda.device(z.device):
+            dz = torch.empty_like(z)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+            p_off, k0 = _grad_ptr(g_off, z)
+            p_diag, k1 = _grad_ptr(g_diag, z)
+            p_dom, k2 = _grad_ptr(g_dom, z)
+            _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
+                                                    n, K, margin, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            del k0, k1, k2
+        return dz, None, None, None, None, None
+
+
+def whitening_terms(z, n_per_domain, n_domains, margin=0.0, eps=1e-5):
+    """(L_off, L_diag, L_dom): the three-value form ShapeVariationalDist_x.compute_whitening_loss returns."""
+    return _WhiteningLoss.apply(z, n_per_domain, n_domains, margin, eps, False)
+
+
+def whitening_folded(z, n_per_domain, n_domains, margin=0.0, eps=1e-5):
+    """(L_off + L_diag, L_dom): the two-value form WT_PSE.compute_whitening_loss returns (algorithms.py:1301)."""
+    return _WhiteningLoss.apply(z, n_per_domain, n_domains, margin, eps, True)
+
+
+def gram_matrix(z, eps=1e-5):
+    """f_cor of algorithms.py:1283 as a B x 16 x 16 tensor (no autograd); exposed for tests/diagnostics."""
+    _require_cuda_f32(z, "z")
+    B, C, H, W = z.shape
+    z = z.contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(z.device):
+        ws_bytes = lib.wtpse_whitening_workspace_bytes(B, H * W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+        losses = torch.empty(4, dtype=torch.float32, device=z.device)
+        gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
+        rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+        _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, H * W, 0, 0, 0.0, float(eps), _ptr(losses), _ptr(gram),
+                                               _ptr(rowstat), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+    return gram
+
+
+class _KdMse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda_f32(a, "a")
+        _require_cuda_f32(b, "b")
+        if a.shape != b.shape:
+            raise ValueError("mse inputs must have the same shape, got %s and %s" % (tuple(a.shape), tuple(b.shape)))
+        a = a.contiguous()
+        b = b.contiguous()
+        N = a.numel()
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            ws_bytes = lib.wtpse_mse_workspace_bytes(N)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=a.device)
+            loss = torch.empty((), dtype=torch.float32, device=a.device)
+            _lib.check(lib.wtpse_mse_forward(_ptr(a), _ptr(b), N, _ptr(loss), _ptr(ws), ws_bytes, _stream_ptr(a.device)))
+        ctx.save_for_backward(a, b)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        need_a, need_b = ctx.needs_input_grad
+        if gout is None or not (need_a or need_b):
+            return None, None
+        lib = _lib.load()
+        with torch.cuda.device(a.device):
+            da = torch.empty_like(a) if need_a else None
+            db = torch.empty_like(b) if need_b else None
+            p_g, keep = _grad_ptr(gout, a)
+            _lib.check(lib.wtpse_mse_backward(_ptr(a), _ptr(b), p_g, a.numel(), _ptr(da), _ptr(db), _stream_ptr(a.device)))
+            del keep
+        return da, db
+
+
+def kd_mse(a, b):
+    """nn.MSELoss(reduction='mean')(a, b) -- ShapeVariationalDist_x.wasser_distance (shape_networks.py:596-597)."""
+    return _KdMse.apply(a, b)
+
+
+class HostPlan:
+    """Plugin-facing host-buffer entry point (include/wtpse_b200.h: wtpse_host_plan_*).
+
+    Takes HOST float32 buffers (numpy arrays or CPU tensors; pinned memory makes the copies
+    asynchronous DMA), runs H2D -> forward -> backward -> D2H and returns when the host buffers are
+    complete.  This is the call bench.py times as ``e2e``."""
+
+    def __init__(self, B, H, W, device=None):
+        self.B, self.H, self.W = int(B), int(H), int(W)
+        self._lib = _lib.load()
+        self._dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wtpse_host_plan_create(self.B, self.H * self.W, ctypes.byref(self._h)))
+
+    def run(self, z_host, n_per_domain, n_domains, margin=0.0, eps=1e-5, grad_w=(1.0, 1.0, 1.0), dz_host=None):
+        if z_host.is_cuda or z_host.dtype != torch.float32 or not z_host.is_contiguous():
+            raise ValueError("z_host must be a contiguous float32 CPU tensor")
+        if tuple(z_host.shape) != (self.B, CHANNELS, self.H, self.W):
+            raise ValueError("z_host shape %s does not match the plan" % (tuple(z_host.shape),))
+        if dz_host is not None and (dz_host.is_cuda or dz_host.shape != z_host.shape or not dz_host.is_contiguous()):
+            raise ValueError("dz_host must be a contiguous CPU tensor shaped like z_host")
+        gw = (ctypes.c_float * 3)(*[float(x) for x in grad_w])
+        out = (ctypes.c_float * 4)()
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wtpse_host_plan_run(self._h, ctypes.c_void_p(z_host.data_ptr()), int(n_per_domain),
+                                                     int(n_domains), float(margin), float(eps), gw, out,
+                                                     ctypes.c_void_p(dz_host.data_ptr()) if dz_host is not None else None))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def close(self):
+        if self._h:
+            self._lib.wtpse_host_plan_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
