@@ -127,6 +127,13 @@ const char* wtpse_profile_kernel_name(int id);
 long long   wtpse_profile_launches(int id);            /* id < 0: all kernels */
 /* Sum of event-timed durations (ms) of kernel `id` since the last reset; synchronises those events. */
 int         wtpse_profile_read(int id, long long* timed_launches, double* total_ms);
+/* Diagnostics: a 16 x int64 DEVICE buffer that receives clock64() at the epilogue kernels' phase
+ * boundaries ([0..7] forward, [8..15] backward); NULL (default) disables the stamps. */
+void        wtpse_debug_set_stamp_buffer(long long* device_buffer16);
+/* Diagnostics: launch each epilogue kernel n times back to back (warm instruction cache experiment). */
+void        wtpse_debug_set_epilogue_repeat(int n);
+/* Tests: use the two-kernel backward (epilogue + apply) even where the fused kernel applies. */
+void        wtpse_debug_force_unfused_backward(int on);
 
 #ifdef __cplusplus
 }

@@ -276,6 +276,42 @@ def test_run_to_run_bit_reproducible():
         assert o[0] == outs[0][0] and o[1] == outs[0][1] and torch.equal(o[2], outs[0][2])
 
 
+def test_fused_backward_is_bitwise_the_two_kernel_backward():
+    """apply_tma_kernel<fused> derives M_b per CTA; it must reproduce epilogue_bwd + apply exactly."""
+    import wtpse_b200 as wb
+
+    lib = wb._lib.load()
+    for B, H, n in ((9, 96, 3), (32, 128, 10), (6, 32, 2)):
+        z = _synth(B, H, H, seed=B).to(_dev())
+        grads = []
+        for unfused in (0, 1):
+            lib.wtpse_debug_force_unfused_backward(unfused)
+            try:
+                zz = z.clone().requires_grad_(True)
+                off, diag, dom = wb.whitening_terms(zz, n, 3)
+                (0.7 * off + 1.9 * diag + 1.3 * dom).backward()
+                grads.append(zz.grad.clone())
+            finally:
+                lib.wtpse_debug_force_unfused_backward(0)
+        assert torch.equal(grads[0], grads[1])
+
+
+def test_many_mmd_samples_fall_back_to_the_epilogue_kernel():
+    """More than 64 samples in the MMD do not fit beside the pipeline stages: two-kernel backward."""
+    import wtpse_b200 as wb
+    from oracle import whitening_np as wnp
+
+    B, n, K = 70, 23, 3
+    z_cpu = _synth(B, 20, 20, seed=70)
+    z = z_cpu.to(_dev()).requires_grad_(True)
+    ins, dom = wb.whitening_folded(z, n, K)
+    (ins + dom).backward()
+    f = wnp.whitening_forward(z_cpu.numpy(), n, K)
+    dz, _ = wnp.whitening_backward(z_cpu.numpy(), f, n, K)
+    assert _close(float(ins), float(f["off"] + f["diag"])) and _close(float(dom), float(f["dom"]), scale=1.0)
+    assert rel_err(z.grad.cpu().numpy(), dz) < TOL
+
+
 def test_dropin_methods_on_reference_shaped_objects():
     """dropin.bind() on stand-ins carrying exactly the attributes the reference's methods read
     (self.margin, self.eps, self.mmd_operator.{batch_size,domain_num}); algorithms.py:1140-1155."""

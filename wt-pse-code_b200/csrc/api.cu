@@ -39,27 +39,33 @@ int sm_count_cached() {
     return cache[dev];
 }
 
+bool g_force_unfused_backward = false;   // diagnostics/tests: exercise the two-kernel backward
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WhitenWorkspace {
     float* partial;
+    int* slot_count;
     float* mmat;
-    double* scratch;
+    void* scratch;
     size_t total;
 };
 
-// K is not known when the workspace is sized; K*K <= B*B + 1 always holds for the domains that can be
-// non-empty, and the MMD never reads blk beyond K*K, so reserve B*B + 64 doubles for it.
+// K is not known when the workspace is sized: reserve the epilogue scratch for K*K <= B*B + 64 domain pairs
+// (check_common rejects more; only domains that can be non-empty matter).
+size_t scratch_bytes_any_k(int B) { return align_up(epilogue_scratch_bytes(B, 1) + (size_t(B) * B + 64) * sizeof(double), 256); }
+
 WhitenWorkspace carve(void* base, int B, long long P, int sms) {
     WhitenWorkspace w;
     size_t off = 0;
     const size_t partial_bytes = align_up(gram_partial_floats(B, P, sms) * sizeof(float), 256);
+    const size_t count_bytes = align_up(size_t(B) * sizeof(int), 256);
     const size_t mmat_bytes = align_up(size_t(B) * 256 * sizeof(float), 256);
-    const size_t scratch_bytes = align_up((epilogue_scratch_doubles(B, 1) + size_t(B) * B + 64) * sizeof(double), 256);
     char* p = static_cast<char*>(base);
     w.partial = reinterpret_cast<float*>(p + off); off += partial_bytes;
+    w.slot_count = reinterpret_cast<int*>(p + off); off += count_bytes;
     w.mmat = reinterpret_cast<float*>(p + off); off += mmat_bytes;
-    w.scratch = reinterpret_cast<double*>(p + off); off += scratch_bytes;
+    w.scratch = p + off; off += scratch_bytes_any_k(B);
     w.total = off;
     return w;
 }
@@ -97,10 +103,9 @@ int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_d
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const GramPlan g = plan_gram(z, B, P, sms);
     cudaError_t e;
-    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, B, P, g, s); }
+    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, w.slot_count, B, P, g, s); }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
-    const EpilogueScratch sc = carve_epilogue_scratch(w.scratch, B, n_domains);
-    { LaunchScope scope(kKernEpilogueFwd, s); e = launch_whiten_epilogue_fwd(w.partial, g, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, sc, s); }
+    { LaunchScope scope(kKernEpilogueFwd, s); e = launch_whiten_epilogue_fwd(w.partial, w.slot_count, g.nslots, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s); }
     if (e != cudaSuccess) return cuda_fail(e, "forward epilogue launch");
     return WTPSE_OK;
 }
@@ -116,18 +121,26 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
     const WhitenWorkspace w = carve(workspace, B, P, sms);
     if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const EpilogueScratch sc = carve_epilogue_scratch(w.scratch, B, n_domains);
     cudaError_t e;
-    { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, sc, s); }
-    if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
-    { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s); }
+    if (apply_can_fuse(z, dz, B, P, n_per_domain, n_domains) && !g_force_unfused_backward) {
+        LaunchScope scope(kKernApply, s);
+        e = launch_apply_fused(z, gram, rowstat, g_off, g_diag, g_dom, dz, B, P, n_per_domain, n_domains, sms, s);
+    } else {
+        { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s); }
+        if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
+        { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s); }
+    }
     if (e != cudaSuccess) return cuda_fail(e, "apply launch");
     return WTPSE_OK;
 }
 
+void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }
+void wtpse_debug_set_epilogue_repeat(int n) { g_epilogue_repeat = n > 0 ? n : 1; }
+void wtpse_debug_force_unfused_backward(int on) { g_force_unfused_backward = on != 0; }
+
 size_t wtpse_mmd_workspace_bytes(int B) {
     if (B <= 0) return 0;
-    return align_up((epilogue_scratch_doubles(B, 1) + size_t(B) * B + 64) * sizeof(double), 256);
+    return scratch_bytes_any_k(B);
 }
 
 static int check_mmd(const void* v, int B, int D, int n, int K) {
@@ -143,10 +156,9 @@ int wtpse_mmd_forward(const float* v, int B, int D, int n_per_domain, int n_doma
     if (int rc = check_mmd(v, B, D, n_per_domain, n_domains)) return rc;
     if (!loss || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
     if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
-    const EpilogueScratch sc = carve_epilogue_scratch(static_cast<double*>(workspace), B, n_domains);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    { LaunchScope scope(kKernMmdFwd, s); e = launch_mmd(v, nullptr, B, n_per_domain, n_domains, loss, nullptr, sc, s); }
+    { LaunchScope scope(kKernMmdFwd, s); e = launch_mmd(v, nullptr, B, n_per_domain, n_domains, loss, nullptr, workspace, s); }
     if (e != cudaSuccess) return cuda_fail(e, "mmd forward launch");
     return WTPSE_OK;
 }
@@ -156,10 +168,9 @@ int wtpse_mmd_backward(const float* v, const float* gout, int B, int D, int n_pe
     if (int rc = check_mmd(v, B, D, n_per_domain, n_domains)) return rc;
     if (!dv || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
     if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
-    const EpilogueScratch sc = carve_epilogue_scratch(static_cast<double*>(workspace), B, n_domains);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    { LaunchScope scope(kKernMmdBwd, s); e = launch_mmd(v, gout, B, n_per_domain, n_domains, nullptr, dv, sc, s); }
+    { LaunchScope scope(kKernMmdBwd, s); e = launch_mmd(v, gout, B, n_per_domain, n_domains, nullptr, dv, workspace, s); }
     if (e != cudaSuccess) return cuda_fail(e, "mmd backward launch");
     return WTPSE_OK;
 }

@@ -15,36 +15,37 @@ struct GramPlan {
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
 size_t gram_partial_floats(int B, long long P, int sm_count);
-cudaError_t launch_gram(const float* z, float* partial, int B, long long P, const GramPlan& g, cudaStream_t stream);
+cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                        cudaStream_t stream);
 
-// forward epilogue: partials -> gram, rowstat, losses
-struct EpilogueScratch {
-    double* gd;     // [B][136] scaled Gram (double)
-    double* stat;   // [B][4]   off_b, diag_b, |v_b|^2, unused
-    double* E;      // [B][B]   exp(-D)
-    double* coef;   // [B][B]   backward: dL/dD_ac + dL/dD_ca
-    double* blk;    // [K*K]    per-domain-pair sums of E
-    double* vd;     // [B][120] upper-triangle vectors (double)
-};
-size_t epilogue_scratch_doubles(int B, int K);
-EpilogueScratch carve_epilogue_scratch(double* base, int B, int K);
+// epilogues (single CTA).  `scratch` is the global fallback for their working set (epilogue_scratch_bytes).
+size_t epilogue_scratch_bytes(int B, int K);
+extern long long* g_epilogue_dbg;
+extern int g_epilogue_repeat;
 
-cudaError_t launch_whiten_epilogue_fwd(const float* partial, const GramPlan& g, int B, long long P, int n_per_domain,
-                                       int n_domains, float margin, float eps, float* losses, float* gram,
-                                       float* rowstat, const EpilogueScratch& s, cudaStream_t stream);
+// forward: partial slots -> gram, rowstat, losses
+cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
+                                       int n_per_domain, int n_domains, float margin, float eps, float* losses,
+                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream);
 
-// backward epilogue: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
+// backward: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
 cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
                                        const float* g_dom, int B, long long P, int n_per_domain, int n_domains,
-                                       float* mmat, const EpilogueScratch& s, cudaStream_t stream);
+                                       float* mmat, void* scratch, cudaStream_t stream);
 
 // standalone compute_MMD.forward / backward on v[B][120]; dv == nullptr selects the forward
 cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,
-                       const EpilogueScratch& s, cudaStream_t stream);
+                       void* scratch, cudaStream_t stream);
 
 // backward apply: dz_b = M_b z_b
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
                          cudaStream_t stream);
+
+// fused backward: every CTA derives M_b for its own samples (no separate epilogue launch)
+bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains);
+cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,
+                               const float* g_diag, const float* g_dom, float* dz, int B, long long P, int n_per_domain,
+                               int n_domains, int sm_count, cudaStream_t stream);
 
 // KD MSE
 size_t mse_partial_doubles(long long N, int sm_count);

@@ -1,4 +1,5 @@
-// Backward stage 2: dz_b = M_b z_b, the adjoint of the Gram, fused with the gradient write.
+// Backward: dz_b = M_b z_b, the adjoint of the Gram, fused with the gradient write -- and, in the
+// fused variant, with the derivation of M_b itself.
 //
 // What autograd derives from the bmm of algorithms.py:1283 (two more passes over z in the reference:
 // grad @ z and grad^T @ z) collapses to ONE 16x16 symmetric matrix per sample applied to every pixel:
@@ -7,8 +8,15 @@
 // Same persistent layout as the forward Gram kernel: contiguous tile ranges per CTA, a producer warp
 // feeding a 3-stage shared-memory ring with 1-D TMA bulk copies, 8 consumer warps with 4 pixels per
 // thread.  M_b (1 KB) sits in shared memory and is read with warp-uniform LDS.128 (broadcast).
+//
+// Fused variant (kFused): instead of a separate single-CTA "backward epilogue" launch that serialises
+// all samples on one SM (~20 us measured), every CTA derives M_b for the one or two samples it owns
+// from the saved Gram: the 120-d vectors of the MMD samples are staged once per CTA (<= 32 KB), then per
+// sample one distance row, one coefficient row and 136 matrix entries (~1 us, overlapped with the
+// producer's first TMA loads).  Same arithmetic as whiten_epilogue_bwd_kernel (mmd_device.cuh).
 #include "common.cuh"
 #include "kernels.h"
+#include "mmd_device.cuh"
 
 namespace wtpse {
 
@@ -20,20 +28,34 @@ constexpr int kThreads = kConsumers + 32;
 constexpr int kTilePx = kConsumers * 4;
 constexpr int kStages = 3;
 constexpr int kStageFloats = kC * kTilePx;
-constexpr size_t kSmemBytes = size_t(kStages) * kStageFloats * sizeof(float) + 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+constexpr int kFusedMaxM = 64;     // MMD samples whose vectors fit beside the pipeline stages
+constexpr size_t kSmemPipe = size_t(kStages) * kStageFloats * sizeof(float);
+constexpr size_t kSmemPlain = kSmemPipe + 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+constexpr size_t kSmemFused = kSmemPlain + (size_t(kFusedMaxM) * kVStride + kFusedMaxM) * sizeof(float) + sizeof(IndexTables) + 16;
 
 __device__ __forceinline__ void st_stream(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+struct FusedArgs {
+    const float* gram;      // [B][16][16]
+    const float* rowstat;   // [B][2]
+    const float *g_off, *g_diag, *g_dom;
+    int B, n, K;
+};
+
+template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
 apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, float* __restrict__ dz, long long P,
-                 long long tiles_per_sample, long long T) {
+                 long long tiles_per_sample, long long T, FusedArgs fa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* msh = stage_buf + size_t(kStages) * kStageFloats;
     uint64_t* full = reinterpret_cast<uint64_t*>(msh + 256);
     uint64_t* empty = full + kStages;
+    float* vbuf = reinterpret_cast<float*>(empty + kStages);          // [kFusedMaxM][124]   (fused only)
+    float* coefrow = vbuf + size_t(kFusedMaxM) * kVStride;            // [kFusedMaxM]
+    IndexTables* tab = reinterpret_cast<IndexTables*>(coefrow + kFusedMaxM);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
@@ -71,6 +93,30 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
         return;
     }
 
+    // ---- fused prologue: everything that does not depend on the sample ------------------------------
+    DomainInfo dom{0, 0, 0, 0};
+    float g_dom = 0.f, w_off = 0.f, w_diag = 0.f;
+    bool need_dom = false;
+    const float denom = float(P - 1);
+    if (kFused) {
+        dom = make_domain(fa.B, fa.n, fa.K);
+        const float g_off = fa.g_off ? __ldg(fa.g_off) : 0.f;
+        const float g_diag = fa.g_diag ? __ldg(fa.g_diag) : 0.f;
+        g_dom = fa.g_dom ? __ldg(fa.g_dom) : 0.f;
+        need_dom = (dom.M > 0) && (g_dom != 0.f);
+        w_off = g_off / (float(fa.B) * float(kOff));
+        w_diag = g_diag / (float(fa.B) * float(kC));
+        build_index_tables(*tab, tid, kConsumers);
+        named_bar_sync(1, kConsumers);
+        if (need_dom) {
+            for (int idx = tid; idx < dom.M * kOff; idx += kConsumers) {
+                const int b = idx / kOff, o = idx - b * kOff;
+                const int ij = tab->off[o];
+                vbuf[size_t(b) * kVStride + o] = __ldg(fa.gram + b * 256 + (ij >> 4) * kC + (ij & 15));
+            }
+        }
+    }
+
     int stage = 0;
     uint32_t phase = 0;
     long long cur_b = -1;
@@ -79,8 +125,30 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
         const long long px0 = (t - b * tiles_per_sample) * kTilePx;
         const long long rem = P - px0;
         if (b != cur_b) {
-            named_bar_sync(1, kConsumers);          // everyone is done with the previous sample's matrix
-            msh[tid] = __ldg(mmat + b * 256 + tid);
+            named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use; vbuf staged
+            if (kFused) {
+                const int bi = int(b);
+                const bool in_mmd = need_dom && bi < dom.M;
+                if (in_mmd) {
+                    for (int c = tid; c < dom.M; c += kConsumers) {
+                        const float D = mmd_distance(vbuf + size_t(bi) * kVStride, vbuf + size_t(c) * kVStride);
+                        coefrow[c] = mmd_coefficient(dom, bi, c, expf(-D));
+                    }
+                    named_bar_sync(1, kConsumers);
+                }
+                if (tid < kTri) {
+                    const int ij = tab->tri[tid], i = ij >> 4, j = ij & 15;
+                    const float g = __ldg(fa.gram + bi * 256 + i * kC + j);
+                    float dom_grad = 0.f;
+                    if (in_mmd && i != j) dom_grad = g_dom * mmd_grad_entry(vbuf, coefrow, dom.M, bi, off_idx(i, j));
+                    const float m = backward_matrix_entry(i, j, g, __ldg(fa.rowstat + bi * 2 + 0),
+                                                          __ldg(fa.rowstat + bi * 2 + 1), w_off, w_diag, dom_grad, denom);
+                    msh[i * kC + j] = m;
+                    msh[j * kC + i] = m;
+                }
+            } else {
+                msh[tid] = __ldg(mmat + b * 256 + tid);
+            }
             named_bar_sync(1, kConsumers);
             cur_b = b;
         }
@@ -145,22 +213,43 @@ apply_generic_kernel(const float* __restrict__ z, const float* __restrict__ mmat
     }
 }
 
+bool tma_ok(const float* z, const float* dz, long long P) {
+    return (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(dz) & 15u) == 0);
+}
+
 }  // namespace
+
+bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains) {
+    long long m = n_domains > 1 ? (long long)n_per_domain * n_domains : 0;
+    if (m > B) m = B;
+    return tma_ok(z, dz, P) && m <= kFusedMaxM;
+}
 
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
                          cudaStream_t stream) {
-    const bool tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(dz) & 15u) == 0);
-    if (tma) {
-        cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+    if (tma_ok(z, dz, P)) {
+        cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemPlain));
         if (e != cudaSuccess) return e;
         const long long tps = (P + kTilePx - 1) / kTilePx;
         const long long T = tps * B;
         const long long G = T < sm_count ? T : sm_count;
-        apply_tma_kernel<<<dim3(unsigned(G)), kThreads, kSmemBytes, stream>>>(z, mmat, dz, P, tps, T);
+        apply_tma_kernel<false><<<dim3(unsigned(G)), kThreads, kSmemPlain, stream>>>(z, mmat, dz, P, tps, T, FusedArgs{});
     } else {
         apply_generic_kernel<<<dim3(unsigned((P + 255) / 256), unsigned(B)), 256, 0, stream>>>(z, mmat, dz, P);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,
+                               const float* g_diag, const float* g_dom, float* dz, int B, long long P, int n_per_domain,
+                               int n_domains, int sm_count, cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemFused));
+    if (e != cudaSuccess) return e;
+    const long long tps = (P + kTilePx - 1) / kTilePx;
+    const long long T = tps * B;
+    const long long G = T < sm_count ? T : sm_count;
+    FusedArgs fa{gram, rowstat, g_off, g_diag, g_dom, B, n_per_domain, n_domains};
+    apply_tma_kernel<true><<<dim3(unsigned(G)), kThreads, kSmemFused, stream>>>(z, nullptr, dz, P, tps, T, fa);
     return cudaGetLastError();
 }
 

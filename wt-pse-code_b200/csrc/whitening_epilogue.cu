@@ -7,86 +7,101 @@
 // Backward: upstream grads + saved Gram -> per-sample symmetric 16x16
 //   coefficient matrix M_b = (S_b + S_b^T)/(P-1) that the apply kernel multiplies into z.
 //
-// The work is O(B*136*slots + B^2*120): microseconds.  It runs as ONE CTA so that every reduction
-// has a fixed order (bit-reproducible run to run, no float atomics) and is evaluated in float64,
-// which keeps the MMD's Kxx + Kyy - 2Kxy cancellation closer to the
-// reference's own float64 result than the reference's float32 path is.
+// The work is O(B*136*slots + B^2*120) -- microseconds -- so these kernels are latency-bound and are
+// built around that (measured with the clock64 stamps below, tools/epilogue_phases.py):
+//   * ONE CTA, fixed reduction orders: bit-reproducible, no float atomics, no grid sync;
+//   * float32 arithmetic like the reference.  B200's FP64 pipe issues ~1 warp instruction per 3
+//     cycles with ~50-cycle dependent latency; a first float64 version of this file spent 25 us per
+//     launch in it.  Accuracy is kept where the MMD needs it by two reformulations instead:
+//       - distances use the difference form sum_e (v_a - v_c)^2, not |x|^2 + |y|^2 - 2x.y
+//         (algorithms.py:65-71), so there is no cancellation in D;
+//       - the kernel value is carried as u = expm1(-D) = E - 1.  Kxx + Kyy - 2Kxy is invariant under
+//         E -> E - 1, so the O(1) parts cancel analytically and the result keeps full relative
+//         precision even when the domains are statistically identical (SURVEY.md section 7's
+//         3.8e-3 fp32-vs-fp64 gap of the reference does not arise).  Only the handful of final
+//         block sums run in float64.
+//   * one warp per sample reduces that sample's slots straight into registers and emits the Gram,
+//     the 120-d vector (shared memory) and off_b / diag_b with one shuffle reduction;
+//   * pairwise distances: one LANE per (a, c) pair, two rows a per warp, LDS.128 on rows padded to
+//     124 floats (conflict-free), so there is no shuffle chain per pair.
 #include <math.h>
 
 #include "common.cuh"
 #include "kernels.h"
+#include "mmd_device.cuh"
 
 namespace wtpse {
 
 namespace {
 
+#define WTPSE_STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[k] = clock64(); } while (0)
+
 constexpr int kEpiThreads = 1024;
 constexpr int kEpiWarps = kEpiThreads / 32;
 constexpr size_t kEpiSmemCap = 200 * 1024;
-
-__device__ __forceinline__ void tri_decode(int e, int& i, int& j) {
-    int r = 0, len = kC;
-    while (e >= len) { e -= len; --len; ++r; }
-    i = r;
-    j = r + e;
-}
-// index of (i,j), i<j, in torch.triu_indices(16,16,1) order (algorithms.py:1305)
-__device__ __forceinline__ int off_idx(int i, int j) { return tri_idx(i, j) - (i + 1); }
-
-// torch.clamp(x, min=0): NaN propagates
-__device__ __forceinline__ double clamp0(double x) { return (x < 0.0) ? 0.0 : x; }
-// clamp_min_(1e-30): NaN propagates
-__device__ __forceinline__ double clamp_tiny(double x) { return (x < 1e-30) ? 1e-30 : x; }
-
-__device__ __forceinline__ int chunk_lo(int k, int n, int B) {
-    const long long v = (long long)n * k;
-    return int(v < B ? v : B);
-}
-
-// features[k] = inputs[n*k : n*(k+1)] with python slice truncation (algorithms.py:107)
-struct DomainInfo {
-    int M;  // samples that enter the MMD: min(B, K*n), 0 when K <= 1
-    int K, n, B;
-    __device__ int domain_of(int a) const { return n > 0 ? a / n : 0; }
-    __device__ int size(int k) const { return chunk_lo(k + 1, n, B) - chunk_lo(k, n, B); }
+// Working set: v [M][124] f32 | U [M][M] f32 | stat [B][2] f32 | blk [K*K] f64 ; shared memory when it fits.
+struct EpiMem {
+    float* v;
+    float* U;
+    float* stat;
+    double* blk;
 };
 
-__device__ __forceinline__ DomainInfo make_domain(int B, int n, int K) {
-    DomainInfo dom{0, K, n, B};
-    const long long m = (long long)K * n;
-    dom.M = K > 1 ? int(m < B ? m : B) : 0;
-    return dom;
+__host__ __device__ inline size_t round4(size_t x) { return (x + 3) & ~size_t(3); }
+__host__ __device__ inline size_t epi_mem_bytes(int B, int M, int K) {
+    const size_t kk = size_t(K > 0 ? K : 1) * size_t(K > 0 ? K : 1);
+    return (round4(size_t(M) * kVStride) + round4(size_t(M) * M) + round4(size_t(B) * 2)) * sizeof(float) + kk * sizeof(double);
 }
 
-// E[a][c] = exp(-max(|v_a - v_c|^2, 1e-30)) for a,c < M ; v has row stride 120 (shared or global)
-__device__ void pairwise_kernel(const double* __restrict__ v, double* __restrict__ E, int M, int warp, int lane) {
-    for (int a = warp; a < M; a += kEpiWarps) {
-        double va[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int e = lane + 32 * q;
-            va[q] = e < kOff ? v[a * kOff + e] : 0.0;
-        }
-        for (int c = a; c < M; ++c) {
-            double d = 0.0;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int e = lane + 32 * q;
-                const double diff = e < kOff ? va[q] - v[c * kOff + e] : 0.0;
-                d = fma(diff, diff, d);
-            }
-            d = warp_sum(d);
-            if (lane == 0) {
-                const double val = exp(-clamp_tiny(d));
-                E[a * M + c] = val;
-                E[c * M + a] = val;
+// kSmem is a template parameter so that the compiler sees shared-space pointers (LDS/STS) instead of
+// generic ones: generic accesses to shared memory go through the address-divergence unit and made
+// every phase of these kernels ~5x slower.
+template <bool kSmem>
+__device__ __forceinline__ EpiMem resolve_mem(void* smem, void* global, int B, int M) {
+    float* base = reinterpret_cast<float*>(kSmem ? smem : global);
+    EpiMem m;
+    m.v = base;
+    m.U = m.v + round4(size_t(M) * kVStride);
+    m.stat = m.U + round4(size_t(M) * M);
+    m.blk = reinterpret_cast<double*>(m.stat + round4(size_t(B) * 2));    // 16-byte aligned by construction
+    return m;
+}
+
+// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all a, c < M: one lane per pair, two rows per warp.
+template <typename F>
+__device__ __forceinline__ void pairwise_rows(const float* __restrict__ v, int M, int warp, int lane, F&& emit) {
+    for (int a0 = 2 * warp; a0 < M; a0 += 2 * kEpiWarps) {
+        const int a1 = (a0 + 1 < M) ? a0 + 1 : a0;
+        const float4* va0 = reinterpret_cast<const float4*>(v + size_t(a0) * kVStride);
+        const float4* va1 = reinterpret_cast<const float4*>(v + size_t(a1) * kVStride);
+        for (int c0 = 0; c0 < M; c0 += 32) {
+            const int c = c0 + lane;
+            if (c < M) {
+                const float4* vc = reinterpret_cast<const float4*>(v + size_t(c) * kVStride);
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll 5
+                for (int e = 0; e < kOff / 4; ++e) {
+                    const float4 y = vc[e], x0 = va0[e], x1 = va1[e];
+                    float d;
+                    d = x0.x - y.x; p0 = fmaf(d, d, p0);
+                    d = x0.y - y.y; p1 = fmaf(d, d, p1);
+                    d = x0.z - y.z; p2 = fmaf(d, d, p2);
+                    d = x0.w - y.w; p3 = fmaf(d, d, p3);
+                    d = x1.x - y.x; q0 = fmaf(d, d, q0);
+                    d = x1.y - y.y; q1 = fmaf(d, d, q1);
+                    d = x1.z - y.z; q2 = fmaf(d, d, q2);
+                    d = x1.w - y.w; q3 = fmaf(d, d, q3);
+                }
+                emit(a0, c, clamp_tiny((p0 + p1) + (p2 + p3)));
+                if (a1 != a0) emit(a1, c, clamp_tiny((q0 + q1) + (q2 + q3)));
             }
         }
     }
 }
 
-// per-domain-pair sums of E, one warp per (k <= l) block, fixed lane-strided order
-__device__ void domain_block_sums(const double* __restrict__ E, const DomainInfo& dom, double* __restrict__ blk,
+// per-domain-pair sums of u = E - 1: one warp per (k <= l) block, fp32 lane partials in a fixed order,
+// float64 across lanes
+__device__ void domain_block_sums(const float* __restrict__ U, const DomainInfo& dom, double* __restrict__ blk,
                                   int first_warp, int nwarps, int warp, int lane) {
     const int K = dom.K;
     for (int pr = warp - first_warp; pr < K * K; pr += nwarps) {
@@ -95,68 +110,40 @@ __device__ void domain_block_sums(const double* __restrict__ E, const DomainInfo
         const int a0 = chunk_lo(k, dom.n, dom.B), a1 = chunk_lo(k + 1, dom.n, dom.B);
         const int c0 = chunk_lo(l, dom.n, dom.B), c1 = chunk_lo(l + 1, dom.n, dom.B);
         const int na = a1 - a0, nc = c1 - c0;
-        double s = 0.0;
+        float s = 0.f;
         for (int q = lane; q < na * nc; q += 32) {
             const int a = a0 + q / nc, c = c0 + q % nc;
-            s += E[a * dom.M + c];
+            s += U[a * dom.M + c];
         }
-        s = warp_sum(s);
-        if (lane == 0) blk[k * K + l] = s;
+        const double t = warp_sum(double(s));
+        if (lane == 0) blk[k * K + l] = t;
     }
 }
 
-// L_dom = sum_{k<l} (Kxx + Kyy - 2Kxy) / (K(K-1)/2)      algorithms.py:110-116, :82-88
-__device__ double mmd_from_blocks(const double* __restrict__ blk, const DomainInfo& dom) {
-    double pen = 0.0;
+// L_dom = sum_{k<l} (Kxx + Kyy - 2Kxy) / (K(K-1)/2)   (algorithms.py:110-116, :82-88) from the u block sums;
+// executed by one warp, one lane per domain pair.  An empty chunk gives 0 * inf = NaN, as torch's
+// mean() over an empty tensor does.
+__device__ float mmd_from_blocks(const double* __restrict__ blk, const DomainInfo& dom, int lane) {
     const int K = dom.K;
-    if (K > 1) {
-        for (int k = 0; k < K; ++k)
-            for (int l = k + 1; l < K; ++l) {
-                const int sk = dom.size(k), sl = dom.size(l);
-                const double nk = double(sk), nl = double(sl);
-                // empty chunk: 0/0 = NaN, as torch's mean() over an empty tensor
-                const double kxx = (sk > 0 ? blk[k * K + k] : 0.0) / (nk * nk);
-                const double kyy = (sl > 0 ? blk[l * K + l] : 0.0) / (nl * nl);
-                const double kxy = ((sk > 0 && sl > 0) ? blk[k * K + l] : 0.0) / (nk * nl);
-                pen += kxx + kyy - 2.0 * kxy;
-            }
-        pen /= double(K) * double(K - 1) / 2.0;
-    }
-    return pen;
-}
-
-// coef_ac = dL/dD_ac + dL/dD_ca  (zero on the diagonal, where clamp_min_(1e-30) is active)
-__device__ void mmd_coefficients(const double* __restrict__ E, const DomainInfo& dom, double* __restrict__ coef, int tid) {
-    const int M = dom.M;
-    const double npairs = double(dom.K) * double(dom.K - 1) / 2.0;
-    for (int idx = tid; idx < M * M; idx += kEpiThreads) {
-        const int a = idx / M, c = idx - a * M;
-        const int ka = dom.domain_of(a), kc = dom.domain_of(c);
-        double w;
-        if (ka == kc) {
-            const double nk = double(dom.size(ka));
-            w = -2.0 * double(dom.K - 1) / (nk * nk);
-        } else {
-            w = 2.0 / (double(dom.size(ka)) * double(dom.size(kc)));
-        }
-        coef[idx] = (a == c) ? 0.0 : E[idx] * w / npairs;
-    }
-}
-
-// d L_dom / d v_b[o] = 2 * sum_c coef_bc (v_b[o] - v_c[o])
-__device__ __forceinline__ double mmd_grad_entry(const double* __restrict__ v, const double* __restrict__ coef, int M,
-                                                 int b, int o) {
-    const double vb = v[b * kOff + o];
+    if (K <= 1) return 0.f;
+    const int npairs = K * (K - 1) / 2;
     double acc = 0.0;
-    for (int c = 0; c < M; ++c) acc = fma(coef[b * M + c], vb - v[c * kOff + o], acc);
-    return 2.0 * acc;
+    for (int pidx = lane; pidx < npairs; pidx += 32) {
+        int k = 0, r = pidx;
+        while (r >= K - 1 - k) { r -= K - 1 - k; ++k; }
+        const int l = k + 1 + r;
+        const float nk = float(dom.size(k)), nl = float(dom.size(l));
+        const double rkk = double(1.0f / (nk * nk)), rll = double(1.0f / (nl * nl)), rkl = double(1.0f / (nk * nl));
+        acc += blk[k * K + k] * rkk + blk[l * K + l] * rll - 2.0 * (blk[k * K + l] * rkl);
+    }
+    acc = warp_sum(acc);
+    return float(acc) / float(npairs);
 }
 
 // ------------------------------------------------------------------------------------------------
 struct FwdParams {
     const float* partial;
-    int tma;
-    long long tps, T, G;
+    const int* slot_count;   // [B] written by the Gram kernel
     int nslots;
     int B;
     long long P;
@@ -165,90 +152,92 @@ struct FwdParams {
     float* losses;
     float* gram;
     float* rowstat;
-    double *gd, *stat, *E, *blk, *vd;
-    int v_in_smem;
+    void* scratch;      // global fallback for EpiMem
+    int in_smem;
+    long long* dbg;     // optional phase timestamps (tools/epilogue_phases.py); nullptr in production
 };
 
+template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(FwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* vs = reinterpret_cast<double*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.B;
     const DomainInfo dom = make_domain(B, p.n, p.K);
-    const double inv = 1.0 / double(p.P - 1);
-
-    // 1. slots -> scaled Gram (+eps on the diagonal)
-    for (int idx = tid; idx < B * kTri; idx += kEpiThreads) {
-        const int b = idx / kTri, e = idx - b * kTri;
-        int cnt = p.nslots;
-        if (p.tma) {
-            const long long first = part_owner((long long)b * p.tps, p.T, p.G);
-            const long long last = part_owner((long long)(b + 1) * p.tps - 1, p.T, p.G);
-            cnt = int(last - first + 1);
-        }
-        double s = 0.0;
-        const float* src = p.partial + ((long long)b * p.nslots) * kTri + e;
-        for (int sl = 0; sl < cnt; ++sl) s += double(src[(long long)sl * kTri]);
-        int i, j;
-        tri_decode(e, i, j);
-        s *= inv;
-        if (i == j) s += double(p.eps);
-        p.gd[idx] = s;
-        p.gram[b * 256 + i * kC + j] = float(s);
-        p.gram[b * 256 + j * kC + i] = float(s);
-        if (i != j) {
-            p.vd[b * kOff + off_idx(i, j)] = s;
-            if (p.v_in_smem && b < dom.M) vs[b * kOff + off_idx(i, j)] = s;
-        }
-    }
+    const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, B, dom.M);
+    const float denom = float(p.P - 1);
+    __shared__ IndexTables tab;
+    build_index_tables(tab, tid, kEpiThreads);
     __syncthreads();
+    WTPSE_STAMP(0);
 
-    // 2. per-sample sums (one warp per sample)
+    // A. one warp per sample: slots -> Gram entries -> gram, v, off_b, diag_b
     for (int b = warp; b < B; b += kEpiWarps) {
-        double off = 0.0, dg = 0.0;
+        const int cnt = __ldg(p.slot_count + b);
+        const float* src = p.partial + ((long long)b * p.nslots) * kTri;
+        float off = 0.f, dg = 0.f;
         for (int e = lane; e < kTri; e += 32) {
-            int i, j;
-            tri_decode(e, i, j);
-            const double g = p.gd[b * kTri + e];
-            if (i == j) dg += fabs(g - 1.0);
-            else off += fabs(g);
+            float s = 0.f;
+            for (int sl = 0; sl < cnt; ++sl) s += __ldg(src + (long long)sl * kTri + e);
+            const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
+            s = s / denom;                                   // .div(HW - 1), algorithms.py:1283
+            if (i == j) {
+                s += p.eps;                                  // + eps * eye
+                dg += fabsf(s - 1.0f);                       // |f_cor_masked_diag - I|, :1297
+                p.gram[b * 256 + i * kC + i] = s;
+            } else {
+                off += fabsf(s);                             // |f_cor_masked|, :1289
+                p.gram[b * 256 + i * kC + j] = s;
+                p.gram[b * 256 + j * kC + i] = s;
+                if (b < dom.M) mem.v[size_t(b) * kVStride + off_idx(i, j)] = s;
+            }
         }
-        off = warp_sum(off);
-        dg = warp_sum(dg);
+        off = warp_sum(off) - p.margin;
+        dg = warp_sum(dg) - p.margin;
         if (lane == 0) {
-            off -= double(p.margin);
-            dg -= double(p.margin);
-            p.stat[b * 4 + 0] = off;
-            p.stat[b * 4 + 1] = dg;
-            p.rowstat[b * 2 + 0] = float(off);
-            p.rowstat[b * 2 + 1] = float(dg);
+            mem.stat[b * 2 + 0] = off;
+            mem.stat[b * 2 + 1] = dg;
+            p.rowstat[b * 2 + 0] = off;
+            p.rowstat[b * 2 + 1] = dg;
         }
     }
-    // 3. pairwise gaussian kernel values (independent of step 2)
-    pairwise_kernel(p.v_in_smem ? vs : p.vd, p.E, dom.M, warp, lane);
     __syncthreads();
+    WTPSE_STAMP(1);
 
-    // 4. instance terms (warp 0), per-domain-pair block sums of E (warps 1..)
+    // B. pairwise u = exp(-D) - 1
+    {
+        float* U = mem.U;
+        const int M = dom.M;
+        pairwise_rows(mem.v, M, warp, lane, [U, M](int a, int c, float D) { U[a * M + c] = expm1f(-D); });
+    }
+    __syncthreads();
+    WTPSE_STAMP(2);
+
+    // C. instance terms (warp 0), per-domain-pair block sums (warps 1..)
     if (warp == 0) {
-        double so = 0.0, sd = 0.0;
+        float so = 0.f, sd = 0.f;
         for (int b = lane; b < B; b += 32) {
-            so += clamp0(p.stat[b * 4 + 0] / double(kOff));
-            sd += clamp0(p.stat[b * 4 + 1] / double(kC));
+            so += clamp0(mem.stat[b * 2 + 0] / float(kOff));   // clamp(off_diag_sum / 120, min=0), :1290
+            sd += clamp0(mem.stat[b * 2 + 1] / float(kC));     // clamp(diag_sum / 16, min=0), :1298
         }
-        so = warp_sum(so) / double(B);
-        sd = warp_sum(sd) / double(B);
+        so = warp_sum(so) / float(B);
+        sd = warp_sum(sd) / float(B);
         if (lane == 0) {
-            p.losses[0] = float(so);
-            p.losses[1] = float(sd);
-            p.losses[3] = float(so + sd);
+            p.losses[0] = so;
+            p.losses[1] = sd;
+            p.losses[3] = so + sd;
         }
     } else if (dom.M > 0) {
-        domain_block_sums(p.E, dom, p.blk, 1, kEpiWarps - 1, warp, lane);
+        domain_block_sums(mem.U, dom, mem.blk, 1, kEpiWarps - 1, warp, lane);
     }
     __syncthreads();
+    WTPSE_STAMP(3);
 
-    // 5. L_dom
-    if (tid == 0) p.losses[2] = float(mmd_from_blocks(p.blk, dom));
+    // D. L_dom
+    if (warp == 0) {
+        const float pen = mmd_from_blocks(mem.blk, dom, lane);
+        if (lane == 0) p.losses[2] = pen;
+    }
+    WTPSE_STAMP(4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -260,60 +249,62 @@ struct BwdParams {
     long long P;
     int n, K;
     float* mmat;
-    double *E, *vd, *coef;
-    int v_in_smem;
+    void* scratch;
+    int in_smem;
+    long long* dbg;
 };
 
+template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(BwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.B;
     const DomainInfo dom = make_domain(B, p.n, p.K);
     const int M = dom.M;
-    const double g_off = p.g_off ? double(*p.g_off) : 0.0;
-    const double g_diag = p.g_diag ? double(*p.g_diag) : 0.0;
-    const double g_dom = p.g_dom ? double(*p.g_dom) : 0.0;
-    double* v = p.v_in_smem ? reinterpret_cast<double*>(smem_raw) : p.vd;
+    const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, B, M);
+    const float g_off = p.g_off ? __ldg(p.g_off) : 0.f;
+    const float g_diag = p.g_diag ? __ldg(p.g_diag) : 0.f;
+    const float g_dom = p.g_dom ? __ldg(p.g_dom) : 0.f;
+    const bool need_dom = (M > 0) && (g_dom != 0.f);      // block-uniform
+    __shared__ IndexTables tab;
+    build_index_tables(tab, tid, kEpiThreads);
+    __syncthreads();
+    WTPSE_STAMP(0);
 
-    // 1. upper-triangle vectors of the samples that enter the MMD
-    for (int idx = tid; idx < M * kOff; idx += kEpiThreads) {
-        const int b = idx / kOff, e = idx - b * kOff;
-        int i = 0, r = e, len = kC - 1;
-        while (r >= len) { r -= len; --len; ++i; }
-        const int j = i + 1 + r;
-        v[idx] = double(p.gram[b * 256 + i * kC + j]);
+    if (need_dom) {
+        // 1. upper-triangle vectors of the samples that enter the MMD
+        for (int idx = tid; idx < M * kOff; idx += kEpiThreads) {
+            const int b = idx / kOff, o = idx - b * kOff;
+            const int ij = tab.off[o];
+            mem.v[size_t(b) * kVStride + o] = __ldg(p.gram + b * 256 + (ij >> 4) * kC + (ij & 15));
+        }
+        __syncthreads();
+        WTPSE_STAMP(1);
+        // 2. symmetric coefficient matrix (stored in U's place)
+        float* coef = mem.U;
+        pairwise_rows(mem.v, M, warp, lane,
+                      [coef, M, &dom](int a, int c, float D) { coef[a * M + c] = mmd_coefficient(dom, a, c, expf(-D)); });
+        __syncthreads();
     }
-    __syncthreads();
-    // 2. E, then the symmetric coefficient matrix
-    pairwise_kernel(v, p.E, M, warp, lane);
-    __syncthreads();
-    if (M > 0) mmd_coefficients(p.E, dom, p.coef, tid);
-    __syncthreads();
+    WTPSE_STAMP(2);
 
-    // 3. M_b[i][j]
-    const double inv = 1.0 / double(p.P - 1);
+    // 3. M_b[i][j] = (S_b + S_b^T)[i][j] / (P - 1)
+    const float denom = float(p.P - 1);
+    const float w_off = g_off / (float(B) * float(kOff));
+    const float w_diag = g_diag / (float(B) * float(kC));
     for (int idx = tid; idx < B * kTri; idx += kEpiThreads) {
         const int b = idx / kTri, e = idx - b * kTri;
-        int i, j;
-        tri_decode(e, i, j);
-        const float g = p.gram[b * 256 + i * kC + j];
-        double s;
-        if (i == j) {
-            const float d = g - 1.0f;   // f_cor_masked_diag - diagonal_matrix in fp32, algorithms.py:1297
-            const double sgn = (d > 0.f) ? 1.0 : ((d < 0.f) ? -1.0 : 0.0);
-            const bool act = (p.rowstat[b * 2 + 1] / float(kC)) >= 0.f;     // clamp(min=0) passes grad at x >= 0
-            s = act ? g_diag * sgn / (double(B) * double(kC)) : 0.0;
-            p.mmat[b * 256 + i * kC + i] = float(2.0 * s * inv);
-        } else {
-            const double sgn = (g > 0.f) ? 1.0 : ((g < 0.f) ? -1.0 : 0.0);
-            const bool act = (p.rowstat[b * 2 + 0] / float(kOff)) >= 0.f;
-            s = act ? g_off * sgn / (double(B) * double(kOff)) : 0.0;
-            if (b < M && g_dom != 0.0) s += g_dom * mmd_grad_entry(v, p.coef, M, b, off_idx(i, j));
-            const float m = float(s * inv);
-            p.mmat[b * 256 + i * kC + j] = m;
-            p.mmat[b * 256 + j * kC + i] = m;
-        }
+        const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
+        const float g = __ldg(p.gram + b * 256 + i * kC + j);
+        float dom_grad = 0.f;
+        if (need_dom && b < M && i != j) dom_grad = g_dom * mmd_grad_entry(mem.v, mem.U + size_t(b) * M, M, b, off_idx(i, j));
+        const float m = backward_matrix_entry(i, j, g, __ldg(p.rowstat + b * 2 + 0), __ldg(p.rowstat + b * 2 + 1), w_off,
+                                              w_diag, dom_grad, denom);
+        p.mmat[b * 256 + i * kC + j] = m;
+        p.mmat[b * 256 + j * kC + i] = m;
     }
+    __syncthreads();
+    WTPSE_STAMP(3);
 }
 
 // ---- standalone compute_MMD.forward on a B x 120 input (algorithms.py:102-121) -------------------
@@ -323,44 +314,54 @@ struct MmdParams {
     int B, n, K;
     float* loss;
     float* dv;
-    double *vd, *E, *coef, *blk;
-    int v_in_smem;
+    void* scratch;
+    int in_smem;
 };
 
-__device__ __forceinline__ double* mmd_stage_vectors(const MmdParams& p, const DomainInfo& dom, double* vs, int tid) {
-    double* v = p.v_in_smem ? vs : p.vd;
-    for (int idx = tid; idx < dom.M * kOff; idx += kEpiThreads) v[idx] = double(p.v32[idx]);
-    return v;
+__device__ __forceinline__ void mmd_stage_vectors(const MmdParams& p, const EpiMem& mem, int M, int tid) {
+    for (int idx = tid; idx < M * kOff; idx += kEpiThreads) {
+        const int b = idx / kOff, o = idx - b * kOff;
+        mem.v[size_t(b) * kVStride + o] = __ldg(p.v32 + idx);
+    }
 }
 
+template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) mmd_fwd_kernel(MmdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DomainInfo dom = make_domain(p.B, p.n, p.K);
-    double* v = mmd_stage_vectors(p, dom, reinterpret_cast<double*>(smem_raw), tid);
+    const int M = dom.M;
+    const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, p.B, M);
+    mmd_stage_vectors(p, mem, M, tid);
     __syncthreads();
-    pairwise_kernel(v, p.E, dom.M, warp, lane);
+    float* U = mem.U;
+    pairwise_rows(mem.v, M, warp, lane, [U, M](int a, int c, float D) { U[a * M + c] = expm1f(-D); });
     __syncthreads();
-    if (dom.M > 0) domain_block_sums(p.E, dom, p.blk, 0, kEpiWarps, warp, lane);
+    if (M > 0) domain_block_sums(mem.U, dom, mem.blk, 0, kEpiWarps, warp, lane);
     __syncthreads();
-    if (tid == 0) p.loss[0] = float(mmd_from_blocks(p.blk, dom));
+    if (warp == 0) {
+        const float pen = mmd_from_blocks(mem.blk, dom, lane);
+        if (lane == 0) p.loss[0] = pen;
+    }
 }
 
+template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) mmd_bwd_kernel(MmdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DomainInfo dom = make_domain(p.B, p.n, p.K);
     const int M = dom.M;
-    double* v = mmd_stage_vectors(p, dom, reinterpret_cast<double*>(smem_raw), tid);
+    const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, p.B, M);
+    mmd_stage_vectors(p, mem, M, tid);
     __syncthreads();
-    pairwise_kernel(v, p.E, M, warp, lane);
+    float* coef = mem.U;
+    pairwise_rows(mem.v, M, warp, lane,
+                  [coef, M, &dom](int a, int c, float D) { coef[a * M + c] = mmd_coefficient(dom, a, c, expf(-D)); });
     __syncthreads();
-    if (M > 0) mmd_coefficients(p.E, dom, p.coef, tid);
-    __syncthreads();
-    const double g = p.gout ? double(*p.gout) : 1.0;
+    const float g = p.gout ? __ldg(p.gout) : 1.f;
     for (int idx = tid; idx < p.B * kOff; idx += kEpiThreads) {
-        const int b = idx / kOff, e = idx - b * kOff;
-        p.dv[idx] = (b < M) ? float(g * mmd_grad_entry(v, p.coef, M, b, e)) : 0.f;
+        const int b = idx / kOff, o = idx - b * kOff;
+        p.dv[idx] = (b < M) ? g * mmd_grad_entry(mem.v, mem.U + size_t(b) * M, M, b, o) : 0.f;
     }
 }
 
@@ -370,9 +371,9 @@ int mmd_samples(int B, int n, int K) {
     return int(m < B ? m : B);
 }
 
-// dynamic shared memory for the double-precision vectors, or 0 when they stay in the global scratch
-size_t vector_smem(const void* fn, int B, int n, int K, int* in_smem, cudaError_t* err) {
-    const size_t bytes = size_t(mmd_samples(B, n, K)) * kOff * sizeof(double);
+// dynamic shared memory for the working set, or 0 when it has to live in the global scratch
+size_t epi_smem(const void* fn, int B, int n, int K, int* in_smem, cudaError_t* err) {
+    const size_t bytes = epi_mem_bytes(B, mmd_samples(B, n, K), K);
     *err = cudaSuccess;
     *in_smem = bytes <= kEpiSmemCap ? 1 : 0;
     if (!*in_smem) return 0;
@@ -382,65 +383,62 @@ size_t vector_smem(const void* fn, int B, int n, int K, int* in_smem, cudaError_
 
 }  // namespace
 
-static size_t blk_doubles(int K) { return size_t(K > 0 ? K : 1) * size_t(K > 0 ? K : 1); }
+int g_epilogue_repeat = 1;             // diagnostics: launch the epilogues this many times back to back
+long long* g_epilogue_dbg = nullptr;   // set through wtpse_debug_set_stamp_buffer (16 x int64 device buffer)
 
-size_t epilogue_scratch_doubles(int B, int K) {
-    return size_t(B) * kTri + size_t(B) * 4 + 2 * size_t(B) * B + blk_doubles(K) + size_t(B) * kOff;
-}
+size_t epilogue_scratch_bytes(int B, int K) { return epi_mem_bytes(B, B, K); }
 
-EpilogueScratch carve_epilogue_scratch(double* base, int B, int K) {
-    EpilogueScratch s;
-    s.gd = base;
-    s.stat = s.gd + size_t(B) * kTri;
-    s.E = s.stat + size_t(B) * 4;
-    s.coef = s.E + size_t(B) * B;
-    s.blk = s.coef + size_t(B) * B;
-    s.vd = s.blk + blk_doubles(K);
-    return s;
-}
-
-cudaError_t launch_whiten_epilogue_fwd(const float* partial, const GramPlan& g, int B, long long P, int n_per_domain,
-                                       int n_domains, float margin, float eps, float* losses, float* gram,
-                                       float* rowstat, const EpilogueScratch& s, cudaStream_t stream) {
+cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
+                                       int n_per_domain, int n_domains, float margin, float eps, float* losses,
+                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream) {
     FwdParams p;
-    p.partial = partial;
-    p.tma = g.tma ? 1 : 0;
-    p.tps = g.tiles_per_sample; p.T = g.T; p.G = g.G; p.nslots = g.nslots;
+    p.partial = partial; p.slot_count = slot_count; p.nslots = nslots;
     p.B = B; p.P = P; p.n = n_per_domain; p.K = n_domains; p.margin = margin; p.eps = eps;
     p.losses = losses; p.gram = gram; p.rowstat = rowstat;
-    p.gd = s.gd; p.stat = s.stat; p.E = s.E; p.blk = s.blk; p.vd = s.vd;
+    p.scratch = scratch; p.dbg = g_epilogue_dbg;
     cudaError_t e;
-    const size_t dyn = vector_smem((const void*)whiten_epilogue_fwd_kernel, B, n_per_domain, n_domains, &p.v_in_smem, &e);
+    const size_t dyn = epi_smem((const void*)whiten_epilogue_fwd_kernel<true>, B, n_per_domain, n_domains, &p.in_smem, &e);
     if (e != cudaSuccess) return e;
-    whiten_epilogue_fwd_kernel<<<1, kEpiThreads, dyn, stream>>>(p);
+    for (int r = 0; r < g_epilogue_repeat; ++r) {
+        if (p.in_smem) whiten_epilogue_fwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
+        else whiten_epilogue_fwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
                                        const float* g_dom, int B, long long P, int n_per_domain, int n_domains,
-                                       float* mmat, const EpilogueScratch& s, cudaStream_t stream) {
+                                       float* mmat, void* scratch, cudaStream_t stream) {
     BwdParams p;
     p.gram = gram; p.rowstat = rowstat; p.g_off = g_off; p.g_diag = g_diag; p.g_dom = g_dom;
     p.B = B; p.P = P; p.n = n_per_domain; p.K = n_domains; p.mmat = mmat;
-    p.E = s.E; p.vd = s.vd; p.coef = s.coef;
+    p.scratch = scratch; p.dbg = g_epilogue_dbg ? g_epilogue_dbg + 8 : nullptr;
     cudaError_t e;
-    const size_t dyn = vector_smem((const void*)whiten_epilogue_bwd_kernel, B, n_per_domain, n_domains, &p.v_in_smem, &e);
+    const size_t dyn = epi_smem((const void*)whiten_epilogue_bwd_kernel<true>, B, n_per_domain, n_domains, &p.in_smem, &e);
     if (e != cudaSuccess) return e;
-    whiten_epilogue_bwd_kernel<<<1, kEpiThreads, dyn, stream>>>(p);
+    for (int r = 0; r < g_epilogue_repeat; ++r) {
+        if (p.in_smem) whiten_epilogue_bwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
+        else whiten_epilogue_bwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
 cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,
-                       const EpilogueScratch& s, cudaStream_t stream) {
+                       void* scratch, cudaStream_t stream) {
     MmdParams p;
     p.v32 = v; p.gout = gout; p.B = B; p.n = n_per_domain; p.K = n_domains; p.loss = loss; p.dv = dv;
-    p.vd = s.vd; p.E = s.E; p.coef = s.coef; p.blk = s.blk;
-    const void* fn = dv ? (const void*)mmd_bwd_kernel : (const void*)mmd_fwd_kernel;
+    p.scratch = scratch;
+    const void* fn = dv ? (const void*)mmd_bwd_kernel<true> : (const void*)mmd_fwd_kernel<true>;
     cudaError_t e;
-    const size_t dyn = vector_smem(fn, B, n_per_domain, n_domains, &p.v_in_smem, &e);
+    const size_t dyn = epi_smem(fn, B, n_per_domain, n_domains, &p.in_smem, &e);
     if (e != cudaSuccess) return e;
-    if (dv) mmd_bwd_kernel<<<1, kEpiThreads, dyn, stream>>>(p);
-    else mmd_fwd_kernel<<<1, kEpiThreads, dyn, stream>>>(p);
+    if (dv) {
+        if (p.in_smem) mmd_bwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
+        else mmd_bwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
+    } else {
+        if (p.in_smem) mmd_fwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
+        else mmd_fwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 

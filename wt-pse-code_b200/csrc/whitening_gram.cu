@@ -83,8 +83,8 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, long long P, long long tiles_per_sample,
-                long long T, int nslots) {
+gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
+                long long tiles_per_sample, long long T, int nslots) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
@@ -155,6 +155,8 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, long l
         if (segment_end) {
             const long long slot = k - part_owner(b * tiles_per_sample, T, G);
             flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+            // the CTA that owns a sample's last tile knows how many slots that sample used
+            if (tid == 0 && (t + 1) % tiles_per_sample == 0) slot_count[b] = int(slot) + 1;
 #pragma unroll
             for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
         }
@@ -165,7 +167,8 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, long l
 // aligned): same arithmetic, plain coalesced scalar loads, one pixel per thread per step.
 // grid = (nslots, B); block = 256.
 __global__ void __launch_bounds__(kConsumers)
-gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, long long P, int nslots) {
+gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
+                    int nslots) {
     __shared__ float red[kConsumerWarps * kTri];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long b = blockIdx.y;
@@ -188,6 +191,7 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, lo
             for (int j = i; j < kC; ++j) acc[tri_idx(i, j)] = fmaf(x[i], x[j], acc[tri_idx(i, j)]);
     }
     flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+    if (slot == 0 && tid == 0) slot_count[b] = nslots;
 }
 
 }  // namespace
@@ -232,13 +236,15 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
     return size_t(B) * size_t(slots) * kTri;
 }
 
-cudaError_t launch_gram(const float* z, float* partial, int B, long long P, const GramPlan& g, cudaStream_t stream) {
+cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                        cudaStream_t stream) {
     if (g.tma) {
         cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
-        gram_tma_kernel<<<dim3(unsigned(g.G)), kThreads, kSmemBytes, stream>>>(z, partial, P, g.tiles_per_sample, g.T, g.nslots);
+        gram_tma_kernel<<<dim3(unsigned(g.G)), kThreads, kSmemBytes, stream>>>(z, partial, slot_count, P, g.tiles_per_sample, g.T,
+                                                                                  g.nslots);
     } else {
-        gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, P, g.nslots);
+        gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, slot_count, P, g.nslots);
     }
     return cudaGetLastError();
 }
