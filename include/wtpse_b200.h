@@ -100,6 +100,48 @@ int wtpse_mse_forward(const float* a, const float* b, int64_t N, float* loss,
 int wtpse_mse_backward(const float* a, const float* b, const float* gout, int64_t N,
                        float* da, float* db, wtpse_stream_t stream);
 
+/* ---- integer label path + coarse-to-fine ROI ----------------------------- */
+
+/*
+ * custom_transforms.py:466-499 (Normalize_tf) + :581-599 (ToTensor), batched on the device:
+ *   image_chw[b][c][h][w] = float(img_hwc[b][h][w][c]) / 127.5 - 1.0      (img_hwc may be NULL to skip)
+ *   label_od = [raw_od <= 200], label_oc = [raw_od <= 50]  as {0,1} floats, [B][1][H][W]
+ * raw_oc is accepted for signature parity; the reference overwrites it completely from the OD mask
+ * (custom_transforms.py:493-494).  Bit-exact.
+ */
+int wtpse_prepare_batch(const unsigned char* img_hwc, const unsigned char* raw_od, const unsigned char* raw_oc,
+                        int B, int H, int W, float* image_chw, float* label_od, float* label_oc,
+                        wtpse_stream_t stream);
+
+size_t wtpse_od_roi_workspace_bytes(void);
+/*
+ * Trainer.py:842-853 and :865-867:
+ *   od_pred = (sigmoid(logits) > threshold) as float          [B][1][HW]
+ *   image  += 1 (IN PLACE, as the reference does)              [B][C][HW]
+ *   image_roi = image * od_pred - 1
+ *   sums[0] = sum(od_pred), sums[1] = sum(od_pred * target_oc), sums[2] = sums[0]/sums[1] (1 if inf/nan)
+ * target_oc and sums may be NULL.  Bit-exact against the same statements executed by ATen on the GPU.
+ */
+int wtpse_od_roi(const float* logits, const float* target_oc, float* image, float* od_pred, float* image_roi,
+                 int B, int C, int64_t HW, float threshold, float* sums,
+                 void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
+/* ---- attention fuse: algorithms.py:1243-1249 (attention_layer :1120-1129) ---------------------- */
+
+size_t wtpse_attention_fuse_workspace_bytes(int B, int64_t P);
+/*
+ * att = sigmoid(w * z_post + b)  (Conv2d(1,1,kernel_size=1) + Sigmoid), weight_bias = DEVICE {w, b}
+ * att_mask = (att > threshold) as float, fuse = coef * emb + att * emb ; emb/fuse are [B][Ce][P].
+ */
+int wtpse_attention_fuse_forward(const float* emb, const float* z_post, const float* weight_bias, float coef,
+                                 int B, int Ce, int64_t P, float threshold,
+                                 float* fuse, float* att_mask, float* att, wtpse_stream_t stream);
+/* d_emb / d_z_post / d_weight_bias ({dw, db}) may each be NULL. */
+int wtpse_attention_fuse_backward(const float* grad_fuse, const float* emb, const float* z_post, const float* att,
+                                  const float* weight_bias, float coef, int B, int Ce, int64_t P,
+                                  float* d_emb, float* d_z_post, float* d_weight_bias,
+                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- host-buffer entry point (plugin-facing, used for the end-to-end number) --------------- */
 
 typedef struct wtpse_host_plan wtpse_host_plan;

@@ -1,0 +1,114 @@
+"""GPU parity for the kernels either side of the loss: integer label path (bit-exact), coarse-to-fine
+ROI step (bit-exact against the reference statements executed by ATen on the same GPU), and the
+attention fuse (fp32 tolerance 1e-5, forward and backward)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def test_prepare_batch_bit_exact_against_reference_golden():
+    import wtpse_b200 as wb
+
+    g = golden("labels_24x32.npz")
+    dev = _dev()
+    raw = torch.from_numpy(g["raw_od"]).to(dev)[None]
+    img = torch.from_numpy(g["img"]).to(dev)[None]
+    image, od, oc = wb.prepare_batch(raw, img)
+    assert np.array_equal(od[0, 0].cpu().numpy(), g["same_od"][..., 0].astype(np.float32))
+    assert np.array_equal(oc[0, 0].cpu().numpy(), g["same_oc"][..., 0].astype(np.float32))
+    assert np.array_equal(image[0].cpu().numpy(), g["same_image"].transpose(2, 0, 1))
+    # a different raw_oc buffer changes nothing (custom_transforms.py:493-494 quirk)
+    _, od2, oc2 = wb.prepare_batch(raw, None, torch.from_numpy(g["raw_oc"]).to(dev)[None])
+    assert np.array_equal(oc2[0, 0].cpu().numpy(), g["diff_oc"][..., 0].astype(np.float32))
+    assert torch.equal(od2, od)
+
+
+def test_prepare_batch_all_byte_values_and_batch_layout():
+    import wtpse_b200 as wb
+    from oracle import labels_np
+
+    rng = np.random.RandomState(0)
+    raw = rng.randint(0, 256, size=(5, 37, 53)).astype(np.uint8)
+    raw[0].flat[:256] = np.arange(256)
+    img = rng.randint(0, 256, size=(5, 37, 53, 3)).astype(np.uint8)
+    image, od, oc = wb.prepare_batch(torch.from_numpy(raw).to(_dev()), torch.from_numpy(img).to(_dev()))
+    for b in range(5):
+        o, c = labels_np.labels_from_raw(raw[b])
+        assert np.array_equal(od[b, 0].cpu().numpy(), o[..., 0].astype(np.float32))
+        assert np.array_equal(oc[b, 0].cpu().numpy(), c[..., 0].astype(np.float32))
+        assert np.array_equal(image[b].cpu().numpy(), labels_np.normalize_image(img[b]).transpose(2, 0, 1))
+
+
+def test_od_roi_bit_exact():
+    import wtpse_b200 as wb
+    from oracle import labels_np
+
+    g = golden("labels_24x32.npz")
+    dev = _dev()
+    logits = torch.from_numpy(g["logits"]).to(dev)
+    image = torch.from_numpy(g["image"]).to(dev)
+    target_oc = torch.from_numpy(g["target_oc"]).to(dev)
+
+    # the reference statements (Trainer.py:842-853, 865-867) executed by ATen on this GPU
+    ref_img = image.clone()
+    ref_pred = (torch.sigmoid(logits) > 0.75).float().detach().float()
+    ref_img += 1
+    ref_roi = ref_img * ref_pred
+    ref_roi -= 1
+    ref_w = torch.sum(ref_pred) / torch.sum(ref_pred * target_oc)
+
+    od_pred, roi, sums = wb.od_roi(logits, image, target_oc)
+    assert torch.equal(od_pred, ref_pred)
+    assert torch.equal(image, ref_img)           # in-place += 1
+    assert torch.equal(roi, ref_roi)
+    assert float(sums[0]) == float(ref_pred.sum()) and float(sums[2]) == float(ref_w)
+    # and the CPU golden, outside the entries whose sigmoid sits within 2 ulp of the threshold
+    amb = labels_np.od_threshold_ambiguous(g["logits"])
+    assert ((od_pred.cpu().numpy() != g["od_pred"]) & ~amb).sum() == 0
+    same = od_pred.cpu().numpy() == g["od_pred"]
+    assert np.array_equal(roi.cpu().numpy()[np.broadcast_to(same, roi.shape)], g["image_roi"][np.broadcast_to(same, roi.shape)])
+    # empty prediction -> pos_weight falls back to 1 (Trainer.py:866-867)
+    _, _, sums0 = wb.od_roi(torch.full_like(logits, -10.0), image.clone(), target_oc)
+    assert float(sums0[0]) == 0.0 and float(sums0[2]) == 1.0
+
+
+@pytest.mark.parametrize("B,Ce,H,W", [(6, 8, 32, 32), (5, 8, 33, 17), (15, 8, 128, 128)])
+def test_attention_fuse_forward_backward(B, Ce, H, W):
+    import wtpse_b200 as wb
+
+    dev = _dev()
+    g = torch.Generator().manual_seed(B * 100 + H)
+    emb = torch.randn(B, Ce, H, W, generator=g).to(dev).requires_grad_(True)
+    zp = (2.0 * torch.randn(B, 1, H, W, generator=g)).to(dev).requires_grad_(True)
+    conv = torch.nn.Conv2d(1, 1, kernel_size=1).to(dev)
+    with torch.no_grad():
+        conv.weight.fill_(0.83)
+        conv.bias.fill_(-0.21)
+    gout = torch.randn(B, Ce, H, W, generator=g).to(dev)
+
+    # reference statements, algorithms.py:1126-1128 and :1243-1249, in float64 for the truth
+    e64, z64 = emb.detach().double().requires_grad_(True), zp.detach().double().requires_grad_(True)
+    w64, b64 = conv.weight.detach().double().requires_grad_(True), conv.bias.detach().double().requires_grad_(True)
+    att64 = torch.sigmoid(torch.nn.functional.conv2d(z64, w64, b64))
+    fuse64 = 0.3 * e64 + att64 * e64
+    fuse64.backward(gout.double())
+
+    fuse, mask = wb.attention_fuse(emb, zp, conv.weight, conv.bias, 0.3)
+    fuse.backward(gout)
+    assert rel_err(fuse.detach().cpu().numpy(), fuse64.detach().cpu().numpy()) < TOL
+    amb = (att64.detach() - 0.75).abs() < 1e-6
+    assert ((mask.double() != (att64.detach() > 0.75).double()) & ~amb).sum() == 0
+    assert not mask.requires_grad
+    assert rel_err(emb.grad.cpu().numpy(), e64.grad.cpu().numpy()) < TOL
+    assert rel_err(zp.grad.cpu().numpy(), z64.grad.cpu().numpy()) < TOL
+    assert abs(float(conv.weight.grad) - float(w64.grad)) <= TOL * abs(float(w64.grad))
+    assert abs(float(conv.bias.grad) - float(b64.grad)) <= TOL * abs(float(b64.grad))

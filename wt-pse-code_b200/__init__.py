@@ -7,6 +7,8 @@ side.  There is no CPU or eager-PyTorch fallback: calls raise if the library is 
 from . import _build, _lib  # noqa: F401
 from .functional import HostPlan, gram_matrix, kd_mse, whitening_folded, whitening_terms  # noqa: F401
 from .mmd import mmd_penalty  # noqa: F401
+from .elementwise import attention_fuse, od_roi, prepare_batch  # noqa: F401
 from . import dropin  # noqa: F401
 
-__all__ = ["whitening_terms", "whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin"]
+__all__ = ["whitening_terms", "whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin",
+           "prepare_batch", "od_roi", "attention_fuse"]

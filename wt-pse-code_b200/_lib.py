@@ -35,6 +35,18 @@ EXPORTS = {
                                      _c.c_void_p]),
     "wtpse_mse_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p,
                                       _c.c_void_p]),
+    "wtpse_prepare_batch": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                       _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "wtpse_od_roi_workspace_bytes": (_c.c_size_t, []),
+    "wtpse_od_roi": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                _c.c_int64, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_attention_fuse_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64]),
+    "wtpse_attention_fuse_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_float, _c.c_int, _c.c_int,
+                                                _c.c_int64, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                _c.c_void_p]),
+    "wtpse_attention_fuse_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                 _c.c_float, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p,
+                                                 _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_profile_enable": (None, [_c.c_int]),
     "wtpse_profile_reset": (None, []),
     "wtpse_profile_kernel_count": (_c.c_int, []),

@@ -205,6 +205,65 @@ int wtpse_mse_backward(const float* a, const float* b, const float* gout, int64_
 }
 
 // ---------------------------------------------------------------------------------------------
+// element-wise kernels either side of the loss
+// ---------------------------------------------------------------------------------------------
+int wtpse_prepare_batch(const unsigned char* img_hwc, const unsigned char* raw_od, const unsigned char* raw_oc, int B, int H,
+                        int W, float* image_chw, float* label_od, float* label_oc, wtpse_stream_t stream) {
+    if (!raw_od || !label_od || !label_oc) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (img_hwc && !image_chw) return fail(WTPSE_ERR_INVALID, "image output missing");
+    if (B <= 0 || H <= 0 || W <= 0) return fail(WTPSE_ERR_INVALID, "bad shape %dx%dx%d", B, H, W);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernLabels, s); e = launch_prepare_batch(img_hwc, raw_od, raw_oc, B, (long long)H * W, image_chw, label_od, label_oc, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "prepare_batch launch");
+    return WTPSE_OK;
+}
+
+size_t wtpse_od_roi_workspace_bytes(void) { return od_roi_workspace_bytes(); }
+
+int wtpse_od_roi(const float* logits, const float* target_oc, float* image, float* od_pred, float* image_roi, int B, int C,
+                 int64_t HW, float threshold, float* sums, void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (!logits || !image || !od_pred || !image_roi || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (B <= 0 || C <= 0 || HW <= 0) return fail(WTPSE_ERR_INVALID, "bad shape");
+    if (workspace_bytes < od_roi_workspace_bytes()) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernLabels, s); e = launch_od_roi(logits, target_oc, image, od_pred, image_roi, B, C, HW, threshold, sums, workspace, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "od_roi launch");
+    return WTPSE_OK;
+}
+
+size_t wtpse_attention_fuse_workspace_bytes(int B, int64_t P) {
+    if (B <= 0 || P <= 0) return 0;
+    return align_up(fuse_bwd_partial_doubles(B, P, sm_count_cached()) * sizeof(double), 256);
+}
+
+int wtpse_attention_fuse_forward(const float* emb, const float* z_post, const float* weight_bias, float coef, int B, int Ce,
+                                 int64_t P, float threshold, float* fuse, float* att_mask, float* att,
+                                 wtpse_stream_t stream) {
+    if (!emb || !z_post || !weight_bias || !fuse || !att_mask || !att) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (B <= 0 || Ce <= 0 || P <= 0) return fail(WTPSE_ERR_INVALID, "bad shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernFuse, s); e = launch_fuse_fwd(emb, z_post, weight_bias, coef, B, Ce, P, threshold, fuse, att_mask, att, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "attention_fuse forward launch");
+    return WTPSE_OK;
+}
+
+int wtpse_attention_fuse_backward(const float* grad_fuse, const float* emb, const float* z_post, const float* att,
+                                  const float* weight_bias, float coef, int B, int Ce, int64_t P, float* d_emb, float* d_z_post,
+                                  float* d_weight_bias, void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (!grad_fuse || !emb || !z_post || !att || !weight_bias || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (B <= 0 || Ce <= 0 || P <= 0) return fail(WTPSE_ERR_INVALID, "bad shape");
+    if (workspace_bytes < wtpse_attention_fuse_workspace_bytes(B, P)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernFuse, s); e = launch_fuse_bwd(grad_fuse, emb, z_post, att, weight_bias, coef, B, Ce, P, d_emb, d_z_post, d_weight_bias, static_cast<double*>(workspace), sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "attention_fuse backward launch");
+    return WTPSE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-buffer plan
 // ---------------------------------------------------------------------------------------------
 struct wtpse_host_plan {

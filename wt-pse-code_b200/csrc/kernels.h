@@ -54,4 +54,18 @@ cudaError_t launch_mse_fwd(const float* a, const float* b, long long N, float* l
 cudaError_t launch_mse_bwd(const float* a, const float* b, const float* gout, long long N, float* da, float* db,
                            int sm_count, cudaStream_t stream);
 
+// element-wise kernels (elementwise.cu)
+cudaError_t launch_prepare_batch(const unsigned char* img, const unsigned char* raw_od, const unsigned char* raw_oc, int B,
+                                 long long HW, float* image, float* label_od, float* label_oc, int sm_count,
+                                 cudaStream_t stream);
+size_t od_roi_workspace_bytes();
+cudaError_t launch_od_roi(const float* logits, const float* target_oc, float* image, float* od_pred, float* image_roi, int B,
+                          int C, long long HW, float thr, float* sums, void* workspace, int sm_count, cudaStream_t stream);
+cudaError_t launch_fuse_fwd(const float* emb, const float* zp, const float* wb, float coef, int B, int Ce, long long P,
+                            float thr, float* fuse, float* mask, float* att, int sm_count, cudaStream_t stream);
+size_t fuse_bwd_partial_doubles(int B, long long P, int sm_count);
+cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, const float* att, const float* wb, float coef,
+                            int B, int Ce, long long P, float* d_emb, float* d_zp, float* d_wb, double* partial, int sm_count,
+                            cudaStream_t stream);
+
 }  // namespace wtpse

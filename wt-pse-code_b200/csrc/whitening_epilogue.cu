@@ -22,8 +22,8 @@
 //         block sums run in float64.
 //   * one warp per sample reduces that sample's slots straight into registers and emits the Gram,
 //     the 120-d vector (shared memory) and off_b / diag_b with one shuffle reduction;
-//   * pairwise distances: one LANE per (a, c) pair, two rows a per warp, LDS.128 on rows padded to
-//     124 floats (conflict-free), so there is no shuffle chain per pair.
+//   * pairwise distances: one LANE per unordered pair a < c (the matrix is symmetric), LDS.128 on rows
+//     padded to 124 floats (conflict-free), so there is no shuffle chain per pair.
 #include <math.h>
 
 #include "common.cuh"
@@ -67,35 +67,20 @@ __device__ __forceinline__ EpiMem resolve_mem(void* smem, void* global, int B, i
     return m;
 }
 
-// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all a, c < M: one lane per pair, two rows per warp.
+// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M, one LANE per pair (no shuffle chain);
+// emit(a, c, D) is expected to fill both (a, c) and (c, a).  Consecutive lanes share a and walk c, so the
+// v_a loads broadcast and the v_c loads hit distinct banks (row stride 124 floats).
 template <typename F>
-__device__ __forceinline__ void pairwise_rows(const float* __restrict__ v, int M, int warp, int lane, F&& emit) {
-    for (int a0 = 2 * warp; a0 < M; a0 += 2 * kEpiWarps) {
-        const int a1 = (a0 + 1 < M) ? a0 + 1 : a0;
-        const float4* va0 = reinterpret_cast<const float4*>(v + size_t(a0) * kVStride);
-        const float4* va1 = reinterpret_cast<const float4*>(v + size_t(a1) * kVStride);
-        for (int c0 = 0; c0 < M; c0 += 32) {
-            const int c = c0 + lane;
-            if (c < M) {
-                const float4* vc = reinterpret_cast<const float4*>(v + size_t(c) * kVStride);
-                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-#pragma unroll 5
-                for (int e = 0; e < kOff / 4; ++e) {
-                    const float4 y = vc[e], x0 = va0[e], x1 = va1[e];
-                    float d;
-                    d = x0.x - y.x; p0 = fmaf(d, d, p0);
-                    d = x0.y - y.y; p1 = fmaf(d, d, p1);
-                    d = x0.z - y.z; p2 = fmaf(d, d, p2);
-                    d = x0.w - y.w; p3 = fmaf(d, d, p3);
-                    d = x1.x - y.x; q0 = fmaf(d, d, q0);
-                    d = x1.y - y.y; q1 = fmaf(d, d, q1);
-                    d = x1.z - y.z; q2 = fmaf(d, d, q2);
-                    d = x1.w - y.w; q3 = fmaf(d, d, q3);
-                }
-                emit(a0, c, clamp_tiny((p0 + p1) + (p2 + p3)));
-                if (a1 != a0) emit(a1, c, clamp_tiny((q0 + q1) + (q2 + q3)));
-            }
-        }
+__device__ __forceinline__ void pairwise_upper(const float* __restrict__ v, int M, int tid, F&& emit) {
+    const int npairs = M * (M - 1) / 2;
+    for (int pidx = tid; pidx < npairs; pidx += kEpiThreads) {
+        // row a of the strict upper triangle that contains flat index pidx (row a starts at a*(2M-a-1)/2)
+        const float t = float(2 * M - 1);
+        int a = int((t - sqrtf(t * t - 8.0f * float(pidx))) * 0.5f);
+        while (a > 0 && a * (2 * M - a - 1) / 2 > pidx) --a;
+        while ((a + 1) * (2 * M - a - 2) / 2 <= pidx) ++a;
+        const int c = a + 1 + (pidx - a * (2 * M - a - 1) / 2);
+        emit(a, c, mmd_distance(v + size_t(a) * kVStride, v + size_t(c) * kVStride));
     }
 }
 
@@ -170,25 +155,42 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
     __syncthreads();
     WTPSE_STAMP(0);
 
-    // A. one warp per sample: slots -> Gram entries -> gram, v, off_b, diag_b
+    // A. one warp per sample: slots -> Gram entries -> gram, v, off_b, diag_b.
+    //    The first three slots are loaded speculatively, together with the slot count, so the warp pays
+    //    one L2 round trip instead of a chain of them (unused slots hold garbage that is never added).
     for (int b = warp; b < B; b += kEpiWarps) {
-        const int cnt = __ldg(p.slot_count + b);
         const float* src = p.partial + ((long long)b * p.nslots) * kTri;
+        float v0[5], v1[5], v2[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = lane + 32 * q;
+            const bool ok = e < kTri;
+            v0[q] = ok ? __ldg(src + e) : 0.f;
+            v1[q] = (ok && p.nslots > 1) ? __ldg(src + kTri + e) : 0.f;
+            v2[q] = (ok && p.nslots > 2) ? __ldg(src + 2 * kTri + e) : 0.f;
+        }
+        const int cnt = __ldg(p.slot_count + b);
         float off = 0.f, dg = 0.f;
-        for (int e = lane; e < kTri; e += 32) {
-            float s = 0.f;
-            for (int sl = 0; sl < cnt; ++sl) s += __ldg(src + (long long)sl * kTri + e);
-            const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
-            s = s / denom;                                   // .div(HW - 1), algorithms.py:1283
-            if (i == j) {
-                s += p.eps;                                  // + eps * eye
-                dg += fabsf(s - 1.0f);                       // |f_cor_masked_diag - I|, :1297
-                p.gram[b * 256 + i * kC + i] = s;
-            } else {
-                off += fabsf(s);                             // |f_cor_masked|, :1289
-                p.gram[b * 256 + i * kC + j] = s;
-                p.gram[b * 256 + j * kC + i] = s;
-                if (b < dom.M) mem.v[size_t(b) * kVStride + off_idx(i, j)] = s;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const int e = lane + 32 * q;
+            if (e < kTri) {
+                float s = v0[q];
+                if (cnt > 1) s += v1[q];
+                if (cnt > 2) s += v2[q];
+                for (int sl = 3; sl < cnt; ++sl) s += __ldg(src + (long long)sl * kTri + e);
+                const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
+                s = s / denom;                                   // .div(HW - 1), algorithms.py:1283
+                if (i == j) {
+                    s += p.eps;                                  // + eps * eye
+                    dg += fabsf(s - 1.0f);                       // |f_cor_masked_diag - I|, :1297
+                    p.gram[b * 256 + i * kC + i] = s;
+                } else {
+                    off += fabsf(s);                             // |f_cor_masked|, :1289
+                    p.gram[b * 256 + i * kC + j] = s;
+                    p.gram[b * 256 + j * kC + i] = s;
+                    if (b < dom.M) mem.v[size_t(b) * kVStride + off_idx(i, j)] = s;
+                }
             }
         }
         off = warp_sum(off) - p.margin;
@@ -207,7 +209,12 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
     {
         float* U = mem.U;
         const int M = dom.M;
-        pairwise_rows(mem.v, M, warp, lane, [U, M](int a, int c, float D) { U[a * M + c] = expm1f(-D); });
+        pairwise_upper(mem.v, M, tid, [U, M](int a, int c, float D) {
+            const float u = expm1f(-D);
+            U[a * M + c] = u;
+            U[c * M + a] = u;
+        });
+        for (int a = tid; a < M; a += kEpiThreads) U[a * M + a] = expm1f(-1e-30f);   // D(a,a) = 0 -> clamp_min_(1e-30)
     }
     __syncthreads();
     WTPSE_STAMP(2);
@@ -282,8 +289,12 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(Bwd
         WTPSE_STAMP(1);
         // 2. symmetric coefficient matrix (stored in U's place)
         float* coef = mem.U;
-        pairwise_rows(mem.v, M, warp, lane,
-                      [coef, M, &dom](int a, int c, float D) { coef[a * M + c] = mmd_coefficient(dom, a, c, expf(-D)); });
+        pairwise_upper(mem.v, M, tid, [coef, M, &dom](int a, int c, float D) {
+            const float E = expf(-D);
+            coef[a * M + c] = mmd_coefficient(dom, a, c, E);
+            coef[c * M + a] = mmd_coefficient(dom, c, a, E);
+        });
+        for (int a = tid; a < M; a += kEpiThreads) coef[a * M + a] = 0.f;
         __syncthreads();
     }
     WTPSE_STAMP(2);
@@ -335,7 +346,12 @@ __global__ void __launch_bounds__(kEpiThreads, 1) mmd_fwd_kernel(MmdParams p) {
     mmd_stage_vectors(p, mem, M, tid);
     __syncthreads();
     float* U = mem.U;
-    pairwise_rows(mem.v, M, warp, lane, [U, M](int a, int c, float D) { U[a * M + c] = expm1f(-D); });
+    pairwise_upper(mem.v, M, tid, [U, M](int a, int c, float D) {
+        const float u = expm1f(-D);
+        U[a * M + c] = u;
+        U[c * M + a] = u;
+    });
+    for (int a = tid; a < M; a += kEpiThreads) U[a * M + a] = expm1f(-1e-30f);
     __syncthreads();
     if (M > 0) domain_block_sums(mem.U, dom, mem.blk, 0, kEpiWarps, warp, lane);
     __syncthreads();
@@ -355,8 +371,12 @@ __global__ void __launch_bounds__(kEpiThreads, 1) mmd_bwd_kernel(MmdParams p) {
     mmd_stage_vectors(p, mem, M, tid);
     __syncthreads();
     float* coef = mem.U;
-    pairwise_rows(mem.v, M, warp, lane,
-                  [coef, M, &dom](int a, int c, float D) { coef[a * M + c] = mmd_coefficient(dom, a, c, expf(-D)); });
+    pairwise_upper(mem.v, M, tid, [coef, M, &dom](int a, int c, float D) {
+        const float E = expf(-D);
+        coef[a * M + c] = mmd_coefficient(dom, a, c, E);
+        coef[c * M + a] = mmd_coefficient(dom, c, a, E);
+    });
+    for (int a = tid; a < M; a += kEpiThreads) coef[a * M + a] = 0.f;
     __syncthreads();
     const float g = p.gout ? __ldg(p.gout) : 1.f;
     for (int idx = tid; idx < p.B * kOff; idx += kEpiThreads) {

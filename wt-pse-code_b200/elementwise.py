@@ -1,0 +1,128 @@
+"""Host side of the element-wise kernels around the loss (include/wtpse_b200.h):
+
+  prepare_batch    custom_transforms.py:466-499 + :581-599  (uint8 image / raw mask -> fp32 image, OD/OC labels)
+  od_roi           Trainer.py:842-853, 865-867              (threshold, in-place image += 1, ROI image, pos weight)
+  attention_fuse   algorithms.py:1243-1249                  (sigmoid(conv1x1(z_post)) gate on the embedding), autograd
+"""
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from .functional import _ptr, _require_cuda_f32, _stream_ptr
+
+
+def _require_cuda_u8(t, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != torch.uint8:
+        raise TypeError("%s must be a CUDA uint8 tensor" % name)
+
+
+def prepare_batch(raw_od, img_hwc=None, raw_oc=None):
+    """raw_od: B x H x W uint8 ; img_hwc: B x H x W x 3 uint8 (optional).
+    Returns (image B x 3 x H x W or None, label_od B x 1 x H x W, label_oc B x 1 x H x W), all float32."""
+    _require_cuda_u8(raw_od, "raw_od")
+    if raw_od.dim() != 3:
+        raise ValueError("raw_od must be B x H x W")
+    B, H, W = raw_od.shape
+    raw_od = raw_od.contiguous()
+    if img_hwc is not None:
+        _require_cuda_u8(img_hwc, "img_hwc")
+        if tuple(img_hwc.shape) != (B, H, W, 3):
+            raise ValueError("img_hwc must be B x H x W x 3 matching raw_od")
+        img_hwc = img_hwc.contiguous()
+    if raw_oc is not None:
+        _require_cuda_u8(raw_oc, "raw_oc")
+        raw_oc = raw_oc.contiguous()
+    lib = _lib.load()
+    dev = raw_od.device
+    with torch.cuda.device(dev):
+        image = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if img_hwc is not None else None
+        od = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+        oc = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+        _lib.check(lib.wtpse_prepare_batch(_ptr(img_hwc), _ptr(raw_od), _ptr(raw_oc), B, H, W, _ptr(image), _ptr(od), _ptr(oc),
+                                           _stream_ptr(dev)))
+    return image, od, oc
+
+
+def od_roi(logits, image, target_oc=None, threshold=0.75):
+    """Returns (od_pred, image_roi, sums) with sums = [sum(od_pred), sum(od_pred*target_oc), pos_weight] (device,
+    no host sync).  `image` is incremented by 1 IN PLACE exactly as Trainer.py:850 does."""
+    _require_cuda_f32(logits, "logits")
+    _require_cuda_f32(image, "image")
+    if not image.is_contiguous():
+        raise ValueError("image must be contiguous (it is updated in place)")
+    B, C = image.shape[0], image.shape[1]
+    HW = image.shape[2] * image.shape[3]
+    if logits.numel() != B * HW:
+        raise ValueError("logits must be B x 1 x H x W")
+    logits = logits.detach().contiguous()
+    if target_oc is not None:
+        _require_cuda_f32(target_oc, "target_oc")
+        target_oc = target_oc.contiguous()
+    lib = _lib.load()
+    dev = image.device
+    with torch.cuda.device(dev):
+        od_pred = torch.empty(B, 1, image.shape[2], image.shape[3], dtype=torch.float32, device=dev)
+        roi = torch.empty_like(image)
+        sums = torch.empty(3, dtype=torch.float32, device=dev)
+        ws_bytes = lib.wtpse_od_roi_workspace_bytes()
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.wtpse_od_roi(_ptr(logits), _ptr(target_oc), _ptr(image), _ptr(od_pred), _ptr(roi), B, C, HW,
+                                    float(threshold), _ptr(sums), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+    return od_pred, roi, sums
+
+
+class _AttentionFuse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, z_post, weight, bias, coef, threshold):
+        _require_cuda_f32(emb, "embedding")
+        _require_cuda_f32(z_post, "z_posterior")
+        if weight.numel() != 1 or bias.numel() != 1:
+            raise ValueError("attention_layer is Conv2d(1, 1, kernel_size=1): one weight and one bias")
+        B, Ce, H, W = emb.shape
+        if z_post.shape[0] != B or z_post.numel() != B * H * W:
+            raise ValueError("z_posterior must be B x 1 x H x W")
+        emb = emb.contiguous()
+        z_post = z_post.contiguous()
+        wb = torch.cat([weight.detach().reshape(1), bias.detach().reshape(1)]).float()
+        lib = _lib.load()
+        dev = emb.device
+        with torch.cuda.device(dev):
+            fuse = torch.empty_like(emb)
+            mask = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+            att = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+            _lib.check(lib.wtpse_attention_fuse_forward(_ptr(emb), _ptr(z_post), _ptr(wb), float(coef), B, Ce, H * W,
+                                                        float(threshold), _ptr(fuse), _ptr(mask), _ptr(att), _stream_ptr(dev)))
+        ctx.save_for_backward(emb, z_post, att, wb)
+        ctx.coef = float(coef)
+        ctx.wshape, ctx.bshape = weight.shape, bias.shape
+        ctx.mark_non_differentiable(mask)
+        return fuse, mask
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_fuse, _g_mask):
+        emb, z_post, att, wb = ctx.saved_tensors
+        if g_fuse is None:
+            return None, None, None, None, None, None
+        B, Ce, H, W = emb.shape
+        need_emb, need_zp, need_w, need_b = ctx.needs_input_grad[:4]
+        g_fuse = g_fuse.contiguous()
+        lib = _lib.load()
+        dev = emb.device
+        with torch.cuda.device(dev):
+            d_emb = torch.empty_like(emb) if need_emb else None
+            d_zp = torch.empty_like(z_post) if need_zp else None
+            d_wb = torch.empty(2, dtype=torch.float32, device=dev) if (need_w or need_b) else None
+            ws_bytes = lib.wtpse_attention_fuse_workspace_bytes(B, H * W)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.wtpse_attention_fuse_backward(_ptr(g_fuse), _ptr(emb), _ptr(z_post), _ptr(att), _ptr(wb), ctx.coef,
+                                                         B, Ce, H * W, _ptr(d_emb), _ptr(d_zp), _ptr(d_wb), _ptr(ws),
+                                                         ws_bytes, _stream_ptr(dev)))
+        d_w = d_wb[0].reshape(ctx.wshape) if need_w else None
+        d_b = d_wb[1].reshape(ctx.bshape) if need_b else None
+        return d_emb, d_zp, d_w, d_b, None, None
+
+
+def attention_fuse(embedding, z_posterior, weight, bias, coef, threshold=0.75):
+    """(fuse_embedding, z_posterior_attention_mask) of algorithms.py:1243-1249."""
+    return _AttentionFuse.apply(embedding, z_posterior, weight, bias, coef, threshold)
