@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"])
     ap.add_argument("--size", type=int, default=WORKLOAD["H"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=6, help="timed iterations of the full WT-PSE train step (0 = skip)")
+    ap.add_argument("--train-size", type=int, default=512)
+    ap.add_argument("--train-batch", type=int, default=16, help="nominal per-GPU batch (the reference uses 3 * (batch // 3))")
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
@@ -314,6 +317,10 @@ def run_ours(args):
            "d2h_bytes_per_step": nbytes + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "api": "wtpse_host_plan_run (pinned host z -> H2D -> fwd -> bwd -> D2H dz + losses)"}
 
+    train = None
+    if args.train_steps > 0:
+        train = time_train_step(args, dev, rank, world, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,11 +363,52 @@ def run_ours(args):
                    "per_gpu_batch": B, "l2": "inputs (%.0f MB, two alternating buffers) larger than L2" % (nbytes / 1e6),
                    "sharding": "independent [K x n] batches per rank, no data-path collective"},
         "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
-        "clocks": clocks, "losses": losses,
+        "clocks": clocks, "losses": losses, "train_step": train,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_train_step(args, dev, rank, world, barrier):
+    """BASELINE configs[2]/[3]: full WT-PSE iteration (4 network updates: reference U-Net backbone in PyTorch/cuDNN
+    + the CUDA shape-loss path) on synthetic fundus-shaped batches, data-parallel over the ranks with one bucketed
+    NCCL all-reduce per backward.  Reported as images/s over all ranks; loader time (device-side generator +
+    bit-exact label kernel) is inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    import wtpse_b200 as wb
+
+    n_per_domain, used = wb.dp.per_rank_batch(args.train_batch * world, world, 3)
+    S = args.train_size
+    ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0)
+    lib = wb._lib.load()
+
+    def one(it):
+        image, od, oc = wb.synthetic.fundus_batch(n_per_domain, 3, S, S, dev, seed=wb.dp.rank_batch_seed(1, rank, it))
+        return ts.step(image, od, oc)
+
+    for it in range(3):
+        one(it)
+    barrier()
+    lib.wtpse_profile_reset()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for it in range(args.train_steps):
+        out = one(3 + it)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.train_steps
+    return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+            "steps": args.train_steps, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
+            "global_batch_used": world * used, "our_kernel_launches": int(lib.wtpse_profile_launches(-1)),
+            "backbone": "PyTorch/cuDNN (fp32, TF32 convs as torch defaults)", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
+            "losses": {k: float(v) for k, v in out.items()}}
 
 
 def main():

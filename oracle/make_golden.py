@@ -157,6 +157,12 @@ def gen_update(alg, sn):
     image = torch.rand(B, 3, H, H, generator=g) * 2 - 1
     image = image + 0.3 * torch.arange(B).view(B, 1, 1, 1).div(n, rounding_mode="floor")   # per-domain shift
     mask = (torch.rand(B, 1, H, H, generator=g) > 0.5).float()
+    # predict() (algorithms.py:1311-1353) in eval mode, BEFORE any train-mode forward touches the BatchNorm
+    # running statistics: pure backbone, pins the PyTorch side of the port from the seed alone
+    main.eval(); shape.eval()
+    with torch.no_grad():
+        pred_logits, pred_pre = main.predict(shape, image)
+    main.train(); shape.train()
     with torch.no_grad():
         emb_main = [t.clone() for t in main.wt_model.forward(image)]
         emb_shape = [t.clone() for t in shape.wt_model.forward(image)]
@@ -173,7 +179,8 @@ def gen_update(alg, sn):
         mu_s = shape.mu_prior(shape.unet_extractor(emb_shape[-1]))
     np.savez_compressed(
         os.path.join(OUT, "update_b6_16x16.npz"),
-        n=n, K=K, margin=0.0, eps=1e-5,
+        n=n, K=K, margin=0.0, eps=1e-5, image=image.numpy(), mask=mask.numpy(),
+        predict_logits=pred_logits.numpy(), predict_pre_sigmoid=pred_pre.numpy(), logits=logits.detach().numpy(),
         main_z0=emb_main[0].numpy(), main_z1=emb_main[1].numpy(),
         shape_z0=emb_shape[0].numpy(), shape_z1=emb_shape[1].numpy(),
         mu_teacher=mu_t.numpy(), mu_student=mu_s.numpy(),

@@ -1,0 +1,107 @@
+"""GPU parity of the reference-facing entry points: WT_PSE.update / ShapeVariationalDist_x.update against the
+loss tuples the unmodified reference returned for the same seed-0 weights and inputs, and the train-step harness."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+HP = {"whitening": True, "margin": 0, "shape_prior": True, "shape_attention": True, "cat_shape": False,
+      "shape_attention_coeffient": 0.3, "shape_start": 0.5, "instance_wt_gm": 1, "domain_wt_gm": 1, "multi-turn": 1}
+
+
+@pytest.fixture(autouse=True)
+def _fp32_backbone():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _close(a, b, tol):
+    return abs(a - b) <= tol * max(abs(b), 1e-12)
+
+
+def test_update_entry_points_match_reference_golden():
+    from wtpse_b200 import segmentation as seg
+
+    g = golden("update_b6_16x16.npz")
+    n, K = int(g["n"]), int(g["K"])
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)                        # same construction order as the reference -> same weights (CPU RNG)
+    main = seg.WT_PSE(3, 1, dict(HP), dev, False, per_domain_batch=n, source_domain_num=K)
+    shape = seg.ShapeVariationalDist_x(dict(HP), dev, 1, number_source_domain=K, batch_size=n)
+    main.to(dev).train(); shape.to(dev).train()
+    image = torch.from_numpy(g["image"]).to(dev)
+    mask = torch.from_numpy(g["mask"]).to(dev)
+
+    logits, att1, att2, ins, dom = main.update(image, mask, step=0, plot_show=0, two_stage_inputs=image, sp_mask=mask,
+                                               two_step=True)
+    assert tuple(logits.shape) == tuple(g["logits_shape"]) and att1 is att2 and att1.shape == mask.shape
+    assert ins.dim() == 0 and dom.dim() == 0 and ins.requires_grad and dom.requires_grad
+    # loss scalars are RNG-free (they see only the whitening features); conv arithmetic differs CPU vs cuDNN
+    assert _close(float(ins), float(g["wt_ins"]), 1e-4), (float(ins), float(g["wt_ins"]))
+    assert abs(float(dom) - float(g["wt_dom"])) <= 1e-5
+
+    kd, tot, ij, ii, dom_s = shape.update(main, image, mask, step=0, plot_show=0, two_stage_inputs=image, two_step=True)
+    assert _close(float(kd), float(g["sh_kd"]), 1e-4)
+    assert _close(float(ij), float(g["sh_ij"]), 1e-4) and _close(float(ii), float(g["sh_ii"]), 1e-4)
+    assert _close(float(tot), float(g["sh_total"]), 1e-4) and abs(float(dom_s) - float(g["sh_dom"])) <= 1e-5
+
+    # the whole thing is differentiable down to the conv weights, and only through real numbers
+    (torch.nn.functional.binary_cross_entropy(torch.sigmoid(logits), mask) + ins + dom).backward()
+    (kd + tot + dom_s).backward()
+    for m in (main, shape):
+        grads = [p.grad for p in m.parameters() if p.grad is not None]
+        assert grads and all(torch.isfinite(x).all() for x in grads)
+    assert main.wt_model.DoubleConv.double_conv[0].weight.grad.abs().max() > 0
+    assert shape.wt_model.DoubleConv2.double_conv[2].weight.grad.abs().max() > 0
+
+
+def test_update_gradients_match_autograd_through_the_reference_operator_sequence():
+    """Same model, same batch: d(loss)/d(conv weights) with the CUDA loss path vs the op-sequence restatement."""
+    from oracle import whitening_torch as wt
+    from wtpse_b200 import segmentation as seg
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    net = seg.DeepWT(3, 16).to(dev)
+    x = torch.randn(6, 3, 48, 40, device=dev)
+    grads = []
+    for use_cuda_path in (True, False):
+        net.zero_grad(set_to_none=True)
+        f = net(x)
+        if use_cuda_path:
+            import wtpse_b200 as wb
+            losses = [wb.whitening_folded(t, 2, 3) for t in f[:2]]
+        else:
+            losses = [wt.wt_pse_whitening_loss(t, 2, 3) for t in f[:2]]
+        sum(a + b for a, b in losses).backward()
+        grads.append(torch.cat([p.grad.reshape(-1) for p in net.parameters()]).clone())
+    err = (grads[0] - grads[1]).abs().max() / grads[1].abs().max()
+    assert err < 1e-4, float(err)
+
+
+def test_train_step_runs_and_learns():
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda:0")
+    ts = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=0)
+    before = [p.detach().clone() for p in ts.model_shape_oc.parameters()][:4]
+    first = None
+    for it in range(3):
+        image, od, oc = wb.synthetic.fundus_batch(2, 3, 64, 64, dev, seed=it)
+        assert image.min() >= -1.0 and image.max() <= 1.0 and set(od.unique().tolist()) <= {0.0, 1.0}
+        assert float((oc * (1 - od)).sum()) == 0.0               # the cup lies inside the disc
+        img_in = image.clone()
+        out = ts.step(image, od, oc)
+        assert torch.equal(image, img_in + 1)                     # Trainer.py:850 mutates the batch in place
+        vals = {k: float(v) for k, v in out.items()}
+        assert all(np.isfinite(v) for v in vals.values()), vals
+        first = first or vals
+    after = [p.detach() for p in ts.model_shape_oc.parameters()][:4]
+    assert any(not torch.equal(a, b) for a, b in zip(before, after))
+    assert set(first) >= {"loss_seg", "ins_wt", "dom_wt", "kd", "ins_ii", "ins_ij", "loss_seg_oc", "kd_oc"}

@@ -1,0 +1,86 @@
+"""CPU checks of the PyTorch side of the entry-point classes (wt-pse-code_b200/segmentation.py): same
+state-dict keys and initialisation stream as the reference, same backbone outputs.  The loss kernels
+themselves need a GPU and are covered by tests/test_gpu_*.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+
+HP = {"whitening": True, "margin": 0, "shape_prior": True, "shape_attention": True, "cat_shape": False,
+      "shape_attention_coeffient": 0.3, "shape_start": 0.5, "instance_wt_gm": 1, "domain_wt_gm": 1, "multi-turn": 1}
+
+
+def _ours(n=2, K=3):
+    from wtpse_b200 import segmentation as seg
+
+    torch.manual_seed(0)
+    main = seg.WT_PSE(3, 1, dict(HP), "cpu", False, per_domain_batch=n, source_domain_num=K)
+    shape = seg.ShapeVariationalDist_x(dict(HP), "cpu", 1, number_source_domain=K, batch_size=n)
+    return main, shape
+
+
+def test_predict_matches_reference_golden():
+    """Seed-0 construction consumes the RNG in the reference's order, so the weights -- and therefore
+    predict() (algorithms.py:1311-1353, pure backbone) -- reproduce what the reference produced."""
+    g = golden("update_b6_16x16.npz")
+    main, shape = _ours(int(g["n"]), int(g["K"]))
+    main.eval(); shape.eval()
+    with torch.no_grad():
+        logits, pre = main.predict(shape, torch.from_numpy(g["image"]))
+    assert rel_err(logits.numpy(), g["predict_logits"]) < 1e-5
+    assert rel_err(pre.numpy(), g["predict_pre_sigmoid"]) < 1e-5
+
+
+def test_whitening_features_match_reference_golden():
+    g = golden("update_b6_16x16.npz")
+    main, shape = _ours(int(g["n"]), int(g["K"]))
+    with torch.no_grad():
+        fm = main.wt_model(torch.from_numpy(g["image"]))
+        fs = shape.wt_model(torch.from_numpy(g["image"]))
+    assert len(fm) == 3 and torch.equal(fm[2], torch.relu(fm[1]))
+    assert rel_err(fm[0].numpy(), g["main_z0"]) < 1e-6 and rel_err(fm[1].numpy(), g["main_z1"]) < 1e-6
+    assert rel_err(fs[0].numpy(), g["shape_z0"]) < 1e-6 and rel_err(fs[1].numpy(), g["shape_z1"]) < 1e-6
+    main.train(); shape.train()
+    with torch.no_grad():
+        mu_t = main.prior_dist.mu_prior(main.prior_dist.unet_extractor(fm[-1], torch.from_numpy(g["mask"])))
+        mu_s = shape.mu_prior(shape.unet_extractor(fs[-1]))
+    assert rel_err(mu_t.numpy(), g["mu_teacher"]) < 1e-5 and rel_err(mu_s.numpy(), g["mu_student"]) < 1e-5
+
+
+def test_parameter_counts_match_survey():
+    main, shape = _ours()
+    assert sum(p.numel() for p in main.parameters()) == 6378661
+    assert sum(p.numel() for p in shape.parameters()) == 3189570
+
+
+def test_state_dict_is_interchangeable_with_the_reference():
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not on this box")
+    alg, sn, _ = ref_shim.load()
+    torch.manual_seed(0)
+    ref_main = alg.WT_PSE(3, 1, dict(HP), "cpu", False, per_domain_batch=2, source_domain_num=3)
+    ref_shape = sn.ShapeVariationalDist_x(dict(HP), "cpu", 1, number_source_domain=3, batch_size=2)
+    main, shape = _ours()
+    for ours, ref in ((main, ref_main), (shape, ref_shape)):
+        a, b = ours.state_dict(), ref.state_dict()
+        assert list(sorted(a)) == list(sorted(b))
+        for k in a:
+            assert torch.equal(a[k], b[k]), k                 # same init stream under the same seed
+        ours.load_state_dict(b, strict=True)
+        ref.load_state_dict(a, strict=True)
+
+
+def test_no_extra_state_for_the_loss():
+    main, shape = _ours()
+    keys = list(main.state_dict()) + list(shape.state_dict())
+    assert not any(k.split(".")[0] in ("i", "reversal_i", "diagonal", "mmd_operator") for k in keys)
+
+
+def test_update_refuses_cpu_tensors():
+    main, _ = _ours()
+    x = torch.randn(6, 3, 16, 16)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        main.update(x, (x[:, :1] > 0).float(), two_stage_inputs=x, two_step=True)

@@ -9,6 +9,9 @@ from .functional import HostPlan, gram_matrix, kd_mse, whitening_folded, whiteni
 from .mmd import mmd_penalty  # noqa: F401
 from .elementwise import attention_fuse, od_roi, prepare_batch  # noqa: F401
 from . import dropin  # noqa: F401
+from . import dp, segmentation, synthetic, train_step  # noqa: F401
+from .segmentation import ShapeVariationalDist_x, WT_PSE  # noqa: F401
+from .train_step import TrainStep  # noqa: F401
 
 __all__ = ["whitening_terms", "whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin",
-           "prepare_batch", "od_roi", "attention_fuse"]
+           "prepare_batch", "od_roi", "attention_fuse", "WT_PSE", "ShapeVariationalDist_x", "TrainStep"]

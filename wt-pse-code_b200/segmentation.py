@@ -1,0 +1,354 @@
+"""The two entry-point classes of the path -- ``WT_PSE`` and ``ShapeVariationalDist_x`` -- with the
+reference's constructor and ``update()`` / ``predict()`` signatures, tuple arities and tensor layouts
+(SURVEY.md 8(a) rows R4/R6, 8(b)), so the reference's Trainer drives them unchanged.
+
+Split of labour (north_star): the segmentation backbone -- U-Net stages, the DeepWT feature extractor,
+the teacher/student shape networks -- stays ordinary PyTorch (cuDNN); the shape-regularization hot path
+inside ``update()`` runs in the CUDA library:
+
+    whitening + MMD loss   wtpse_whitening_forward/backward        (algorithms.py:1261-1264, shape_networks.py:545-549)
+    KD MSE                 wtpse_mse_forward/backward              (shape_networks.py:529)
+    attention fuse         wtpse_attention_fuse_forward/backward   (algorithms.py:1243-1249)
+
+Module/parameter names follow the reference's state-dict keys (``inc.conv1.weight``,
+``wt_model.DoubleConv.double_conv.0.weight``, ``prior_dist.mu_prior.4.bias`` ...), so checkpoints written by
+either implementation load into the other with ``strict=True``.  No parameter or buffer is added for the loss.
+
+Reference quirks that are reproduced on purpose: losses summed over 2
+embeddings but divided by 3; the ``instance_wt_loss2`` overwrite-and-double in the shape update; the shape
+network's MMD always using 3 domains; the teacher mean NOT detached in the KD loss; the
+``normal(mu, std) * std + mu`` re-parameterisation.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as wf
+from .elementwise import attention_fuse
+
+BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
+
+
+def _norm(planes):
+    return nn.BatchNorm2d(planes)            # norm='bn' everywhere on the trained path (algorithms.py:1174)
+
+
+class ConvD(nn.Module):
+    """Encoder stage: [maxpool] -> conv-bn -> conv-bn-relu -> conv-bn-relu (algorithms.py:877-917)."""
+
+    def __init__(self, inplanes, planes, first=False):
+        super().__init__()
+        self.first = first
+        self.conv1, self.bn1 = nn.Conv2d(inplanes, planes, 3, padding=1), _norm(planes)
+        self.conv2, self.bn2 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
+        self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
+
+    def forward(self, x):
+        if not self.first:
+            x = F.max_pool2d(x, 2)
+        x = self.bn1(self.conv1(x))                      # no activation after the first conv
+        x = F.relu(self.bn2(self.conv2(x)), inplace=True)
+        return F.relu(self.bn3(self.conv3(x)), inplace=True)
+
+
+class ConvU(nn.Module):
+    """Decoder stage: [conv-bn-relu] -> bilinear x2 -> 1x1 conv-bn-relu -> cat(skip) -> conv-bn-relu
+    (algorithms.py:920-962)."""
+
+    def __init__(self, planes, first=False):
+        super().__init__()
+        self.first = first
+        if not first:
+            self.conv1, self.bn1 = nn.Conv2d(2 * planes, planes, 3, padding=1), _norm(planes)
+        self.conv2, self.bn2 = nn.Conv2d(planes, planes // 2, 1), _norm(planes // 2)
+        self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
+
+    def forward(self, x, skip):
+        if not self.first:
+            x = F.relu(self.bn1(self.conv1(x)), inplace=True)
+        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        x = F.relu(self.bn2(self.conv2(x)), inplace=True)
+        x = torch.cat([skip, x], 1)
+        return F.relu(self.bn3(self.conv3(x)), inplace=True)
+
+
+class _UNetTrunk(nn.Module):
+    """down1..down4 / up1..up4 shared by all three U-Nets (widths 16-32-64-128-256)."""
+
+    def _build_trunk(self, n=BASE_WIDTH):
+        self.down1, self.down2 = ConvD(n, 2 * n), ConvD(2 * n, 4 * n)
+        self.down3, self.down4 = ConvD(4 * n, 8 * n), ConvD(8 * n, 16 * n)
+        self.up1 = ConvU(16 * n, first=True)
+        self.up2, self.up3, self.up4 = ConvU(8 * n), ConvU(4 * n), ConvU(2 * n)
+
+    def _trunk(self, x1):
+        x2 = self.down1(x1)
+        x3 = self.down2(x2)
+        x4 = self.down3(x3)
+        x5 = self.down4(x4)
+        x = self.up1(x5, x4)
+        x = self.up2(x, x3)
+        x = self.up3(x, x2)
+        return self.up4(x, x1)
+
+
+class _DoubleConv(nn.Module):
+    """conv-bn-relu x2; state-dict keys double_conv.{0,1,3,4} (algorithms.py:398-413)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
+                                         nn.Conv2d(cout, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
+
+    def forward(self, x):
+        return self.double_conv(x)
+
+
+class _DoubleConvWT(nn.Module):
+    """conv-relu-conv, no norm; keys double_conv.{0,2} (algorithms.py:416-428)."""
+
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(inplace=True),
+                                         nn.Conv2d(cout, cout, 3, padding=1))
+
+    def forward(self, x):
+        return self.double_conv(x)
+
+
+class DeepWT(nn.Module):
+    """Whitening feature extractor (algorithms.py:1080-1117): returns [z0, z1, relu(z1)]; z0 and z1 -- both
+    PRE-activation, the InstanceNorm of the reference is constructed but commented out -- feed the
+    whitening loss, the last one feeds the shape networks."""
+
+    def __init__(self, input_channel, out_channel, whitening=True):
+        super().__init__()
+        self.whitening = whitening
+        if whitening:
+            self.DoubleConv = _DoubleConvWT(input_channel, out_channel)
+            self.DoubleConv2 = _DoubleConvWT(out_channel, out_channel)
+
+    def forward(self, x):
+        if not self.whitening:
+            return [x]
+        z0 = self.DoubleConv(x)
+        z1 = self.DoubleConv2(F.relu(z0))
+        return [z0, z1, F.relu(z1)]
+
+
+def _head(cin, mid, cout):
+    return nn.Sequential(nn.Conv2d(cin, cin, 1), nn.ReLU(), nn.Conv2d(cin, mid, 1), nn.ReLU(), nn.Conv2d(mid, cout, 1))
+
+
+class ShapeVariationalDist_y_x(_UNetTrunk):
+    """Teacher shape network p(shape | mask, features) (algorithms.py:979-1075)."""
+
+    def __init__(self, hparams, device, n_channels, bilinear, n_classes, wt=True, prior=True, number_source_domain=3):
+        super().__init__()
+        self.device, self.prior, self.wt = device, prior, hparams["whitening"]
+        self.number_source_domain = number_source_domain
+        n = BASE_WIDTH
+        if self.wt:
+            self.inc = _DoubleConv(n_channels, n)
+            self.fusion = nn.Sequential(nn.Conv2d(2 * n, n, 1), nn.ReLU())
+        else:
+            self.inc = _DoubleConv(n_channels + 1, n)
+        self._build_trunk(n)
+        self.mu_prior = _head(2 * n, 8, n_classes)
+        self.logvar_prior = _head(2 * n, 8, n_classes)
+
+    def unet_extractor(self, inputs, mask):
+        if self.wt:
+            x1 = self.fusion(torch.cat([self.inc(mask), inputs], 1))
+        else:
+            x1 = self.inc(torch.cat([mask, inputs], 1))
+        return self._trunk(x1)
+
+    def sample_forward(self, inputs, mask=None, training=True):
+        fm = self.unet_extractor(inputs, mask)
+        mu = self.mu_prior(fm)
+        if not training:
+            return mu
+        logvar = self.logvar_prior(fm)
+        return self.reparameterization(mu, logvar), mu
+
+    def reparameterization(self, mu, logvar):
+        std = torch.exp(logvar / 2)
+        return mu + std * torch.randn_like(std)          # algorithms.py:1068-1075
+
+
+class attention_layer(nn.Module):  # noqa: N801  (reference name; key attention_layer.layer1.*)
+    def __init__(self, channel1, channel2):
+        super().__init__()
+        self.layer1 = nn.Conv2d(channel1, channel2, kernel_size=1)
+
+    def forward(self, x):
+        x1 = self.layer1(x)
+        return torch.sigmoid(x1), x1
+
+
+class _MmdConfig:
+    """Stands in for the reference's compute_MMD instance: only (domain_num, batch_size) are state."""
+
+    def __init__(self, domain_num, batch_size):
+        self.domain_num, self.batch_size = domain_num, batch_size
+
+    def forward(self, inputs, **kwargs):
+        from .mmd import mmd_penalty
+        return mmd_penalty(inputs, self.batch_size, self.domain_num)
+
+
+class WT_PSE(_UNetTrunk):
+    """Segmentation network + shape regularisation (algorithms.py:1134-1353)."""
+
+    def __init__(self, n_channels, n_classes, hparams, device, two_step, per_domain_batch=8, source_domain_num=3,
+                 feature_dim=8, bilinear=True):
+        super().__init__()
+        self.n_channels, self.n_classes, self.device, self.hparams = n_channels, n_classes, device, hparams
+        self.eps = 1e-5
+        self.two_step, self.per_domain_batch, self.number_source_domain = two_step, per_domain_batch, source_domain_num
+        self.whitening, self.cat_shape, self.margin = hparams["whitening"], hparams["cat_shape"], hparams["margin"]
+        self.dim = BASE_WIDTH
+        self.mmd_operator = _MmdConfig(domain_num=source_domain_num, batch_size=per_domain_batch)
+        n = BASE_WIDTH
+        self.wt_model = DeepWT(3, n, whitening=self.whitening)
+        self.inc = ConvD(n_channels, n, first=True)
+        self._build_trunk(n)
+        fuse_dim = feature_dim
+        if hparams["shape_prior"]:
+            self.prior_dist = ShapeVariationalDist_y_x(hparams, device, 1, bilinear, n_classes=1, wt=self.whitening,
+                                                       prior=True, number_source_domain=source_domain_num)
+            if self.cat_shape:
+                fuse_dim = feature_dim + 1
+        self.mu = nn.Sequential(nn.Conv2d(2 * n, 2 * n, 1), nn.ReLU(), nn.Conv2d(2 * n, feature_dim, 1))
+        self.outc = nn.Sequential(nn.Conv2d(fuse_dim, n_classes, 1))
+        self.attention_layer = attention_layer(1, 1)
+
+    # -- backbone (PyTorch) -----------------------------------------------------------------------
+    def embed(self, inputs):
+        return self.mu(self._trunk(self.inc(inputs)))
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def compute_whitening_loss(self, z):
+        """(instance_loss, domain_loss) -- algorithms.py:1277-1309, one CUDA forward + one fused backward."""
+        return wf.whitening_folded(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
+                                   float(self.eps))
+
+    def update(self, inputs, mask, step=0, plot_show=0, two_stage_inputs=None, sp_mask=None, two_step=False):
+        embedding = self.embed(inputs)
+        attention_mask = 0
+        feats = None
+        if self.hparams["shape_prior"]:
+            feats = self.wt_model(two_stage_inputs if two_step else inputs)
+            z_post, _z_post_mu = self.prior_dist.sample_forward(feats[-1], mask, training=True)
+            if self.hparams["shape_attention"]:
+                lay = self.attention_layer.layer1
+                embedding_f, attention_mask = attention_fuse(embedding, z_post, lay.weight, lay.bias,
+                                                             self.hparams["shape_attention_coeffient"])
+            else:
+                embedding_f = embedding
+            embedding = torch.cat([embedding_f, z_post], 1) if self.cat_shape else embedding_f
+        instance_wt_loss, domain_wt_loss = 0, 0
+        if self.hparams["whitening"]:
+            num_embeddings = len(feats)
+            for k in range(num_embeddings - 1):                       # two embeddings ...
+                ins_k, dom_k = self.compute_whitening_loss(feats[k])
+                instance_wt_loss = instance_wt_loss + ins_k
+                domain_wt_loss = domain_wt_loss + dom_k
+            instance_wt_loss = instance_wt_loss / num_embeddings      # ... divided by three (algorithms.py:1266-1267)
+            domain_wt_loss = domain_wt_loss / num_embeddings
+        output = self.outc(embedding)
+        if self.hparams["shape_prior"]:
+            return output, attention_mask, attention_mask, instance_wt_loss, domain_wt_loss
+        return output, 0, 0, 0, 0
+
+    def predict(self, learn_x_network, inputs_all):
+        if self.two_step:
+            inputs, two_stage_inputs = inputs_all[0], inputs_all[1]
+        else:
+            inputs = two_stage_inputs = inputs_all
+        embedding = self.embed(inputs)
+        pre_sigmoid = None
+        if self.hparams["shape_prior"]:
+            feats = learn_x_network.wt_model(two_stage_inputs)
+            z_post = learn_x_network.sample_forward(feats[-1], training=False)
+            if self.hparams["shape_attention"]:
+                att, pre_sigmoid = self.attention_layer(z_post)
+                fuse = self.hparams["shape_attention_coeffient"] * embedding + att * embedding
+            else:
+                fuse = embedding
+            embedding = torch.cat([fuse, z_post], 1) if self.cat_shape else fuse
+        return self.outc(embedding), pre_sigmoid
+
+
+class ShapeVariationalDist_x(_UNetTrunk):
+    """Student shape network p(shape | features) with its distillation update (shape_networks.py:415-597)."""
+
+    def __init__(self, hparams, device, n_classes, number_source_domain=3, batch_size=3):
+        super().__init__()
+        self.device, self.batch_size, self.hparams = device, batch_size, hparams
+        self.wt = self.whitening = hparams["whitening"]
+        self.number_source_domain = number_source_domain
+        self.eps, self.margin, self.dim = 1e-5, hparams["margin"], BASE_WIDTH
+        n = BASE_WIDTH
+        self.wt_model = DeepWT(3, n, whitening=self.whitening)
+        if not self.wt:
+            self.inc = _DoubleConv(3, n)
+        self._build_trunk(n)
+        self.mmd_operator = _MmdConfig(domain_num=3, batch_size=batch_size)      # literal 3, shape_networks.py:448
+        self.mu_prior = _head(2 * n, 8, n_classes)
+        self.logvar_prior = _head(2 * n, 8, n_classes)
+
+    def unet_extractor(self, inputs):
+        return self._trunk(inputs if self.wt else self.inc(inputs))
+
+    @staticmethod
+    def _scrub_nan(t):
+        # shape_networks.py:490-492 / :504-506: `if isnan(t).any(): t = nan_to_num(t); t[t == inf] = 0`.
+        # Same result without the host sync of the python `if`: the whole tensor is replaced only when it
+        # contains a NaN (the follow-up `t[t == inf] = 0` can never fire after nan_to_num).
+        return torch.where(torch.isnan(t).any(), torch.nan_to_num(t), t)
+
+    def sample_forward(self, inputs, training):
+        fm = self.unet_extractor(inputs)
+        mu = self._scrub_nan(self.mu_prior(fm))
+        if not training:
+            return mu
+        logvar = self.logvar_prior(fm)
+        return self.reparameterization(mu, logvar), mu
+
+    def reparameterization(self, mu, logvar):
+        std = self._scrub_nan(torch.exp(logvar / 2))
+        return torch.normal(mu, std) * std + mu              # shape_networks.py:507-509
+
+    def compute_whitening_loss(self, z):
+        """(off_diagonal_loss, diagonal_loss, domain_loss) -- shape_networks.py:561-594."""
+        return wf.whitening_terms(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
+                                  float(self.eps))
+
+    def wasser_distance(self, prior_space_mu, posterior_space_mu):
+        return wf.kd_mse(prior_space_mu, posterior_space_mu)            # nn.MSELoss(reduction='mean'), :596-597
+
+    def update(self, main_network, inputs, mask, step=0, plot_show=0, two_stage_inputs=None, two_step=False):
+        if not self.hparams["whitening"]:
+            return 0, 0, 0, 0, 0
+        x = two_stage_inputs if two_step else inputs
+        teacher_feats = main_network.wt_model(x)
+        student_feats = self.wt_model(x)
+        # teacher: features + mask (its mean is NOT detached: gradients reach main_network and are discarded
+        # by the caller's zero_grad, shape_networks.py:524); student: features only
+        _z_post, z_post_mu = main_network.prior_dist.sample_forward(teacher_feats[-1], mask, training=True)
+        _z_pre, z_pre_mu = self.sample_forward(student_feats[-1], training=True)
+        kd_loss = self.wasser_distance(z_post_mu, z_pre_mu)
+        # (the two attention_layer forwards at shape_networks.py:531-535 have no effect on any output)
+        off_sum, diag_last, dom_sum = 0, 0, 0
+        num_embeddings = len(student_feats)
+        for k in range(num_embeddings - 1):
+            off_k, diag_k, dom_k = self.compute_whitening_loss(student_feats[k])
+            off_sum = off_sum + off_k
+            diag_last = diag_k + diag_k           # `a, instance_wt_loss2, b = f(); instance_wt_loss2 += instance_wt_loss2`
+            dom_sum = dom_sum + dom_k
+        instance_ij = off_sum / num_embeddings
+        instance_ii = diag_last / num_embeddings
+        domain = dom_sum / num_embeddings
+        return kd_loss, instance_ij + instance_ii, instance_ij, instance_ii, domain

@@ -1,0 +1,90 @@
+"""One training iteration of WT-PSE: the body of ``Trainer.train_epoch`` (Trainer.py:762-925) as a harness
+that takes a device batch and returns device scalars (no per-loss ``.item()`` host syncs).
+
+Four sub-steps, exactly in the reference's order and with its loss definitions:
+  1. OD segmentation net   BCE(sigmoid(out), od) + w_i * ins + w_d * dom          Trainer.py:779-805
+  2. OD shape net          kd + w_i * ins_total + w_d * dom                        Trainer.py:811-825
+  -- coarse-to-fine: od_pred = sigmoid(out) > 0.75 ; image += 1 ; roi = image * od_pred - 1   :842-853 --
+  3. OC segmentation net   BCE-with-logits(out * od_pred, oc, pos_weight) + ...    Trainer.py:856-892
+  4. OC shape net                                                                  Trainer.py:896-914
+Adam(lr 5e-4, betas (0.9, 0.99)) per network (train.py:120-138).  With a process group, each backward is
+followed by one bucketed all-reduce of that network's gradients (dp.FlatGradBucket); the gradients the
+shape update deposits into the segmentation network (teacher not detached) are never reduced.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import segmentation as seg
+from .dp import FlatGradBucket
+from .elementwise import od_roi
+
+DEFAULT_HPARAMS = {   # hparams_registry.py:75-93
+    "whitening": True, "margin": 0, "shape_prior": True, "shape_attention": True, "cat_shape": False,
+    "shape_attention_coeffient": 0.3, "shape_start": 0.5, "instance_wt_gm": 1, "domain_wt_gm": 1, "multi-turn": 1,
+}
+
+
+class TrainStep:
+    def __init__(self, n_per_domain, n_domains=3, device="cuda", hparams=None, lr=5e-4, seed=0, process_group=None):
+        self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
+        self.device = torch.device(device)
+        torch.manual_seed(seed)                                   # identical initial weights on every rank
+        mk = lambda two_step: seg.WT_PSE(3, 1, self.hp, self.device, two_step, per_domain_batch=n_per_domain,
+                                         source_domain_num=n_domains)
+        sh = lambda: seg.ShapeVariationalDist_x(self.hp, self.device, 1, number_source_domain=n_domains,
+                                                batch_size=n_per_domain)
+        self.model, self.model_shape = mk(False).to(self.device), sh().to(self.device)
+        self.model_oc, self.model_shape_oc = mk(True).to(self.device), sh().to(self.device)
+        self.nets = (self.model, self.model_shape, self.model_oc, self.model_shape_oc)
+        for m in self.nets:
+            m.train()
+        self.buckets = [FlatGradBucket(m, process_group) for m in self.nets]
+        self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99)) for m in self.nets]
+        self.iteration = 0
+
+    def _finish(self, idx, loss):
+        loss.backward()
+        self.buckets[idx].allreduce_mean()
+        self.optims[idx].step()
+
+    def step(self, image, target_od, target_oc):
+        """image B x 3 x H x W in [-1, 1] (MUTATED in place: += 1, as Trainer.py:850 does); targets B x 1 x H x W.
+        Returns a dict of 0-dim device tensors."""
+        hp = self.hp
+        wi, wd = hp["instance_wt_gm"], hp["domain_wt_gm"]
+        out = {}
+        # ---- 1. OD segmentation ---------------------------------------------------------------------
+        self.buckets[0].zero()
+        output, _, _, ins, dom = self.model.update(image, target_od, step=self.iteration, plot_show=0,
+                                                   two_stage_inputs=image, sp_mask=target_od, two_step=True)
+        loss_seg = F.binary_cross_entropy(torch.sigmoid(output), target_od)
+        self._finish(0, loss_seg + wi * ins + wd * dom)
+        out.update(loss_seg=loss_seg.detach(), ins_wt=ins.detach(), dom_wt=dom.detach())
+        # ---- 2. OD shape network --------------------------------------------------------------------
+        for _ in range(hp["multi-turn"]):
+            self.buckets[1].zero()
+            kd, ins_s, ins_ij, ins_ii, dom_s = self.model_shape.update(self.model, image, target_od, step=self.iteration,
+                                                                      plot_show=0, two_stage_inputs=image, two_step=True)
+            self._finish(1, kd + wi * ins_s + wd * dom_s)
+        out.update(kd=kd.detach(), ins_wt_shape=ins_s.detach(), ins_ij=ins_ij.detach(), ins_ii=ins_ii.detach(),
+                   dom_wt_shape=dom_s.detach())
+        # ---- coarse-to-fine ROI (one kernel; also yields the BCE pos_weight without a host sync) ------
+        od_pred, image_roi, sums = od_roi(output, image, target_oc, 0.75)
+        pos_weight = sums[2]
+        # ---- 3. OC segmentation ---------------------------------------------------------------------
+        self.buckets[2].zero()
+        output_oc, _, _, ins_oc, dom_oc = self.model_oc.update(image_roi, target_oc, step=self.iteration, plot_show=0,
+                                                               two_stage_inputs=image_roi, two_step=True)
+        loss_seg_oc = F.binary_cross_entropy_with_logits(output_oc * od_pred, target_oc, pos_weight=pos_weight)
+        self._finish(2, loss_seg_oc + wi * ins_oc + wd * dom_oc)
+        out.update(loss_seg_oc=loss_seg_oc.detach(), ins_wt_oc=ins_oc.detach(), dom_wt_oc=dom_oc.detach())
+        # ---- 4. OC shape network --------------------------------------------------------------------
+        for _ in range(hp["multi-turn"]):
+            self.buckets[3].zero()
+            kd_oc, ins_s_oc, _, _, dom_s_oc = self.model_shape_oc.update(self.model_oc, image_roi, target_oc,
+                                                                        step=self.iteration, plot_show=0,
+                                                                        two_stage_inputs=image_roi, two_step=True)
+            self._finish(3, kd_oc + wi * ins_s_oc + wd * dom_s_oc)
+        out.update(kd_oc=kd_oc.detach(), ins_wt_shape_oc=ins_s_oc.detach(), dom_wt_shape_oc=dom_s_oc.detach())
+        self.iteration += 1
+        return out
