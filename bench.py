@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--train-size", type=int, default=512)
     ap.add_argument("--train-batch", type=int, default=16, help="nominal per-GPU batch (the reference uses 3 * (batch // 3))")
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
+    ap.add_argument("--debug-backward-mode", type=int, default=0)
+    ap.add_argument("--debug-round-robin", type=int, default=1)
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
 
@@ -233,6 +235,8 @@ def run_ours(args):
     margin, eps = WORKLOAD["margin"], WORKLOAD["eps"]
     pix = B * H * W
     lib = wb._lib.load()
+    lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
+    lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
 
     # two resident input batches, alternated, each 4x the 126 MB L2 -> no timed step finds its input in L2
     zs = [synth_batch(B, H, W, seed=1234 + 17 * rank + i, device=dev).requires_grad_(True) for i in range(2)]
@@ -407,7 +411,7 @@ def time_train_step(args, dev, rank, world, barrier):
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
             "steps": args.train_steps, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
             "global_batch_used": world * used, "our_kernel_launches": int(lib.wtpse_profile_launches(-1)),
-            "backbone": "PyTorch/cuDNN (fp32, TF32 convs as torch defaults)", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
+            "backbone": "PyTorch/cuDNN, channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}
 
 

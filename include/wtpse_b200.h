@@ -174,8 +174,11 @@ int         wtpse_profile_read(int id, long long* timed_launches, double* total_
 void        wtpse_debug_set_stamp_buffer(long long* device_buffer16);
 /* Diagnostics: launch each epilogue kernel n times back to back (warm instruction cache experiment). */
 void        wtpse_debug_set_epilogue_repeat(int n);
-/* Tests: use the two-kernel backward (epilogue + apply) even where the fused kernel applies. */
-void        wtpse_debug_force_unfused_backward(int on);
+/* Tests/diagnostics: backward variant. 0 (default) per-sample M_b kernel + round-robin apply chained by
+ * programmatic dependent launch; 1 M_b derived inside the apply kernel; 2 single-CTA epilogue + apply. */
+void        wtpse_debug_set_backward_mode(int mode);
+/* Diagnostics: round-robin instead of contiguous tile schedule in the unfused apply kernel. */
+void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
 
 #ifdef __cplusplus
 }

@@ -276,24 +276,25 @@ def test_run_to_run_bit_reproducible():
         assert o[0] == outs[0][0] and o[1] == outs[0][1] and torch.equal(o[2], outs[0][2])
 
 
-def test_fused_backward_is_bitwise_the_two_kernel_backward():
-    """apply_tma_kernel<fused> derives M_b per CTA; it must reproduce epilogue_bwd + apply exactly."""
+def test_backward_variants_are_bitwise_identical():
+    """Per-sample M_b kernel + round-robin apply (default), M_b derived inside the apply kernel, and the single-CTA
+    epilogue + apply share their arithmetic (mmd_device.cuh): same bits."""
     import wtpse_b200 as wb
 
     lib = wb._lib.load()
     for B, H, n in ((9, 96, 3), (32, 128, 10), (6, 32, 2)):
         z = _synth(B, H, H, seed=B).to(_dev())
         grads = []
-        for unfused in (0, 1):
-            lib.wtpse_debug_force_unfused_backward(unfused)
+        for mode in (0, 1, 2):
+            lib.wtpse_debug_set_backward_mode(mode)
             try:
                 zz = z.clone().requires_grad_(True)
                 off, diag, dom = wb.whitening_terms(zz, n, 3)
                 (0.7 * off + 1.9 * diag + 1.3 * dom).backward()
                 grads.append(zz.grad.clone())
             finally:
-                lib.wtpse_debug_force_unfused_backward(0)
-        assert torch.equal(grads[0], grads[1])
+                lib.wtpse_debug_set_backward_mode(0)
+        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
 
 
 def test_many_mmd_samples_fall_back_to_the_epilogue_kernel():

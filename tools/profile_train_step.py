@@ -9,7 +9,7 @@ if os.environ.get("CUDNN_BENCHMARK", "0") == "1":
     torch.backends.cudnn.benchmark = True
 dev = torch.device("cuda:0")
 S = int(os.environ.get("SIZE", "512"))
-ts = wb.TrainStep(n_per_domain=5, n_domains=3, device=dev, seed=0)
+ts = wb.TrainStep(n_per_domain=5, n_domains=3, device=dev, seed=0, channels_last=os.environ.get('CHANNELS_LAST', '0') == '1')
 def one(it):
     image, od, oc = wb.synthetic.fundus_batch(5, 3, S, S, dev, seed=it)
     return ts.step(image, od, oc)

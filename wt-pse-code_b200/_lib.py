@@ -55,7 +55,8 @@ EXPORTS = {
     "wtpse_profile_read": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_double)]),
     "wtpse_debug_set_stamp_buffer": (None, [_c.c_void_p]),
     "wtpse_debug_set_epilogue_repeat": (None, [_c.c_int]),
-    "wtpse_debug_force_unfused_backward": (None, [_c.c_int]),
+    "wtpse_debug_set_backward_mode": (None, [_c.c_int]),
+    "wtpse_debug_set_apply_round_robin": (None, [_c.c_int]),
     "wtpse_host_plan_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     "wtpse_host_plan_destroy": (None, [_c.c_void_p]),
     "wtpse_host_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,

@@ -39,7 +39,7 @@ int sm_count_cached() {
     return cache[dev];
 }
 
-bool g_force_unfused_backward = false;   // diagnostics/tests: exercise the two-kernel backward
+int g_backward_mode = 0;                  // see wtpse_whitening_backward
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -122,9 +122,17 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
     if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (apply_can_fuse(z, dz, B, P, n_per_domain, n_domains) && !g_force_unfused_backward) {
+    // g_backward_mode: 0 = per-sample M_b kernel + round-robin apply chained by programmatic dependent launch (default),
+    //                  1 = M_b derived inside the apply kernel (one launch, contiguous tile ranges),
+    //                  2 = single-CTA epilogue + apply (also the fallback for very many MMD samples)
+    if (g_backward_mode == 1 && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
         LaunchScope scope(kKernApply, s);
         e = launch_apply_fused(z, gram, rowstat, g_off, g_diag, g_dom, dz, B, P, n_per_domain, n_domains, sms, s);
+    } else if (g_backward_mode != 2 && mmat_multi_cta_ok(B, n_per_domain, n_domains)) {
+        LaunchScope scope(kKernApply, s);            // one scope: an event between the two would defeat the overlap
+        e = launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s);
+        if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
+        e = launch_apply(z, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/true);
     } else {
         { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s); }
         if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
@@ -136,7 +144,8 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
 
 void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }
 void wtpse_debug_set_epilogue_repeat(int n) { g_epilogue_repeat = n > 0 ? n : 1; }
-void wtpse_debug_force_unfused_backward(int on) { g_force_unfused_backward = on != 0; }
+void wtpse_debug_set_backward_mode(int mode) { g_backward_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
+void wtpse_debug_set_apply_round_robin(int chunk) { g_apply_round_robin = chunk > 0 ? chunk : 0; }
 
 size_t wtpse_mmd_workspace_bytes(int B) {
     if (B <= 0) return 0;

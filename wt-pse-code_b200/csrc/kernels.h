@@ -22,6 +22,7 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
 size_t epilogue_scratch_bytes(int B, int K);
 extern long long* g_epilogue_dbg;
 extern int g_epilogue_repeat;
+extern int g_apply_round_robin;
 
 // forward: partial slots -> gram, rowstat, losses
 cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
@@ -33,13 +34,19 @@ cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, 
                                        const float* g_dom, int B, long long P, int n_per_domain, int n_domains,
                                        float* mmat, void* scratch, cudaStream_t stream);
 
+// backward stage 1, one CTA per sample (triggers programmatic dependents immediately)
+bool mmat_multi_cta_ok(int B, int n_per_domain, int n_domains);
+cudaError_t launch_whiten_mmat(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
+                               const float* g_dom, int B, long long P, int n_per_domain, int n_domains, float* mmat,
+                               cudaStream_t stream);
+
 // standalone compute_MMD.forward / backward on v[B][120]; dv == nullptr selects the forward
 cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,
                        void* scratch, cudaStream_t stream);
 
 // backward apply: dz_b = M_b z_b
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
-                         cudaStream_t stream);
+                         cudaStream_t stream, bool programmatic_dependent = false);
 
 // fused backward: every CTA derives M_b for its own samples (no separate epilogue launch)
 bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains);

@@ -318,6 +318,57 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(Bwd
     WTPSE_STAMP(3);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward stage 1, multi-CTA: one CTA per sample derives M_b (same arithmetic as the single-CTA
+// kernel above, parallel over samples).  It triggers its dependents at once (griddepcontrol), so the
+// apply kernel launched behind it with programmatic stream serialisation starts streaming z while the
+// matrices are still being computed, and only waits right before it reads the first M_b.
+constexpr int kMmatThreads = 256;
+
+__global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x;
+    const int B = p.B, b = blockIdx.x;
+    const DomainInfo dom = make_domain(B, p.n, p.K);
+    const int M = dom.M;
+    float* vbuf = reinterpret_cast<float*>(smem_raw);                 // [M][124]
+    float* coefrow = vbuf + round4(size_t(M) * kVStride);            // [M]
+    __shared__ IndexTables tab;
+    build_index_tables(tab, tid, kMmatThreads);
+    const float g_off = p.g_off ? __ldg(p.g_off) : 0.f;
+    const float g_diag = p.g_diag ? __ldg(p.g_diag) : 0.f;
+    const float g_dom = p.g_dom ? __ldg(p.g_dom) : 0.f;
+    const bool in_mmd = (M > 0) && (g_dom != 0.f) && (b < M);         // block-uniform
+    __syncthreads();
+    if (in_mmd) {
+        for (int idx = tid; idx < M * kOff; idx += kMmatThreads) {
+            const int c = idx / kOff, o = idx - c * kOff;
+            const int ij = tab.off[o];
+            vbuf[size_t(c) * kVStride + o] = __ldg(p.gram + c * 256 + (ij >> 4) * kC + (ij & 15));
+        }
+        __syncthreads();
+        for (int c = tid; c < M; c += kMmatThreads) {
+            const float D = mmd_distance(vbuf + size_t(b) * kVStride, vbuf + size_t(c) * kVStride);
+            coefrow[c] = mmd_coefficient(dom, b, c, expf(-D));
+        }
+        __syncthreads();
+    }
+    const float denom = float(p.P - 1);
+    const float w_off = g_off / (float(B) * float(kOff));
+    const float w_diag = g_diag / (float(B) * float(kC));
+    if (tid < kTri) {
+        const int ij = tab.tri[tid], i = ij >> 4, j = ij & 15;
+        const float g = __ldg(p.gram + b * 256 + i * kC + j);
+        float dom_grad = 0.f;
+        if (in_mmd && i != j) dom_grad = g_dom * mmd_grad_entry(vbuf, coefrow, M, b, off_idx(i, j));
+        const float m = backward_matrix_entry(i, j, g, __ldg(p.rowstat + b * 2 + 0), __ldg(p.rowstat + b * 2 + 1), w_off,
+                                              w_diag, dom_grad, denom);
+        p.mmat[b * 256 + i * kC + j] = m;
+        p.mmat[b * 256 + j * kC + i] = m;
+    }
+}
+
 // ---- standalone compute_MMD.forward on a B x 120 input (algorithms.py:102-121) -------------------
 struct MmdParams {
     const float* v32;
@@ -440,6 +491,28 @@ cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, 
         if (p.in_smem) whiten_epilogue_bwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
         else whiten_epilogue_bwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
     }
+    return cudaGetLastError();
+}
+
+bool mmat_multi_cta_ok(int B, int n_per_domain, int n_domains) {
+    const size_t M = size_t(mmd_samples(B, n_per_domain, n_domains));
+    return (round4(M * kVStride) + round4(M)) * sizeof(float) <= kEpiSmemCap;
+}
+
+cudaError_t launch_whiten_mmat(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
+                               const float* g_dom, int B, long long P, int n_per_domain, int n_domains, float* mmat,
+                               cudaStream_t stream) {
+    BwdParams p;
+    p.gram = gram; p.rowstat = rowstat; p.g_off = g_off; p.g_diag = g_diag; p.g_dom = g_dom;
+    p.B = B; p.P = P; p.n = n_per_domain; p.K = n_domains; p.mmat = mmat;
+    p.scratch = nullptr; p.in_smem = 1; p.dbg = nullptr;
+    const size_t M = size_t(mmd_samples(B, n_per_domain, n_domains));
+    const size_t dyn = (round4(M * kVStride) + round4(M)) * sizeof(float);
+    if (dyn > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(whiten_mmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn));
+        if (e != cudaSuccess) return e;
+    }
+    whiten_mmat_kernel<<<B, kMmatThreads, dyn, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -21,10 +21,7 @@ class FlatGradBucket:
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)       # autograd accumulates in place into the view
-            off += p.numel()
+        self._rebind()
 
     def zero(self):
         """Replaces optimizer.zero_grad()/module.zero_grad() (Trainer.py:767-768): one memset, views stay bound."""
@@ -38,7 +35,9 @@ class FlatGradBucket:
     def _rebind(self):
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # a view with the parameter's own strides (channels-last weights keep their layout, as the
+            # gradient-layout contract and the fused optimizers require); autograd accumulates in place into it
+            p.grad = torch.as_strided(self.flat, p.size(), p.stride(), storage_offset=off)
             off += p.numel()
 
     def allreduce_mean(self):
