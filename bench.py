@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
     ap.add_argument("--debug-backward-mode", type=int, default=0)
     ap.add_argument("--debug-round-robin", type=int, default=1)
+    ap.add_argument("--debug-gram-round-robin", type=int, default=0)
+    ap.add_argument("--debug-two-stage-epilogue", type=int, default=1)
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
 
@@ -237,6 +239,8 @@ def run_ours(args):
     lib = wb._lib.load()
     lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
     lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
+    lib.wtpse_debug_set_gram_round_robin(args.debug_gram_round_robin)
+    lib.wtpse_debug_set_two_stage_epilogue(args.debug_two_stage_epilogue)
 
     # two resident input batches, alternated, each 4x the 126 MB L2 -> no timed step finds its input in L2
     zs = [synth_batch(B, H, W, seed=1234 + 17 * rank + i, device=dev).requires_grad_(True) for i in range(2)]

@@ -39,6 +39,7 @@ int sm_count_cached() {
     return cache[dev];
 }
 
+int g_two_stage_epilogue = 1;            // forward: per-sample reduce kernel (B CTAs) + single-CTA MMD; 0 = one single-CTA kernel
 int g_backward_mode = 0;                  // see wtpse_whitening_backward
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -47,6 +48,8 @@ struct WhitenWorkspace {
     float* partial;
     int* slot_count;
     float* mmat;
+    float* vd;
+    float* statd;
     void* scratch;
     size_t total;
 };
@@ -65,6 +68,8 @@ WhitenWorkspace carve(void* base, int B, long long P, int sms) {
     w.partial = reinterpret_cast<float*>(p + off); off += partial_bytes;
     w.slot_count = reinterpret_cast<int*>(p + off); off += count_bytes;
     w.mmat = reinterpret_cast<float*>(p + off); off += mmat_bytes;
+    w.vd = reinterpret_cast<float*>(p + off); off += align_up(size_t(B) * 124 * sizeof(float), 256);
+    w.statd = reinterpret_cast<float*>(p + off); off += align_up(size_t(B) * 2 * sizeof(float), 256);
     w.scratch = p + off; off += scratch_bytes_any_k(B);
     w.total = off;
     return w;
@@ -105,7 +110,15 @@ int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_d
     cudaError_t e;
     { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, w.slot_count, B, P, g, s); }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
-    { LaunchScope scope(kKernEpilogueFwd, s); e = launch_whiten_epilogue_fwd(w.partial, w.slot_count, g.nslots, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s); }
+    if (g_two_stage_epilogue) {
+        LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
+        e = launch_gram_reduce(w.partial, w.slot_count, g, B, P, n_per_domain, n_domains, margin, eps, gram, rowstat, w.vd, w.statd, s);
+        if (e != cudaSuccess) return cuda_fail(e, "gram reduce launch");
+        e = launch_whiten_epilogue_fwd(nullptr, nullptr, 0, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s, w.vd, w.statd, true);
+    } else {
+        LaunchScope scope(kKernEpilogueFwd, s);
+        e = launch_whiten_epilogue_fwd(w.partial, w.slot_count, g.nslots, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "forward epilogue launch");
     return WTPSE_OK;
 }
@@ -145,6 +158,8 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
 void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }
 void wtpse_debug_set_epilogue_repeat(int n) { g_epilogue_repeat = n > 0 ? n : 1; }
 void wtpse_debug_set_backward_mode(int mode) { g_backward_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
+void wtpse_debug_set_gram_round_robin(int on) { g_gram_round_robin = on != 0; if (on) g_two_stage_epilogue = 1; }
+void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = (on != 0 || g_gram_round_robin) ? 1 : 0; }
 void wtpse_debug_set_apply_round_robin(int chunk) { g_apply_round_robin = chunk > 0 ? chunk : 0; }
 
 size_t wtpse_mmd_workspace_bytes(int B) {

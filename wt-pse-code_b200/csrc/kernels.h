@@ -11,6 +11,7 @@ struct GramPlan {
     long long T;                 // total tiles
     long long G;                 // grid (CTAs)
     int nslots;                  // partial slots per sample
+    bool round_robin;            // tiles dealt round-robin (slot = CTA index) instead of one contiguous range per CTA
 };
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
@@ -27,7 +28,14 @@ extern int g_apply_round_robin;
 // forward: partial slots -> gram, rowstat, losses
 cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
                                        int n_per_domain, int n_domains, float margin, float eps, float* losses,
-                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream);
+                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream,
+                                       const float* vd = nullptr, const float* statd = nullptr, bool pre_reduced = false);
+
+// forward stage 2a (round-robin Gram schedule): one CTA per sample reduces the per-CTA partials
+cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, const GramPlan& g, int B, long long P, int n_per_domain, int n_domains,
+                               float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
+                               cudaStream_t stream);
+extern int g_gram_round_robin;
 
 // backward: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
 cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,

@@ -139,6 +139,9 @@ struct FwdParams {
     float* rowstat;
     void* scratch;      // global fallback for EpiMem
     int in_smem;
+    const float* vd;    // pre-reduced mode (after gram_reduce_kernel): [B][124] vectors and [B][2] row statistics
+    const float* statd;
+    int pre_reduced;
     long long* dbg;     // optional phase timestamps (tools/epilogue_phases.py); nullptr in production
 };
 
@@ -158,6 +161,15 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
     // A. one warp per sample: slots -> Gram entries -> gram, v, off_b, diag_b.
     //    The first three slots are loaded speculatively, together with the slot count, so the warp pays
     //    one L2 round trip instead of a chain of them (unused slots hold garbage that is never added).
+    if (p.pre_reduced) {
+        // the per-sample work was done by gram_reduce_kernel (one CTA per sample): just stage its results
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        for (int idx = tid; idx < dom.M * kOff; idx += kEpiThreads) {
+            const int b = idx / kOff, o = idx - b * kOff;
+            mem.v[size_t(b) * kVStride + o] = __ldg(p.vd + size_t(b) * kVStride + o);
+        }
+        for (int idx = tid; idx < 2 * B; idx += kEpiThreads) mem.stat[idx] = __ldg(p.statd + idx);
+    } else
     for (int b = warp; b < B; b += kEpiWarps) {
         const float* src = p.partial + ((long long)b * p.nslots) * kTri;
         float v0[5], v1[5], v2[5];
@@ -245,6 +257,95 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
         if (lane == 0) p.losses[2] = pen;
     }
     WTPSE_STAMP(4);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward stage 2a for the round-robin Gram schedule: every CTA of the Gram kernel holds a partial for
+// (almost) every sample, so the slot reduction is done by one CTA PER SAMPLE, in a fixed order, together with
+// everything else that is per-sample (Gram entries, 120-d vector, off_b, diag_b).  The single-CTA epilogue
+// that follows only does the MMD and the final sums.
+constexpr int kReduceParts = 4;
+constexpr int kReduceThreads = kTri * kReduceParts;   // 544
+
+struct ReduceParams {
+    const float* partial;     // [B][G][136]
+    const int* slot_count;    // contiguous schedule: slots used per sample (nullptr for round-robin)
+    long long tps, T, G;      // G = slots per sample
+    int B;
+    long long P;
+    int n, K;
+    float margin, eps;
+    float* gram;
+    float* rowstat;
+    float* vd;                // [B][124]
+    float* statd;             // [B][2]
+};
+
+__global__ void __launch_bounds__(kReduceThreads) gram_reduce_kernel(ReduceParams p) {
+    __shared__ float red[kReduceParts][kTri];
+    __shared__ float wred[2][8];
+    __shared__ IndexTables tab;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x;
+    const int e = tid % kTri, part = tid / kTri;
+    build_index_tables(tab, tid, kReduceThreads);
+    asm volatile("griddepcontrol.wait;" ::: "memory");               // partials come from the Gram kernel
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int G = int(p.G);
+    const int per = (G + kReduceParts - 1) / kReduceParts;
+    const int k0 = part * per, k1 = (k0 + per < G) ? k0 + per : G;
+    // CTA k of the Gram kernel touched this sample iff its first tile at or after the sample start lies inside it
+    const long long tb = (long long)b * p.tps, te = tb + p.tps;
+    const int rb = int(tb % G);
+    const int cnt = p.slot_count ? __ldg(p.slot_count + b) : 0;
+    const float* src = p.partial + ((long long)b * G) * kTri + e;
+    float s = 0.f;
+    for (int k = k0; k < k1; k += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int kk = k + u;
+            const int r = kk - rb + (kk < rb ? G : 0);
+            const bool valid = p.slot_count ? (kk < cnt) : (tb + r < te);
+            v[u] = (kk < k1 && valid) ? __ldg(src + (long long)kk * kTri) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    red[part][e] = s;
+    __syncthreads();
+    float off = 0.f, dg = 0.f;
+    if (tid < kTri) {
+        float g = ((red[0][e] + red[1][e]) + red[2][e]) + red[3][e];
+        const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
+        g = g / float(p.P - 1);                              // .div(HW - 1), algorithms.py:1283
+        if (i == j) {
+            g += p.eps;
+            dg = fabsf(g - 1.0f);
+            p.gram[b * 256 + i * kC + i] = g;
+        } else {
+            off = fabsf(g);
+            p.gram[b * 256 + i * kC + j] = g;
+            p.gram[b * 256 + j * kC + i] = g;
+            p.vd[size_t(b) * kVStride + off_idx(i, j)] = g;
+        }
+    }
+    if (warp < 5) {                                          // the 136 entry threads live in warps 0..4
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if (lane == 0) { wred[0][warp] = off; wred[1][warp] = dg; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float so = 0.f, sd = 0.f;
+        for (int w = 0; w < 5; ++w) { so += wred[0][w]; sd += wred[1][w]; }
+        so -= p.margin;
+        sd -= p.margin;
+        p.rowstat[b * 2 + 0] = so;
+        p.rowstat[b * 2 + 1] = sd;
+        p.statd[b * 2 + 0] = so;
+        p.statd[b * 2 + 1] = sd;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -459,17 +560,54 @@ long long* g_epilogue_dbg = nullptr;   // set through wtpse_debug_set_stamp_buff
 
 size_t epilogue_scratch_bytes(int B, int K) { return epi_mem_bytes(B, B, K); }
 
+cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, const GramPlan& g, int B, long long P, int n_per_domain, int n_domains,
+                               float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
+                               cudaStream_t stream) {
+    ReduceParams p;
+    p.partial = partial; p.tps = g.tiles_per_sample; p.T = g.T; p.B = B; p.P = P;
+    p.G = g.nslots;                                   // == grid size for the round-robin schedule
+    p.slot_count = g.round_robin ? nullptr : slot_count;
+    p.n = n_per_domain; p.K = n_domains; p.margin = margin; p.eps = eps;
+    p.gram = gram; p.rowstat = rowstat; p.vd = vd; p.statd = statd;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(B));
+    cfg.blockDim = dim3(kReduceThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gram_reduce_kernel, p);
+}
+
 cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
                                        int n_per_domain, int n_domains, float margin, float eps, float* losses,
-                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream) {
+                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream, const float* vd,
+                                       const float* statd, bool pre_reduced) {
     FwdParams p;
     p.partial = partial; p.slot_count = slot_count; p.nslots = nslots;
     p.B = B; p.P = P; p.n = n_per_domain; p.K = n_domains; p.margin = margin; p.eps = eps;
     p.losses = losses; p.gram = gram; p.rowstat = rowstat;
     p.scratch = scratch; p.dbg = g_epilogue_dbg;
+    p.vd = vd; p.statd = statd; p.pre_reduced = pre_reduced ? 1 : 0;
     cudaError_t e;
     const size_t dyn = epi_smem((const void*)whiten_epilogue_fwd_kernel<true>, B, n_per_domain, n_domains, &p.in_smem, &e);
     if (e != cudaSuccess) return e;
+    if (pre_reduced) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(1);
+        cfg.blockDim = dim3(kEpiThreads);
+        cfg.dynamicSmemBytes = p.in_smem ? dyn : 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return p.in_smem ? cudaLaunchKernelEx(&cfg, whiten_epilogue_fwd_kernel<true>, p)
+                         : cudaLaunchKernelEx(&cfg, whiten_epilogue_fwd_kernel<false>, p);
+    }
     for (int r = 0; r < g_epilogue_repeat; ++r) {
         if (p.in_smem) whiten_epilogue_fwd_kernel<true><<<1, kEpiThreads, dyn, stream>>>(p);
         else whiten_epilogue_fwd_kernel<false><<<1, kEpiThreads, 0, stream>>>(p);
