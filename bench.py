@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
     ap.add_argument("--debug-backward-mode", type=int, default=0)
     ap.add_argument("--debug-round-robin", type=int, default=1)
-    ap.add_argument("--debug-gram-round-robin", type=int, default=0)
+    ap.add_argument("--debug-gram-group", type=int, default=-1)
     ap.add_argument("--debug-two-stage-epilogue", type=int, default=1)
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
@@ -239,7 +239,8 @@ def run_ours(args):
     lib = wb._lib.load()
     lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
     lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
-    lib.wtpse_debug_set_gram_round_robin(args.debug_gram_round_robin)
+    if args.debug_gram_group >= 0:
+        lib.wtpse_debug_set_gram_group(args.debug_gram_group)
     lib.wtpse_debug_set_two_stage_epilogue(args.debug_two_stage_epilogue)
 
     # two resident input batches, alternated, each 4x the 126 MB L2 -> no timed step finds its input in L2

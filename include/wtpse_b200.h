@@ -179,8 +179,9 @@ void        wtpse_debug_set_epilogue_repeat(int n);
 void        wtpse_debug_set_backward_mode(int mode);
 /* Diagnostics: round-robin instead of contiguous tile schedule in the unfused apply kernel. */
 void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
-/* Diagnostics: Gram tile schedule, 1 round-robin (implies the two-stage epilogue), 0 (default) contiguous ranges. */
-void        wtpse_debug_set_gram_round_robin(int on);
+/* Diagnostics: Gram tile schedule = CTAs per group (a group owns a contiguous tile range and deals it round-robin
+ * to its members): 1 contiguous range per CTA, 0 pure round-robin, else a divisor of the grid size. */
+void        wtpse_debug_set_gram_group(int ctas_per_group);
 /* Diagnostics: forward epilogue as per-sample reduce kernel + single-CTA MMD (1, default) or one single-CTA kernel (0). */
 void        wtpse_debug_set_two_stage_epilogue(int on);
 

@@ -298,27 +298,29 @@ def test_backward_variants_are_bitwise_identical():
 
 
 def test_forward_schedules_agree():
-    """Round-robin Gram + per-sample reduce kernel (default) vs contiguous ranges + in-epilogue reduction: same
-    math, different summation order -> equal to fp32 rounding; both bit-reproducible run to run."""
+    """Gram tile schedules (contiguous ranges, grouped, pure round-robin) x epilogue variants (per-sample reduce
+    kernel + single-CTA MMD, or one single-CTA kernel): same math, different summation order -> equal to fp32
+    rounding; each bit-reproducible run to run."""
     import wtpse_b200 as wb
 
     lib = wb._lib.load()
     for B, H, W, n in ((9, 96, 96, 3), (32, 128, 128, 10), (6, 32, 20, 2), (3, 300, 300, 1), (200, 16, 16, 66)):
         z = _synth(B, H, W, seed=B + 1).to(_dev())
         res = []
-        for rr in (1, 0, 1):
-            lib.wtpse_debug_set_gram_round_robin(rr)
-            lib.wtpse_debug_set_two_stage_epilogue(rr)          # rr=0 also exercises the one-kernel epilogue
+        for grp, two_stage in ((0, 1), (1, 0), (0, 1), (4, 1), (2, 0), (37, 1)):
+            lib.wtpse_debug_set_gram_group(grp)                  # 0 = pure round-robin, 1 = contiguous ranges
+            lib.wtpse_debug_set_two_stage_epilogue(two_stage)
             try:
                 off, diag, dom = wb.whitening_terms(z, n, 3)
                 res.append((float(off), float(diag), float(dom), wb.gram_matrix(z).clone()))
             finally:
-                lib.wtpse_debug_set_gram_round_robin(0)
+                lib.wtpse_debug_set_gram_group(1)
                 lib.wtpse_debug_set_two_stage_epilogue(1)
         assert res[0][:3] == res[2][:3] and torch.equal(res[0][3], res[2][3])          # reproducible
-        for a, b in zip(res[0][:3], res[1][:3]):
-            assert _close(a, b, tol=2e-6, scale=1e-3)
-        assert rel_err(res[0][3].cpu().numpy(), res[1][3].cpu().numpy()) < 2e-6
+        for other in res[1:]:
+            for a, b in zip(res[0][:3], other[:3]):
+                assert _close(a, b, tol=2e-6, scale=1e-3)
+            assert rel_err(res[0][3].cpu().numpy(), other[3].cpu().numpy()) < 2e-6
 
 
 def test_many_mmd_samples_fall_back_to_the_epilogue_kernel():

@@ -11,7 +11,8 @@ struct GramPlan {
     long long T;                 // total tiles
     long long G;                 // grid (CTAs)
     int nslots;                  // partial slots per sample
-    bool round_robin;            // tiles dealt round-robin (slot = CTA index) instead of one contiguous range per CTA
+    bool round_robin;            // group > 1
+    int group;                   // CTAs per group: the group owns a contiguous tile range and deals it round-robin
 };
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
@@ -35,7 +36,7 @@ cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_cou
 cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, const GramPlan& g, int B, long long P, int n_per_domain, int n_domains,
                                float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
                                cudaStream_t stream);
-extern int g_gram_round_robin;
+extern int g_gram_group;
 
 // backward: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
 cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,

@@ -566,7 +566,7 @@ cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, cons
     ReduceParams p;
     p.partial = partial; p.tps = g.tiles_per_sample; p.T = g.T; p.B = B; p.P = P;
     p.G = g.nslots;                                   // == grid size for the round-robin schedule
-    p.slot_count = g.round_robin ? nullptr : slot_count;
+    p.slot_count = slot_count;
     p.n = n_per_domain; p.K = n_domains; p.margin = margin; p.eps = eps;
     p.gram = gram; p.rowstat = rowstat; p.vd = vd; p.statd = statd;
     cudaLaunchConfig_t cfg{};

@@ -19,8 +19,10 @@ namespace wtpse {
 
 namespace {
 
-// 7 consumer warps + 1 producer warp = 256 threads: ptxas sizes the register budget for the block
-// rounded up to 128 threads, and the 136 accumulators + 64 staged inputs need > 168 registers.
+// 7 consumer warps + 1 producer warp = 256 threads: the 136 accumulators + 64 staged inputs need 255 registers, so
+// 256 threads is the most an SM holds (a 9th warp pushes ptxas to 168 registers and spills).  Folding the producer
+// into a consumer warp (8 consumers, 1024-pixel tiles) was tried and is slower (110 vs 102 us): the issuing lane's
+// waits on the ring stall its warp and couple the look-ahead to the consumers' pace.
 constexpr int kConsumers = 224;
 constexpr int kConsumerWarps = kConsumers / 32;
 constexpr int kThreads = kConsumers + 32;       // + producer warp
@@ -82,9 +84,38 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4
     }
 }
 
+// Tile schedule.  The G CTAs form G/g groups of g; each group owns one contiguous range of tiles and deals it
+// round-robin to its members (member r takes tiles r, r+g, ... of the range).  g = 1: one contiguous range per
+// CTA; g = G: pure round-robin.  Every member flushes one partial for EVERY sample its group's range touches
+// (zeros if it happened to get no tile of it), so the slot bookkeeping is uniform:
+//   slot(b, CTA) = (group - first group touching b) * g + r,   slot_count[b] = (#groups touching b) * g.
+struct TileWalk {
+    long long R0, R1;      // group range
+    long long g, r;        // group size, member index
+    long long b_first, b_last;
+    __device__ TileWalk(long long k, long long G, long long T, long long tps, long long group) {
+        g = group;
+        const long long Gg = G / g, grp = k / g;
+        r = k - grp * g;
+        R0 = part_begin(grp, T, Gg);
+        R1 = part_begin(grp + 1, T, Gg);
+        b_first = R0 / tps;
+        b_last = (R1 - 1) / tps;
+    }
+    // [first, end) of this CTA's tiles inside sample b, step g
+    __device__ void segment(long long b, long long tps, long long& first, long long& end) const {
+        const long long s0 = b * tps > R0 ? b * tps : R0;
+        const long long s1 = (b + 1) * tps < R1 ? (b + 1) * tps : R1;
+        long long d = (r - (s0 - R0)) % g;
+        if (d < 0) d += g;
+        first = s0 + d;
+        end = s1;
+    }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
-                long long tiles_per_sample, long long T, int nslots, int round_robin) {
+                long long tiles_per_sample, long long T, int nslots, int group) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
@@ -94,12 +125,7 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the (tiny) dependents get resident early
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
-    // tile schedule: round-robin over the grid (CTA k takes tiles k, k+G, ...: all CTAs stream adjacent tiles at the
-    // same time, which DRAM likes ~10 % better) or one contiguous range per CTA (few samples per CTA, few flushes)
-    const bool rr = round_robin != 0;
-    const long long t0 = rr ? k : part_begin(k, T, G);
-    const long long t1 = rr ? T : part_begin(k + 1, T, G);
-    const long long tstep = rr ? G : 1;
+    const TileWalk walk(k, G, T, tiles_per_sample, group);
 
     if (tid == 0) {
 #pragma unroll
@@ -116,19 +142,22 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = t0; t < t1; t += tstep) {
-                mbar_wait(&empty[stage], phase ^ 1);
-                const long long b = t / tiles_per_sample;
-                const long long px0 = (t - b * tiles_per_sample) * kTilePx;
-                const long long rem = P - px0;
-                const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
-                const uint32_t bytes = npx * 4u;
-                mbar_arrive_expect_tx(&full[stage], bytes * kC);
-                const float* src = z + (b * kC) * P + px0;
-                float* dst = stage_buf + size_t(stage) * kStageFloats;
+            for (long long b = walk.b_first; b <= walk.b_last; ++b) {
+                long long t, tend;
+                walk.segment(b, tiles_per_sample, t, tend);
+                for (; t < tend; t += walk.g) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+                    const long long rem = P - px0;
+                    const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
+                    const uint32_t bytes = npx * 4u;
+                    mbar_arrive_expect_tx(&full[stage], bytes * kC);
+                    const float* src = z + (b * kC) * P + px0;
+                    float* dst = stage_buf + size_t(stage) * kStageFloats;
 #pragma unroll
-                for (int c = 0; c < kC; ++c) tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    for (int c = 0; c < kC; ++c) tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
             }
         }
         return;
@@ -141,33 +170,32 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
 
     int stage = 0;
     uint32_t phase = 0;
-    for (long long t = t0; t < t1; t += tstep) {
-        const long long b = t / tiles_per_sample;
-        const long long px0 = (t - b * tiles_per_sample) * kTilePx;
-        const long long rem = P - px0;
-        mbar_wait(&full[stage], phase);
-        if (4LL * tid < rem) {
-            const float* src = stage_buf + size_t(stage) * kStageFloats + 4 * tid;
-            float4 x[kC];
+    const long long Gg = G / walk.g, grp = k / walk.g;
+    for (long long b = walk.b_first; b <= walk.b_last; ++b) {
+        long long t, tend;
+        walk.segment(b, tiles_per_sample, t, tend);
+        for (; t < tend; t += walk.g) {
+            const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+            const long long rem = P - px0;
+            mbar_wait(&full[stage], phase);
+            if (4LL * tid < rem) {
+                const float* src = stage_buf + size_t(stage) * kStageFloats + 4 * tid;
+                float4 x[kC];
 #pragma unroll
-            for (int c = 0; c < kC; ++c) x[c] = *reinterpret_cast<const float4*>(src + c * kTilePx);
-            gram_accumulate(acc, x);
+                for (int c = 0; c < kC; ++c) x[c] = *reinterpret_cast<const float4*>(src + c * kTilePx);
+                gram_accumulate(acc, x);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-
-        const bool segment_end = (t + tstep >= t1) || ((t + tstep) / tiles_per_sample != b);
-        if (segment_end) {
-            // round-robin: slot = CTA index (the reduce kernel knows which CTAs touch a sample);
-            // contiguous: slot = position among the CTAs that share the sample
-            const long long slot = rr ? k : k - part_owner(b * tiles_per_sample, T, G);
-            flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
-            // contiguous: the CTA that owns a sample's last tile knows how many slots that sample used
-            if (!rr && tid == 0 && (t + 1) % tiles_per_sample == 0) slot_count[b] = int(slot) + 1;
+        const long long first_grp = part_owner(b * tiles_per_sample, T, Gg);
+        const long long slot = (grp - first_grp) * walk.g + walk.r;
+        flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+        // the group that owns a sample's last tile knows how many slots that sample used
+        if (tid == 0 && walk.r == 0 && (b + 1) * tiles_per_sample <= walk.R1) slot_count[b] = int((grp - first_grp + 1) * walk.g);
 #pragma unroll
-            for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
-        }
+        for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
     }
 }
 
@@ -204,26 +232,31 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, in
 
 }  // namespace
 
-// Gram tile schedule: 0 = one contiguous range per CTA (default), 1 = round-robin.  Round-robin gives DRAM the same
-// ~10 % better locality it gives the apply kernel, but every CTA then touches every sample and pays one 136-value
-// cross-thread flush per sample (32 instead of 1-2): measured 123 us vs 104 us at 32x16x512x512, so it stays off.
-int g_gram_round_robin = 0;
+// Gram tile schedule: CTAs per group (see TileWalk).  1 = one contiguous range per CTA, 0 = pure round-robin.
+// Round-robin gives DRAM the same ~10 % better locality it gives the apply kernel, but every CTA then touches every
+// sample and pays one 136-value cross-thread flush per sample (32 instead of 1-2): 123 us vs 104 us at 32x16x512x512.
+int g_gram_group = 1;
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count) {
     GramPlan g;
     g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
     g.round_robin = false;
+    g.group = 1;
     if (g.tma) {
         g.tiles_per_sample = (P + kTilePx - 1) / kTilePx;
         g.T = g.tiles_per_sample * B;
         g.G = g.T < sm_count ? g.T : sm_count;
-        g.round_robin = g_gram_round_robin != 0;
+        long long grp = g_gram_group;
+        if (grp <= 0 || grp > g.G) grp = g.G;                    // 0 = pure round-robin
+        if (g.G % grp != 0) grp = 1;
+        g.group = int(grp);
+        g.round_robin = grp > 1;
+        const long long Gg = g.G / grp;
         int nslots = 1;
-        if (g.round_robin) nslots = int(g.G);
-        else for (int b = 0; b < B; ++b) {
-            const long long first = part_owner((long long)b * g.tiles_per_sample, g.T, g.G);
-            const long long last = part_owner((long long)(b + 1) * g.tiles_per_sample - 1, g.T, g.G);
-            if (last - first + 1 > nslots) nslots = int(last - first + 1);
+        for (int b = 0; b < B; ++b) {
+            const long long first = part_owner((long long)b * g.tiles_per_sample, g.T, Gg);
+            const long long last = part_owner((long long)(b + 1) * g.tiles_per_sample - 1, g.T, Gg);
+            if ((last - first + 1) * grp > nslots) nslots = int((last - first + 1) * grp);
         }
         g.nslots = nslots;
     } else {
@@ -249,7 +282,7 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
     long long slots_gen = (2LL * sm_count + B - 1) / B;
     if (slots_gen < 1) slots_gen = 1;
     long long slots = slots_tma > slots_gen ? slots_tma : slots_gen;
-    if (G > slots) slots = G;      // round-robin schedule: one slot per CTA
+    if (2 * G > slots) slots = 2 * G;      // grouped / round-robin schedules: at most (#groups touching a sample) * g <= 2G slots
     return size_t(B) * size_t(slots) * kTri;
 }
 
@@ -259,7 +292,7 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
         cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
         gram_tma_kernel<<<dim3(unsigned(g.G)), kThreads, kSmemBytes, stream>>>(z, partial, slot_count, P, g.tiles_per_sample, g.T,
-                                                                                  g.nslots, g.round_robin ? 1 : 0);
+                                                                                  g.nslots, g.group);
     } else {
         gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, slot_count, P, g.nslots);
     }
