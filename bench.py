@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--track", default="whitening", choices=["whitening", "wavelet"],
+                    help="wavelet = BASELINE configs[1] as literally written (Track W, parity unpinned); not the default")
     ap.add_argument("--e2e-steps", type=int, default=10, help="steps of the host-buffer (PCIe-bound) loop")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline leg")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"])
@@ -420,8 +422,57 @@ def time_train_step(args, dev, rank, world, barrier):
             "losses": {k: float(v) for k, v in out.items()}}
 
 
+def run_wavelet(args):
+    """Track W side bench: db2 J=4 L1 detail loss fwd+bwd on 32x2x512x512 maps (BASELINE configs[1] verbatim).
+    PARITY UNPINNED (no wavelet code in the reference); reported for completeness, never the headline."""
+    import torch
+
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, C, H, W, J, wv = 32, 2, args.size, args.size, 4, "db2"
+    xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev), 1).requires_grad_(True) for _ in range(4)]
+    one = torch.ones((), device=dev)
+
+    def step(i):
+        x = xs[i % 4]
+        x.grad = None
+        loss = wb.wavelet_shape_loss(x, wv, J)
+        loss.backward(one)
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        loss = step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    elems = B * C * H * W
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_PEAK_GBS
+    algo = 8.0 * elems                      # SURVEY 8(d) Track W: 4N read forward + 4N written backward
+    moved = 4.0 * elems * (8.0 / 3.0) * 2   # what the per-level kernels move: (read + write) * 4/3 per pass, two passes
+    print(json.dumps({
+        "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": B * H * W / (ms * 1e-3) / 1e6,
+        "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "db2 DWT J=4 L1 detail-coefficient loss fwd+bwd, %dx%dx%dx%d softmax maps" % (B, C, H, W),
+                   "l2": "four alternating 67 MB inputs (each below the 126 MB L2: the 268 MB rotation is not)"},
+        "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},
+        "loss": float(loss.detach())}))
+
+
 def main():
     args = parse_args()
+    if args.track == "wavelet" and args.impl != "reference":
+        return run_wavelet(args)
     if args.impl == "reference":
         run_reference_arm(args)
     else:

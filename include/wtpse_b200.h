@@ -142,6 +142,24 @@ int wtpse_attention_fuse_backward(const float* grad_fuse, const float* emb, cons
                                   float* d_emb, float* d_z_post, float* d_weight_bias,
                                   void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/* ---- Track W: wavelet transform + detail-coefficient shape loss -- PARITY UNPINNED --------------
+ * The reference contains no wavelet code; these entry points replace nothing in it.
+ * Conventions (oracle/wavelet_np.py): orthonormal Haar (wavelet = 0) / db2 (wavelet = 1), periodic
+ * extension, Mallat-packed coefficients with the input's shape, J levels, H and W divisible by 2^J.
+ * x / coef are [nmaps][H][W] fp32 (nmaps = batch * channels). */
+size_t wtpse_wavelet_workspace_bytes(int nmaps, int H, int W, int J);
+int wtpse_dwt2d_forward(const float* x, int nmaps, int H, int W, int wavelet, int J, float* coef,
+                        void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+/* Synthesis == adjoint (orthonormal); scale is an optional DEVICE scalar multiplied into x. */
+int wtpse_dwt2d_inverse(const float* coef, int nmaps, int H, int W, int wavelet, int J, float* x,
+                        const float* scale, void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+/* loss = (1/nmaps) sum_maps sum_j w_j mean|detail_j| ; grad_coef receives dloss/dcoef (Mallat layout), so
+ * the backward is wtpse_dwt2d_inverse(grad_coef, ..., scale = upstream gradient).  level_weights is a HOST
+ * array of J floats (NULL = all ones). */
+int wtpse_wavelet_loss_forward(const float* x, int nmaps, int H, int W, int wavelet, int J,
+                               const float* level_weights, float* loss, float* grad_coef,
+                               void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- host-buffer entry point (plugin-facing, used for the end-to-end number) --------------- */
 
 typedef struct wtpse_host_plan wtpse_host_plan;

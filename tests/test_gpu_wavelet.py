@@ -1,0 +1,92 @@
+"""Track W (wavelet) GPU tests.  PARITY UNPINNED: the reference has no wavelet code, so these check the CUDA
+kernels against this repository's own float64 specification (oracle/wavelet_np.py) and against the identities
+every orthonormal DWT satisfies: perfect reconstruction, Parseval, adjointness."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _maps(shape, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+@pytest.mark.parametrize("wavelet", ["haar", "db2"])
+@pytest.mark.parametrize("shape,J", [((3, 2, 32, 32), 3), ((2, 2, 64, 48), 4), ((1, 1, 16, 80), 2), ((4, 2, 8, 8), 1)])
+def test_dwt_matches_spec_and_identities(wavelet, shape, J):
+    import wtpse_b200 as wb
+    from oracle import wavelet_np as wn
+
+    x_cpu = _maps(shape, seed=sum(shape) + J)
+    x = x_cpu.to(_dev())
+    c = wb.dwt2d(x, wavelet, J)
+    assert rel_err(c.cpu().numpy(), wn.dwt2d(x_cpu.numpy(), wavelet, J)) < TOL
+    # perfect reconstruction and Parseval
+    xr = wb.idwt2d(c, wavelet, J)
+    assert rel_err(xr.cpu().numpy(), x_cpu.numpy()) < TOL
+    assert abs(float((c.double() ** 2).sum()) - float((x.double() ** 2).sum())) <= TOL * float((x.double() ** 2).sum())
+    # adjoint identity <W x, y> = <x, W^T y>
+    y = _maps(shape, seed=99).to(_dev())
+    lhs = float((c.double() * y.double()).sum())
+    rhs = float((x.double() * wb.idwt2d(y, wavelet, J).double()).sum())
+    assert abs(lhs - rhs) <= TOL * max(abs(lhs), 1.0)
+    # autograd through the transform pair
+    xg = x.clone().requires_grad_(True)
+    (wb.dwt2d(xg, wavelet, J) * y).sum().backward()
+    assert rel_err(xg.grad.cpu().numpy(), wn.idwt2d(y.cpu().numpy(), wavelet, J)) < TOL
+
+
+@pytest.mark.parametrize("wavelet,J,weights", [("haar", 3, None), ("db2", 4, None), ("db2", 2, (0.5, 2.0)), ("haar", 1, (3.0,))])
+def test_wavelet_shape_loss_forward_backward(wavelet, J, weights):
+    import wtpse_b200 as wb
+    from oracle import wavelet_np as wn
+
+    # softmax OC/OD-like probability maps: B x 2 x H x W
+    logits = _maps((5, 2, 64, 64), seed=J)
+    p_cpu = torch.softmax(3.0 * logits, dim=1)
+    p = p_cpu.to(_dev()).requires_grad_(True)
+    loss = wb.wavelet_shape_loss(p, wavelet, J, weights)
+    (1.7 * loss).backward()
+    ref_loss, ref_grad = wn.shape_loss(p_cpu.numpy(), wavelet, J, weights)
+    assert abs(float(loss) - ref_loss) <= TOL * abs(ref_loss)
+    assert rel_err(p.grad.cpu().numpy(), 1.7 * ref_grad) < TOL
+    # run-to-run reproducible
+    loss2 = wb.wavelet_shape_loss(p.detach(), wavelet, J, weights)
+    assert float(loss2) == float(loss)
+
+
+def test_wavelet_contract_errors():
+    import wtpse_b200 as wb
+
+    x = torch.randn(2, 2, 24, 24, device=_dev())
+    with pytest.raises(wb._lib.WtpseError):
+        wb.dwt2d(x, "haar", 4)                      # 24 not divisible by 16
+    with pytest.raises(ValueError):
+        wb.dwt2d(x, "sym8", 1)
+    with pytest.raises(RuntimeError):
+        wb.dwt2d(x.cpu(), "haar", 1)
+
+
+def test_wavelet_full_size_properties():
+    """BASELINE configs[1] as literally written: 32 x 2 x 512 x 512, db2, J = 4."""
+    import wtpse_b200 as wb
+
+    x = torch.rand(32, 2, 512, 512, device=_dev())
+    c = wb.dwt2d(x, "db2", 4)
+    assert rel_err(wb.idwt2d(c, "db2", 4).cpu().numpy(), x.cpu().numpy()) < TOL
+    e0, e1 = float((x.double() ** 2).sum()), float((c.double() ** 2).sum())
+    assert abs(e0 - e1) <= TOL * e0
+    xg = x.clone().requires_grad_(True)
+    loss = wb.wavelet_shape_loss(xg, "db2", 4)
+    loss.backward()
+    # the loss is 1-homogeneous in x: <grad, x> == loss (Euler), a size-independent gradient check
+    assert abs(float((xg.grad.double() * x.double()).sum()) - float(loss)) <= 1e-4 * float(loss)

@@ -47,6 +47,14 @@ EXPORTS = {
     "wtpse_attention_fuse_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                  _c.c_float, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p,
                                                  _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_wavelet_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "wtpse_dwt2d_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                       _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_dwt2d_inverse": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p,
+                                       _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_wavelet_loss_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                              _c.POINTER(_c.c_float), _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                              _c.c_size_t, _c.c_void_p]),
     "wtpse_profile_enable": (None, [_c.c_int]),
     "wtpse_profile_reset": (None, []),
     "wtpse_profile_kernel_count": (_c.c_int, []),

@@ -288,6 +288,67 @@ int wtpse_attention_fuse_backward(const float* grad_fuse, const float* emb, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// Track W: wavelet transform + L1 detail loss (parity unpinned, see include/wtpse_b200.h)
+// ---------------------------------------------------------------------------------------------
+static int check_wavelet(const void* p, int nmaps, int H, int W, int wavelet, int J) {
+    if (!p) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (wavelet != 0 && wavelet != 1) return fail(WTPSE_ERR_INVALID, "wavelet must be 0 (haar) or 1 (db2)");
+    if (nmaps <= 0 || H <= 0 || W <= 0 || J < 1 || J > 16) return fail(WTPSE_ERR_INVALID, "bad shape / level count");
+    if ((H % (1 << J)) || (W % (1 << J))) return fail(WTPSE_ERR_INVALID, "H=%d and W=%d must be divisible by 2^J=%d", H, W, 1 << J);
+    if (wavelet == 1 && ((H >> (J - 1)) < 4 || (W >> (J - 1)) < 4)) return fail(WTPSE_ERR_INVALID, "db2 needs at least 4 samples at the coarsest level");
+    return WTPSE_OK;
+}
+
+size_t wtpse_wavelet_workspace_bytes(int nmaps, int H, int W, int J) {
+    if (nmaps <= 0 || H <= 0 || W <= 0 || J < 1) return 0;
+    return align_up(wavelet_scratch_floats(nmaps, H, W) * sizeof(float), 256) +
+           align_up(wavelet_partial_doubles(nmaps, H, W, J) * sizeof(double), 256);
+}
+
+static float* wavelet_scratch(void* ws) { return static_cast<float*>(ws); }
+static double* wavelet_partials(void* ws, int nmaps, int H, int W) {
+    return reinterpret_cast<double*>(static_cast<char*>(ws) + align_up(wavelet_scratch_floats(nmaps, H, W) * sizeof(float), 256));
+}
+
+int wtpse_dwt2d_forward(const float* x, int nmaps, int H, int W, int wavelet, int J, float* coef, void* workspace,
+                        size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_wavelet(x, nmaps, H, W, wavelet, J)) return rc;
+    if (!coef || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (workspace_bytes < wtpse_wavelet_workspace_bytes(nmaps, H, W, J)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernWaveletFwd, s); e = launch_dwt(x, nmaps, H, W, wavelet ? 4 : 2, J, coef, wavelet_scratch(workspace), nullptr, nullptr, nullptr, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "dwt launch");
+    return WTPSE_OK;
+}
+
+int wtpse_dwt2d_inverse(const float* coef, int nmaps, int H, int W, int wavelet, int J, float* x, const float* scale,
+                        void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_wavelet(coef, nmaps, H, W, wavelet, J)) return rc;
+    if (!x || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (workspace_bytes < wtpse_wavelet_workspace_bytes(nmaps, H, W, J)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernWaveletBwd, s); e = launch_idwt(coef, nmaps, H, W, wavelet ? 4 : 2, J, x, wavelet_scratch(workspace), scale, s); }
+    if (e != cudaSuccess) return cuda_fail(e, "idwt launch");
+    return WTPSE_OK;
+}
+
+int wtpse_wavelet_loss_forward(const float* x, int nmaps, int H, int W, int wavelet, int J, const float* level_weights,
+                               float* loss, float* grad_coef, void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_wavelet(x, nmaps, H, W, wavelet, J)) return rc;
+    if (!loss || !grad_coef || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (workspace_bytes < wtpse_wavelet_workspace_bytes(nmaps, H, W, J)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    float w[16];
+    for (int j = 0; j < J; ++j) w[j] = level_weights ? level_weights[j] : 1.0f;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernWaveletFwd, s); e = launch_dwt(x, nmaps, H, W, wavelet ? 4 : 2, J, grad_coef, wavelet_scratch(workspace), w, loss, wavelet_partials(workspace, nmaps, H, W), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "wavelet loss launch");
+    return WTPSE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-buffer plan
 // ---------------------------------------------------------------------------------------------
 struct wtpse_host_plan {

@@ -84,4 +84,12 @@ cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, c
                             int B, int Ce, long long P, float* d_emb, float* d_zp, float* d_wb, double* partial, int sm_count,
                             cudaStream_t stream);
 
+// Track W (wavelet.cu)
+size_t wavelet_scratch_floats(long long nmaps, int H, int W);
+size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);
+cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J, float* coef, float* scratch,
+                       const float* weights_host, float* loss, double* partial, cudaStream_t stream);
+cudaError_t launch_idwt(const float* coef, int nmaps, int H, int W, int taps, int J, float* x, float* scratch,
+                        const float* scale, cudaStream_t stream);
+
 }  // namespace wtpse
