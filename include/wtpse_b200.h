@@ -175,6 +175,15 @@ void wtpse_host_plan_destroy(wtpse_host_plan* plan);
 int  wtpse_host_plan_run(wtpse_host_plan* plan, const float* z_host,
                          int n_per_domain, int n_domains, float margin, float eps,
                          const float grad_w[3], float losses_host[4], float* dz_host);
+/*
+ * Asynchronous form: enqueue one step (same work as _run) and return; the host buffers of a step are complete
+ * after wtpse_host_plan_wait(), or after the second-next submit (two device slots alternate, so the D2H of one
+ * step overlaps the H2D of the next on the full-duplex link).  Each step needs its own host buffers until then.
+ */
+int  wtpse_host_plan_submit(wtpse_host_plan* plan, const float* z_host,
+                            int n_per_domain, int n_domains, float margin, float eps,
+                            const float grad_w[3], float losses_host[4], float* dz_host);
+int  wtpse_host_plan_wait(wtpse_host_plan* plan);
 
 /* ---- launch accounting / in-step kernel timing (used by bench.py, not by the reference path) - */
 

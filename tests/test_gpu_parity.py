@@ -385,6 +385,22 @@ def test_host_plan_matches_device_path():
     assert torch.equal(dz_host, z.grad.cpu())
 
 
+def test_host_plan_pipelined_submissions():
+    """Asynchronous submit()/wait(): four steps in flight over two device slots return what run() returns."""
+    import wtpse_b200 as wb
+
+    zs = [_synth(6, 32, 32, seed=40 + i).pin_memory() for i in range(4)]
+    dzs = [torch.empty_like(z).pin_memory() for z in zs]
+    plan = wb.HostPlan(6, 32, 32)
+    outs = [plan.submit(z, 2, 3, 0.0, 1e-5, (1.0, 0.5, 2.0), dz) for z, dz in zip(zs, dzs)]
+    plan.wait()
+    for z, dz, out in zip(zs, dzs, outs):
+        ref_dz = torch.empty_like(z)
+        ref = plan.run(z, 2, 3, 0.0, 1e-5, (1.0, 0.5, 2.0), ref_dz)
+        assert (out[0], out[1], out[2]) == ref and torch.equal(dz, ref_dz)
+    plan.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties + the op-sequence restatement on the GPU
 # ---------------------------------------------------------------------------------------------

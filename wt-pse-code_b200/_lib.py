@@ -71,6 +71,9 @@ EXPORTS = {
     "wtpse_host_plan_destroy": (None, [_c.c_void_p]),
     "wtpse_host_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
                                        _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.c_void_p]),
+    "wtpse_host_plan_submit": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
+                                          _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _c.c_void_p]),
+    "wtpse_host_plan_wait": (_c.c_int, [_c.c_void_p]),
 }
 
 

@@ -164,9 +164,24 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
     if (p.pre_reduced) {
         // the per-sample work was done by gram_reduce_kernel (one CTA per sample): just stage its results
         asm volatile("griddepcontrol.wait;" ::: "memory");
-        for (int idx = tid; idx < dom.M * kOff; idx += kEpiThreads) {
-            const int b = idx / kOff, o = idx - b * kOff;
-            mem.v[size_t(b) * kVStride + o] = __ldg(p.vd + size_t(b) * kVStride + o);
+        // rows are 124 floats in both places: copy them as float4, four independent loads in flight per thread
+        {
+            const float4* src4 = reinterpret_cast<const float4*>(p.vd);
+            float4* dst4 = reinterpret_cast<float4*>(mem.v);
+            const int n4 = dom.M * (kVStride / 4);
+            for (int base = 0; base < n4; base += 4 * kEpiThreads) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * kEpiThreads + tid;
+                    v[u] = idx < n4 ? __ldg(src4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * kEpiThreads + tid;
+                    if (idx < n4) dst4[idx] = v[u];
+                }
+            }
         }
         for (int idx = tid; idx < 2 * B; idx += kEpiThreads) mem.stat[idx] = __ldg(p.statd + idx);
     } else
@@ -443,10 +458,29 @@ __global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) 
     const bool in_mmd = (M > 0) && (g_dom != 0.f) && (b < M);         // block-uniform
     __syncthreads();
     if (in_mmd) {
-        for (int idx = tid; idx < M * kOff; idx += kMmatThreads) {
-            const int c = idx / kOff, o = idx - c * kOff;
-            const int ij = tab.off[o];
-            vbuf[size_t(c) * kVStride + o] = __ldg(p.gram + c * 256 + (ij >> 4) * kC + (ij & 15));
+        // stage the vectors of all MMD samples: batches of 8 independent gathers per thread (one DRAM/L2 round trip
+        // per batch instead of one per element)
+        for (int base = 0; base < M * kOff; base += 8 * kMmatThreads) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kMmatThreads + tid;
+                if (idx < M * kOff) {
+                    const int c = idx / kOff, o = idx - c * kOff;
+                    const int ij = tab.off[o];
+                    v[u] = __ldg(p.gram + c * 256 + (ij >> 4) * kC + (ij & 15));
+                } else {
+                    v[u] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int idx = base + u * kMmatThreads + tid;
+                if (idx < M * kOff) {
+                    const int c = idx / kOff, o = idx - c * kOff;
+                    vbuf[size_t(c) * kVStride + o] = v[u];
+                }
+            }
         }
         __syncthreads();
         for (int c = tid; c < M; c += kMmatThreads) {

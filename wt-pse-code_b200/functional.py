@@ -201,6 +201,28 @@ class HostPlan:
                                                      ctypes.c_void_p(dz_host.data_ptr()) if dz_host is not None else None))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def submit(self, z_host, n_per_domain, n_domains, margin=0.0, eps=1e-5, grad_w=(1.0, 1.0, 1.0), dz_host=None):
+        """Asynchronous run(): returns a ctypes float[4] that holds (L_off, L_diag, L_dom, L_off+L_diag) once wait()
+        -- or the second-next submit() -- has returned.  Two device slots alternate, so consecutive steps overlap
+        their PCIe transfers; every in-flight step needs its own host buffers."""
+        if z_host.is_cuda or z_host.dtype != torch.float32 or not z_host.is_contiguous():
+            raise ValueError("z_host must be a contiguous float32 CPU tensor")
+        if tuple(z_host.shape) != (self.B, CHANNELS, self.H, self.W):
+            raise ValueError("z_host shape %s does not match the plan" % (tuple(z_host.shape),))
+        if dz_host is not None and (dz_host.is_cuda or dz_host.shape != z_host.shape or not dz_host.is_contiguous()):
+            raise ValueError("dz_host must be a contiguous CPU tensor shaped like z_host")
+        gw = (ctypes.c_float * 3)(*[float(x) for x in grad_w])
+        out = (ctypes.c_float * 4)()
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wtpse_host_plan_submit(self._h, ctypes.c_void_p(z_host.data_ptr()), int(n_per_domain),
+                                                        int(n_domains), float(margin), float(eps), gw, out,
+                                                        ctypes.c_void_p(dz_host.data_ptr()) if dz_host is not None else None))
+        return out
+
+    def wait(self):
+        with torch.cuda.device(self._dev):
+            _lib.check(self._lib.wtpse_host_plan_wait(self._h))
+
     def close(self):
         if self._h:
             self._lib.wtpse_host_plan_destroy(self._h)
