@@ -60,10 +60,11 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
     float* coefrow = vbuf + size_t(kFusedMaxM) * kVStride;            // [kFusedMaxM]
     IndexTables* tab = reinterpret_cast<IndexTables*>(coefrow + kFusedMaxM);
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // e.g. the next Gram kernel: it waits for us itself
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
-    // tile schedule: contiguous range per CTA (stride 1) or round-robin over the grid (stride G; experiment for
-    // DRAM row locality: at any moment the CTAs then stream adjacent tiles)
+    // tile schedule: one contiguous range per CTA, or blocks of tiles dealt round-robin over the grid (default: at any
+    // moment the CTAs then stream adjacent tiles of every channel row)
     // round_robin = c > 0: blocks of c consecutive tiles dealt round-robin to the CTAs (block q -> CTA q % G)
     const long long chunk = fa.round_robin;
     const bool rr = chunk > 0;

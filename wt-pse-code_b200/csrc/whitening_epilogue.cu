@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
     const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, B, dom.M);
     const float denom = float(p.P - 1);
     __shared__ IndexTables tab;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // dependents wait for our completion themselves
     build_index_tables(tab, tid, kEpiThreads);
     __syncthreads();
     WTPSE_STAMP(0);
@@ -452,6 +453,7 @@ __global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) 
     float* coefrow = vbuf + round4(size_t(M) * kVStride);            // [M]
     __shared__ IndexTables tab;
     build_index_tables(tab, tid, kMmatThreads);
+    asm volatile("griddepcontrol.wait;" ::: "memory");             // inputs may come from the kernel right before us
     const float g_off = p.g_off ? __ldg(p.g_off) : 0.f;
     const float g_diag = p.g_diag ? __ldg(p.g_diag) : 0.f;
     const float g_dom = p.g_dom ? __ldg(p.g_dom) : 0.f;
@@ -684,8 +686,17 @@ cudaError_t launch_whiten_mmat(const float* gram, const float* rowstat, const fl
         cudaError_t e = cudaFuncSetAttribute(whiten_mmat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn));
         if (e != cudaSuccess) return e;
     }
-    whiten_mmat_kernel<<<B, kMmatThreads, dyn, stream>>>(p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(B));
+    cfg.blockDim = dim3(kMmatThreads);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, whiten_mmat_kernel, p);
 }
 
 cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,

@@ -136,6 +136,9 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
         fence_mbar_init();
     }
     __syncthreads();
+    // launched with programmatic stream serialisation: everything above overlapped the previous kernel's tail; z
+    // (and the workspace) may only be touched once that kernel has completed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == kConsumerWarps) {
         // ---------------- producer: one lane issues the bulk copies ----------------
@@ -291,8 +294,18 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
     if (g.tma) {
         cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
-        gram_tma_kernel<<<dim3(unsigned(g.G)), kThreads, kSmemBytes, stream>>>(z, partial, slot_count, P, g.tiles_per_sample, g.T,
-                                                                                  g.nslots, g.group);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned(g.G));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, gram_tma_kernel, z, partial, slot_count, (long long)P, g.tiles_per_sample, g.T, g.nslots,
+                                  g.group);
     } else {
         gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, slot_count, P, g.nslots);
     }
