@@ -1,4 +1,5 @@
-"""Print clock64 deltas between the epilogue kernels' phases (diagnostic; needs a GPU)."""
+"""Print clock64 deltas between the phases of the single-CTA epilogue kernels (diagnostic; needs a GPU).
+Forces the one-kernel forward epilogue and the single-CTA backward epilogue (debug modes), which carry the stamps."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -6,6 +7,8 @@ import wtpse_b200 as wb
 
 B, H, n = (int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (32, 512, 10)
 lib = wb._lib.load()
+lib.wtpse_debug_set_two_stage_epilogue(0)
+lib.wtpse_debug_set_backward_mode(2)
 lib.wtpse_debug_set_epilogue_repeat(int(os.environ.get("REPEAT", "1")))
 dev = torch.device("cuda:0")
 z = (0.3 * torch.randn(B, 16, H, H, device=dev) + 0.2 * torch.randn(B, 16, 1, 1, device=dev)).requires_grad_(True)

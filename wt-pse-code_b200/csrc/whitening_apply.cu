@@ -1,5 +1,4 @@
-// Backward: dz_b = M_b z_b, the adjoint of the Gram, fused with the gradient write -- and, in the
-// fused variant, with the derivation of M_b itself.
+// Backward: dz_b = M_b z_b, the adjoint of the Gram, fused with the gradient write.
 //
 // What autograd derives from the bmm of algorithms.py:1283 (two more passes over z in the reference:
 // grad @ z and grad^T @ z) collapses to ONE 16x16 symmetric matrix per sample applied to every pixel:
@@ -11,11 +10,14 @@
 // adjacent 4 KB pieces of each of the 16 channel rows at the same time, which is worth 10 % of DRAM
 // throughput over giving every CTA its own contiguous range (2 368 scattered streams).
 //
-// Fused variant (kFused): instead of a separate single-CTA "backward epilogue" launch that serialises
-// all samples on one SM (~20 us measured), every CTA derives M_b for the one or two samples it owns
-// from the saved Gram: the 120-d vectors of the MMD samples are staged once per CTA (<= 32 KB), then per
-// sample one distance row, one coefficient row and 136 matrix entries (~1 us, overlapped with the
-// producer's first TMA loads).  Same arithmetic as whiten_epilogue_bwd_kernel (mmd_device.cuh).
+// Default path (apply_tma_kernel<false>): the matrices come from whiten_mmat_kernel (one CTA per sample,
+// whitening_epilogue.cu); this kernel is launched as its programmatic dependent, so z is already streaming
+// while the matrices are derived, and the consumers wait (griddepcontrol.wait) only before the first M_b read.
+//
+// Alternative (apply_tma_kernel<true>, wtpse_debug_set_backward_mode(1)): every CTA derives M_b itself for the
+// one or two samples of its CONTIGUOUS tile range -- one launch instead of two, but without the round-robin
+// schedule's DRAM locality (188 us vs 176 us for the pair at 32x16x512x512).  Same arithmetic (mmd_device.cuh),
+// bitwise-equal results (tests/test_gpu_parity.py).
 #include "common.cuh"
 #include "kernels.h"
 #include "mmd_device.cuh"

@@ -4,12 +4,19 @@
 // Forward  (algorithms.py:1283-1307 after the bmm, compute_MMD.forward algorithms.py:102-121):
 //   partial Gram slots -> f_cor = G/(P-1) + eps*I -> off_b, diag_b -> L_off, L_diag
 //   -> 120-d upper-triangle vectors -> pairwise exp(-D) -> L_dom.
+//   gram_reduce_kernel           one CTA per sample: slot reduction, Gram, vector, off_b, diag_b
+//   whiten_epilogue_fwd_kernel   ONE CTA: instance terms, pairwise kernel values, block sums, L_dom
+//                                (also able to do the per-sample part itself: wtpse_debug_set_two_stage_epilogue(0))
 // Backward: upstream grads + saved Gram -> per-sample symmetric 16x16
 //   coefficient matrix M_b = (S_b + S_b^T)/(P-1) that the apply kernel multiplies into z.
+//   whiten_mmat_kernel           one CTA per sample (default)
+//   whiten_epilogue_bwd_kernel   ONE CTA for all samples (fallback for very many MMD samples, debug mode 2)
 //
 // The work is O(B*136*slots + B^2*120) -- microseconds -- so these kernels are latency-bound and are
 // built around that (measured with the clock64 stamps below, tools/epilogue_phases.py):
-//   * ONE CTA, fixed reduction orders: bit-reproducible, no float atomics, no grid sync;
+//   * a single SM issues at most 4 warp instructions per cycle: whatever is per-sample runs as one CTA per
+//     sample; only the genuinely all-to-all part (the MMD) runs in one CTA, with fixed reduction orders:
+//     bit-reproducible, no float atomics, no grid sync;
 //   * float32 arithmetic like the reference.  B200's FP64 pipe issues ~1 warp instruction per 3
 //     cycles with ~50-cycle dependent latency; a first float64 version of this file spent 25 us per
 //     launch in it.  Accuracy is kept where the MMD needs it by two reformulations instead:
@@ -20,10 +27,13 @@
 //         precision even when the domains are statistically identical (SURVEY.md section 7's
 //         3.8e-3 fp32-vs-fp64 gap of the reference does not arise).  Only the handful of final
 //         block sums run in float64.
-//   * one warp per sample reduces that sample's slots straight into registers and emits the Gram,
-//     the 120-d vector (shared memory) and off_b / diag_b with one shuffle reduction;
+//   * dependent loads are issued in batches (speculative slot loads, 8-deep gathers) so a phase pays one
+//     L2/DRAM round trip, not one per element;
 //   * pairwise distances: one LANE per unordered pair a < c (the matrix is symmetric), LDS.128 on rows
-//     padded to 124 floats (conflict-free), so there is no shuffle chain per pair.
+//     padded to 124 floats (conflict-free), so there is no shuffle chain per pair;
+//   * index tables live in shared memory and the kernels are templated on shared-vs-global working set
+//     (per-lane indexing of __constant__ memory and generic pointers to shared memory both serialise
+//     in the address-divergence unit).
 #include <math.h>
 
 #include "common.cuh"
