@@ -25,6 +25,7 @@ size_t epilogue_scratch_bytes(int B, int K);
 extern long long* g_epilogue_dbg;
 extern int g_epilogue_repeat;
 extern int g_apply_round_robin;
+extern int g_l2_evict_first;
 
 // forward: partial slots -> gram, rowstat, losses
 cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,

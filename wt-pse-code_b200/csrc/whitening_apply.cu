@@ -47,6 +47,7 @@ struct FusedArgs {
     const float *g_off, *g_diag, *g_dom;
     int B, n, K;
     int round_robin;
+    int l2_hint;            // 1: TMA loads carry an L2 evict-first policy (z is read once)
 };
 
 template <bool kFused>
@@ -88,6 +89,8 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
 
     if (warp == kConsumerWarps) {
         if (lane == 0) {
+            const uint64_t policy = make_evict_first_policy();
+            const bool g_use_hint = fa.l2_hint != 0;
             int stage = 0;
             uint32_t phase = 0;
             for (long long j = t0; j < t1; ++j) {
@@ -103,7 +106,10 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
                 const float* src = z + (b * kC) * P + px0;
                 float* dst = stage_buf + size_t(stage) * kStageFloats;
 #pragma unroll
-                for (int c = 0; c < kC; ++c) tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                for (int c = 0; c < kC; ++c) {
+                        if (g_use_hint) tma_load_1d_hint(dst + c * kTilePx, src + c * P, bytes, &full[stage], policy);
+                        else tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                    }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
@@ -245,6 +251,9 @@ bool tma_ok(const float* z, const float* dz, long long P) {
 // any moment the 148 CTAs stream ADJACENT tiles of each channel row (0 = one contiguous range per CTA).
 // Measured at 32x16x512x512: contiguous 184 us, round-robin 1: 167-171 us, 2: 168 us, 4: 180 us, 8: 181 us.
 int g_apply_round_robin = 1;
+// L2 evict-first policy on the TMA loads of z (read exactly once; keeps the dz write-back lines in L2 longer).
+// Measured: step 281.5 -> 276 us, apply 174.9 -> 171.4 us, gram 104.2 -> 102.7 us.
+int g_l2_evict_first = 1;
 
 bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains) {
     long long m = n_domains > 1 ? (long long)n_per_domain * n_domains : 0;
@@ -262,6 +271,7 @@ cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, lo
         const long long G = T < sm_count ? T : sm_count;
         FusedArgs fa{};
         fa.round_robin = g_apply_round_robin;   // 0 = contiguous ranges, c > 0 = round-robin blocks of c tiles
+        fa.l2_hint = g_l2_evict_first;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(unsigned(G));
         cfg.blockDim = dim3(kThreads);
@@ -287,7 +297,7 @@ cudaError_t launch_apply_fused(const float* z, const float* gram, const float* r
     const long long tps = (P + kTilePx - 1) / kTilePx;
     const long long T = tps * B;
     const long long G = T < sm_count ? T : sm_count;
-    FusedArgs fa{gram, rowstat, g_off, g_diag, g_dom, B, n_per_domain, n_domains, 0};
+    FusedArgs fa{gram, rowstat, g_off, g_diag, g_dom, B, n_per_domain, n_domains, 0, g_l2_evict_first};
     apply_tma_kernel<true><<<dim3(unsigned(G)), kThreads, kSmemFused, stream>>>(z, nullptr, dz, P, tps, T, fa);
     return cudaGetLastError();
 }

@@ -115,7 +115,7 @@ struct TileWalk {
 
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
-                long long tiles_per_sample, long long T, int nslots, int group) {
+                long long tiles_per_sample, long long T, int nslots, int group, int hint) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
@@ -143,6 +143,8 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
     if (warp == kConsumerWarps) {
         // ---------------- producer: one lane issues the bulk copies ----------------
         if (lane == 0) {
+            const uint64_t policy = make_evict_first_policy();
+            const bool g_use_hint = hint != 0;
             int stage = 0;
             uint32_t phase = 0;
             for (long long b = walk.b_first; b <= walk.b_last; ++b) {
@@ -158,7 +160,10 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
                     const float* src = z + (b * kC) * P + px0;
                     float* dst = stage_buf + size_t(stage) * kStageFloats;
 #pragma unroll
-                    for (int c = 0; c < kC; ++c) tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                    for (int c = 0; c < kC; ++c) {
+                        if (g_use_hint) tma_load_1d_hint(dst + c * kTilePx, src + c * P, bytes, &full[stage], policy);
+                        else tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                    }
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
             }
@@ -305,7 +310,7 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return cudaLaunchKernelEx(&cfg, gram_tma_kernel, z, partial, slot_count, (long long)P, g.tiles_per_sample, g.T, g.nslots,
-                                  g.group);
+                                  g.group, g_l2_evict_first);
     } else {
         gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, slot_count, P, g.nslots);
     }
