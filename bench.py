@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--train-steps", type=int, default=6, help="timed iterations of the full WT-PSE train step (0 = skip)")
     ap.add_argument("--train-size", type=int, default=512)
+    ap.add_argument("--train-graph", type=int, default=1, help="replay the train iteration as a CUDA graph")
     ap.add_argument("--train-batch", type=int, default=16, help="nominal per-GPU batch (the reference uses 3 * (batch // 3))")
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
     ap.add_argument("--debug-backward-mode", type=int, default=0)
@@ -407,12 +408,24 @@ def time_train_step(args, dev, rank, world, barrier):
     ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0)
     lib = wb._lib.load()
 
+    mode = "eager"
+
+    def batch(it):
+        return wb.synthetic.fundus_batch(n_per_domain, 3, S, S, dev, seed=wb.dp.rank_batch_seed(1, rank, it))
+
     def one(it):
-        image, od, oc = wb.synthetic.fundus_batch(n_per_domain, 3, S, S, dev, seed=wb.dp.rank_batch_seed(1, rank, it))
-        return ts.step(image, od, oc)
+        image, od, oc = batch(it)
+        return ts.replay(image, od, oc) if mode == "cuda-graph" else ts.step(image, od, oc)
 
     for it in range(3):
         one(it)
+    if args.train_graph:
+        try:                                              # the whole iteration as one CUDA graph (no host syncs on the path)
+            ts.capture(*batch(100))
+            mode = "cuda-graph"
+            one(101)
+        except Exception as exc:                          # report, do not hide: the eager path is still the product
+            mode = "eager (graph capture failed: %s)" % str(exc).splitlines()[0][:120]
     barrier()
     lib.wtpse_profile_reset()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -427,7 +440,7 @@ def time_train_step(args, dev, rank, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / args.train_steps
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
-            "steps": args.train_steps, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
+            "steps": args.train_steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
             "global_batch_used": world * used, "our_kernel_launches": int(lib.wtpse_profile_launches(-1)),
             "backbone": "PyTorch/cuDNN, channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}

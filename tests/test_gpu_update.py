@@ -85,6 +85,26 @@ def test_update_gradients_match_autograd_through_the_reference_operator_sequence
     assert err < 1e-4, float(err)
 
 
+def test_reparameterisation_equals_torch_normal():
+    """The capturable spelling of `torch.normal(mu, std) * std + mu` draws the same numbers and has the same gradients."""
+    from wtpse_b200 import segmentation as seg
+
+    dev = torch.device("cuda:0")
+    net = seg.ShapeVariationalDist_x(dict(HP), dev, 1, number_source_domain=3, batch_size=2)
+    mu = torch.randn(6, 1, 16, 16, device=dev, requires_grad=True)
+    logvar = torch.randn(6, 1, 16, 16, device=dev, requires_grad=True)
+    torch.manual_seed(11)
+    ours = net.reparameterization(mu, logvar)
+    ours.sum().backward()
+    g_ours = (mu.grad.clone(), logvar.grad.clone())
+    mu.grad = logvar.grad = None
+    torch.manual_seed(11)
+    std = torch.exp(logvar / 2)
+    ref = torch.normal(mu, std) * std + mu               # shape_networks.py:507-509 verbatim
+    ref.sum().backward()
+    assert torch.equal(ours, ref) and torch.equal(g_ours[0], mu.grad) and torch.allclose(g_ours[1], logvar.grad, rtol=1e-6, atol=0)
+
+
 def test_train_step_runs_and_learns():
     import wtpse_b200 as wb
 
@@ -105,3 +125,33 @@ def test_train_step_runs_and_learns():
     after = [p.detach() for p in ts.model_shape_oc.parameters()][:4]
     assert any(not torch.equal(a, b) for a, b in zip(before, after))
     assert set(first) >= {"loss_seg", "ins_wt", "dom_wt", "kd", "ins_ii", "ins_ij", "loss_seg_oc", "kd_oc"}
+
+
+def test_train_step_cuda_graph_replay_matches_eager():
+    """One iteration replayed from a CUDA graph gives the losses of the eager iteration on the same weights/batch
+    (the RNG only feeds the re-parameterisation, which no loss scalar depends on)."""
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda:0")
+    batches = [wb.synthetic.fundus_batch(2, 3, 64, 64, dev, seed=50 + i) for i in range(3)]
+    eager = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=1)
+    graph = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=1)
+    graph.capture(*[t.clone() for t in batches[0]], warmup=0)
+    # capture itself ran no real step (warmup=0 and graph capture only records): both start from the same weights
+    for it, (img, od, oc) in enumerate(batches):
+        a = eager.step(img.clone(), od, oc)
+        b = graph.replay(img.clone(), od, oc)
+        vals = {k: float(v) for k, v in b.items()}
+        assert all(np.isfinite(v) for v in vals.values()), vals
+        if it == 0:
+            # same weights, same batch: every loss scalar that does not depend on the re-parameterisation noise agrees.
+            # (Later iterations diverge legitimately: the logits see z_posterior, i.e. the RNG, and the two runs
+            # draw different noise, so their weights differ after the first optimizer step.)
+            # Sub-step 1's whitening losses see only the initial weights; everything after the first optimizer step has
+            # already absorbed the (different) noise through the segmentation loss, so it only has to be close.
+            for k in ("ins_wt", "dom_wt"):
+                assert abs(float(a[k]) - float(b[k])) <= 2e-4 * max(abs(float(a[k])), 1e-3), (k, float(a[k]), float(b[k]))
+            for k in ("kd", "ins_ii", "ins_ij", "ins_wt_oc"):
+                assert abs(float(a[k]) - float(b[k])) <= 0.05 * max(abs(float(a[k])), 1e-3), (k, float(a[k]), float(b[k]))
+    first_kd = float(graph.replay(*batches[0])["kd"])          # replay() returns the graph's static output tensors
+    assert float(graph.replay(*batches[0])["kd"]) != first_kd  # same batch again: the weights moved, the graph keeps training

@@ -319,7 +319,11 @@ class ShapeVariationalDist_x(_UNetTrunk):
 
     def reparameterization(self, mu, logvar):
         std = self._scrub_nan(torch.exp(logvar / 2))
-        return torch.normal(mu, std) * std + mu              # shape_networks.py:507-509
+        # shape_networks.py:507-509: `torch.normal(mu, std) * std + mu`.  torch.normal(mean, std) draws randn * std + mean
+        # from the same generator stream and passes no gradient to its arguments; written out
+        # that way it has no host-side `std >= 0` check, so the iteration stays CUDA-graph capturable.
+        sampled = (torch.randn_like(std) * std + mu).detach()
+        return sampled * std + mu
 
     def compute_whitening_loss(self, z):
         """(off_diagonal_loss, diagonal_loss, domain_loss) -- shape_networks.py:561-594."""

@@ -46,7 +46,9 @@ class TrainStep:
                 m.to(memory_format=torch.channels_last)
         self.buckets = [FlatGradBucket(m, process_group) for m in self.nets]
         fused = bool(fused_adam) and self.device.type == "cuda"       # one multi-tensor kernel per optimizer step
-        self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused) for m in self.nets]
+        self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused, capturable=fused)
+                       for m in self.nets]
+        self._graph = None
         self.iteration = 0
 
     def _finish(self, idx, loss):
@@ -95,3 +97,32 @@ class TrainStep:
         out.update(kd_oc=kd_oc.detach(), ins_wt_shape_oc=ins_s_oc.detach(), dom_wt_shape_oc=dom_s_oc.detach())
         self.iteration += 1
         return out
+
+    # ---- CUDA-graph replay of the whole iteration --------------------------------------
+    def capture(self, image, target_od, target_oc, warmup=3):
+        """Record one full iteration (all four sub-steps, ~5 000 kernel launches, the NCCL all-reduces included)
+        into a CUDA graph on static input buffers.  Possible because nothing on the path synchronises the host:
+        the losses stay on the device, the ROI pos-weight is computed by a kernel, the NaN scrubs are `where`s.
+        Call once with a representative batch; afterwards `replay()` copies a new batch in and launches the graph."""
+        self._static = [image.clone(), target_od.clone(), target_oc.clone()]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                                   # allocator / cuDNN / optimizer state warm-up
+                self._static[0].copy_(image)
+                self.step(*self._static)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self._static[0].copy_(image)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._static_out = self.step(*self._static)
+        return self
+
+    def replay(self, image, target_od, target_oc):
+        if self._graph is None:
+            raise RuntimeError("call capture() first")
+        self._static[0].copy_(image)
+        self._static[1].copy_(target_od)
+        self._static[2].copy_(target_oc)
+        self._graph.replay()
+        return self._static_out
