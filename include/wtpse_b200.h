@@ -206,6 +206,8 @@ void        wtpse_debug_set_epilogue_repeat(int n);
 void        wtpse_debug_set_backward_mode(int mode);
 /* Diagnostics: round-robin instead of contiguous tile schedule in the unfused apply kernel. */
 void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
+/* Diagnostics (Track W): 1 all levels fused per 64x64 tile where the shape allows, 0 (default) per-level kernels. */
+void        wtpse_debug_set_wavelet_fused(int on);
 /* Diagnostics: L2 evict-first policy on the TMA loads of z in the Gram and apply kernels. */
 void        wtpse_debug_set_l2_hint(int on);
 /* Diagnostics: Gram tile schedule = CTAs per group (a group owns a contiguous tile range and deals it round-robin

@@ -21,7 +21,8 @@ def _maps(shape, seed=0):
 
 
 @pytest.mark.parametrize("wavelet", ["haar", "db2"])
-@pytest.mark.parametrize("shape,J", [((3, 2, 32, 32), 3), ((2, 2, 64, 48), 4), ((1, 1, 16, 80), 2), ((4, 2, 8, 8), 1)])
+@pytest.mark.parametrize("shape,J", [((3, 2, 32, 32), 3), ((2, 2, 64, 48), 4), ((1, 1, 16, 80), 2), ((4, 2, 8, 8), 1),
+                                     ((2, 2, 128, 64), 4), ((1, 2, 64, 192), 3), ((3, 1, 64, 64), 1), ((1, 1, 256, 128), 2)])
 def test_dwt_matches_spec_and_identities(wavelet, shape, J):
     import wtpse_b200 as wb
     from oracle import wavelet_np as wn
@@ -62,6 +63,30 @@ def test_wavelet_shape_loss_forward_backward(wavelet, J, weights):
     # run-to-run reproducible
     loss2 = wb.wavelet_shape_loss(p.detach(), wavelet, J, weights)
     assert float(loss2) == float(loss)
+
+
+@pytest.mark.parametrize("wavelet", ["haar", "db2"])
+def test_fused_and_per_level_kernels_agree(wavelet):
+    """All-levels-in-one-pass tiles (64x64 + halo in shared memory) vs one kernel per level."""
+    import wtpse_b200 as wb
+
+    lib = wb._lib.load()
+    x = torch.rand(3, 2, 128, 192, device=_dev())
+    y = torch.randn(3, 2, 128, 192, device=_dev())
+    outs = []
+    for fused in (1, 0):
+        lib.wtpse_debug_set_wavelet_fused(fused)
+        try:
+            xg = x.clone().requires_grad_(True)
+            loss = wb.wavelet_shape_loss(xg, wavelet, 4, (1.0, 0.5, 0.25, 2.0))
+            loss.backward()
+            outs.append((wb.dwt2d(x, wavelet, 4), wb.idwt2d(y, wavelet, 4), float(loss), xg.grad.clone()))
+        finally:
+            lib.wtpse_debug_set_wavelet_fused(0)
+    assert rel_err(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy()) < 2e-6
+    assert rel_err(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy()) < 2e-6
+    assert abs(outs[0][2] - outs[1][2]) <= 2e-6 * abs(outs[1][2])
+    assert rel_err(outs[0][3].cpu().numpy(), outs[1][3].cpu().numpy()) < 2e-6
 
 
 def test_wavelet_contract_errors():
