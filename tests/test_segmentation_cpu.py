@@ -84,3 +84,33 @@ def test_update_refuses_cpu_tensors():
     x = torch.randn(6, 3, 16, 16)
     with pytest.raises(RuntimeError, match="no CPU implementation"):
         main.update(x, (x[:, :1] > 0).float(), two_stage_inputs=x, two_step=True)
+
+
+def test_dropin_install_rebinds_the_reference_classes():
+    """dropin.install() swaps the hot-path methods on the reference's own classes (and uninstall restores them)."""
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference tree not on this box")
+    import wtpse_b200 as wb
+
+    alg, sn, _ = ref_shim.load()
+    torch.manual_seed(0)
+    ref_main = alg.WT_PSE(3, 1, dict(HP), "cpu", False, per_domain_batch=2, source_domain_num=3)
+    ref_shape = sn.ShapeVariationalDist_x(dict(HP), "cpu", 1, number_source_domain=3, batch_size=2)
+    z = torch.randn(6, 16, 8, 8)
+    before = ref_main.compute_whitening_loss(z)
+    saved = wb.dropin.install(alg, sn)
+    try:
+        assert alg.WT_PSE.compute_whitening_loss is wb.dropin.wt_pse_compute_whitening_loss
+        assert sn.ShapeVariationalDist_x.wasser_distance is wb.dropin.shape_wasser_distance
+        # the rebound methods read the reference's own attributes and route into the CUDA path (which refuses CPU input)
+        for call in (lambda: ref_main.compute_whitening_loss(z), lambda: ref_shape.compute_whitening_loss(z),
+                     lambda: ref_shape.wasser_distance(z[:, :1], z[:, 1:2]),
+                     lambda: ref_main.mmd_operator.forward(torch.randn(6, 120))):
+            with pytest.raises(RuntimeError, match="no CPU implementation"):
+                call()
+    finally:
+        wb.dropin.uninstall(saved)
+    after = ref_main.compute_whitening_loss(z)
+    assert float(before[0]) == float(after[0]) and float(before[1]) == float(after[1])

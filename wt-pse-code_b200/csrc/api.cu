@@ -114,6 +114,7 @@ int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_d
         LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
         e = launch_gram_reduce(w.partial, w.slot_count, g, B, P, n_per_domain, n_domains, margin, eps, gram, rowstat, w.vd, w.statd, s);
         if (e != cudaSuccess) return cuda_fail(e, "gram reduce launch");
+        profile_count_kernel(kKernGramReduce);
         e = launch_whiten_epilogue_fwd(nullptr, nullptr, 0, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s, w.vd, w.statd, true);
     } else {
         LaunchScope scope(kKernEpilogueFwd, s);
@@ -145,6 +146,7 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
         LaunchScope scope(kKernApply, s);            // one scope: an event between the two would defeat the overlap
         e = launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s);
         if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
+        profile_count_kernel(kKernMmat);
         e = launch_apply(z, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/true);
     } else {
         { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s); }

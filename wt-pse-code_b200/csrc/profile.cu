@@ -25,7 +25,7 @@ constexpr size_t kMaxPairs = 1 << 16;
 const char* kNames[kKernCount] = {"gram_tma_kernel", "whiten_epilogue_fwd_kernel", "whiten_epilogue_bwd_kernel",
                                   "apply_tma_kernel", "mmd_fwd_kernel", "mmd_bwd_kernel", "mse_fwd_kernels",
                                   "mse_bwd_kernel", "fuse_kernels", "label_kernels", "wavelet_fwd_kernels",
-                                  "wavelet_bwd_kernels"};
+                                  "wavelet_bwd_kernels", "gram_reduce_kernel", "whiten_mmat_kernel"};
 
 thread_local Pair t_open = {nullptr, nullptr, -1};
 
@@ -50,6 +50,8 @@ void profile_record_begin(int id, cudaStream_t s) {
     cudaEventRecord(p.a, s);
     t_open = p;
 }
+
+void profile_count_kernel(int id) { g_launches[id].fetch_add(1, std::memory_order_relaxed); }
 
 void profile_record_end(int id, cudaStream_t s) {
     if (t_open.id != id) return;

@@ -20,12 +20,17 @@ enum KernelId {
     kKernLabels,
     kKernWaveletFwd,
     kKernWaveletBwd,
+    kKernGramReduce,      // counted only: timed inside the kKernEpilogueFwd scope
+    kKernMmat,            // counted only: timed inside the kKernApply scope
     kKernCount
 };
 
 const char* kernel_name(int id);
 void profile_record_begin(int id, cudaStream_t s);
 void profile_record_end(int id, cudaStream_t s);
+// a scope that brackets two kernels (chained by programmatic dependent launch, so no event may sit between them)
+// counts the second one here
+void profile_count_kernel(int id);
 
 struct LaunchScope {
     int id;
