@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--debug-round-robin", type=int, default=1)
     ap.add_argument("--debug-gram-group", type=int, default=-1)
     ap.add_argument("--debug-l2-hint", type=int, default=-1)
+    ap.add_argument("--debug-gram-variant", type=int, default=-1)
     ap.add_argument("--debug-two-stage-epilogue", type=int, default=1)
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
@@ -243,6 +244,8 @@ def run_ours(args):
     lib = wb._lib.load()
     lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
     lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
+    if args.debug_gram_variant >= 0:
+        lib.wtpse_debug_set_gram_variant(args.debug_gram_variant)
     if args.debug_l2_hint >= 0:
         lib.wtpse_debug_set_l2_hint(args.debug_l2_hint)
     if args.debug_gram_group >= 0:

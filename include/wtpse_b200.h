@@ -213,6 +213,8 @@ void        wtpse_debug_set_l2_hint(int on);
 /* Diagnostics: Gram tile schedule = CTAs per group (a group owns a contiguous tile range and deals it round-robin
  * to its members): 1 contiguous range per CTA, 0 pure round-robin, else a divisor of the grid size. */
 void        wtpse_debug_set_gram_group(int ctas_per_group);
+/* Diagnostics: Gram kernel variant, 0 one thread per pixel quad (255 registers, 8 warps/SM), 1 two threads per quad. */
+void        wtpse_debug_set_gram_variant(int variant);
 /* Diagnostics: forward epilogue as per-sample reduce kernel + single-CTA MMD (1, default) or one single-CTA kernel (0). */
 void        wtpse_debug_set_two_stage_epilogue(int on);
 

@@ -307,15 +307,18 @@ def test_forward_schedules_agree():
     for B, H, W, n in ((9, 96, 96, 3), (32, 128, 128, 10), (6, 32, 20, 2), (3, 300, 300, 1), (200, 16, 16, 66)):
         z = _synth(B, H, W, seed=B + 1).to(_dev())
         res = []
-        for grp, two_stage in ((0, 1), (1, 0), (0, 1), (4, 1), (2, 0), (37, 1)):
+        for grp, two_stage, variant in ((0, 1, 0), (1, 0, 0), (0, 1, 0), (4, 1, 0), (2, 0, 0), (37, 1, 0),
+                                        (1, 1, 1), (0, 1, 1), (4, 0, 1)):
             lib.wtpse_debug_set_gram_group(grp)                  # 0 = pure round-robin, 1 = contiguous ranges
             lib.wtpse_debug_set_two_stage_epilogue(two_stage)
+            lib.wtpse_debug_set_gram_variant(variant)            # 1 = two threads per pixel quad
             try:
                 off, diag, dom = wb.whitening_terms(z, n, 3)
                 res.append((float(off), float(diag), float(dom), wb.gram_matrix(z).clone()))
             finally:
                 lib.wtpse_debug_set_gram_group(1)
                 lib.wtpse_debug_set_two_stage_epilogue(1)
+                lib.wtpse_debug_set_gram_variant(0)
         assert res[0][:3] == res[2][:3] and torch.equal(res[0][3], res[2][3])          # reproducible
         for other in res[1:]:
             for a, b in zip(res[0][:3], other[:3]):

@@ -68,6 +68,7 @@ EXPORTS = {
     "wtpse_debug_set_l2_hint": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_fused": (None, [_c.c_int]),
     "wtpse_debug_set_gram_group": (None, [_c.c_int]),
+    "wtpse_debug_set_gram_variant": (None, [_c.c_int]),
     "wtpse_debug_set_two_stage_epilogue": (None, [_c.c_int]),
     "wtpse_host_plan_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     "wtpse_host_plan_destroy": (None, [_c.c_void_p]),

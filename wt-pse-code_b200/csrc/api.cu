@@ -160,6 +160,7 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
 void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }
 void wtpse_debug_set_epilogue_repeat(int n) { g_epilogue_repeat = n > 0 ? n : 1; }
 void wtpse_debug_set_backward_mode(int mode) { g_backward_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
+void wtpse_debug_set_gram_variant(int v) { g_gram_variant = v == 1 ? 1 : 0; }
 void wtpse_debug_set_gram_group(int ctas_per_group) { g_gram_group = ctas_per_group >= 0 ? ctas_per_group : 1; }
 void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = on != 0; }
 void wtpse_debug_set_wavelet_fused(int on) { g_wavelet_fused = on != 0; }

@@ -126,4 +126,34 @@ __host__ __device__ __forceinline__ long long part_owner(long long t, long long 
     return ((t + 1) * G - 1) / T;
 }
 
+
+// Tile schedule.  The G CTAs form G/g groups of g; each group owns one contiguous range of tiles and deals it
+// round-robin to its members (member r takes tiles r, r+g, ... of the range).  g = 1: one contiguous range per
+// CTA; g = G: pure round-robin.  Every member flushes one partial for EVERY sample its group's range touches
+// (zeros if it happened to get no tile of it), so the slot bookkeeping is uniform:
+//   slot(b, CTA) = (group - first group touching b) * g + r,   slot_count[b] = (#groups touching b) * g.
+struct TileWalk {
+    long long R0, R1;      // group range
+    long long g, r;        // group size, member index
+    long long b_first, b_last;
+    __device__ TileWalk(long long k, long long G, long long T, long long tps, long long group) {
+        g = group;
+        const long long Gg = G / g, grp = k / g;
+        r = k - grp * g;
+        R0 = part_begin(grp, T, Gg);
+        R1 = part_begin(grp + 1, T, Gg);
+        b_first = R0 / tps;
+        b_last = (R1 - 1) / tps;
+    }
+    // [first, end) of this CTA's tiles inside sample b, step g
+    __device__ void segment(long long b, long long tps, long long& first, long long& end) const {
+        const long long s0 = b * tps > R0 ? b * tps : R0;
+        const long long s1 = (b + 1) * tps < R1 ? (b + 1) * tps : R1;
+        long long d = (r - (s0 - R0)) % g;
+        if (d < 0) d += g;
+        first = s0 + d;
+        end = s1;
+    }
+};
+
 }  // namespace wtpse

@@ -13,6 +13,7 @@ struct GramPlan {
     int nslots;                  // partial slots per sample
     bool round_robin;            // group > 1
     int group;                   // CTAs per group: the group owns a contiguous tile range and deals it round-robin
+    int variant;                 // 0: one thread per pixel quad (whitening_gram.cu), 1: two threads per quad (..._split.cu)
 };
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
@@ -38,6 +39,10 @@ cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, cons
                                float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
                                cudaStream_t stream);
 extern int g_gram_group;
+extern int g_gram_variant;
+long long gram_split_tile_px();
+cudaError_t launch_gram_split(const float* z, float* partial, int* slot_count, long long P, const GramPlan& g,
+                              cudaStream_t stream);
 
 // backward: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
 cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,

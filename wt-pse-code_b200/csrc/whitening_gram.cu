@@ -84,35 +84,6 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4
     }
 }
 
-// Tile schedule.  The G CTAs form G/g groups of g; each group owns one contiguous range of tiles and deals it
-// round-robin to its members (member r takes tiles r, r+g, ... of the range).  g = 1: one contiguous range per
-// CTA; g = G: pure round-robin.  Every member flushes one partial for EVERY sample its group's range touches
-// (zeros if it happened to get no tile of it), so the slot bookkeeping is uniform:
-//   slot(b, CTA) = (group - first group touching b) * g + r,   slot_count[b] = (#groups touching b) * g.
-struct TileWalk {
-    long long R0, R1;      // group range
-    long long g, r;        // group size, member index
-    long long b_first, b_last;
-    __device__ TileWalk(long long k, long long G, long long T, long long tps, long long group) {
-        g = group;
-        const long long Gg = G / g, grp = k / g;
-        r = k - grp * g;
-        R0 = part_begin(grp, T, Gg);
-        R1 = part_begin(grp + 1, T, Gg);
-        b_first = R0 / tps;
-        b_last = (R1 - 1) / tps;
-    }
-    // [first, end) of this CTA's tiles inside sample b, step g
-    __device__ void segment(long long b, long long tps, long long& first, long long& end) const {
-        const long long s0 = b * tps > R0 ? b * tps : R0;
-        const long long s1 = (b + 1) * tps < R1 ? (b + 1) * tps : R1;
-        long long d = (r - (s0 - R0)) % g;
-        if (d < 0) d += g;
-        first = s0 + d;
-        end = s1;
-    }
-};
-
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
                 long long tiles_per_sample, long long T, int nslots, int group, int hint) {
@@ -244,14 +215,17 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, in
 // Round-robin gives DRAM the same ~10 % better locality it gives the apply kernel, but every CTA then touches every
 // sample and pays one 136-value cross-thread flush per sample (32 instead of 1-2): 123 us vs 104 us at 32x16x512x512.
 int g_gram_group = 1;
+int g_gram_variant = 0;
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count) {
     GramPlan g;
     g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
     g.round_robin = false;
     g.group = 1;
+    g.variant = g_gram_variant;
     if (g.tma) {
-        g.tiles_per_sample = (P + kTilePx - 1) / kTilePx;
+        const long long tile_px = g.variant == 1 ? gram_split_tile_px() : kTilePx;
+        g.tiles_per_sample = (P + tile_px - 1) / tile_px;
         g.T = g.tiles_per_sample * B;
         g.G = g.T < sm_count ? g.T : sm_count;
         long long grp = g_gram_group;
@@ -282,7 +256,7 @@ GramPlan plan_gram(const float* z, int B, long long P, int sm_count) {
 
 size_t gram_partial_floats(int B, long long P, int sm_count) {
     // upper bound over both paths: nslots <= sm_count + 1 for the persistent path and <= 2*sm_count for the generic one
-    const long long tps = (P + kTilePx - 1) / kTilePx;
+    const long long tps = (P + 640 - 1) / 640;      // smallest tile of the two variants
     long long T = tps * B;
     long long G = T < sm_count ? T : sm_count;
     long long per_cta = (T + G - 1) / G;
@@ -296,6 +270,7 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
 
 cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
                         cudaStream_t stream) {
+    if (g.tma && g.variant == 1) return launch_gram_split(z, partial, slot_count, P, g, stream);
     if (g.tma) {
         cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
