@@ -50,8 +50,83 @@ struct LevelArgs {
     int partial_base;
 };
 
+// One thread -> TWO horizontally adjacent half-resolution sites (j, j+1): their input patches overlap in TAPS-2
+// columns, so a row costs one 128-bit load (+ one 64-bit load for db2) instead of two / four 64-bit loads, and every
+// sub-band is written as a float2.  Requires w % 4 == 0 (the launcher falls back to dwt_level_kernel otherwise).
+template <int TAPS, bool kLoss>
+__global__ void __launch_bounds__(kBx * kBy) dwt_level2_kernel(LevelArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int h2 = a.h >> 1, w2 = a.w >> 1;
+    const int j = 2 * (blockIdx.x * kBx + threadIdx.x), i = blockIdx.y * kBy + threadIdx.y, m = blockIdx.z;
+    float absum = 0.f;
+    if (i < h2 && j < w2) {
+        const float* src = a.in + (long long)m * a.in_map;
+        float lo0[TAPS], hi0[TAPS], lo1[TAPS], hi1[TAPS];
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            int r = 2 * i + k;
+            if (r >= a.h) r -= a.h;
+            const float* row = src + (long long)r * a.in_ld;
+            float x[TAPS + 2];
+            const float4 v = __ldg(reinterpret_cast<const float4*>(row + 2 * j));      // 2j % 4 == 0, w % 4 == 0
+            x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w;
+            if (TAPS == 4) {
+                int c = 2 * j + 4;
+                if (c >= a.w) c -= a.w;
+                const float2 u = __ldg(reinterpret_cast<const float2*>(row + c));
+                x[TAPS] = u.x; x[TAPS + 1] = u.y;
+            }
+            float s0 = 0.f, d0 = 0.f, s1 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int l = 0; l < TAPS; ++l) {
+                s0 = fmaf(Bank<TAPS>::h(l), x[l], s0); d0 = fmaf(Bank<TAPS>::g(l), x[l], d0);
+                s1 = fmaf(Bank<TAPS>::h(l), x[l + 2], s1); d1 = fmaf(Bank<TAPS>::g(l), x[l + 2], d1);
+            }
+            lo0[k] = s0; hi0[k] = d0; lo1[k] = s1; hi1[k] = d1;
+        }
+        float2 LL = make_float2(0.f, 0.f), LH = LL, HL = LL, HH = LL;
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            LL.x = fmaf(Bank<TAPS>::h(k), lo0[k], LL.x); LL.y = fmaf(Bank<TAPS>::h(k), lo1[k], LL.y);
+            LH.x = fmaf(Bank<TAPS>::h(k), hi0[k], LH.x); LH.y = fmaf(Bank<TAPS>::h(k), hi1[k], LH.y);
+            HL.x = fmaf(Bank<TAPS>::g(k), lo0[k], HL.x); HL.y = fmaf(Bank<TAPS>::g(k), lo1[k], HL.y);
+            HH.x = fmaf(Bank<TAPS>::g(k), hi0[k], HH.x); HH.y = fmaf(Bank<TAPS>::g(k), hi1[k], HH.y);
+        }
+        if (a.ll) *reinterpret_cast<float2*>(a.ll + (long long)m * a.ll_map + (long long)i * a.ll_ld + j) = LL;
+        float* det = a.det + (long long)m * a.det_map;
+        if (kLoss) {
+            const float sc = a.det_scale;
+            absum = (fabsf(LH.x) + fabsf(LH.y) + fabsf(HL.x) + fabsf(HL.y) + fabsf(HH.x) + fabsf(HH.y)) * sc;
+            auto sg = [&](float v) { return v > 0.f ? sc : (v < 0.f ? -sc : 0.f); };
+            LH = make_float2(sg(LH.x), sg(LH.y));
+            HL = make_float2(sg(HL.x), sg(HL.y));
+            HH = make_float2(sg(HH.x), sg(HH.y));
+            if (a.zero_ll) *reinterpret_cast<float2*>(det + (long long)i * a.det_ld + j) = make_float2(0.f, 0.f);
+        }
+        *reinterpret_cast<float2*>(det + (long long)i * a.det_ld + w2 + j) = LH;
+        *reinterpret_cast<float2*>(det + (long long)(h2 + i) * a.det_ld + j) = HL;
+        *reinterpret_cast<float2*>(det + (long long)(h2 + i) * a.det_ld + w2 + j) = HH;
+    }
+    if (kLoss) {
+        __shared__ double red[kBx * kBy / 32];
+        double s = warp_sum(double(absum));
+        const int t = threadIdx.y * kBx + threadIdx.x;
+        if ((t & 31) == 0) red[t >> 5] = s;
+        __syncthreads();
+        if (t == 0) {
+            double tot = 0.0;
+#pragma unroll
+            for (int q = 0; q < kBx * kBy / 32; ++q) tot += red[q];
+            a.partial[a.partial_base + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
+        }
+    }
+}
+
 template <int TAPS, bool kLoss>
 __global__ void __launch_bounds__(kBx * kBy) dwt_level_kernel(LevelArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int h2 = a.h >> 1, w2 = a.w >> 1;
     const int j = blockIdx.x * kBx + threadIdx.x, i = blockIdx.y * kBy + threadIdx.y, m = blockIdx.z;
     float absum = 0.f;
@@ -127,6 +202,8 @@ struct SynthArgs {
 // adjoint of dwt_level_kernel: out[2i'+pr][2j'+pc] = sum_{m,n} f_r[2m+pr] f_c[2n+pc] * band[i'-m][j'-n]
 template <int TAPS>
 __global__ void __launch_bounds__(kBx * kBy) idwt_level_kernel(SynthArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int h2 = a.h >> 1, w2 = a.w >> 1;
     const int jp = blockIdx.x * kBx + threadIdx.x, ip = blockIdx.y * kBy + threadIdx.y, mp = blockIdx.z;
     if (ip >= h2 || jp >= w2) return;
@@ -399,6 +476,20 @@ __global__ void __launch_bounds__(1024) wavelet_loss_final_kernel(const double* 
     }
 }
 
+template <typename Kernel, typename Args>
+cudaError_t launch_pss(Kernel kernel, dim3 grid, dim3 block, cudaStream_t stream, const Args& args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 dim3 level_grid(int h, int w, int nmaps) { return dim3((w / 2 + kBx - 1) / kBx, (h / 2 + kBy - 1) / kBy, nmaps); }
 
 }  // namespace
@@ -471,15 +562,19 @@ cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J,
         a.det_scale = loss_mode ? weights_host[j] / (3.0f * float(h / 2) * float(w / 2) * float(nmaps)) : 0.f;
         a.zero_ll = (loss_mode && last) ? 1 : 0;
         a.partial = partial; a.partial_base = pbase;
-        const dim3 g = level_grid(h, w, nmaps), b(kBx, kBy);
+        const bool wide = (w % 4 == 0) && (w >= 8);                                   // two sites per thread
+        const dim3 b(kBx, kBy);
+        const dim3 g = wide ? dim3((w / 4 + kBx - 1) / kBx, (h / 2 + kBy - 1) / kBy, nmaps) : level_grid(h, w, nmaps);
+        cudaError_t e;
         if (loss_mode) {
-            if (taps == 2) dwt_level_kernel<2, true><<<g, b, 0, stream>>>(a);
-            else dwt_level_kernel<4, true><<<g, b, 0, stream>>>(a);
+            if (wide) e = taps == 2 ? launch_pss(dwt_level2_kernel<2, true>, g, b, stream, a) : launch_pss(dwt_level2_kernel<4, true>, g, b, stream, a);
+            else e = taps == 2 ? launch_pss(dwt_level_kernel<2, true>, g, b, stream, a) : launch_pss(dwt_level_kernel<4, true>, g, b, stream, a);
             pbase += int(g.x * g.y * g.z);
         } else {
-            if (taps == 2) dwt_level_kernel<2, false><<<g, b, 0, stream>>>(a);
-            else dwt_level_kernel<4, false><<<g, b, 0, stream>>>(a);
+            if (wide) e = taps == 2 ? launch_pss(dwt_level2_kernel<2, false>, g, b, stream, a) : launch_pss(dwt_level2_kernel<4, false>, g, b, stream, a);
+            else e = taps == 2 ? launch_pss(dwt_level_kernel<2, false>, g, b, stream, a) : launch_pss(dwt_level_kernel<4, false>, g, b, stream, a);
         }
+        if (e != cudaSuccess) return e;
     }
     if (loss_mode) wavelet_loss_final_kernel<<<1, 1024, 0, stream>>>(partial, pbase, loss);
     return cudaGetLastError();
@@ -517,8 +612,8 @@ cudaError_t launch_idwt(const float* coef, int nmaps, int H, int W, int taps, in
         }
         a.h = h; a.w = w; a.nmaps = nmaps;
         const dim3 g = level_grid(h, w, nmaps), b(kBx, kBy);
-        if (taps == 2) idwt_level_kernel<2><<<g, b, 0, stream>>>(a);
-        else idwt_level_kernel<4><<<g, b, 0, stream>>>(a);
+        const cudaError_t e = taps == 2 ? launch_pss(idwt_level_kernel<2>, g, b, stream, a) : launch_pss(idwt_level_kernel<4>, g, b, stream, a);
+        if (e != cudaSuccess) return e;
     }
     return cudaGetLastError();
 }
