@@ -420,8 +420,10 @@ def time_train_step(args, dev, rank, world, barrier):
         image, od, oc = batch(it)
         return ts.replay(image, od, oc) if mode == "cuda-graph" else ts.step(image, od, oc)
 
+    lib.wtpse_profile_reset()
     for it in range(3):
         one(it)
+    kernels_per_iteration = int(lib.wtpse_profile_launches(-1)) // 3          # counted on the eager warm-up iterations
     if args.train_graph:
         try:                                              # the whole iteration as one CUDA graph (no host syncs on the path)
             ts.capture(*batch(100))
@@ -444,7 +446,7 @@ def time_train_step(args, dev, rank, world, barrier):
     ms = float(t.item()) / args.train_steps
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
             "steps": args.train_steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
-            "global_batch_used": world * used, "our_kernel_launches": int(lib.wtpse_profile_launches(-1)),
+            "global_batch_used": world * used, "our_kernels_per_iteration": kernels_per_iteration,
             "backbone": "PyTorch/cuDNN, channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}
 
