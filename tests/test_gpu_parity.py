@@ -29,6 +29,11 @@ def _close(a, b, tol=TOL, scale=0.0):
     return abs(a - b) <= tol * max(abs(b), scale, 1e-300)
 
 
+def _rel_err_dev(a, b):
+    """max-abs normalised error computed on the device (full-size tensors stay in HBM)."""
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
 def _synth(B, H, W, seed=1234, offset=True):
     g = torch.Generator().manual_seed(seed)
     z = 0.3 * torch.randn(B, 16, H, W, generator=g)
@@ -407,7 +412,7 @@ def test_host_plan_pipelined_submissions():
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties + the op-sequence restatement on the GPU
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("B,H,W,n", [(32, 512, 512, 10), (16, 1024, 1024, 5)])
+@pytest.mark.parametrize("B,H,W,n", [(32, 512, 512, 10), (16, 1024, 1024, 5), (64, 1024, 1024, 21)])
 def test_full_size_properties(B, H, W, n):
     import wtpse_b200 as wb
     from oracle import whitening_torch as wt
@@ -426,14 +431,15 @@ def test_full_size_properties(B, H, W, n):
     (r_off + r_diag + r_dom).backward()
     assert _close(float(off), float(r_off)) and _close(float(diag), float(r_diag))
     assert _close(float(dom), float(r_dom), scale=1.0)
-    assert rel_err(dz.cpu().numpy(), zr.grad.cpu().numpy()) < TOL
+    assert _rel_err_dev(dz, zr.grad) < TOL
+    del zr, r_G
     # (2) homogeneity: G(a z) = a^2 G(z)
     G2 = wb.gram_matrix(2.0 * z, eps=0.0)
-    assert rel_err(G2.cpu().numpy(), 4.0 * G.cpu().numpy()) < 1e-6
+    assert _rel_err_dev(G2, 4.0 * G) < 1e-6
     # (3) pixel permutation invariance of the Gram (sum over pixels), exact up to summation order
     perm = torch.randperm(H * W, device=dev)
     Gp = wb.gram_matrix(z.view(B, 16, -1)[:, :, perm].view_as(z).contiguous(), eps=0.0)
-    assert rel_err(Gp.cpu().numpy(), G.cpu().numpy()) < 1e-5
+    assert _rel_err_dev(Gp, G) < 1e-5
     # (4) adjoint identity: <dz_b, z_b> = sum_ij M_ij G_ij (P-1) with dz = M z  =>  check via a second apply:
     #     the loss is degree-2 homogeneous in z through G, so <dz, z> = 2 * sum_b <dL/dG_b, G_b - eps I>
     zr2 = z.clone().requires_grad_(True)
