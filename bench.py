@@ -40,6 +40,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--wavelet-split", type=int, default=-1, help="Track W fused plan: -1 auto, 0 whole map resident, 1 level 1 streamed")
+    ap.add_argument("--wavelet-tiles", type=int, default=1, help="Track W: level 1 of the streamed plan as TMA pipelines (1) or per-thread loads (0)")
+    ap.add_argument("--wavelet-cluster-max", type=int, default=8, help="Track W: largest cluster size of the resident stage")
+    ap.add_argument("--wavelet-resident", type=int, default=1, help="Track W: 0 = per-level kernels instead of the cluster-resident kernel")
     ap.add_argument("--track", default="whitening", choices=["whitening", "wavelet"],
                     help="wavelet = BASELINE configs[1] as literally written (Track W, parity unpinned); not the default")
     ap.add_argument("--e2e-steps", type=int, default=20, help="steps of the host-buffer (PCIe-bound) loop")
@@ -461,37 +465,76 @@ def run_wavelet(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
     B, C, H, W, J, wv = 32, 2, args.size, args.size, 4, "db2"
+    from wtpse_b200 import wavelet as wvm
+    from wtpse_b200.functional import _ptr, _stream_ptr
+
+    lib = wb._lib.load()
+    lib.wtpse_debug_set_wavelet_resident(int(args.wavelet_resident))
+    lib.wtpse_debug_set_wavelet_split(int(args.wavelet_split))
+    lib.wtpse_debug_set_wavelet_cluster_max(int(args.wavelet_cluster_max))
+    lib.wtpse_debug_set_wavelet_tiles(int(args.wavelet_tiles))
+    cs = wvm.resident_cluster_size(H, W, wv, J)
     xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev), 1).requires_grad_(True) for _ in range(4)]
     one = torch.ones((), device=dev)
 
-    def step(i):
+    def step_autograd(i):                   # the public API: autograd Function, fresh output tensors every call
         x = xs[i % 4]
         x.grad = None
         loss = wb.wavelet_shape_loss(x, wv, J)
         loss.backward(one)
         return loss
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for i in range(args.steps):
-        loss = step(i)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / args.steps
+    # the same launches through the C ABI with preallocated outputs (no Python autograd bookkeeping between them)
+    nmaps = B * C
+    nbytes = lib.wtpse_wavelet_workspace_bytes(nmaps, H, W, J)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss_abi = torch.zeros((), device=dev)
+    grad = torch.empty(B, C, H, W, device=dev)
+    gcoef = torch.empty(B, C, H, W, device=dev)
+    st = _stream_ptr(dev)
+
+    def step_abi(i):
+        x = xs[i % 4]
+        if cs:
+            wb._lib.check(lib.wtpse_wavelet_loss_resident(_ptr(x), nmaps, H, W, 1, J, None, None, _ptr(loss_abi), _ptr(grad),
+                                                          _ptr(ws), nbytes, st))
+            wb._lib.check(lib.wtpse_scale_unless_one(_ptr(grad), grad.numel(), _ptr(one), st))
+        else:
+            wb._lib.check(lib.wtpse_wavelet_loss_forward(_ptr(x), nmaps, H, W, 1, J, None, _ptr(loss_abi), _ptr(gcoef), _ptr(ws),
+                                                         nbytes, st))
+            wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(gcoef), nmaps, H, W, 1, J, _ptr(grad), _ptr(one), _ptr(ws), nbytes, st))
+        return loss_abi
+
+    def timed(step):
+        for i in range(max(args.warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            out = step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / args.steps, out
+
+    ms_autograd, loss_ag = timed(step_autograd)
+    ms, loss = timed(step_abi)
+    assert abs(float(loss) - float(loss_ag)) <= 1e-6 * abs(float(loss_ag)), (float(loss), float(loss_ag))
     elems = B * C * H * W
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
         os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_PEAK_GBS
     algo = 8.0 * elems                      # SURVEY 8(d) Track W: 4N read forward + 4N written backward
-    moved = 4.0 * elems * (8.0 / 3.0) * 2   # what the per-level kernels move: (read + write) * 4/3 per pass, two passes
+    # bytes the kernels actually move: resident = one read + one write; per-level = (read + write) * 4/3 per pass, two passes
+    moved = algo if cs else 4.0 * elems * (8.0 / 3.0) * 2
     print(json.dumps({
         "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": B * H * W / (ms * 1e-3) / 1e6,
         "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "db2 DWT J=4 L1 detail-coefficient loss fwd+bwd, %dx%dx%dx%d softmax maps" % (B, C, H, W),
-                   "l2": "four alternating 67 MB inputs (each below the 126 MB L2: the 268 MB rotation is not)"},
+                   "l2": "four alternating 67 MB inputs (each below the 126 MB L2: the 268 MB rotation is not)",
+                   "path": ("fused plan (wavelet-split=%d), resident stage in clusters of %d CTAs" % (args.wavelet_split, cs)) if cs else "one kernel per level",
+                   "timed_through": "C ABI, preallocated outputs"},
+        "autograd_ms_per_step": ms_autograd,
         "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None,
                      "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},

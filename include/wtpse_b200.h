@@ -160,6 +160,28 @@ int wtpse_wavelet_loss_forward(const float* x, int nmaps, int H, int W, int wave
                                const float* level_weights, float* loss, float* grad_coef,
                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/*
+ * Fused loss + gradient path: ONE pass over x for the loss and dloss/dx, no coefficient buffer in HBM.
+ *  - whole map resident (wavelet_resident.cu): every H x W map is held in the distributed shared memory of one
+ *    thread-block cluster (row bands, 1-D TMA loads, filter-overlap rows exchanged through DSMEM); all J analysis
+ *    levels, the L1 reduction and the whole synthesis of the gradient run shared-to-shared;
+ *  - level 1 streamed (wavelet_stream.cu): level 1 (3/4 of all coefficients) goes global-to-global with the detail
+ *    bands reduced to one byte of packed signs per site, and the low-low band (a quarter of the map) is what the
+ *    cluster-resident kernel works on.  Chosen automatically for maps that would need a cluster of more than 2 CTAs.
+ * wtpse_wavelet_resident_cluster returns the cluster size of the resident stage (1, 2, 4, 8) or 0 when no fused plan
+ * exists for the shape (W not divisible by 2^(J+1), a low-low band that does not fit a cluster, ...) -- use the
+ * per-level entry points above then.
+ * grad_x (may be NULL: loss only) receives upstream * dloss/dx; upstream is an optional DEVICE scalar (NULL = 1).
+ * Workspace: wtpse_wavelet_workspace_bytes.
+ */
+int wtpse_wavelet_resident_cluster(int H, int W, int wavelet, int J);
+int wtpse_wavelet_loss_resident(const float* x, int nmaps, int H, int W, int wavelet, int J,
+                                const float* level_weights, const float* upstream, float* loss, float* grad_x,
+                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+/* data[0..n) *= *scale unless *scale == 1 (decided on the device; no host synchronisation).  Used by the autograd
+ * backward of the resident path: the gradient was already written for upstream = 1. */
+int wtpse_scale_unless_one(float* data, int64_t n, const float* scale, wtpse_stream_t stream);
+
 /* ---- host-buffer entry point (plugin-facing, used for the end-to-end number) --------------- */
 
 typedef struct wtpse_host_plan wtpse_host_plan;
@@ -208,6 +230,14 @@ void        wtpse_debug_set_backward_mode(int mode);
 void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
 /* Diagnostics (Track W): 1 all levels fused per 64x64 tile where the shape allows, 0 (default) per-level kernels. */
 void        wtpse_debug_set_wavelet_fused(int on);
+/* Diagnostics: 0 makes wtpse_wavelet_resident_cluster report 0 for every shape (callers fall back to the per-level path). */
+void        wtpse_debug_set_wavelet_resident(int on);
+/* Diagnostics: fused-plan choice, -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed whenever possible. */
+void        wtpse_debug_set_wavelet_split(int mode);
+/* Diagnostics: level 1 of the streamed plan as persistent TMA pipelines (1, default) or with per-thread global loads (0). */
+void        wtpse_debug_set_wavelet_tiles(int on);
+/* Diagnostics: largest cluster size the resident planner may pick (1..8, default 8). */
+void        wtpse_debug_set_wavelet_cluster_max(int cs);
 /* Diagnostics: L2 evict-first policy on the TMA loads of z in the Gram and apply kernels. */
 void        wtpse_debug_set_l2_hint(int on);
 /* Diagnostics: Gram tile schedule = CTAs per group (a group owns a contiguous tile range and deals it round-robin

@@ -89,6 +89,94 @@ def test_fused_and_per_level_kernels_agree(wavelet):
     assert rel_err(outs[0][3].cpu().numpy(), outs[1][3].cpu().numpy()) < 2e-6
 
 
+@pytest.mark.parametrize("wavelet", ["haar", "db2"])
+@pytest.mark.parametrize("shape,J", [((40, 2, 64, 64), 3),        # 80 maps: every cluster loops over several maps
+                                     ((3, 2, 96, 160), 3),        # non-power-of-two sides
+                                     ((2, 1, 256, 256), 5),
+                                     ((5, 1, 32, 64), 4),
+                                     ((2, 2, 48, 64), 4),         # whole map: one CTA, the halo wraps onto itself
+                                     ((3, 1, 64, 128), 1),        # J = 1: the streamed plan has no resident stage
+                                     ((2, 1, 64, 72), 2),         # W % 32 != 0: level 1 falls back to per-thread loads
+                                     ((1, 2, 512, 512), 4)])
+def test_fused_plans_match_per_level_path(wavelet, shape, J):
+    """The fused loss + gradient plans (whole map resident in a cluster's distributed shared memory; level 1 streamed +
+    low-low band resident) against the per-level kernels: loss, gradient, a second backward through the retained graph,
+    the loss-only call."""
+    import wtpse_b200 as wb
+    from wtpse_b200 import wavelet as wv
+
+    lib = wb._lib.load()
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(J + shape[0])).to(_dev())
+    weights = tuple(0.5 + 0.25 * j for j in range(J))
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        loss = wb.wavelet_shape_loss(xg, wavelet, J, weights)
+        (0.3 * loss).backward(retain_graph=True)
+        g1 = xg.grad.clone()
+        xg.grad = None
+        (2.0 * loss).backward()                  # second pass through the retained graph
+        return float(loss), g1, xg.grad.clone(), float(wb.wavelet_shape_loss(x, wavelet, J, weights))
+
+    try:
+        lib.wtpse_debug_set_wavelet_resident(0)
+        assert wv.resident_cluster_size(shape[-2], shape[-1], wavelet, J) == 0
+        l_p, g_p, g2_p, lo_p = run()
+        assert lo_p == l_p
+        lib.wtpse_debug_set_wavelet_resident(1)
+        for split, cmax, tiles in ((0, 8, 1), (1, 8, 1), (1, 2, 1), (1, 8, 0), (-1, 8, 1)):
+            lib.wtpse_debug_set_wavelet_split(split)
+            lib.wtpse_debug_set_wavelet_cluster_max(cmax)
+            lib.wtpse_debug_set_wavelet_tiles(tiles)
+            assert wv.resident_cluster_size(shape[-2], shape[-1], wavelet, J) > 0, (split, cmax)
+            l_r, g_r, g2_r, lo_r = run()
+            assert abs(l_r - l_p) <= 2e-6 * abs(l_p) and lo_r == l_r, (split, cmax)
+            assert rel_err(g_r.cpu().numpy(), g_p.cpu().numpy()) < 2e-6, (split, cmax)
+            assert rel_err(g2_r.cpu().numpy(), g2_p.cpu().numpy()) < 2e-6, (split, cmax)
+            assert rel_err(g2_r.cpu().numpy(), (g_r / 0.3 * 2.0).cpu().numpy()) < 2e-6, (split, cmax)
+    finally:
+        lib.wtpse_debug_set_wavelet_resident(1)
+        lib.wtpse_debug_set_wavelet_split(-1)
+        lib.wtpse_debug_set_wavelet_cluster_max(8)
+        lib.wtpse_debug_set_wavelet_tiles(1)
+
+
+def test_fused_plan_covers_maps_too_large_for_a_cluster():
+    """1024 x 1024 (BASELINE configs[4]): 4 MB per map does not fit a cluster, its 512 x 512 low-low band does."""
+    import wtpse_b200 as wb
+    from wtpse_b200 import wavelet as wv
+
+    lib = wb._lib.load()
+    assert wv.resident_cluster_size(1024, 1024, "db2", 5) == 8
+    x = torch.rand(2, 2, 1024, 1024, device=_dev())
+    res = []
+    for resident in (1, 0):
+        lib.wtpse_debug_set_wavelet_resident(resident)
+        try:
+            xg = x.clone().requires_grad_(True)
+            loss = wb.wavelet_shape_loss(xg, "db2", 5)
+            loss.backward()
+            res.append((float(loss), xg.grad.clone()))
+        finally:
+            lib.wtpse_debug_set_wavelet_resident(1)
+    assert abs(res[0][0] - res[1][0]) <= 2e-6 * abs(res[1][0])
+    assert rel_err(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 2e-6
+
+
+def test_resident_path_reproducible_and_unit_upstream():
+    import wtpse_b200 as wb
+
+    x = torch.rand(32, 2, 128, 128, device=_dev())
+    outs = []
+    for _ in range(2):
+        xg = x.clone().requires_grad_(True)
+        loss = wb.wavelet_shape_loss(xg, "db2", 4)
+        loss.backward()                              # upstream gradient exactly 1: the scale kernel exits early
+        outs.append((float(loss), xg.grad.clone()))
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1])
+    assert abs(float((outs[0][1].double() * x.double()).sum()) - outs[0][0]) <= 1e-4 * outs[0][0]
+
+
 def test_wavelet_contract_errors():
     import wtpse_b200 as wb
 

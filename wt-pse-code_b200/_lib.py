@@ -66,6 +66,15 @@ EXPORTS = {
     "wtpse_debug_set_backward_mode": (None, [_c.c_int]),
     "wtpse_debug_set_apply_round_robin": (None, [_c.c_int]),
     "wtpse_debug_set_l2_hint": (None, [_c.c_int]),
+    "wtpse_wavelet_resident_cluster": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "wtpse_wavelet_loss_resident": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                               _c.POINTER(_c.c_float), _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                               _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_scale_unless_one": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p]),
+    "wtpse_debug_set_wavelet_resident": (None, [_c.c_int]),
+    "wtpse_debug_set_wavelet_split": (None, [_c.c_int]),
+    "wtpse_debug_set_wavelet_tiles": (None, [_c.c_int]),
+    "wtpse_debug_set_wavelet_cluster_max": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_fused": (None, [_c.c_int]),
     "wtpse_debug_set_gram_group": (None, [_c.c_int]),
     "wtpse_debug_set_gram_variant": (None, [_c.c_int]),

@@ -164,6 +164,10 @@ void wtpse_debug_set_gram_variant(int v) { g_gram_variant = v == 1 ? 1 : 0; }
 void wtpse_debug_set_gram_group(int ctas_per_group) { g_gram_group = ctas_per_group >= 0 ? ctas_per_group : 1; }
 void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = on != 0; }
 void wtpse_debug_set_wavelet_fused(int on) { g_wavelet_fused = on != 0; }
+void wtpse_debug_set_wavelet_resident(int on) { g_wavelet_resident = on != 0; }
+void wtpse_debug_set_wavelet_tiles(int on) { g_wavelet_tiles = on != 0; }
+void wtpse_debug_set_wavelet_split(int mode) { g_wavelet_split = mode < 0 ? -1 : (mode ? 1 : 0); }
+void wtpse_debug_set_wavelet_cluster_max(int cs) { g_wavelet_cluster_max = cs < 1 ? 1 : (cs > 8 ? 8 : cs); }
 void wtpse_debug_set_l2_hint(int on) { g_l2_evict_first = on != 0; }
 void wtpse_debug_set_apply_round_robin(int chunk) { g_apply_round_robin = chunk > 0 ? chunk : 0; }
 
@@ -306,8 +310,9 @@ static int check_wavelet(const void* p, int nmaps, int H, int W, int wavelet, in
 
 size_t wtpse_wavelet_workspace_bytes(int nmaps, int H, int W, int J) {
     if (nmaps <= 0 || H <= 0 || W <= 0 || J < 1) return 0;
+    // + one double per CTA of the resident kernel (at most one CTA per SM)
     return align_up(wavelet_scratch_floats(nmaps, H, W) * sizeof(float), 256) +
-           align_up(wavelet_partial_doubles(nmaps, H, W, J) * sizeof(double), 256);
+           align_up((wavelet_partial_doubles(nmaps, H, W, J) + wavelet_stream_partials(nmaps, H, W) + 1024) * sizeof(double), 256);
 }
 
 static float* wavelet_scratch(void* ws) { return static_cast<float*>(ws); }
@@ -350,6 +355,52 @@ int wtpse_wavelet_loss_forward(const float* x, int nmaps, int H, int W, int wave
     cudaError_t e;
     { LaunchScope scope(kKernWaveletFwd, s); e = launch_dwt(x, nmaps, H, W, wavelet ? 4 : 2, J, grad_coef, wavelet_scratch(workspace), w, loss, wavelet_partials(workspace, nmaps, H, W), s); }
     if (e != cudaSuccess) return cuda_fail(e, "wavelet loss launch");
+    return WTPSE_OK;
+}
+
+int wtpse_wavelet_resident_cluster(int H, int W, int wavelet, int J) {
+    if (!g_wavelet_resident || (wavelet != 0 && wavelet != 1) || H <= 0 || W <= 0 || J < 1 || J > 16) return 0;
+    if ((H % (1 << J)) || (W % (1 << J))) return 0;
+    if (wavelet == 1 && ((H >> (J - 1)) < 4 || (W >> (J - 1)) < 4)) return 0;
+    const int taps = wavelet ? 4 : 2;
+    switch (wavelet_fused_plan(H, W, taps, J)) {
+        case 1: return wavelet_resident_cluster(H, W, taps, J);
+        case 2: return J > 1 ? wavelet_resident_cluster(H / 2, W / 2, taps, J - 1) : 1;
+        default: return 0;
+    }
+}
+
+int wtpse_wavelet_loss_resident(const float* x, int nmaps, int H, int W, int wavelet, int J, const float* level_weights,
+                                const float* upstream, float* loss, float* grad_x, void* workspace, size_t workspace_bytes,
+                                wtpse_stream_t stream) {
+    if (int rc = check_wavelet(x, nmaps, H, W, wavelet, J)) return rc;
+    if (!loss || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (wtpse_wavelet_resident_cluster(H, W, wavelet, J) == 0)
+        return fail(WTPSE_ERR_INVALID, "a %d x %d map (J=%d) does not fit the cluster-resident path; use wtpse_wavelet_loss_forward", H, W, J);
+    if (workspace_bytes < wtpse_wavelet_workspace_bytes(nmaps, H, W, J)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    float w[16];
+    for (int j = 0; j < J; ++j) w[j] = level_weights ? level_weights[j] : 1.0f;
+    const int taps = wavelet ? 4 : 2;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    {
+        LaunchScope scope(kKernWaveletFwd, s);
+        if (wavelet_fused_plan(H, W, taps, J) == 2)
+            e = launch_wavelet_loss_split(x, nmaps, H, W, taps, J, w, upstream, loss, grad_x, wavelet_scratch(workspace),
+                                          wavelet_partials(workspace, nmaps, H, W), sm_count_cached(), s);
+        else
+            e = launch_wavelet_resident(x, nmaps, H, W, taps, J, w, upstream, loss, grad_x, wavelet_partials(workspace, nmaps, H, W), s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "fused wavelet loss launch");
+    return WTPSE_OK;
+}
+
+int wtpse_scale_unless_one(float* data, int64_t n, const float* scale, wtpse_stream_t stream) {
+    if (n < 0 || (n > 0 && (!data || !scale))) return fail(WTPSE_ERR_INVALID, "null pointer / negative size");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernWaveletBwd, s); e = launch_scale_unless_one(data, n, scale, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "scale launch");
     return WTPSE_OK;
 }
 

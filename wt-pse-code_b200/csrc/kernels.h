@@ -99,4 +99,29 @@ cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J,
 cudaError_t launch_idwt(const float* coef, int nmaps, int H, int W, int taps, int J, float* x, float* scratch,
                         const float* scale, cudaStream_t stream);
 
+cudaError_t launch_wavelet_loss_final(const double* partial, int n, float* loss, cudaStream_t stream);
+
+// Track W, cluster-resident fused loss + gradient (wavelet_resident.cu)
+extern int g_wavelet_resident;
+extern int g_wavelet_cluster_max;
+int wavelet_resident_cluster(int H, int W, int taps, int J);        // cluster size, 0 = the map does not fit
+cudaError_t launch_wavelet_resident(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
+                                    const float* upstream, float* loss, float* grad, double* partial, cudaStream_t stream,
+                                    int* n_partials = nullptr);
+// streaming level 1 + resident levels 2..J (wavelet_stream.cu)
+extern int g_wavelet_split;
+int wavelet_fused_plan(int H, int W, int taps, int J);             // 0 none, 1 whole map resident, 2 level 1 streamed
+size_t wavelet_stream_partials(int nmaps, int H, int W);
+cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
+                                      const float* upstream, float* loss, float* grad, float* scratch, double* partial,
+                                      int sm_count, cudaStream_t stream);
+// level 1 of the streamed plan as persistent TMA pipelines (wavelet_tiles.cu); R = 0: shape not taken
+extern int g_wavelet_tiles;
+void wavelet_tile_plan(int H, int W, int taps, bool has_ll, int* R_fwd, int* S_fwd, int* R_inv, int* S_inv);
+cudaError_t launch_dwt1_tiles(const float* x, float* ll, unsigned char* sg, int nmaps, int H, int W, int taps, int R, int S,
+                              float sc, bool grad, double* partial, int sm_count, cudaStream_t stream, int* n_partials);
+cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float* out, int nmaps, int H, int W, int taps, int R,
+                               int S, float sc, const float* upstream, bool has_ll, int sm_count, cudaStream_t stream);
+cudaError_t launch_scale_unless_one(float* data, long long n, const float* scale, int sm_count, cudaStream_t stream);
+
 }  // namespace wtpse

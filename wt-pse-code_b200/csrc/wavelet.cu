@@ -14,30 +14,13 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "wavelet_bank.cuh"
 
 namespace wtpse {
 
 namespace {
 
 constexpr int kBx = 32, kBy = 8;
-
-template <int TAPS>
-struct Bank;
-template <>
-struct Bank<2> {
-    __device__ static float h(int k) { return 0.70710678118654752f; }
-    __device__ static float g(int k) { return k == 0 ? 0.70710678118654752f : -0.70710678118654752f; }
-};
-template <>
-struct Bank<4> {
-    // db2: h = [1+s3, 3+s3, 3-s3, 1-s3] / (4 sqrt2),  g[k] = (-1)^k h[3-k]
-    __device__ static float h(int k) {
-        return k == 0 ? 0.48296291314453414f : k == 1 ? 0.83651630373780790f : k == 2 ? 0.22414386804201339f : -0.12940952255126037f;
-    }
-    __device__ static float g(int k) {
-        return k == 0 ? -0.12940952255126037f : k == 1 ? -0.22414386804201339f : k == 2 ? 0.83651630373780790f : -0.48296291314453414f;
-    }
-};
 
 struct LevelArgs {
     const float* in;  long long in_map; int in_ld;      // h x w block of every map
@@ -577,6 +560,11 @@ cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J,
         if (e != cudaSuccess) return e;
     }
     if (loss_mode) wavelet_loss_final_kernel<<<1, 1024, 0, stream>>>(partial, pbase, loss);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wavelet_loss_final(const double* partial, int n, float* loss, cudaStream_t stream) {
+    wavelet_loss_final_kernel<<<1, 1024, 0, stream>>>(partial, n, loss);
     return cudaGetLastError();
 }
 

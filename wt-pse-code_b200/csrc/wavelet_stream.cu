@@ -1,0 +1,268 @@
+// Track W, streaming level-1 kernels + the plan that combines them with the cluster-resident kernel.
+// PARITY UNPINNED (see wavelet.cu / oracle/wavelet_np.py).
+//
+// A 512 x 512 map needs a cluster of 8 CTAs to be resident, so only ~15 maps are in flight on 148 SMs and every level
+// costs two cluster barriers.  Peeling the FIRST level off fixes both: level 1 holds 3/4 of all coefficients, needs
+// no inter-CTA exchange at all when it streams from / to global memory, and what is left (the low-low band, a quarter
+// of the map) is small enough for clusters of 2..4 with several clusters per SM.
+//   A  dwt1_stream_kernel   x -> LL1 (fp32, N/4) + packed signs of the level-1 detail bands (1 byte per site, N/4 bytes)
+//                           + partial sums of |d1|;                     reads 4N, writes 1.25N bytes
+//   B  wavelet_resident_kernel on LL1 (levels 2..J, in place: LL1 -> dL/dLL1), everything in shared memory
+//   C  idwt1_stream_kernel  dL/dLL1 + signs -> dL/dx (times the upstream gradient);  reads 1.25N, writes 4N bytes
+// A and C walk down the rows of a 4-column strip with the overlapping rows carried in registers (wavelet_level.cuh),
+// 128-bit coalesced loads / stores, no shared memory, every SM busy.
+#include <math.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "wavelet_level.cuh"
+
+namespace wtpse {
+
+namespace {
+
+constexpr int kStreamThreads = 128;
+
+struct StreamFwdArgs {
+    const float* x;         // [nmaps][H][W]
+    float* ll;              // [nmaps][H/2][W/2]
+    unsigned char* sg;      // [nmaps][H/2][W/2]
+    int H, W, seg;
+    float sc;               // w_1 / (3 * H/2 * W/2 * nmaps)
+    double* partial;        // one per CTA
+};
+
+template <int TAPS, bool kGrad>
+__global__ void __launch_bounds__(kStreamThreads, 7) dwt1_stream_kernel(StreamFwdArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, pairs = W >> 2;
+    const int nseg = (h2 + a.seg - 1) / a.seg;
+    const int t = blockIdx.x * kStreamThreads + threadIdx.x, m = blockIdx.y;
+    float ab = 0.f;
+    if (t < nseg * pairs) {
+        const int jj = t % pairs, si = t / pairs;
+        const int i0 = si * a.seg, i1 = min(i0 + a.seg, h2), c0 = 4 * jj;
+        int c4 = c0 + 4;
+        if (c4 >= W) c4 -= W;
+        const long long map_elems = (long long)H * W;
+        const float* src = a.x + (long long)m * map_elems;
+        float* ll = a.ll + (long long)m * h2 * w2 + (long long)i0 * w2 + 2 * jj;
+        unsigned char* sg = a.sg + (long long)m * h2 * w2 + (long long)i0 * w2 + 2 * jj;
+        // raw columns 4jj .. 4jj+TAPS+1 of one input row; rows past the end wrap to the top of the map
+        struct Raw { float4 v; float2 u; };
+        auto load_row = [&](const float* row) {
+            Raw r;
+            r.v = __ldg(reinterpret_cast<const float4*>(row + c0));
+            r.u = TAPS == 4 ? __ldg(reinterpret_cast<const float2*>(row + c4)) : make_float2(0.f, 0.f);
+            return r;
+        };
+        auto filter = [&](const Raw& r, float& lo0, float& hi0, float& lo1, float& hi1) {
+            float x[TAPS + 2];
+            x[0] = r.v.x; x[1] = r.v.y; x[2] = r.v.z; x[3] = r.v.w;
+            if (TAPS == 4) { x[TAPS] = r.u.x; x[TAPS + 1] = r.u.y; }
+            row_filter<TAPS>(x, lo0, hi0, lo1, hi1);
+        };
+        const float* rp = src + (long long)(2 * i0) * W;           // 2*i0 + TAPS-3 < H: the carried rows never wrap
+        float lo0[TAPS], hi0[TAPS], lo1[TAPS], hi1[TAPS];
+#pragma unroll
+        for (int k = 0; k < TAPS - 2; ++k) filter(load_row(rp + (long long)k * W), lo0[k], hi0[k], lo1[k], hi1[k]);
+        rp += (long long)(TAPS - 2) * W;                           // the two NEW rows of output row i0
+        auto new_rows = [&](int i, Raw& ra, Raw& rb) {
+            const float* p = rp;
+            if (TAPS == 4 && i == h2 - 1) p -= map_elems;           // rows H, H+1 -> 0, 1
+            ra = load_row(p);
+            rb = load_row(p + W);
+        };
+        // software pipeline: the loads of output rows i+1 .. i+kDepth are in flight while row i is computed.  One SM
+        // needs ~90 KB in flight to cover the loaded HBM latency at its share of the bandwidth; a thread holds
+        // kDepth * 48 B, so depth 1 (what the compiler does by itself) stalls at half the bandwidth.
+        constexpr int kDepth = 3;
+        Raw ra[kDepth] = {}, rb[kDepth] = {};
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            if (i0 + d < i1) new_rows(i0 + d, ra[d], rb[d]);
+            rp += 2 * W;
+        }
+        for (int ib = i0; ib < i1; ib += kDepth) {
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+                const int i = ib + d;
+                if (i < i1) {
+                    const Raw ca = ra[d], cb = rb[d];
+                    if (i + kDepth < i1) new_rows(i + kDepth, ra[d], rb[d]);
+                    rp += 2 * W;
+                    filter(ca, lo0[TAPS - 2], hi0[TAPS - 2], lo1[TAPS - 2], hi1[TAPS - 2]);
+                    filter(cb, lo0[TAPS - 1], hi0[TAPS - 1], lo1[TAPS - 1], hi1[TAPS - 1]);
+                    float2 LL, LH, HL, HH;
+                    col_filter<TAPS>(lo0, hi0, lo1, hi1, LL, LH, HL, HH);
+                    *reinterpret_cast<float2*>(ll) = LL;
+                    ab += abs_sum(LH, HL, HH) * a.sc;
+                    if (kGrad) *reinterpret_cast<unsigned short*>(sg) = static_cast<unsigned short>(sign_pack2(LH, HL, HH));
+                    ll += w2;
+                    sg += w2;
+#pragma unroll
+                    for (int k = 0; k < TAPS - 2; ++k) {
+                        lo0[k] = lo0[k + 2]; hi0[k] = hi0[k + 2]; lo1[k] = lo1[k + 2]; hi1[k] = hi1[k + 2];
+                    }
+                }
+            }
+        }
+    }
+    __shared__ double red[kStreamThreads / 32];
+    const double s = warp_sum(double(ab));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < kStreamThreads / 32; ++q) tot += red[q];
+        a.partial[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+    }
+}
+
+struct StreamInvArgs {
+    const float* gll;           // [nmaps][H/2][W/2] gradient wrt the low-low band (ignored when !kHasLL)
+    const unsigned char* sg;    // [nmaps][H/2][W/2]
+    float* out;                 // [nmaps][H][W]
+    int H, W, seg;
+    float sc;
+    const float* upstream;      // optional device scalar
+};
+
+template <int TAPS, bool kHasLL>
+__global__ void __launch_bounds__(kStreamThreads) idwt1_stream_kernel(StreamInvArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, pairs = w2 >> 1;
+    const int nseg = (h2 + a.seg - 1) / a.seg;
+    const int t = blockIdx.x * kStreamThreads + threadIdx.x, m = blockIdx.y;
+    if (t >= nseg * pairs) return;
+    const int q = t % pairs, si = t / pairs;
+    const int i0 = si * a.seg, i1 = min(i0 + a.seg, h2);
+    const int c0 = 2 * q, cm = c0 ? c0 - 1 : w2 - 1;
+    const float* gl = a.gll + (long long)m * h2 * w2;
+    const unsigned char* sp = a.sg + (long long)m * h2 * w2;
+    float* out = a.out + (long long)m * H * W + (long long)(2 * i0) * W + 4 * q;
+    const float gs = a.upstream ? __ldg(a.upstream) : 1.0f;
+    // raw operands of one coefficient row: low-low gradient and packed signs of columns 2q, 2q+1 and (db2) 2q-1
+    struct Raw { float2 l01; float lm; unsigned b01, bm; };
+    auto load_row = [&](int r) {
+        Raw v;
+        if (r < 0) r += h2;
+        const long long o = (long long)r * w2;
+        v.l01 = kHasLL ? __ldg(reinterpret_cast<const float2*>(gl + o + c0)) : make_float2(0.f, 0.f);
+        v.b01 = __ldg(reinterpret_cast<const unsigned short*>(sp + o + c0));
+        v.lm = (TAPS == 4 && kHasLL) ? __ldg(gl + o + cm) : 0.f;
+        v.bm = TAPS == 4 ? unsigned(__ldg(sp + o + cm)) : 0u;
+        return v;
+    };
+    float pL[4] = {0.f, 0.f, 0.f, 0.f}, pH[4] = {0.f, 0.f, 0.f, 0.f};
+    if (TAPS == 4) {
+        const Raw v = load_row(i0 - 1);
+        col_synth_vals<TAPS>(v.l01, v.lm, v.b01, v.bm, a.sc, pL, pH);
+    }
+    // software pipeline, two coefficient rows ahead (a row is five registers)
+    Raw r0 = load_row(i0), r1 = load_row(min(i0 + 1, i1 - 1));
+    for (int i = i0; i < i1; ++i) {
+        const Raw r2 = load_row(min(i + 2, i1 - 1));
+        float cL[4], cH[4];
+        col_synth_vals<TAPS>(r0.l01, r0.lm, r0.b01, r0.bm, a.sc, cL, cH);
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            float o[4];
+            row_synth<TAPS>(cL, cH, pL, pH, pr, o);
+            *reinterpret_cast<float4*>(out + (long long)pr * W) = make_float4(o[0] * gs, o[1] * gs, o[2] * gs, o[3] * gs);
+        }
+        out += 2 * W;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { pL[k] = cL[k]; pH[k] = cH[k]; }
+        r0 = r1;
+        r1 = r2;
+    }
+}
+
+template <typename Kernel, typename Args>
+cudaError_t launch_stream(Kernel kernel, dim3 grid, cudaStream_t stream, const Args& args, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kStreamThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
+int stream_seg(int h2) { return h2 >= 64 ? 16 : (h2 >= 16 ? 8 : h2); }
+
+}  // namespace
+
+int g_wavelet_split = -1;       // -1: automatic, 0: whole map resident (when it fits), 1: level 1 streamed (when possible)
+
+static bool split_possible(int H, int W, int taps, int J) {
+    if ((W % 8) || (H % 2) || H < 4 || W < 8) return false;
+    if (taps == 4 && (H < 4 || W < 8)) return false;
+    return J == 1 || wavelet_resident_cluster(H / 2, W / 2, taps, J - 1) > 0;
+}
+
+// 0: no fused path; 1: whole map resident; 2: level 1 streamed, levels 2..J resident
+int wavelet_fused_plan(int H, int W, int taps, int J) {
+    const int whole = wavelet_resident_cluster(H, W, taps, J);
+    const bool split = split_possible(H, W, taps, J);
+    if (g_wavelet_split == 0) return whole ? 1 : 0;
+    if (g_wavelet_split == 1) return split ? 2 : (whole ? 1 : 0);
+    // automatic: a map that needs a cluster of more than 2 CTAs leaves SMs idle and pays two cluster barriers per level
+    if (whole && whole <= 2) return 1;
+    return split ? 2 : (whole ? 1 : 0);
+}
+
+size_t wavelet_stream_partials(int nmaps, int H, int W) {
+    const int h2 = H / 2, seg = stream_seg(h2);
+    const int nseg = (h2 + seg - 1) / seg;
+    const size_t per_map = (size_t(nseg) * (W / 4) + kStreamThreads - 1) / kStreamThreads;
+    return per_map * nmaps;
+}
+
+cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
+                                      const float* upstream, float* loss, float* grad, float* scratch, double* partial,
+                                      int sm_count, cudaStream_t stream) {
+    const int h2 = H / 2, w2 = W / 2, seg = stream_seg(h2);
+    const int nseg = (h2 + seg - 1) / seg;
+    float* ll = scratch;
+    unsigned char* sg = reinterpret_cast<unsigned char*>(scratch + size_t(nmaps) * h2 * w2);
+    const float sc = weights_host[0] / (3.0f * float(h2) * float(w2) * float(nmaps));
+    int Rf, Sf, Ri, Si;
+    wavelet_tile_plan(H, W, taps, J > 1, &Rf, &Sf, &Ri, &Si);
+    cudaError_t e;
+    int np = 0;
+    if (Rf) {
+        e = launch_dwt1_tiles(x, ll, sg, nmaps, H, W, taps, Rf, Sf, sc, grad != nullptr, partial, sm_count, stream, &np);
+    } else {
+        StreamFwdArgs fa;
+        fa.x = x; fa.ll = ll; fa.sg = sg; fa.H = H; fa.W = W; fa.seg = seg; fa.sc = sc; fa.partial = partial;
+        const dim3 gf(unsigned((size_t(nseg) * (W / 4) + kStreamThreads - 1) / kStreamThreads), nmaps);
+        if (grad) e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, true>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, true>, gf, stream, fa, false);
+        else e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, false>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, false>, gf, stream, fa, false);
+        np = int(gf.x * gf.y);
+    }
+    if (e != cudaSuccess) return e;
+    if (J > 1) {
+        int nb = 0;
+        e = launch_wavelet_resident(ll, nmaps, h2, w2, taps, J - 1, weights_host + 1, nullptr, nullptr, grad ? ll : nullptr,
+                                    partial + np, stream, &nb);
+        if (e != cudaSuccess) return e;
+        np += nb;
+    }
+    e = launch_wavelet_loss_final(partial, np, loss, stream);
+    if (e != cudaSuccess || !grad) return e;
+    if (Ri) return launch_idwt1_tiles(ll, sg, grad, nmaps, H, W, taps, Ri, Si, sc, upstream, J > 1, sm_count, stream);
+    StreamInvArgs ia;
+    ia.gll = ll; ia.sg = sg; ia.out = grad; ia.H = H; ia.W = W; ia.seg = seg; ia.sc = sc; ia.upstream = upstream;
+    const dim3 gi(unsigned((size_t(nseg) * (w2 / 2) + kStreamThreads - 1) / kStreamThreads), nmaps);
+    if (J > 1) return taps == 2 ? launch_stream(idwt1_stream_kernel<2, true>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, true>, gi, stream, ia, false);
+    return taps == 2 ? launch_stream(idwt1_stream_kernel<2, false>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, false>, gi, stream, ia, false);
+}
+
+}  // namespace wtpse

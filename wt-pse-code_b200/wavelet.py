@@ -65,14 +65,13 @@ def idwt2d(coef, wavelet="haar", J=1):
 
 
 class _WaveletLoss(torch.autograd.Function):
+    """Per-level path: forward writes dloss/dcoef, backward is one inverse transform scaled by the upstream gradient.
+    Used when a map does not fit the cluster-resident kernel (wtpse_wavelet_resident_cluster == 0)."""
+
     @staticmethod
     def forward(ctx, x, wavelet, J, weights):
         x, nmaps, H, W, wid, J = _prep(x, wavelet, J)
-        w = None
-        if weights is not None:
-            if len(weights) != J:
-                raise ValueError("need one weight per level")
-            w = (ctypes.c_float * J)(*[float(v) for v in weights])
+        w = _weights(weights, J)
         lib = _lib.load()
         with torch.cuda.device(x.device):
             gcoef = torch.empty_like(x)
@@ -102,7 +101,74 @@ class _WaveletLoss(torch.autograd.Function):
         return dx, None, None, None
 
 
+def _weights(weights, J):
+    if weights is None:
+        return None
+    if len(weights) != J:
+        raise ValueError("need one weight per level")
+    return (ctypes.c_float * J)(*[float(v) for v in weights])
+
+
+def _resident_call(x, nmaps, H, W, wid, J, weights, upstream, want_grad):
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x) if want_grad else None
+        ws, nbytes = _ws(lib, x, nmaps, H, W, J)
+        p_up, keep = (None, None) if upstream is None else _grad_ptr(upstream, x)
+        _lib.check(lib.wtpse_wavelet_loss_resident(_ptr(x), nmaps, H, W, wid, J, _weights(weights, J), p_up, _ptr(loss),
+                                                   None if grad is None else _ptr(grad), _ptr(ws), nbytes,
+                                                   _stream_ptr(x.device)))
+        del keep
+    return loss, grad
+
+
+class _WaveletLossResident(torch.autograd.Function):
+    """Cluster-resident path: ONE kernel reads every map once, keeps it in the distributed shared memory of a
+    thread-block cluster through all J levels and writes dloss/dx (for upstream = 1) in the same pass.  The backward
+    then only rescales that buffer -- on the device, and only if the upstream gradient is not exactly 1."""
+
+    @staticmethod
+    def forward(ctx, x, wavelet, J, weights):
+        x, nmaps, H, W, wid, J = _prep(x, wavelet, J)
+        want_grad = ctx.needs_input_grad[0]
+        loss, grad = _resident_call(x, nmaps, H, W, wid, J, weights, None, want_grad)
+        ctx.cfg = (nmaps, H, W, wid, J, weights)
+        ctx.unit_grad = grad                    # consumed (scaled in place and handed out) by the first backward
+        ctx.save_for_backward(x)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        if gout is None:
+            return None, None, None, None
+        nmaps, H, W, wid, J, weights = ctx.cfg
+        (x,) = ctx.saved_tensors
+        grad, ctx.unit_grad = ctx.unit_grad, None
+        if grad is None:
+            # a second backward through a retained graph: recompute with the upstream gradient folded in
+            _, grad = _resident_call(x, nmaps, H, W, wid, J, weights, gout, True)
+            return grad, None, None, None
+        lib = _lib.load()
+        with torch.cuda.device(grad.device):
+            p_g, keep = _grad_ptr(gout, grad)
+            _lib.check(lib.wtpse_scale_unless_one(_ptr(grad), grad.numel(), p_g, _stream_ptr(grad.device)))
+            del keep
+        return grad, None, None, None
+
+
+def resident_cluster_size(H, W, wavelet="haar", J=1):
+    """Cluster size the resident kernel would use for H x W maps (0: not resident-capable, per-level path)."""
+    return int(_lib.load().wtpse_wavelet_resident_cluster(int(H), int(W), WAVELETS[wavelet], int(J)))
+
+
 def wavelet_shape_loss(maps, wavelet="haar", J=3, weights=None):
     """(1/N) sum_maps sum_j w_j mean|detail_j|: L1 sparsity of the detail sub-bands of every H x W map
     (e.g. softmax optic-cup / optic-disc probability maps, B x 2 x H x W)."""
-    return _WaveletLoss.apply(maps, wavelet, J, None if weights is None else tuple(weights))
+    if wavelet not in WAVELETS:
+        raise ValueError("wavelet must be one of %s" % sorted(WAVELETS))
+    weights = None if weights is None else tuple(weights)
+    if maps.is_cuda and maps.dim() >= 2 and resident_cluster_size(maps.shape[-2], maps.shape[-1], wavelet, J):
+        return _WaveletLossResident.apply(maps, wavelet, J, weights)
+    return _WaveletLoss.apply(maps, wavelet, J, weights)
