@@ -104,7 +104,7 @@ cudaError_t launch_wavelet_loss_final(const double* partial, int n, float* loss,
 // Track W, cluster-resident fused loss + gradient (wavelet_resident.cu)
 extern int g_wavelet_resident;
 extern int g_wavelet_cluster_max;
-int wavelet_resident_cluster(int H, int W, int taps, int J);        // cluster size, 0 = the map does not fit
+int wavelet_resident_cluster(int H, int W, int taps, int J, int nmaps = 0);   // cluster size, 0 = the map does not fit
 cudaError_t launch_wavelet_resident(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
                                     const float* upstream, float* loss, float* grad, double* partial, cudaStream_t stream,
                                     int* n_partials = nullptr);
@@ -121,7 +121,8 @@ void wavelet_tile_plan(int H, int W, int taps, bool has_ll, int* R_fwd, int* S_f
 cudaError_t launch_dwt1_tiles(const float* x, float* ll, unsigned char* sg, int nmaps, int H, int W, int taps, int R, int S,
                               float sc, bool grad, double* partial, int sm_count, cudaStream_t stream, int* n_partials);
 cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float* out, int nmaps, int H, int W, int taps, int R,
-                               int S, float sc, const float* upstream, bool has_ll, int sm_count, cudaStream_t stream);
+                               int S, float sc, const float* upstream, bool has_ll, const double* partial, int n_partials,
+                               float* loss, int sm_count, cudaStream_t stream);
 cudaError_t launch_scale_unless_one(float* data, long long n, const float* scale, int sm_count, cudaStream_t stream);
 
 }  // namespace wtpse

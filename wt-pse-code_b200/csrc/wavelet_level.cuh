@@ -21,7 +21,10 @@ __device__ __forceinline__ unsigned sign_pack2(const float2& LH, const float2& H
     return ca | (cb << 8);
 }
 
-// low/high-pass along W of one input row: x[0..TAPS+1] are the input columns 4jj .. 4jj+TAPS+1 (periodic)
+// low/high-pass along W of one input row: x[0..TAPS+1] are the input columns 4jj .. 4jj+TAPS+1 (periodic).
+// Scalar FFMA on purpose: the packed fma.rn.f32x2 form (two sites per instruction, 11 % fewer instructions in the
+// level-1 analysis kernel) was measured SLOWER on B200 -- FFMA2 holds the FMA pipe for two cycles, issue utilisation
+// fell from 65 % to 54 % and the kernel went from 31.1k to 33.7k active cycles.
 template <int TAPS>
 __device__ __forceinline__ void row_filter(const float (&x)[TAPS + 2], float& lo0, float& hi0, float& lo1, float& hi1) {
     float s0 = 0.f, d0 = 0.f, s1 = 0.f, d1 = 0.f;
@@ -54,8 +57,8 @@ __device__ __forceinline__ float abs_sum(const float2& LH, const float2& HL, con
 // Column synthesis of one coefficient row for the output sites A = 2q and B = 2q+1.  l01 / b01: low-low gradient and
 // packed signs of columns 2q, 2q+1; lm / bm: of column 2q-1 (periodic; only db2 reads it).  The detail gradient of a
 // site is sc * sign.  tL / tH [A parity 0, A parity 1, B parity 0, B parity 1]: low-row / high-row content of the
-// four output columns 4q .. 4q+3.
-template <int TAPS>
+// four output columns 4q .. 4q+3.  Every output is one multiply + a chain of FMAs (4 terms for db2, 2 for Haar).
+template <int TAPS, bool kHasLL = true>
 __device__ __forceinline__ void col_synth_vals(const float2& l01, float lm, unsigned b01, unsigned bm, float sc, float (&tL)[4],
                                                float (&tH)[4]) {
     const float lh0 = sign_value(b01, 0), hl0 = sign_value(b01, 2), hh0 = sign_value(b01, 4);
@@ -63,9 +66,9 @@ __device__ __forceinline__ void col_synth_vals(const float2& l01, float lm, unsi
 #pragma unroll
     for (int pc = 0; pc < 2; ++pc) {
         const float h = Bank<TAPS>::h(pc), hs = Bank<TAPS>::h(pc) * sc, gs = Bank<TAPS>::g(pc) * sc;
-        tL[pc] = fmaf(h, l01.x, gs * lh0);
+        tL[pc] = kHasLL ? fmaf(h, l01.x, gs * lh0) : gs * lh0;
         tH[pc] = fmaf(hs, hl0, gs * hh0);
-        tL[2 + pc] = fmaf(h, l01.y, gs * lh1);
+        tL[2 + pc] = kHasLL ? fmaf(h, l01.y, gs * lh1) : gs * lh1;
         tH[2 + pc] = fmaf(hs, hl1, gs * hh1);
     }
     if (TAPS == 4) {
@@ -73,23 +76,28 @@ __device__ __forceinline__ void col_synth_vals(const float2& l01, float lm, unsi
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {
             const float h = Bank<TAPS>::h(2 + pc), hs = Bank<TAPS>::h(2 + pc) * sc, gs = Bank<TAPS>::g(2 + pc) * sc;
-            // site A (column 2q) takes its second tap from column 2q-1, site B (2q+1) from column 2q
-            tL[pc] += fmaf(h, lm, gs * lhm);
+            // second tap: site A (column 2q) takes it from column 2q-1, site B (2q+1) from column 2q.  Two short
+            // independent chains per output instead of one 4-deep chain: the single chain was measured slower
+            // (issue utilisation 74 % -> 63 % in the level-1 synthesis kernel).
+            tL[pc] += kHasLL ? fmaf(h, lm, gs * lhm) : gs * lhm;
             tH[pc] += fmaf(hs, hlm, gs * hhm);
-            tL[2 + pc] += fmaf(h, l01.x, gs * lh0);
+            tL[2 + pc] += kHasLL ? fmaf(h, l01.x, gs * lh0) : gs * lh0;
             tH[2 + pc] += fmaf(hs, hl0, gs * hh0);
         }
     }
 }
 
-// Row synthesis: output row 2i + pr from the column-synthesised coefficient rows i (c) and i-1 (p)
+// Row synthesis: output row 2i + pr, times gs, from the column-synthesised coefficient rows i (c) and i-1 (p)
 template <int TAPS>
 __device__ __forceinline__ void row_synth(const float (&cL)[4], const float (&cH)[4], const float (&pL)[4], const float (&pH)[4],
-                                          int pr, float (&o)[4]) {
+                                          int pr, float gs, float (&o)[4]) {
+    const float h0 = Bank<TAPS>::h(pr) * gs, g0 = Bank<TAPS>::g(pr) * gs;
+    const float h1 = TAPS == 4 ? Bank<TAPS>::h(TAPS == 4 ? 2 + pr : 0) * gs : 0.f;
+    const float g1 = TAPS == 4 ? Bank<TAPS>::g(TAPS == 4 ? 2 + pr : 0) * gs : 0.f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        o[k] = fmaf(Bank<TAPS>::h(pr), cL[k], Bank<TAPS>::g(pr) * cH[k]);
-        if (TAPS == 4) o[k] += fmaf(Bank<TAPS>::h(2 + pr), pL[k], Bank<TAPS>::g(2 + pr) * pH[k]);
+        o[k] = fmaf(h0, cL[k], g0 * cH[k]);
+        if (TAPS == 4) o[k] += fmaf(h1, pL[k], g1 * pH[k]);
     }
 }
 

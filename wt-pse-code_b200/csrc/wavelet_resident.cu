@@ -33,6 +33,7 @@ constexpr int kResThreads = 512;
 constexpr int kResMaxJ = 6;
 constexpr int kResSmemLimit = 227 * 1024;
 constexpr int kResChunk = 32 * 1024;            // bytes per bulk copy
+constexpr int kResLoadChunks = 4;               // the band of the input map arrives in this many row chunks, one mbarrier each
 
 struct ResidentArgs {
     const float* x;
@@ -70,7 +71,7 @@ __host__ __device__ inline ResLayout res_layout(int Rb, int W, int J, int halo) 
     o.red = off;
     off += (kResThreads / 32) * 8;
     o.bar = off;
-    off += 16;
+    off += 8 * kResLoadChunks;
     o.total = off;
     return o;
 }
@@ -92,8 +93,11 @@ __device__ __forceinline__ void row_pair(const float* row, int c0, int w, float&
 
 // Analysis of one level, shared to shared.  in: own rows from row 0, the TAPS-2 overlap rows right after them.
 // ll_off < 0: the low-low band is not needed (deepest level).  sg: own rows only (the caller skips the halo row).
+// wait_bar != nullptr (level 1 only): the input arrives in row chunks of wait_rpc rows, chunk c on wait_bar[c]; a task
+// starts as soon as the chunks holding its rows have landed instead of waiting for the whole band.
 template <int TAPS, bool kGrad>
-__device__ __forceinline__ void fwd_level(int in_off, int w, int rows_out, int ll_off, int sg_off, float sc, double& acc) {
+__device__ __forceinline__ void fwd_level(int in_off, int w, int rows_out, int ll_off, int sg_off, float sc, double& acc,
+                                          uint64_t* wait_bar = nullptr, int wait_rpc = 1, uint32_t wait_phase = 0) {
     extern __shared__ __align__(128) unsigned char smem[];
     const float* in = reinterpret_cast<const float*>(smem + in_off);
     float* ll = reinterpret_cast<float*>(smem + (ll_off < 0 ? 0 : ll_off));
@@ -106,6 +110,10 @@ __device__ __forceinline__ void fwd_level(int in_off, int w, int rows_out, int l
     for (int t = threadIdx.x; t < ntasks; t += kResThreads) {
         const int jj = t % pairs, si = t / pairs;
         const int i0 = si * seg, i1 = min(i0 + seg, rows_out), c0 = 4 * jj;
+        if (wait_bar) {
+            const int c_hi = min(kResLoadChunks - 1, (2 * i1 + TAPS - 3) / wait_rpc);      // overlap rows: last chunk
+            for (int c = (2 * i0) / wait_rpc; c <= c_hi; ++c) mbar_wait(&wait_bar[c], wait_phase);
+        }
         float lo0[TAPS], hi0[TAPS], lo1[TAPS], hi1[TAPS];
 #pragma unroll
         for (int k = 0; k < TAPS - 2; ++k) row_pair<TAPS>(in + (2 * i0 + k) * w, c0, w, lo0[k], hi0[k], lo1[k], hi1[k]);
@@ -172,10 +180,10 @@ __device__ __forceinline__ void inv_level(int gll_off, int sg_off, int wj, int r
 #pragma unroll
             for (int pr = 0; pr < 2; ++pr) {
                 float o[4];
-                row_synth<TAPS>(cL, cH, pL, pH, pr, o);
+                row_synth<TAPS>(cL, cH, pL, pH, pr, gs, o);
                 if (kGlobal) {
                     *reinterpret_cast<float4*>(gout + (long long)(2 * i + pr) * out_ld + 4 * q) =
-                        make_float4(o[0] * gs, o[1] * gs, o[2] * gs, o[3] * gs);
+                        make_float4(o[0], o[1], o[2], o[3]);
                 } else {
                     *reinterpret_cast<float4*>(outs + (2 * i + pr) * out_ld + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
                 }
@@ -214,22 +222,31 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
     const long long map_elems = (long long)H * W;
     const bool sync_cluster = (TAPS > 2);          // Haar bands are independent
 
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
+        for (int c = 0; c < kResLoadChunks; ++c) mbar_init(&bar[c], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // launched programmatically behind the level-1 analysis kernel
 
     const uint64_t policy = make_evict_first_policy();
+    const int rpc = (Rb + kResLoadChunks - 1) / kResLoadChunks;        // rows per load chunk
     auto issue_load = [&](int map) {               // one thread
-        const uint32_t band = uint32_t(Rb) * W * 4u, halo = uint32_t(HALO) * W * 4u;
-        mbar_arrive_expect_tx(bar, band + halo);
-        const char* src = reinterpret_cast<const char*>(a.x + map * map_elems + (long long)r * Rb * W);
-        for (uint32_t o = 0; o < band; o += kResChunk)
-            tma_load_1d_hint(smem + lay.x + o, src + o, min(uint32_t(kResChunk), band - o), bar, policy);
-        if (HALO) {
-            const int hr = int(((r + 1) * Rb) % H);
-            tma_load_1d_hint(smem + lay.x + band, a.x + map * map_elems + (long long)hr * W, halo, bar, policy);
+        const float* band = a.x + map * map_elems + (long long)r * Rb * W;
+        for (int c = 0; c < kResLoadChunks; ++c) {
+            const int r0 = min(c * rpc, Rb), r1 = min(r0 + rpc, Rb);
+            const bool last = (c == kResLoadChunks - 1);
+            const uint32_t bytes = uint32_t(r1 - r0) * W * 4u, halo = last ? uint32_t(HALO) * W * 4u : 0u;
+            mbar_arrive_expect_tx(&bar[c], bytes + halo);
+            const char* src = reinterpret_cast<const char*>(band + (long long)r0 * W);
+            unsigned char* dst = smem + lay.x + size_t(r0) * W * 4u;
+            for (uint32_t o = 0; o < bytes; o += kResChunk)
+                tma_load_1d_hint(dst + o, src + o, min(uint32_t(kResChunk), bytes - o), &bar[c], policy);
+            if (halo) {
+                const int hr = int(((r + 1) * Rb) % H);
+                tma_load_1d_hint(smem + lay.x + size_t(Rb) * W * 4u, a.x + map * map_elems + (long long)hr * W, halo, &bar[c], policy);
+            }
         }
     };
     if (threadIdx.x == 0 && cid < a.nmaps) issue_load(cid);
@@ -243,10 +260,10 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
             if (sync_cluster) cluster.sync();
             else __syncthreads();
         }
-        mbar_wait(bar, phase);
-        phase ^= 1;
         // ---- analysis ----
-        fwd_level<TAPS, kGrad>(lay.x, W, Rb >> 1, J > 1 ? lay.l[1] + (W >> 1) * 4 : -1, lay.s[1] + (W >> 1), a.scale[0], acc);
+        fwd_level<TAPS, kGrad>(lay.x, W, Rb >> 1, J > 1 ? lay.l[1] + (W >> 1) * 4 : -1, lay.s[1] + (W >> 1), a.scale[0], acc,
+                               bar, rpc, phase);
+        phase ^= 1;
         __syncthreads();                            // the band buffer is free: prefetch the cluster's next map
         if (threadIdx.x == 0 && map + ncl < a.nmaps) issue_load(map + ncl);
         for (int j = 2; j <= J; ++j) {
@@ -320,11 +337,13 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
     cfg.gridDim = dim3(a.cs);
     cfg.dynamicSmemBytes = size_t(smem);
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = a.cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int ncl = 0;
@@ -332,6 +351,7 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
     if (e != cudaSuccess) return e;
     if (ncl < 1) return cudaErrorLaunchOutOfResources;
     cfg.gridDim = dim3(unsigned(min(ncl, a.nmaps)) * a.cs);
+    cfg.numAttrs = 2;
     *grid_out = int(cfg.gridDim.x);
     return cudaLaunchKernelEx(&cfg, kernel, a);
 }
@@ -341,19 +361,24 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
 int g_wavelet_resident = 1;
 int g_wavelet_cluster_max = 8;      // diagnostics: largest cluster size the planner may pick
 
-int wavelet_resident_cluster(int H, int W, int taps, int J) {
+// Cluster size for H x W maps: the SMALLEST cluster whose bands fit (fewer, larger bands: every level costs two cluster
+// barriers and a DSMEM copy whatever the band size -- measured at 32 x 2 maps of 256 x 256, J = 3: clusters of 2 / 4 / 8
+// -> 79.8 / 82 / 91 us for the whole streamed plan), widened only while a batch is too small to occupy the GPU.
+int wavelet_resident_cluster(int H, int W, int taps, int J, int nmaps) {
     if (J < 1 || J > kResMaxJ || (W % (1 << (J + 1))) || (H % (1 << J))) return 0;
     if ((long long)H * W > (1ll << 24)) return 0;
-    for (int cs = 8; cs >= 1; cs >>= 1) {
-        if (cs > g_wavelet_cluster_max) continue;
+    int best = 0;
+    for (int cs = 1; cs <= 8 && cs <= g_wavelet_cluster_max; cs <<= 1) {
         if (H % cs) continue;
         const int Rb = H / cs;
         if (Rb % (1 << J)) continue;
         if ((long long)(Rb + taps - 2) * W * 4 > kResSmemLimit) continue;
         if (res_layout(Rb, W, J, taps - 2).total > kResSmemLimit) continue;
-        return cs;
+        if (best == 0) best = cs;
+        else if (nmaps > 0 && (long long)nmaps * best < 64) best = cs;
+        else break;
     }
-    return 0;
+    return best;
 }
 
 // loss == nullptr: the caller runs the final reduction itself over partial[0 .. *n_partials).  grad may alias x (every
@@ -363,7 +388,7 @@ cudaError_t launch_wavelet_resident(const float* x, int nmaps, int H, int W, int
                                     int* n_partials) {
     ResidentArgs a;
     a.x = x; a.grad = grad; a.upstream = upstream; a.H = H; a.W = W; a.J = J; a.nmaps = nmaps;
-    a.cs = wavelet_resident_cluster(H, W, taps, J);
+    a.cs = wavelet_resident_cluster(H, W, taps, J, nmaps);
     if (a.cs == 0) return cudaErrorInvalidValue;
     for (int j = 1; j <= J; ++j) a.scale[j - 1] = weights_host[j - 1] / (3.0f * float(H >> j) * float(W >> j) * float(nmaps));
     a.partial = partial;

@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kStreamThreads) idwt1_stream_kernel(StreamInvA
 #pragma unroll
         for (int pr = 0; pr < 2; ++pr) {
             float o[4];
-            row_synth<TAPS>(cL, cH, pL, pH, pr, o);
-            *reinterpret_cast<float4*>(out + (long long)pr * W) = make_float4(o[0] * gs, o[1] * gs, o[2] * gs, o[3] * gs);
+            row_synth<TAPS>(cL, cH, pL, pH, pr, gs, o);
+            *reinterpret_cast<float4*>(out + (long long)pr * W) = make_float4(o[0], o[1], o[2], o[3]);
         }
         out += 2 * W;
 #pragma unroll
@@ -255,9 +255,10 @@ cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, i
         if (e != cudaSuccess) return e;
         np += nb;
     }
+    // the synthesis pipeline sums the loss partials itself (one launch less); without it, a separate reduction
+    if (grad && Ri) return launch_idwt1_tiles(ll, sg, grad, nmaps, H, W, taps, Ri, Si, sc, upstream, J > 1, partial, np, loss, sm_count, stream);
     e = launch_wavelet_loss_final(partial, np, loss, stream);
     if (e != cudaSuccess || !grad) return e;
-    if (Ri) return launch_idwt1_tiles(ll, sg, grad, nmaps, H, W, taps, Ri, Si, sc, upstream, J > 1, sm_count, stream);
     StreamInvArgs ia;
     ia.gll = ll; ia.sg = sg; ia.out = grad; ia.H = H; ia.W = W; ia.seg = seg; ia.sc = sc; ia.upstream = upstream;
     const dim3 gi(unsigned((size_t(nseg) * (w2 / 2) + kStreamThreads - 1) / kStreamThreads), nmaps);

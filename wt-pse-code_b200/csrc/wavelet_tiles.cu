@@ -24,6 +24,8 @@ namespace {
 
 constexpr int kTileConsumers = 512;
 constexpr int kTileThreads = kTileConsumers + 32;
+constexpr int kInvConsumers = 512;
+constexpr int kInvThreads = kInvConsumers + 32;
 constexpr int kTileSmem = 216 * 1024;
 constexpr uint32_t kTileChunk = 32 * 1024;
 
@@ -163,72 +165,99 @@ struct TileInvArgs {
     int H, W, nmaps, R, stages;
     float sc;
     const float* upstream;
+    const double* partial;      // loss partials of the preceding kernels, summed in fixed order by CTA 0 ...
+    int n_partials;
+    float* loss;                // ... into loss (nullptr: somebody else does it)
+};
+
+// The nmaps * H/2 coefficient rows are cut into one contiguous range per CTA (balanced to a row; with 2 CTAs per SM
+// whole strips would leave a quarter of the SMs one strip short), each range into pieces of at most R rows that do
+// not cross a map.
+struct RowPieces {
+    long long r, e;
+    int h2, R;
+    __device__ RowPieces(long long total, int h2_, int R_) : h2(h2_), R(R_) {
+        r = total * blockIdx.x / gridDim.x;
+        e = total * (blockIdx.x + 1) / gridDim.x;
+    }
+    __device__ bool next(long long& m, int& i_first, int& len) {
+        if (r >= e) return false;
+        m = r / h2;
+        i_first = int(r - m * h2);
+        len = int(min((long long)min(R, h2 - i_first), e - r));
+        r += len;
+        return true;
+    }
 };
 
 template <int TAPS, bool kHasLL>
-__global__ void __launch_bounds__(kTileThreads, 1) idwt1_tile_kernel(TileInvArgs a) {
+__global__ void __launch_bounds__(kInvThreads, 1) idwt1_tile_kernel(TileInvArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    constexpr int TOP = TAPS / 2 - 1;                       // coefficient rows above the strip
+    constexpr int TOP = TAPS / 2 - 1;                       // coefficient rows above the piece
     const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, R = a.R, S = a.stages;
-    const int rows_in = R + TOP;
-    const uint32_t ll_bytes = kHasLL ? uint32_t(rows_in) * w2 * 4u : 0u, sg_bytes = uint32_t(rows_in) * w2;
-    const uint32_t stage_bytes = ll_bytes + ((sg_bytes + 15u) & ~15u);
+    const uint32_t ll_cap = kHasLL ? uint32_t(R + TOP) * w2 * 4u : 0u;
+    const uint32_t stage_bytes = ll_cap + ((uint32_t(R + TOP) * w2 + 15u) & ~15u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(S) * stage_bytes);
     uint64_t* empty = full + S;
-    const int spm = h2 / R;
-    const long long T = (long long)a.nmaps * spm;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kTileConsumers / 32);
+            mbar_init(&empty[s], kInvConsumers / 32);
         }
         fence_mbar_init();
     }
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp == kTileConsumers / 32) {
+    RowPieces pieces((long long)a.nmaps * h2, h2, R);
+    long long m;
+    int i_first, len;
+    if (warp == kInvConsumers / 32) {
         if (lane == 0) {
-            int n = 0;
-            for (long long t = blockIdx.x; t < T; t += gridDim.x, ++n) {
+            for (int n = 0; pieces.next(m, i_first, len); ++n) {
                 const int s = n % S;
                 if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
-                const long long m = t / spm;
-                const int r0 = R * int(t % spm) - TOP;      // first coefficient row needed (-1: wraps to the bottom)
+                const int rows_in = len + TOP;
+                const int r0 = i_first - TOP;               // first coefficient row needed (-1: wraps to the bottom)
+                const int wrap = r0 < 0 ? -r0 : 0;
                 unsigned char* dst = smem + size_t(s) * stage_bytes;
                 const float* gl = a.gll + m * (long long)h2 * w2;
                 const unsigned char* sp = a.sg + m * (long long)h2 * w2;
-                mbar_arrive_expect_tx(&full[s], ll_bytes + sg_bytes);
-                const int wrap = r0 < 0 ? -r0 : 0;          // rows taken from the bottom of the map
+                mbar_arrive_expect_tx(&full[s], uint32_t(rows_in) * w2 * (kHasLL ? 5u : 1u));
                 if (wrap) {
                     if (kHasLL) tile_bulk(dst, gl + (long long)(h2 - wrap) * w2, uint32_t(wrap) * w2 * 4u, &full[s], 0, false);
-                    tile_bulk(dst + ll_bytes, sp + (long long)(h2 - wrap) * w2, uint32_t(wrap) * w2, &full[s], 0, false);
+                    tile_bulk(dst + ll_cap, sp + (long long)(h2 - wrap) * w2, uint32_t(wrap) * w2, &full[s], 0, false);
                 }
                 if (kHasLL)
                     tile_bulk(dst + size_t(wrap) * w2 * 4u, gl + (long long)(r0 + wrap) * w2, uint32_t(rows_in - wrap) * w2 * 4u, &full[s], 0, false);
-                tile_bulk(dst + ll_bytes + size_t(wrap) * w2, sp + (long long)(r0 + wrap) * w2, uint32_t(rows_in - wrap) * w2, &full[s], 0, false);
+                tile_bulk(dst + ll_cap + size_t(wrap) * w2, sp + (long long)(r0 + wrap) * w2, uint32_t(rows_in - wrap) * w2, &full[s], 0, false);
             }
+        }
+        __syncwarp();
+        if (a.loss && blockIdx.x == 0) {                    // fixed-order sum of the loss partials, once this CTA's loads are queued
+            double s = 0.0;
+            for (int i = lane; i < a.n_partials; i += 32) s += a.partial[i];
+            s = warp_sum(s);
+            if (lane == 0) a.loss[0] = float(s);
         }
     } else {
         const float gs = a.upstream ? __ldg(a.upstream) : 1.0f;
         const int pairs = w2 >> 1;
-        int seg = (R * pairs) / kTileConsumers;
-        if (seg < 1) seg = 1;
-        const int nseg = (R + seg - 1) / seg;
-        const int ntasks = nseg * pairs;
-        int n = 0;
-        for (long long t = blockIdx.x; t < T; t += gridDim.x, ++n) {
+        for (int n = 0; pieces.next(m, i_first, len); ++n) {
             const int s = n % S;
+            const int groups = max(1, kInvConsumers / pairs);             // row groups that fit the consumer threads
+            const int seg = (len + groups - 1) / groups;
+            const int nseg = (len + seg - 1) / seg;
+            const int ntasks = nseg * pairs;
             mbar_wait(&full[s], (n / S) & 1);
-            const float* gl = reinterpret_cast<const float*>(smem + size_t(s) * stage_bytes);           // row 0 = row above the strip (db2)
-            const unsigned char* sp = smem + size_t(s) * stage_bytes + ll_bytes;
-            const long long m = t / spm;
-            float* obase = a.out + m * (long long)H * W + (long long)(2 * R) * (t % spm) * W;
-            for (int task = threadIdx.x; task < ntasks; task += kTileConsumers) {
+            const float* gl = reinterpret_cast<const float*>(smem + size_t(s) * stage_bytes);           // row 0 = row above the piece (db2)
+            const unsigned char* sp = smem + size_t(s) * stage_bytes + ll_cap;
+            float* obase = a.out + m * (long long)H * W + (long long)(2 * i_first) * W;
+            for (int task = threadIdx.x; task < ntasks; task += kInvConsumers) {
                 const int q = task % pairs, si = task / pairs;
-                const int i0 = si * seg, i1 = min(i0 + seg, R);
+                const int i0 = si * seg, i1 = min(i0 + seg, len);
                 const int c0 = 2 * q, cm = c0 ? c0 - 1 : w2 - 1;
                 auto synth = [&](int r, float (&tL)[4], float (&tH)[4]) {       // r: buffer row
                     float2 l01 = make_float2(0.f, 0.f);
@@ -240,7 +269,7 @@ __global__ void __launch_bounds__(kTileThreads, 1) idwt1_tile_kernel(TileInvArgs
                         if (kHasLL) lm = gl[r * w2 + cm];
                         bm = sp[r * w2 + cm];
                     }
-                    col_synth_vals<TAPS>(l01, lm, b01, bm, a.sc, tL, tH);
+                    col_synth_vals<TAPS, kHasLL>(l01, lm, b01, bm, a.sc, tL, tH);
                 };
                 float pL[4] = {0.f, 0.f, 0.f, 0.f}, pH[4] = {0.f, 0.f, 0.f, 0.f};
                 if (TAPS == 4) synth(i0, pL, pH);                               // coefficient row i0-1 = buffer row i0
@@ -251,8 +280,8 @@ __global__ void __launch_bounds__(kTileThreads, 1) idwt1_tile_kernel(TileInvArgs
 #pragma unroll
                     for (int pr = 0; pr < 2; ++pr) {
                         float o[4];
-                        row_synth<TAPS>(cL, cH, pL, pH, pr, o);
-                        *reinterpret_cast<float4*>(out + (long long)pr * W) = make_float4(o[0] * gs, o[1] * gs, o[2] * gs, o[3] * gs);
+                        row_synth<TAPS>(cL, cH, pL, pH, pr, gs, o);
+                        *reinterpret_cast<float4*>(out + (long long)pr * W) = make_float4(o[0], o[1], o[2], o[3]);
                     }
                     out += 2 * W;
 #pragma unroll
@@ -273,12 +302,12 @@ int divisor_at_most(int n, int cap) {
 }
 
 template <typename Kernel, typename Args>
-cudaError_t launch_tile(Kernel kernel, int grid, size_t smem, cudaStream_t stream, const Args& args, bool pdl) {
+cudaError_t launch_tile(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t stream, const Args& args, bool pdl) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kTileThreads);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -308,13 +337,14 @@ void wavelet_tile_plan(int H, int W, int taps, bool has_ll, int* R_fwd, int* S_f
     }
     {   // synthesis: ~8 rows per consumer thread
         const int pairs = w2 / 2;
-        int R = divisor_at_most(h2, max(1, 8 * kTileConsumers / pairs));
+        int R = divisor_at_most(h2, max(1, 8 * kInvConsumers / pairs));
         auto stage_of = [&](int r) {
             const size_t rows = size_t(r + taps / 2 - 1);
             return (has_ll ? rows * w2 * 4 : 0) + ((rows * w2 + 15) & ~size_t(15));
         };
-        while (R > 1 && 2 * stage_of(R) > size_t(kTileSmem)) R = divisor_at_most(h2, R - 1);
-        const int S = int(std::min<size_t>(4, kTileSmem / stage_of(R)));
+        const size_t budget = size_t(kTileSmem);
+        while (R > 1 && 2 * stage_of(R) > budget) R = divisor_at_most(h2, R - 1);
+        const int S = int(std::min<size_t>(4, budget / stage_of(R)));
         if (S >= 2) { *R_inv = R; *S_inv = S; }
     }
 }
@@ -327,22 +357,24 @@ cudaError_t launch_dwt1_tiles(const float* x, float* ll, unsigned char* sg, int 
     const int grid = int(std::min<long long>(sm_count, T));
     const size_t smem = size_t(S) * (2 * R + taps - 2) * W * 4 + size_t(2 * S) * sizeof(uint64_t);
     *n_partials = grid;
-    if (grad) return taps == 2 ? launch_tile(dwt1_tile_kernel<2, true>, grid, smem, stream, a, false) : launch_tile(dwt1_tile_kernel<4, true>, grid, smem, stream, a, false);
-    return taps == 2 ? launch_tile(dwt1_tile_kernel<2, false>, grid, smem, stream, a, false) : launch_tile(dwt1_tile_kernel<4, false>, grid, smem, stream, a, false);
+    if (grad) return taps == 2 ? launch_tile(dwt1_tile_kernel<2, true>, grid, kTileThreads, smem, stream, a, false) : launch_tile(dwt1_tile_kernel<4, true>, grid, kTileThreads, smem, stream, a, false);
+    return taps == 2 ? launch_tile(dwt1_tile_kernel<2, false>, grid, kTileThreads, smem, stream, a, false) : launch_tile(dwt1_tile_kernel<4, false>, grid, kTileThreads, smem, stream, a, false);
 }
 
 cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float* out, int nmaps, int H, int W, int taps, int R,
-                               int S, float sc, const float* upstream, bool has_ll, int sm_count, cudaStream_t stream) {
+                               int S, float sc, const float* upstream, bool has_ll, const double* partial, int n_partials,
+                               float* loss, int sm_count, cudaStream_t stream) {
     TileInvArgs a;
     a.gll = gll; a.sg = sg; a.out = out; a.H = H; a.W = W; a.nmaps = nmaps; a.R = R; a.stages = S; a.sc = sc; a.upstream = upstream;
+    a.partial = partial; a.n_partials = n_partials; a.loss = loss;
     const int w2 = W / 2;
-    const long long T = (long long)nmaps * (H / 2 / R);
-    const int grid = int(std::min<long long>(sm_count, T));
-    const size_t rows = size_t(R + taps / 2 - 1);
-    const size_t stage = (has_ll ? rows * w2 * 4 : 0) + ((rows * w2 + 15) & ~size_t(15));
+    const long long rows = (long long)nmaps * (H / 2);
+    const int grid = int(std::min<long long>(sm_count, std::max<long long>(1, rows / 8)));
+    const size_t srows = size_t(R + taps / 2 - 1);
+    const size_t stage = (has_ll ? srows * w2 * 4 : 0) + ((srows * w2 + 15) & ~size_t(15));
     const size_t smem = size_t(S) * stage + size_t(2 * S) * sizeof(uint64_t);
-    if (has_ll) return taps == 2 ? launch_tile(idwt1_tile_kernel<2, true>, grid, smem, stream, a, false) : launch_tile(idwt1_tile_kernel<4, true>, grid, smem, stream, a, false);
-    return taps == 2 ? launch_tile(idwt1_tile_kernel<2, false>, grid, smem, stream, a, false) : launch_tile(idwt1_tile_kernel<4, false>, grid, smem, stream, a, false);
+    if (has_ll) return taps == 2 ? launch_tile(idwt1_tile_kernel<2, true>, grid, kInvThreads, smem, stream, a, true) : launch_tile(idwt1_tile_kernel<4, true>, grid, kInvThreads, smem, stream, a, true);
+    return taps == 2 ? launch_tile(idwt1_tile_kernel<2, false>, grid, kInvThreads, smem, stream, a, true) : launch_tile(idwt1_tile_kernel<4, false>, grid, kInvThreads, smem, stream, a, true);
 }
 
 }  // namespace wtpse
