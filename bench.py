@@ -40,7 +40,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--wavelet-name", default="db2", choices=["haar", "db2"])
+    ap.add_argument("--wavelet-levels", type=int, default=4)
+    ap.add_argument("--wavelet-batch", type=int, default=32)
     ap.add_argument("--wavelet-split", type=int, default=-1, help="Track W fused plan: -1 auto, 0 whole map resident, 1 level 1 streamed")
+    ap.add_argument("--wavelet-peel-max", type=int, default=8, help="Track W: most levels streamed before the resident stage")
     ap.add_argument("--wavelet-tiles", type=int, default=1, help="Track W: level 1 of the streamed plan as TMA pipelines (1) or per-thread loads (0)")
     ap.add_argument("--wavelet-cluster-max", type=int, default=8, help="Track W: largest cluster size of the resident stage")
     ap.add_argument("--wavelet-resident", type=int, default=1, help="Track W: 0 = per-level kernels instead of the cluster-resident kernel")
@@ -464,7 +468,8 @@ def run_wavelet(args):
 
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    B, C, H, W, J, wv = 32, 2, args.size, args.size, 4, "db2"
+    B, C, H, W, J, wv = args.wavelet_batch, 2, args.size, args.size, args.wavelet_levels, args.wavelet_name
+    wid = {"haar": 0, "db2": 1}[wv]
     from wtpse_b200 import wavelet as wvm
     from wtpse_b200.functional import _ptr, _stream_ptr
 
@@ -473,6 +478,7 @@ def run_wavelet(args):
     lib.wtpse_debug_set_wavelet_split(int(args.wavelet_split))
     lib.wtpse_debug_set_wavelet_cluster_max(int(args.wavelet_cluster_max))
     lib.wtpse_debug_set_wavelet_tiles(int(args.wavelet_tiles))
+    lib.wtpse_debug_set_wavelet_peel_max(int(args.wavelet_peel_max))
     cs = wvm.resident_cluster_size(H, W, wv, J)
     xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev), 1).requires_grad_(True) for _ in range(4)]
     one = torch.ones((), device=dev)
@@ -496,13 +502,13 @@ def run_wavelet(args):
     def step_abi(i):
         x = xs[i % 4]
         if cs:
-            wb._lib.check(lib.wtpse_wavelet_loss_resident(_ptr(x), nmaps, H, W, 1, J, None, None, _ptr(loss_abi), _ptr(grad),
+            wb._lib.check(lib.wtpse_wavelet_loss_resident(_ptr(x), nmaps, H, W, wid, J, None, None, _ptr(loss_abi), _ptr(grad),
                                                           _ptr(ws), nbytes, st))
             wb._lib.check(lib.wtpse_scale_unless_one(_ptr(grad), grad.numel(), _ptr(one), st))
         else:
-            wb._lib.check(lib.wtpse_wavelet_loss_forward(_ptr(x), nmaps, H, W, 1, J, None, _ptr(loss_abi), _ptr(gcoef), _ptr(ws),
+            wb._lib.check(lib.wtpse_wavelet_loss_forward(_ptr(x), nmaps, H, W, wid, J, None, _ptr(loss_abi), _ptr(gcoef), _ptr(ws),
                                                          nbytes, st))
-            wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(gcoef), nmaps, H, W, 1, J, _ptr(grad), _ptr(one), _ptr(ws), nbytes, st))
+            wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(gcoef), nmaps, H, W, wid, J, _ptr(grad), _ptr(one), _ptr(ws), nbytes, st))
         return loss_abi
 
     def timed(step):
@@ -530,7 +536,7 @@ def run_wavelet(args):
         "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": B * H * W / (ms * 1e-3) / 1e6,
         "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "db2 DWT J=4 L1 detail-coefficient loss fwd+bwd, %dx%dx%dx%d softmax maps" % (B, C, H, W),
+        "config": {"workload": "%s DWT J=%d L1 detail-coefficient loss fwd+bwd, %dx%dx%dx%d softmax maps" % (wv, J, B, C, H, W),
                    "l2": "four alternating 67 MB inputs (each below the 126 MB L2: the 268 MB rotation is not)",
                    "path": ("fused plan (wavelet-split=%d), resident stage in clusters of %d CTAs" % (args.wavelet_split, cs)) if cs else "one kernel per level",
                    "timed_through": "C ABI, preallocated outputs"},

@@ -236,6 +236,8 @@ void        wtpse_debug_set_wavelet_resident(int on);
 void        wtpse_debug_set_wavelet_split(int mode);
 /* Diagnostics: level 1 of the streamed plan as persistent TMA pipelines (1, default) or with per-thread global loads (0). */
 void        wtpse_debug_set_wavelet_tiles(int on);
+/* Diagnostics: most levels the streamed plan may run global-to-global before the resident stage (default 8; 1 = level 1 only). */
+void        wtpse_debug_set_wavelet_peel_max(int levels);
 /* Diagnostics: largest cluster size the resident planner may pick (1..8, default 8). */
 void        wtpse_debug_set_wavelet_cluster_max(int cs);
 /* Diagnostics: L2 evict-first policy on the TMA loads of z in the Gram and apply kernels. */

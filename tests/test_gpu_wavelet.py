@@ -142,25 +142,58 @@ def test_fused_plans_match_per_level_path(wavelet, shape, J):
 
 
 def test_fused_plan_covers_maps_too_large_for_a_cluster():
-    """1024 x 1024 (BASELINE configs[4]): 4 MB per map does not fit a cluster, its 512 x 512 low-low band does."""
+    """1024 x 1024 (BASELINE configs[4]): 4 MB per map does not fit a cluster.  The streamed plan peels levels until the
+    low-low band fits a cluster of <= 2 CTAs (two levels here: 256 x 256 bands); with one peeled level the 512 x 512
+    bands go resident in clusters of 8.  Both against the per-level kernels."""
     import wtpse_b200 as wb
     from wtpse_b200 import wavelet as wv
 
     lib = wb._lib.load()
-    assert wv.resident_cluster_size(1024, 1024, "db2", 5) == 8
     x = torch.rand(2, 2, 1024, 1024, device=_dev())
     res = []
-    for resident in (1, 0):
-        lib.wtpse_debug_set_wavelet_resident(resident)
-        try:
+    try:
+        for resident, peel, cs in ((1, 8, 2), (1, 1, 8), (0, 8, 0)):
+            lib.wtpse_debug_set_wavelet_resident(resident)
+            lib.wtpse_debug_set_wavelet_peel_max(peel)
+            assert wv.resident_cluster_size(1024, 1024, "db2", 5) == cs
             xg = x.clone().requires_grad_(True)
             loss = wb.wavelet_shape_loss(xg, "db2", 5)
             loss.backward()
             res.append((float(loss), xg.grad.clone()))
-        finally:
-            lib.wtpse_debug_set_wavelet_resident(1)
-    assert abs(res[0][0] - res[1][0]) <= 2e-6 * abs(res[1][0])
-    assert rel_err(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) < 2e-6
+    finally:
+        lib.wtpse_debug_set_wavelet_resident(1)
+        lib.wtpse_debug_set_wavelet_peel_max(8)
+    for l, g in res[:2]:
+        assert abs(l - res[2][0]) <= 2e-6 * abs(res[2][0])
+        assert rel_err(g.cpu().numpy(), res[2][1].cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("wavelet", ["haar", "db2"])
+def test_streamed_plan_with_every_level_streamed(wavelet):
+    """1024 x 1024, J = 2: the 512 x 512 low-low band would need a cluster of 8, level 2 can stream -> nothing goes
+    resident (reported cluster size 1).  Shapes with no fused plan at all report 0 and take the per-level path."""
+    import wtpse_b200 as wb
+    from wtpse_b200 import wavelet as wv
+
+    lib = wb._lib.load()
+    assert wv.resident_cluster_size(64, 96, wavelet, 5) == 0        # 96 % 2^(J+1) != 0 and 48, 24 .. are not tileable
+    x = torch.rand(1, 2, 1024, 1024, generator=torch.Generator().manual_seed(5)).to(_dev())
+    res = []
+    try:
+        for resident, peel, cs in ((1, 8, 1), (1, 1, 8), (0, 8, 0)):
+            lib.wtpse_debug_set_wavelet_resident(resident)
+            lib.wtpse_debug_set_wavelet_peel_max(peel)
+            assert wv.resident_cluster_size(1024, 1024, wavelet, 2) == cs
+            xg = x.clone().requires_grad_(True)
+            loss = wb.wavelet_shape_loss(xg, wavelet, 2, (1.0, 2.0))
+            (0.5 * loss).backward()
+            res.append((float(loss), xg.grad.clone()))
+    finally:
+        lib.wtpse_debug_set_wavelet_resident(1)
+        lib.wtpse_debug_set_wavelet_peel_max(8)
+    for l, g in res[:2]:
+        assert abs(l - res[2][0]) <= 2e-6 * abs(res[2][0])
+        assert rel_err(g.cpu().numpy(), res[2][1].cpu().numpy()) < 2e-6
 
 
 def test_resident_path_reproducible_and_unit_upstream():

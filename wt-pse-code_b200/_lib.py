@@ -74,6 +74,7 @@ EXPORTS = {
     "wtpse_debug_set_wavelet_resident": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_split": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_tiles": (None, [_c.c_int]),
+    "wtpse_debug_set_wavelet_peel_max": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_cluster_max": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_fused": (None, [_c.c_int]),
     "wtpse_debug_set_gram_group": (None, [_c.c_int]),

@@ -166,6 +166,7 @@ void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = on != 0
 void wtpse_debug_set_wavelet_fused(int on) { g_wavelet_fused = on != 0; }
 void wtpse_debug_set_wavelet_resident(int on) { g_wavelet_resident = on != 0; }
 void wtpse_debug_set_wavelet_tiles(int on) { g_wavelet_tiles = on != 0; }
+void wtpse_debug_set_wavelet_peel_max(int k) { g_wavelet_peel_max = k < 1 ? 1 : k; }
 void wtpse_debug_set_wavelet_split(int mode) { g_wavelet_split = mode < 0 ? -1 : (mode ? 1 : 0); }
 void wtpse_debug_set_wavelet_cluster_max(int cs) { g_wavelet_cluster_max = cs < 1 ? 1 : (cs > 8 ? 8 : cs); }
 void wtpse_debug_set_l2_hint(int on) { g_l2_evict_first = on != 0; }
@@ -365,7 +366,7 @@ int wtpse_wavelet_resident_cluster(int H, int W, int wavelet, int J) {
     const int taps = wavelet ? 4 : 2;
     switch (wavelet_fused_plan(H, W, taps, J)) {
         case 1: return wavelet_resident_cluster(H, W, taps, J);
-        case 2: return J > 1 ? wavelet_resident_cluster(H / 2, W / 2, taps, J - 1) : 1;
+        case 2: { int cs = 0; wavelet_stream_levels(H, W, taps, J, 0, &cs); return cs; }
         default: return 0;
     }
 }
@@ -385,7 +386,7 @@ int wtpse_wavelet_loss_resident(const float* x, int nmaps, int H, int W, int wav
     cudaError_t e;
     {
         LaunchScope scope(kKernWaveletFwd, s);
-        if (wavelet_fused_plan(H, W, taps, J) == 2)
+        if (wavelet_fused_plan(H, W, taps, J, nmaps) == 2)
             e = launch_wavelet_loss_split(x, nmaps, H, W, taps, J, w, upstream, loss, grad_x, wavelet_scratch(workspace),
                                           wavelet_partials(workspace, nmaps, H, W), sm_count_cached(), s);
         else

@@ -110,7 +110,9 @@ cudaError_t launch_wavelet_resident(const float* x, int nmaps, int H, int W, int
                                     int* n_partials = nullptr);
 // streaming level 1 + resident levels 2..J (wavelet_stream.cu)
 extern int g_wavelet_split;
-int wavelet_fused_plan(int H, int W, int taps, int J);             // 0 none, 1 whole map resident, 2 level 1 streamed
+extern int g_wavelet_peel_max;
+int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps = 0);          // 0 none, 1 whole map resident, 2 streamed plan
+int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs);  // streamed levels k (0: no such plan)
 size_t wavelet_stream_partials(int nmaps, int H, int W);
 cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
                                       const float* upstream, float* loss, float* grad, float* scratch, double* partial,

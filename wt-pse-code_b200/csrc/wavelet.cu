@@ -478,8 +478,10 @@ dim3 level_grid(int h, int w, int nmaps) { return dim3((w / 2 + kBx - 1) / kBx, 
 }  // namespace
 
 size_t wavelet_scratch_floats(long long nmaps, int H, int W) {
-    // ping-pong low-low buffers: H/2 x W/2 and H/4 x W/4 per map
-    return size_t(nmaps) * (size_t(H / 2) * (W / 2) + size_t(H / 4) * (W / 4));
+    // per-level path: ping-pong low-low buffers (H/2 x W/2 and H/4 x W/4 per map).  Streamed plan: the low-low bands
+    // of all peeled levels (< N/3 floats) + their packed sign planes (< N/3 bytes) + alignment.
+    const size_t n = size_t(nmaps) * H * W;
+    return n / 3 + n / 12 + 16 * 256 + size_t(nmaps) * (size_t(H / 2) * (W / 2) + size_t(H / 4) * (W / 4)) / 64;
 }
 
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J) {

@@ -200,17 +200,43 @@ int stream_seg(int h2) { return h2 >= 64 ? 16 : (h2 >= 16 ? 8 : h2); }
 }  // namespace
 
 int g_wavelet_split = -1;       // -1: automatic, 0: whole map resident (when it fits), 1: level 1 streamed (when possible)
+int g_wavelet_peel_max = 8;     // diagnostics: most levels the streamed plan may peel off before the resident stage
 
-static bool split_possible(int H, int W, int taps, int J) {
-    if ((W % 8) || (H % 2) || H < 4 || W < 8) return false;
-    if (taps == 4 && (H < 4 || W < 8)) return false;
-    return J == 1 || wavelet_resident_cluster(H / 2, W / 2, taps, J - 1) > 0;
+static bool level_streamable(int H, int W, int taps) {
+    return !(W % 8) && !(H % 2) && H >= 4 && W >= 8 && (taps == 2 || (H >= 4 && W >= 8));
+}
+static bool level_tiled(int H, int W, int taps, bool has_ll) {
+    int Rf, Sf, Ri, Si;
+    wavelet_tile_plan(H, W, taps, has_ll, &Rf, &Sf, &Ri, &Si);
+    return Rf > 0 && Ri > 0;
 }
 
-// 0: no fused path; 1: whole map resident; 2: level 1 streamed, levels 2..J resident
-int wavelet_fused_plan(int H, int W, int taps, int J) {
-    const int whole = wavelet_resident_cluster(H, W, taps, J);
-    const bool split = split_possible(H, W, taps, J);
+// Streamed plan: the first k levels run global-to-global (TMA tile pipelines; level 1 may fall back to the per-thread
+// kernels), the remaining J-k levels in the cluster-resident kernel on the k-th low-low band.  k grows while that band
+// would still need a cluster of more than 2 CTAs (a 1024 x 1024 map peels two levels: 63 us of resident stage on
+// 512 x 512 bands in clusters of 8 become a second streamed level plus clusters of 2).  k == J: nothing resident.
+// Returns k, 0 if the plan does not exist; *cs = cluster size of the resident stage (1 when k == J).
+int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs) {
+    *cs = 0;
+    if (!level_streamable(H, W, taps)) return 0;
+    int best_k = 0, best_cs = 0;
+    for (int k = 1; k <= J && k <= g_wavelet_peel_max; ++k) {
+        // levels 2..k go through the tile pipelines only
+        if (k > 1 && !(level_streamable(H >> (k - 1), W >> (k - 1), taps) && level_tiled(H >> (k - 1), W >> (k - 1), taps, k < J))) break;
+        if (k == J) { best_k = k; best_cs = 1; break; }
+        const int c = wavelet_resident_cluster(H >> k, W >> k, taps, J - k, nmaps);
+        if (c > 0) { best_k = k; best_cs = c; }
+        if (c == 1 || c == 2) break;
+    }
+    *cs = best_cs;
+    return best_k;
+}
+
+// 0: no fused path; 1: whole map resident; 2: streamed plan
+int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps) {
+    const int whole = wavelet_resident_cluster(H, W, taps, J, nmaps);
+    int cs;
+    const bool split = wavelet_stream_levels(H, W, taps, J, nmaps, &cs) > 0;
     if (g_wavelet_split == 0) return whole ? 1 : 0;
     if (g_wavelet_split == 1) return split ? 2 : (whole ? 1 : 0);
     // automatic: a map that needs a cluster of more than 2 CTAs leaves SMs idle and pays two cluster barriers per level
@@ -222,48 +248,83 @@ size_t wavelet_stream_partials(int nmaps, int H, int W) {
     const int h2 = H / 2, seg = stream_seg(h2);
     const int nseg = (h2 + seg - 1) / seg;
     const size_t per_map = (size_t(nseg) * (W / 4) + kStreamThreads - 1) / kStreamThreads;
-    return per_map * nmaps;
+    return per_map * nmaps + 16 * 1024;          // + one per CTA of every tile-pipeline launch
 }
 
+// scratch (floats): low-low bands LL_1 .. LL_k back to back, then the packed sign planes S_1 .. S_k (bytes)
 cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, int taps, int J, const float* weights_host,
                                       const float* upstream, float* loss, float* grad, float* scratch, double* partial,
                                       int sm_count, cudaStream_t stream) {
-    const int h2 = H / 2, w2 = W / 2, seg = stream_seg(h2);
-    const int nseg = (h2 + seg - 1) / seg;
-    float* ll = scratch;
-    unsigned char* sg = reinterpret_cast<unsigned char*>(scratch + size_t(nmaps) * h2 * w2);
-    const float sc = weights_host[0] / (3.0f * float(h2) * float(w2) * float(nmaps));
-    int Rf, Sf, Ri, Si;
-    wavelet_tile_plan(H, W, taps, J > 1, &Rf, &Sf, &Ri, &Si);
-    cudaError_t e;
-    int np = 0;
-    if (Rf) {
-        e = launch_dwt1_tiles(x, ll, sg, nmaps, H, W, taps, Rf, Sf, sc, grad != nullptr, partial, sm_count, stream, &np);
-    } else {
-        StreamFwdArgs fa;
-        fa.x = x; fa.ll = ll; fa.sg = sg; fa.H = H; fa.W = W; fa.seg = seg; fa.sc = sc; fa.partial = partial;
-        const dim3 gf(unsigned((size_t(nseg) * (W / 4) + kStreamThreads - 1) / kStreamThreads), nmaps);
-        if (grad) e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, true>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, true>, gf, stream, fa, false);
-        else e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, false>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, false>, gf, stream, fa, false);
-        np = int(gf.x * gf.y);
+    int cs;
+    const int k = wavelet_stream_levels(H, W, taps, J, nmaps, &cs);
+    if (k < 1) return cudaErrorInvalidValue;
+    float* ll[16];
+    unsigned char* sg[16];
+    {
+        float* p = scratch;
+        for (int i = 1; i <= k; ++i) { ll[i] = p; p += size_t(nmaps) * (H >> i) * (W >> i); }
+        unsigned char* q = reinterpret_cast<unsigned char*>(p);
+        for (int i = 1; i <= k; ++i) { sg[i] = q; q += (size_t(nmaps) * (H >> i) * (W >> i) + 255) & ~size_t(255); }
     }
-    if (e != cudaSuccess) return e;
-    if (J > 1) {
+    auto scale_of = [&](int i) { return weights_host[i - 1] / (3.0f * float(H >> i) * float(W >> i) * float(nmaps)); };
+    cudaError_t e = cudaSuccess;
+    int np = 0;
+    // ---- analysis, levels 1..k ----
+    for (int i = 1; i <= k; ++i) {
+        const int Hi = H >> (i - 1), Wi = W >> (i - 1);             // input of this level
+        const float* in = i == 1 ? x : ll[i - 1];
+        int Rf, Sf, Ri, Si, n = 0;
+        wavelet_tile_plan(Hi, Wi, taps, i < J, &Rf, &Sf, &Ri, &Si);
+        if (Rf) {
+            e = launch_dwt1_tiles(in, ll[i], sg[i], nmaps, Hi, Wi, taps, Rf, Sf, scale_of(i), grad != nullptr, partial + np, sm_count, stream, &n);
+        } else {
+            const int h2 = Hi / 2, seg = stream_seg(h2), nseg = (h2 + seg - 1) / seg;
+            StreamFwdArgs fa;
+            fa.x = in; fa.ll = ll[i]; fa.sg = sg[i]; fa.H = Hi; fa.W = Wi; fa.seg = seg; fa.sc = scale_of(i); fa.partial = partial + np;
+            const dim3 gf(unsigned((size_t(nseg) * (Wi / 4) + kStreamThreads - 1) / kStreamThreads), nmaps);
+            if (grad) e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, true>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, true>, gf, stream, fa, false);
+            else e = taps == 2 ? launch_stream(dwt1_stream_kernel<2, false>, gf, stream, fa, false) : launch_stream(dwt1_stream_kernel<4, false>, gf, stream, fa, false);
+            n = int(gf.x * gf.y);
+        }
+        if (e != cudaSuccess) return e;
+        np += n;
+    }
+    // ---- levels k+1..J resident, in place on LL_k ----
+    if (k < J) {
         int nb = 0;
-        e = launch_wavelet_resident(ll, nmaps, h2, w2, taps, J - 1, weights_host + 1, nullptr, nullptr, grad ? ll : nullptr,
+        e = launch_wavelet_resident(ll[k], nmaps, H >> k, W >> k, taps, J - k, weights_host + k, nullptr, nullptr, grad ? ll[k] : nullptr,
                                     partial + np, stream, &nb);
         if (e != cudaSuccess) return e;
         np += nb;
     }
-    // the synthesis pipeline sums the loss partials itself (one launch less); without it, a separate reduction
-    if (grad && Ri) return launch_idwt1_tiles(ll, sg, grad, nmaps, H, W, taps, Ri, Si, sc, upstream, J > 1, partial, np, loss, sm_count, stream);
-    e = launch_wavelet_loss_final(partial, np, loss, stream);
-    if (e != cudaSuccess || !grad) return e;
-    StreamInvArgs ia;
-    ia.gll = ll; ia.sg = sg; ia.out = grad; ia.H = H; ia.W = W; ia.seg = seg; ia.sc = sc; ia.upstream = upstream;
-    const dim3 gi(unsigned((size_t(nseg) * (w2 / 2) + kStreamThreads - 1) / kStreamThreads), nmaps);
-    if (J > 1) return taps == 2 ? launch_stream(idwt1_stream_kernel<2, true>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, true>, gi, stream, ia, false);
-    return taps == 2 ? launch_stream(idwt1_stream_kernel<2, false>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, false>, gi, stream, ia, false);
+    if (!grad) return launch_wavelet_loss_final(partial, np, loss, stream);
+    // ---- synthesis, levels k..1: dL/dLL_i + signs_i -> dL/dLL_{i-1} (written over LL_{i-1}) ... -> dL/dx ----
+    bool loss_done = false;
+    for (int i = k; i >= 1; --i) {
+        const int Hi = H >> (i - 1), Wi = W >> (i - 1);             // output of this level
+        float* out = i == 1 ? grad : ll[i - 1];
+        const float* up = i == 1 ? upstream : nullptr;
+        const bool has_ll = i < J;
+        int Rf, Sf, Ri, Si;
+        wavelet_tile_plan(Hi, Wi, taps, has_ll, &Rf, &Sf, &Ri, &Si);
+        if (Ri) {
+            // the last synthesis kernel sums the loss partials itself (one launch less)
+            const bool fold = (i == 1);
+            e = launch_idwt1_tiles(ll[i], sg[i], out, nmaps, Hi, Wi, taps, Ri, Si, scale_of(i), up, has_ll, partial, np,
+                                   fold ? loss : nullptr, sm_count, stream);
+            loss_done = loss_done || fold;
+        } else {
+            const int h2 = Hi / 2, seg = stream_seg(h2), nseg = (h2 + seg - 1) / seg;
+            StreamInvArgs ia;
+            ia.gll = ll[i]; ia.sg = sg[i]; ia.out = out; ia.H = Hi; ia.W = Wi; ia.seg = seg; ia.sc = scale_of(i); ia.upstream = up;
+            const dim3 gi(unsigned((size_t(nseg) * (Wi / 4) + kStreamThreads - 1) / kStreamThreads), nmaps);
+            if (has_ll) e = taps == 2 ? launch_stream(idwt1_stream_kernel<2, true>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, true>, gi, stream, ia, false);
+            else e = taps == 2 ? launch_stream(idwt1_stream_kernel<2, false>, gi, stream, ia, false) : launch_stream(idwt1_stream_kernel<4, false>, gi, stream, ia, false);
+        }
+        if (e != cudaSuccess) return e;
+    }
+    if (!loss_done) e = launch_wavelet_loss_final(partial, np, loss, stream);
+    return e;
 }
 
 }  // namespace wtpse
