@@ -532,6 +532,10 @@ def run_wavelet(args):
     algo = 8.0 * elems                      # SURVEY 8(d) Track W: 4N read forward + 4N written backward
     # bytes the kernels actually move: resident = one read + one write; per-level = (read + write) * 4/3 per pass, two passes
     moved = algo if cs else 4.0 * elems * (8.0 / 3.0) * 2
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if cs and os.path.exists(tpath) and (B, C, H, W, J, wv) == (32, 2, 512, 512, 4, "db2"):
+        traffic = json.load(open(tpath)).get("wavelet_fused_step_32x2x512x512_db2_J4")
     print(json.dumps({
         "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": B * H * W / (ms * 1e-3) / 1e6,
         "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
@@ -542,7 +546,7 @@ def run_wavelet(args):
                    "timed_through": "C ABI, preallocated outputs"},
         "autograd_ms_per_step": ms_autograd,
         "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                      "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},
         "loss": float(loss.detach())}))
 
