@@ -466,8 +466,15 @@ def run_wavelet(args):
 
     import wtpse_b200 as wb
 
+    import torch.distributed as dist
+
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:                           # independent maps: every rank its own batch, no data-path collective
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(1234 + rank)
     B, C, H, W, J, wv = args.wavelet_batch, 2, args.size, args.size, args.wavelet_levels, args.wavelet_name
     wid = {"haar": 0, "db2": 1}[wv]
     from wtpse_b200 import wavelet as wvm
@@ -515,13 +522,18 @@ def run_wavelet(args):
         for i in range(max(args.warmup, 3)):
             step(i)
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for i in range(args.steps):
             out = step(i)
         ev1.record()
         torch.cuda.synchronize()
-        return ev0.elapsed_time(ev1) / args.steps, out
+        t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)        # max over ranks, on the device
+        return float(t), out
 
     ms_autograd, loss_ag = timed(step_autograd)
     ms, loss = timed(step_abi)
@@ -536,16 +548,20 @@ def run_wavelet(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if cs and os.path.exists(tpath) and (B, C, H, W, J, wv) == (32, 2, 512, 512, 4, "db2"):
         traffic = json.load(open(tpath)).get("wavelet_fused_step_32x2x512x512_db2_J4")
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
     print(json.dumps({
-        "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": B * H * W / (ms * 1e-3) / 1e6,
-        "unit": "Mpix/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+        "metric": "wavelet shape-loss fwd+bwd Mpix/s (Track W, parity unpinned)", "value": world * B * H * W / (ms * 1e-3) / 1e6,
+        "unit": "Mpix/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "%s DWT J=%d L1 detail-coefficient loss fwd+bwd, %dx%dx%dx%d softmax maps" % (wv, J, B, C, H, W),
                    "l2": "four alternating 67 MB inputs (each below the 126 MB L2: the 268 MB rotation is not)",
                    "path": ("fused plan (wavelet-split=%d), resident stage in clusters of %d CTAs" % (args.wavelet_split, cs)) if cs else "one kernel per level",
                    "timed_through": "C ABI, preallocated outputs"},
         "autograd_ms_per_step": ms_autograd,
-        "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "per": "GPU",
                      "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                      "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},
         "loss": float(loss.detach())}))

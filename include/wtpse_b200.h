@@ -228,8 +228,6 @@ void        wtpse_debug_set_epilogue_repeat(int n);
 void        wtpse_debug_set_backward_mode(int mode);
 /* Diagnostics: round-robin instead of contiguous tile schedule in the unfused apply kernel. */
 void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
-/* Diagnostics (Track W): 1 all levels fused per 64x64 tile where the shape allows, 0 (default) per-level kernels. */
-void        wtpse_debug_set_wavelet_fused(int on);
 /* Diagnostics: 0 makes wtpse_wavelet_resident_cluster report 0 for every shape (callers fall back to the per-level path). */
 void        wtpse_debug_set_wavelet_resident(int on);
 /* Diagnostics: fused-plan choice, -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed whenever possible. */

@@ -76,7 +76,6 @@ EXPORTS = {
     "wtpse_debug_set_wavelet_tiles": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_peel_max": (None, [_c.c_int]),
     "wtpse_debug_set_wavelet_cluster_max": (None, [_c.c_int]),
-    "wtpse_debug_set_wavelet_fused": (None, [_c.c_int]),
     "wtpse_debug_set_gram_group": (None, [_c.c_int]),
     "wtpse_debug_set_gram_variant": (None, [_c.c_int]),
     "wtpse_debug_set_two_stage_epilogue": (None, [_c.c_int]),

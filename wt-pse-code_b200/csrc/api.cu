@@ -163,7 +163,6 @@ void wtpse_debug_set_backward_mode(int mode) { g_backward_mode = (mode >= 0 && m
 void wtpse_debug_set_gram_variant(int v) { g_gram_variant = v == 1 ? 1 : 0; }
 void wtpse_debug_set_gram_group(int ctas_per_group) { g_gram_group = ctas_per_group >= 0 ? ctas_per_group : 1; }
 void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = on != 0; }
-void wtpse_debug_set_wavelet_fused(int on) { g_wavelet_fused = on != 0; }
 void wtpse_debug_set_wavelet_resident(int on) { g_wavelet_resident = on != 0; }
 void wtpse_debug_set_wavelet_tiles(int on) { g_wavelet_tiles = on != 0; }
 void wtpse_debug_set_wavelet_peel_max(int k) { g_wavelet_peel_max = k < 1 ? 1 : k; }

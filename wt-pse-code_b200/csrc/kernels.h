@@ -91,7 +91,6 @@ cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, c
                             cudaStream_t stream);
 
 // Track W (wavelet.cu)
-extern int g_wavelet_fused;
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);
 cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J, float* coef, float* scratch,

@@ -224,221 +224,6 @@ __global__ void __launch_bounds__(kBx * kBy) idwt_level_kernel(SynthArgs a) {
     *reinterpret_cast<float2*>(out + (long long)(2 * ip + 1) * a.out_ld + 2 * jp) = make_float2(o10 * sc, o11 * sc);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fully fused variants: ALL J levels in one pass over shared-memory tiles (one read of the map, one write of the
-// coefficients / gradient; the per-level kernels above move 4/3 * (read + write)).  A CTA owns a T x T tile of
-// one map.  Forward: the tile is staged with the (TAPS-2)*(2^J-1) pixel halo the deepest level needs (periodic
-// wrap), then every level is computed shared-to-shared, each level writing only the detail coefficients of its
-// own (T/2^j)^2 region.  Inverse: the mirror image with a (TAPS/2-1)-coefficient halo on the low side per level.
-constexpr int kFuseT = 64;
-constexpr int kFuseThreads = 256;
-constexpr int kFuseMaxJ = 4;
-
-struct FusedFwdArgs {
-    const float* x;
-    float* coef;
-    int H, W, J, nmaps;
-    float scale[kFuseMaxJ];     // loss mode: w_j / (3 * (H>>j) * (W>>j) * nmaps), j = 1..J
-    double* partial;
-};
-
-template <int TAPS, bool kLoss>
-__global__ void __launch_bounds__(kFuseThreads) dwt_fused_kernel(FusedFwdArgs a) {
-    extern __shared__ __align__(16) float fsm[];
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;            // 32 x 8 thread grid, no divisions below
-    const int c0 = blockIdx.x * kFuseT, r0 = blockIdx.y * kFuseT, m = blockIdx.z;
-    const int J = a.J;
-    const int halo0 = (TAPS - 2) * ((1 << J) - 1);
-    const int n0 = kFuseT + halo0;
-    const int n1 = kFuseT / 2 + (TAPS - 2) * ((1 << (J - 1)) - 1);
-    // ping-pong level buffers as OFFSETS into fsm (a runtime-indexed pointer array would make every access a
-    // generic load instead of LDS)
-    const int boff[2] = {0, n0 * n0};
-    int* rowoff = reinterpret_cast<int*>(fsm + n0 * n0 + n1 * n1);
-    int* coloff = rowoff + n0;
-    const float* src = a.x + (long long)m * a.H * a.W;
-    float* dst = a.coef + (long long)m * a.H * a.W;
-
-    // periodic wrap, once per row / column
-    for (int i = tid; i < n0; i += kFuseThreads) {
-        rowoff[i] = ((r0 + i) % a.H) * a.W;
-        coloff[i] = (c0 + i) % a.W;
-    }
-    __syncthreads();
-    // stage the tile (+ halo), 64-bit loads (n0, c0 and W are even: a pair never straddles the wrap)
-    const int n0h = n0 >> 1;
-    for (int i = ty; i < n0; i += 8) {
-        const float* row = src + rowoff[i];
-        for (int jj = tx; jj < n0h; jj += 32)
-            *reinterpret_cast<float2*>(fsm + i * n0 + 2 * jj) = __ldg(reinterpret_cast<const float2*>(row + coloff[2 * jj]));
-    }
-    __syncthreads();
-
-    float absum = 0.f;
-    int nprev = n0;
-    for (int j = 1; j <= J; ++j) {
-        const int own = kFuseT >> j;
-        const int nj = own + (TAPS - 2) * ((1 << (J - j)) - 1);
-        const int in_off = ((j - 1) & 1) ? boff[1] : boff[0];
-        const int out_off = (j & 1) ? boff[1] : boff[0];
-        const int hq = a.H >> j, wq = a.W >> j;
-        const float sc = kLoss ? a.scale[j - 1] : 0.f;
-        float* d_ll = dst + (r0 >> j) * a.W + (c0 >> j);                  // own-region origins in the Mallat layout
-        float* d_lh = d_ll + wq;
-        float* d_hl = d_ll + hq * a.W;
-        float* d_hh = d_hl + wq;
-        for (int i = ty; i < nj; i += 8) {
-            for (int jj = tx; jj < nj; jj += 32) {
-                float lo[TAPS], hi[TAPS];
-#pragma unroll
-                for (int k = 0; k < TAPS; ++k) {
-                    const int roff = in_off + (2 * i + k) * nprev + 2 * jj;
-                    float x[TAPS];
-#pragma unroll
-                    for (int l = 0; l < TAPS; l += 2) {
-                        const float2 v = *reinterpret_cast<const float2*>(fsm + roff + l);
-                        x[l] = v.x;
-                        x[l + 1] = v.y;
-                    }
-                    float s = 0.f, d = 0.f;
-#pragma unroll
-                    for (int l = 0; l < TAPS; ++l) { s = fmaf(Bank<TAPS>::h(l), x[l], s); d = fmaf(Bank<TAPS>::g(l), x[l], d); }
-                    lo[k] = s;
-                    hi[k] = d;
-                }
-                float LL = 0.f, LH = 0.f, HL = 0.f, HH = 0.f;
-#pragma unroll
-                for (int k = 0; k < TAPS; ++k) {
-                    LL = fmaf(Bank<TAPS>::h(k), lo[k], LL);
-                    LH = fmaf(Bank<TAPS>::h(k), hi[k], LH);
-                    HL = fmaf(Bank<TAPS>::g(k), lo[k], HL);
-                    HH = fmaf(Bank<TAPS>::g(k), hi[k], HH);
-                }
-                fsm[out_off + i * nj + jj] = LL;
-                if (i < own && jj < own) {
-                    const int o = i * a.W + jj;
-                    if (kLoss) {
-                        absum += (fabsf(LH) + fabsf(HL) + fabsf(HH)) * sc;
-                        d_lh[o] = LH > 0.f ? sc : (LH < 0.f ? -sc : 0.f);
-                        d_hl[o] = HL > 0.f ? sc : (HL < 0.f ? -sc : 0.f);
-                        d_hh[o] = HH > 0.f ? sc : (HH < 0.f ? -sc : 0.f);
-                        if (j == J) d_ll[o] = 0.f;
-                    } else {
-                        d_lh[o] = LH;
-                        d_hl[o] = HL;
-                        d_hh[o] = HH;
-                        if (j == J) d_ll[o] = LL;
-                    }
-                }
-            }
-        }
-        nprev = nj;
-        __syncthreads();
-    }
-    if (kLoss) {
-        __shared__ double red[kFuseThreads / 32];
-        const double s = warp_sum(double(absum));
-        if ((tid & 31) == 0) red[tid >> 5] = s;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-#pragma unroll
-            for (int q = 0; q < kFuseThreads / 32; ++q) tot += red[q];
-            a.partial[(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = tot;
-        }
-    }
-}
-
-struct FusedInvArgs {
-    const float* coef;
-    float* x;
-    int H, W, J, nmaps;
-    const float* scale;
-};
-
-template <int TAPS>
-__global__ void __launch_bounds__(kFuseThreads) idwt_fused_kernel(FusedInvArgs a) {
-    extern __shared__ __align__(16) float fsm[];
-    constexpr int HM = TAPS / 2 - 1;                       // low-side halo in coefficients per level
-    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-    const int c0 = blockIdx.x * kFuseT, r0 = blockIdx.y * kFuseT, m = blockIdx.z;
-    const int J = a.J;
-    const float* src = a.coef + (long long)m * a.H * a.W;
-    float* dst = a.x + (long long)m * a.H * a.W;
-
-    // index ranges [ra[j], rb[j]) x [ca[j], cb[j]) of LL_j needed to rebuild the own tile of LL_0 = x (kept in shared
-    // memory: indexing a local array with the runtime level would spill it)
-    __shared__ int ra[kFuseMaxJ + 1], rb[kFuseMaxJ + 1], ca[kFuseMaxJ + 1], cb[kFuseMaxJ + 1];
-    if (tid == 0) {
-        ra[0] = r0; rb[0] = r0 + kFuseT; ca[0] = c0; cb[0] = c0 + kFuseT;
-        for (int j = 1; j <= kFuseMaxJ; ++j) {
-            ra[j] = (ra[j - 1] >> 1) - HM; rb[j] = ((rb[j - 1] - 1) >> 1) + 1;
-            ca[j] = (ca[j - 1] >> 1) - HM; cb[j] = ((cb[j - 1] - 1) >> 1) + 1;
-        }
-    }
-    constexpr int cap = kFuseT / 2 + HM + 1;               // largest range below level 0
-    // offsets into fsm, not pointers (keeps the accesses LDS/STS): two LL buffers, then [3][rows][cols] details
-    constexpr int kLL1 = cap * cap, kDet = 2 * cap * cap;
-    int* rowoff = reinterpret_cast<int*>(fsm + 5 * cap * cap);
-    int* coloff = rowoff + cap;
-    __syncthreads();
-
-    auto wrap = [](int v, int n) { v %= n; return v < 0 ? v + n : v; };
-    const float sc = a.scale ? __ldg(a.scale) : 1.0f;
-    for (int j = J; j >= 1; --j) {
-        const int raj = ra[j], caj = ca[j];
-        const int rows = rb[j] - raj, cols = cb[j] - caj;
-        const int hq = a.H >> j, wq = a.W >> j;
-        for (int i = tid; i < cap; i += kFuseThreads) {
-            if (i < rows) rowoff[i] = wrap(raj + i, hq) * a.W;
-            if (i < cols) coloff[i] = wrap(caj + i, wq);
-        }
-        __syncthreads();
-        const int plane = rows * cols;
-        for (int i = ty; i < rows; i += 8) {
-            const float* top = src + rowoff[i];
-            const float* bot = top + hq * a.W;
-            for (int jj = tx; jj < cols; jj += 32) {
-                const int gc = coloff[jj], q = i * cols + jj;
-                if (j == J) fsm[((J & 1) ? kLL1 : 0) + q] = __ldg(top + gc);    // coarsest approximation
-                fsm[kDet + q] = __ldg(top + wq + gc);                        // LH
-                fsm[kDet + plane + q] = __ldg(bot + gc);                     // HL
-                fsm[kDet + 2 * plane + q] = __ldg(bot + wq + gc);            // HH
-            }
-        }
-        __syncthreads();
-        const int ll_off = (j & 1) ? kLL1 : 0, o_off = ((j - 1) & 1) ? kLL1 : 0;
-        const int ra1 = ra[j - 1], ca1 = ca[j - 1];
-        const int orow = rb[j - 1] - ra1, ocol = cb[j - 1] - ca1;
-        for (int oi = ty; oi < orow; oi += 8) {
-            const int r = ra1 + oi;
-            const int ip = (r >> 1) - raj, pr = r & 1;
-            for (int oj = tx; oj < ocol; oj += 32) {
-                const int c = ca1 + oj;
-                const int jp = (c >> 1) - caj, pc = c & 1;
-                float acc = 0.f;
-#pragma unroll
-                for (int mm = 0; mm < TAPS / 2; ++mm) {
-                    const float hr = pr ? Bank<TAPS>::h(2 * mm + 1) : Bank<TAPS>::h(2 * mm);
-                    const float gr_ = pr ? Bank<TAPS>::g(2 * mm + 1) : Bank<TAPS>::g(2 * mm);
-#pragma unroll
-                    for (int nn = 0; nn < TAPS / 2; ++nn) {
-                        const int q = (ip - mm) * cols + (jp - nn);
-                        const float LL = fsm[ll_off + q], LH = fsm[kDet + q], HL = fsm[kDet + plane + q], HH = fsm[kDet + 2 * plane + q];
-                        const float hc = pc ? Bank<TAPS>::h(2 * nn + 1) : Bank<TAPS>::h(2 * nn);
-                        const float gc_ = pc ? Bank<TAPS>::g(2 * nn + 1) : Bank<TAPS>::g(2 * nn);
-                        const float tL = fmaf(hc, LL, gc_ * LH), tH = fmaf(hc, HL, gc_ * HH);
-                        acc += fmaf(hr, tL, gr_ * tH);
-                    }
-                }
-                if (j == 1) dst[r * a.W + c] = acc * sc;
-                else fsm[o_off + oi * ocol + oj] = acc;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 __global__ void __launch_bounds__(1024) wavelet_loss_final_kernel(const double* __restrict__ partial, int n,
                                                                   float* __restrict__ loss) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -493,38 +278,9 @@ size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J) {
     return n;
 }
 
-// mode 0: coefficients -> coef (Mallat layout, same shape as x).  mode 1: loss + gradient coefficients -> coef.
-// 1 = all levels fused per 64x64 tile (one read + one write of the map; correct and tested, but at T = 64 the db2 halo
-// doubles the level-1 work and the kernels are instruction-bound: 125 + 134 us vs 80 + 72 us for the per-level
-// kernels at 32x2x512x512), 0 = one kernel per level (default).
-int g_wavelet_fused = 0;
-
-static bool fused_ok(int H, int W, int J) { return g_wavelet_fused && J <= kFuseMaxJ && H % kFuseT == 0 && W % kFuseT == 0; }
-
+// loss == nullptr: coefficients -> coef (Mallat layout, same shape as x).  Otherwise loss + gradient coefficients -> coef.
 cudaError_t launch_dwt(const float* x, int nmaps, int H, int W, int taps, int J, float* coef, float* scratch,
                        const float* weights_host, float* loss, double* partial, cudaStream_t stream) {
-    if (fused_ok(H, W, J)) {
-        FusedFwdArgs a;
-        a.x = x; a.coef = coef; a.H = H; a.W = W; a.J = J; a.nmaps = nmaps; a.partial = partial;
-        for (int j = 1; j <= J; ++j)
-            a.scale[j - 1] = loss ? weights_host[j - 1] / (3.0f * float(H >> j) * float(W >> j) * float(nmaps)) : 0.f;
-        const int n0 = kFuseT + (taps - 2) * ((1 << J) - 1);
-        const int n1 = kFuseT / 2 + (taps - 2) * ((1 << (J - 1)) - 1);
-        const size_t smem = size_t(n0 * n0 + n1 * n1) * sizeof(float) + 2 * size_t(n0) * sizeof(int);
-        const dim3 g(W / kFuseT, H / kFuseT, nmaps);
-        cudaError_t e = cudaSuccess;
-#define WTPSE_FUSED_FWD(T_, L_)                                                                                       \
-    do {                                                                                                              \
-        if (smem > 48 * 1024) e = cudaFuncSetAttribute(dwt_fused_kernel<T_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
-        if (e == cudaSuccess) dwt_fused_kernel<T_, L_><<<g, kFuseThreads, smem, stream>>>(a);                      \
-    } while (0)
-        if (loss) { if (taps == 2) WTPSE_FUSED_FWD(2, true); else WTPSE_FUSED_FWD(4, true); }
-        else { if (taps == 2) WTPSE_FUSED_FWD(2, false); else WTPSE_FUSED_FWD(4, false); }
-#undef WTPSE_FUSED_FWD
-        if (e != cudaSuccess) return e;
-        if (loss) wavelet_loss_final_kernel<<<1, 1024, 0, stream>>>(partial, int(g.x * g.y * g.z), loss);
-        return cudaGetLastError();
-    }
     const long long map = (long long)H * W;
     float* s0 = scratch;
     float* s1 = scratch + size_t(nmaps) * (H / 2) * (W / 2);
@@ -573,16 +329,6 @@ cudaError_t launch_wavelet_loss_final(const double* partial, int n, float* loss,
 // Inverse (== adjoint) transform: coef (Mallat layout) -> x, optionally scaled by a device scalar.
 cudaError_t launch_idwt(const float* coef, int nmaps, int H, int W, int taps, int J, float* x, float* scratch,
                         const float* scale, cudaStream_t stream) {
-    if (fused_ok(H, W, J)) {
-        FusedInvArgs a;
-        a.coef = coef; a.x = x; a.H = H; a.W = W; a.J = J; a.nmaps = nmaps; a.scale = scale;
-        const int cap = kFuseT / 2 + (taps / 2 - 1) + 1;
-        const size_t smem = size_t(5 * cap * cap) * sizeof(float) + 2 * size_t(cap) * sizeof(int);
-        const dim3 g(W / kFuseT, H / kFuseT, nmaps);
-        if (taps == 2) idwt_fused_kernel<2><<<g, kFuseThreads, smem, stream>>>(a);
-        else idwt_fused_kernel<4><<<g, kFuseThreads, smem, stream>>>(a);
-        return cudaGetLastError();
-    }
     const long long map = (long long)H * W;
     float* s0 = scratch;
     float* s1 = scratch + size_t(nmaps) * (H / 2) * (W / 2);
