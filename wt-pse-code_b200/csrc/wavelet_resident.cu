@@ -363,22 +363,20 @@ int g_wavelet_cluster_max = 8;      // diagnostics: largest cluster size the pla
 
 // Cluster size for H x W maps: the SMALLEST cluster whose bands fit (fewer, larger bands: every level costs two cluster
 // barriers and a DSMEM copy whatever the band size -- measured at 32 x 2 maps of 256 x 256, J = 3: clusters of 2 / 4 / 8
-// -> 79.8 / 82 / 91 us for the whole streamed plan), widened only while a batch is too small to occupy the GPU.
-int wavelet_resident_cluster(int H, int W, int taps, int J, int nmaps) {
+// -> 79.8 / 82 / 91 us for the whole streamed plan; widening the cluster for small batches did not pay either: 8 x 2 maps
+// of 256 x 256, clusters of 2 / 4 -> 17.3 / 17.8 us).
+int wavelet_resident_cluster(int H, int W, int taps, int J, int /*nmaps*/) {
     if (J < 1 || J > kResMaxJ || (W % (1 << (J + 1))) || (H % (1 << J))) return 0;
     if ((long long)H * W > (1ll << 24)) return 0;
-    int best = 0;
     for (int cs = 1; cs <= 8 && cs <= g_wavelet_cluster_max; cs <<= 1) {
         if (H % cs) continue;
         const int Rb = H / cs;
         if (Rb % (1 << J)) continue;
         if ((long long)(Rb + taps - 2) * W * 4 > kResSmemLimit) continue;
         if (res_layout(Rb, W, J, taps - 2).total > kResSmemLimit) continue;
-        if (best == 0) best = cs;
-        else if (nmaps > 0 && (long long)nmaps * best < 64) best = cs;
-        else break;
+        return cs;
     }
-    return best;
+    return 0;
 }
 
 // loss == nullptr: the caller runs the final reduction itself over partial[0 .. *n_partials).  grad may alias x (every
