@@ -161,16 +161,19 @@ int wtpse_wavelet_loss_forward(const float* x, int nmaps, int H, int W, int wave
                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
 /*
- * Fused loss + gradient path: ONE pass over x for the loss and dloss/dx, no coefficient buffer in HBM.
+ * Fused loss + gradient path: the loss AND dloss/dx from one call, no coefficient buffer in HBM (the L1 loss needs only
+ * sign(d) of a detail coefficient: three 2-bit codes per site).
  *  - whole map resident (wavelet_resident.cu): every H x W map is held in the distributed shared memory of one
  *    thread-block cluster (row bands, 1-D TMA loads, filter-overlap rows exchanged through DSMEM); all J analysis
- *    levels, the L1 reduction and the whole synthesis of the gradient run shared-to-shared;
- *  - level 1 streamed (wavelet_stream.cu): level 1 (3/4 of all coefficients) goes global-to-global with the detail
- *    bands reduced to one byte of packed signs per site, and the low-low band (a quarter of the map) is what the
- *    cluster-resident kernel works on.  Chosen automatically for maps that would need a cluster of more than 2 CTAs.
- * wtpse_wavelet_resident_cluster returns the cluster size of the resident stage (1, 2, 4, 8) or 0 when no fused plan
- * exists for the shape (W not divisible by 2^(J+1), a low-low band that does not fit a cluster, ...) -- use the
- * per-level entry points above then.
+ *    levels, the L1 reduction and the whole synthesis of the gradient run shared-to-shared: 8 B per element of HBM
+ *    traffic.  Chosen when the smallest cluster that holds a map has <= 2 CTAs.
+ *  - streamed plan (wavelet_stream.cu, wavelet_tiles.cu): the first k levels go global-to-global through persistent
+ *    TMA pipelines (detail bands reduced to one byte of packed signs per site), k growing until the k-th low-low band
+ *    fits a cluster of <= 2 CTAs (512 x 512 maps: k = 1; 1024 x 1024: k = 2); that band is what the cluster-resident
+ *    kernel then works on, in place.
+ * wtpse_wavelet_resident_cluster returns the cluster size of the resident stage (1, 2, 4, 8; 1 also when every level
+ * is streamed) or 0 when no fused plan exists for the shape (e.g. W not divisible by 2^(J+1) with level widths that
+ * are not multiples of 32) -- use the per-level entry points above then.
  * grad_x (may be NULL: loss only) receives upstream * dloss/dx; upstream is an optional DEVICE scalar (NULL = 1).
  * Workspace: wtpse_wavelet_workspace_bytes.
  */
