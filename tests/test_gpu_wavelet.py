@@ -172,6 +172,53 @@ def test_streamed_plan_with_every_level_streamed(wavelet):
         assert rel_err(g.cpu().numpy(), res[2][1].cpu().numpy()) < 2e-6
 
 
+def test_fused_plans_random_shapes_and_determinism():
+    """Seeded sweep over map sizes / level counts / batch sizes: whatever plan the planner picks must agree with the
+    per-level kernels, and five repeated launches must be bit-identical (a race between the TMA ring, the cluster
+    barriers and the DSMEM halo copies would show up as run-to-run differences)."""
+    import random
+
+    import wtpse_b200 as wb
+    from wtpse_b200 import wavelet as wv
+
+    lib = wb._lib.load()
+    rng = random.Random(20261018)
+    cases = 0
+    while cases < 28:
+        H = rng.choice([32, 48, 64, 96, 128, 160, 192, 256, 320, 384, 512])
+        W = rng.choice([32, 64, 96, 128, 160, 256, 384, 512, 640])
+        wavelet = rng.choice(["haar", "db2"])
+        J = rng.randint(1, 5)
+        if H % (1 << J) or W % (1 << J) or (wavelet == "db2" and min(H, W) >> (J - 1) < 4):
+            continue
+        nmaps = rng.choice([1, 2, 3, 7, 16, 37, 70])
+        if nmaps * H * W > 12 * 1024 * 1024:
+            continue
+        cases += 1
+        x = torch.rand(nmaps, 1, H, W, generator=torch.Generator().manual_seed(cases)).to(_dev())
+        weights = tuple(rng.choice([0.25, 1.0, 3.0]) for _ in range(J))
+
+        def run():
+            xg = x.clone().requires_grad_(True)
+            loss = wb.wavelet_shape_loss(xg, wavelet, J, weights)
+            loss.backward()
+            return loss.detach().clone(), xg.grad.clone()
+
+        fused_available = wv.resident_cluster_size(H, W, wavelet, J) > 0
+        l0, g0 = run()
+        for _ in range(4):
+            l1, g1 = run()
+            assert torch.equal(l0, l1) and torch.equal(g0, g1), (H, W, wavelet, J, nmaps)
+        if fused_available:
+            lib.wtpse_debug_set_wavelet_resident(0)
+            try:
+                lp, gp = run()
+            finally:
+                lib.wtpse_debug_set_wavelet_resident(1)
+            assert abs(float(l0) - float(lp)) <= 2e-6 * abs(float(lp)), (H, W, wavelet, J, nmaps)
+            assert rel_err(g0.cpu().numpy(), gp.cpu().numpy()) < 2e-6, (H, W, wavelet, J, nmaps)
+
+
 def test_resident_path_reproducible_and_unit_upstream():
     import wtpse_b200 as wb
 
