@@ -19,6 +19,10 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "wavelet_level.cuh"
@@ -330,8 +334,20 @@ __global__ void __launch_bounds__(256) scale_unless_one_kernel(float* __restrict
 template <int TAPS, bool kGrad>
 cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stream, int* grid_out) {
     auto kernel = wavelet_resident_kernel<TAPS, kGrad>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    // the shared-memory opt-in and the cluster occupancy are queried once per (device, cluster size, footprint)
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> clusters_that_fit;
+    static std::map<int, int> opted_in;             // device -> largest dynamic shared-memory size opted into
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    const auto key = std::make_tuple(dev, a.cs, smem);
+    int ncl = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = clusters_that_fit.find(key);
+        if (it != clusters_that_fit.end()) ncl = it->second;
+    }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kResThreads);
     cfg.gridDim = dim3(a.cs);
@@ -346,10 +362,18 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int ncl = 0;
-    e = cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg);
-    if (e != cudaSuccess) return e;
-    if (ncl < 1) return cudaErrorLaunchOutOfResources;
+    if (ncl == 0) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (opted_in[dev] < smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            opted_in[dev] = smem;
+        }
+        e = cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg);
+        if (e != cudaSuccess) return e;
+        if (ncl < 1) return cudaErrorLaunchOutOfResources;
+        clusters_that_fit[key] = ncl;
+    }
     cfg.gridDim = dim3(unsigned(min(ncl, a.nmaps)) * a.cs);
     cfg.numAttrs = 2;
     *grid_out = int(cfg.gridDim.x);

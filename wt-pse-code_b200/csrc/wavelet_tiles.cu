@@ -13,6 +13,9 @@
 #include <math.h>
 
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -303,8 +306,23 @@ int divisor_at_most(int n, int cap) {
 
 template <typename Kernel, typename Args>
 cudaError_t launch_tile(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t stream, const Args& args, bool pdl) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    // shared-memory opt-in: once per (kernel, device, footprint).  Keyed by the function pointer: instantiations with
+    // the same signature share this template instance.
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> opted_in;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), dev);
+        auto it = opted_in.find(key);
+        if (it == opted_in.end() || it->second < smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            opted_in[key] = smem;
+        }
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(threads);
