@@ -364,7 +364,7 @@ int wtpse_wavelet_resident_cluster(int H, int W, int wavelet, int J) {
     if (wavelet == 1 && ((H >> (J - 1)) < 4 || (W >> (J - 1)) < 4)) return 0;
     const int taps = wavelet ? 4 : 2;
     switch (wavelet_fused_plan(H, W, taps, J)) {
-        case 1: return wavelet_resident_cluster(H, W, taps, J);
+        case 1: return taps == 2 ? 1 : wavelet_resident_cluster(H, W, taps, J);       // Haar: independent bands, no cluster
         case 2: { int cs = 0; wavelet_stream_levels(H, W, taps, J, 0, &cs); return cs; }
         default: return 0;
     }

@@ -217,9 +217,15 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int HALO = TAPS - 2;
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned cs = cluster.num_blocks(), r = cluster.block_rank();
-    const unsigned nxt = (r + 1) % cs, prv = (r + cs - 1) % cs;
-    const int cid = blockIdx.x / cs, ncl = gridDim.x / cs;
+    // db2: a.cs CTAs of one cluster share a map (bands coupled through the filter overlap), work item = map.
+    // Haar: the filters do not overlap, so a band of rows (a multiple of 2^J) is a work item of its own: no cluster,
+    // a.cs = bands per map, every CTA walks items (map, band) with the grid as stride.
+    constexpr bool kBands = (TAPS == 2);
+    const unsigned cs = kBands ? unsigned(a.cs) : cluster.num_blocks();
+    const unsigned rank = kBands ? 0u : cluster.block_rank();
+    const unsigned nxt = (rank + 1) % cs, prv = (rank + cs - 1) % cs;
+    const int first = kBands ? int(blockIdx.x) : int(blockIdx.x / cs), stride = kBands ? int(gridDim.x) : int(gridDim.x / cs);
+    const int n_items = kBands ? a.nmaps * int(cs) : a.nmaps;
     const int H = a.H, W = a.W, J = a.J, Rb = H / int(cs);
     const ResLayout lay = res_layout(Rb, W, J, HALO);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + lay.bar);
@@ -236,7 +242,9 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
 
     const uint64_t policy = make_evict_first_policy();
     const int rpc = (Rb + kResLoadChunks - 1) / kResLoadChunks;        // rows per load chunk
-    auto issue_load = [&](int map) {               // one thread
+    auto issue_load = [&](int item) {              // one thread
+        const int map = kBands ? item / int(cs) : item;
+        const unsigned r = kBands ? unsigned(item) % cs : rank;
         const float* band = a.x + map * map_elems + (long long)r * Rb * W;
         for (int c = 0; c < kResLoadChunks; ++c) {
             const int r0 = min(c * rpc, Rb), r1 = min(r0 + rpc, Rb);
@@ -253,14 +261,16 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
             }
         }
     };
-    if (threadIdx.x == 0 && cid < a.nmaps) issue_load(cid);
+    if (threadIdx.x == 0 && first < n_items) issue_load(first);
 
     const float gs = (kGrad && a.upstream) ? __ldg(a.upstream) : 1.0f;
     double acc = 0.0;
     uint32_t phase = 0;
-    for (int map = cid; map < a.nmaps; map += ncl) {
+    for (int item = first; item < n_items; item += stride) {
+        const int map = kBands ? item / int(cs) : item;
+        const unsigned r = kBands ? unsigned(item) % cs : rank;
         // the neighbours may still be copying halo rows of the previous map out of this CTA's level buffers
-        if (map != cid) {
+        if (item != first) {
             if (sync_cluster) cluster.sync();
             else __syncthreads();
         }
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(kResThreads, 1) wavelet_resident_kernel(Reside
                                bar, rpc, phase);
         phase ^= 1;
         __syncthreads();                            // the band buffer is free: prefetch the cluster's next map
-        if (threadIdx.x == 0 && map + ncl < a.nmaps) issue_load(map + ncl);
+        if (threadIdx.x == 0 && item + stride < n_items) issue_load(item + stride);
         for (int j = 2; j <= J; ++j) {
             const int wi = W >> (j - 1), ri = Rb >> (j - 1);           // input band of this level
             if (sync_cluster) {
@@ -350,12 +360,13 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
     }
     cudaLaunchConfig_t cfg{};
     cfg.blockDim = dim3(kResThreads);
-    cfg.gridDim = dim3(a.cs);
+    const int cluster = TAPS == 2 ? 1 : a.cs;      // Haar: a.cs independent bands per map, no cluster
+    cfg.gridDim = dim3(cluster);
     cfg.dynamicSmemBytes = size_t(smem);
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = a.cs;
+    attr[0].val.clusterDim.x = cluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -374,7 +385,8 @@ cudaError_t launch_resident_t(const ResidentArgs& a, int smem, cudaStream_t stre
         if (ncl < 1) return cudaErrorLaunchOutOfResources;
         clusters_that_fit[key] = ncl;
     }
-    cfg.gridDim = dim3(unsigned(min(ncl, a.nmaps)) * a.cs);
+    const long long items = TAPS == 2 ? (long long)a.nmaps * a.cs : a.nmaps;
+    cfg.gridDim = dim3(unsigned(min((long long)ncl, items)) * cluster);
     cfg.numAttrs = 2;
     *grid_out = int(cfg.gridDim.x);
     return cudaLaunchKernelEx(&cfg, kernel, a);
@@ -392,6 +404,22 @@ int g_wavelet_cluster_max = 8;      // diagnostics: largest cluster size the pla
 int wavelet_resident_cluster(int H, int W, int taps, int J, int /*nmaps*/) {
     if (J < 1 || J > kResMaxJ || (W % (1 << (J + 1))) || (H % (1 << J))) return 0;
     if ((long long)H * W > (1ll << 24)) return 0;
+    if (taps == 2) {
+        // Haar: number of independent row bands per map.  The largest band (a multiple of 2^J rows dividing H) whose
+        // buffers leave room for two CTAs per SM; failing that the smallest band, if it fits at all.
+        int best = 0;
+        for (int nb = 1; nb <= (H >> J); ++nb) {
+            if (H % nb) continue;
+            const int Rb = H / nb;
+            if (Rb % (1 << J)) continue;
+            const long long tot = (long long)Rb * W * 4 * 3 / 2;          // coarse bound, avoids int overflow below
+            if (tot > (1ll << 28)) continue;
+            const int smem = res_layout(Rb, W, J, 0).total;
+            if (smem <= kResSmemLimit) best = nb;                           // keeps shrinking while it still fits ...
+            if (smem <= 110 * 1024) break;                                  // ... until two CTAs fit an SM
+        }
+        return best;
+    }
     for (int cs = 1; cs <= 8 && cs <= g_wavelet_cluster_max; cs <<= 1) {
         if (H % cs) continue;
         const int Rb = H / cs;

@@ -225,8 +225,8 @@ int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs) {
         if (k > 1 && !(level_streamable(H >> (k - 1), W >> (k - 1), taps) && level_tiled(H >> (k - 1), W >> (k - 1), taps, k < J))) break;
         if (k == J) { best_k = k; best_cs = 1; break; }
         const int c = wavelet_resident_cluster(H >> k, W >> k, taps, J - k, nmaps);
-        if (c > 0) { best_k = k; best_cs = c; }
-        if (c == 1 || c == 2) break;
+        if (c > 0) { best_k = k; best_cs = taps == 2 ? 1 : c; }
+        if (c > 0 && (taps == 2 || c <= 2)) break;
     }
     *cs = best_cs;
     return best_k;
@@ -239,8 +239,16 @@ int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps) {
     const bool split = wavelet_stream_levels(H, W, taps, J, nmaps, &cs) > 0;
     if (g_wavelet_split == 0) return whole ? 1 : 0;
     if (g_wavelet_split == 1) return split ? 2 : (whole ? 1 : 0);
-    // automatic: a map that needs a cluster of more than 2 CTAs leaves SMs idle and pays two cluster barriers per level
-    if (whole && whole <= 2) return 1;
+    // automatic.  db2: a map that needs a cluster of more than 2 CTAs leaves SMs idle and pays two cluster barriers per
+    // level -> streamed plan.  Haar: row bands are independent work items (no cluster, any map size), one kernel and
+    // 8 B per element, but its deep levels have little parallelism per band.  Measured, fused band kernel vs streamed
+    // plan, 32 x 2 maps: 1024^2, J = 1 / 3 / 5: 106 / 146 / 177 us vs 120 / 165 / 177; 512^2: 35 / 47 / 55 vs 37 / 46 / 48.
+    if (whole && taps == 2) {
+        const long long px = (long long)H * W;
+        if (J <= 2 || px >= (1ll << 20) || px <= (1ll << 16) || !split) return 1;
+    } else if (whole && whole <= 2) {
+        return 1;
+    }
     return split ? 2 : (whole ? 1 : 0);
 }
 
