@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the train-step backbone")
     ap.add_argument("--wavelet-name", default="db2", choices=["haar", "db2"])
     ap.add_argument("--wavelet-levels", type=int, default=4)
     ap.add_argument("--wavelet-batch", type=int, default=32)
@@ -414,6 +415,8 @@ def time_train_step(args, dev, rank, world, barrier):
 
     import wtpse_b200 as wb
 
+    # fixed shapes: let cuDNN time its algorithms once (during the eager warm-up iterations, before the graph capture)
+    torch.backends.cudnn.benchmark = bool(args.train_cudnn_benchmark)
     n_per_domain, used = wb.dp.per_rank_batch(args.train_batch * world, world, 3)
     S = args.train_size
     ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0)
@@ -455,7 +458,7 @@ def time_train_step(args, dev, rank, world, barrier):
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
             "steps": args.train_steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
             "global_batch_used": world * used, "our_kernels_per_iteration": kernels_per_iteration,
-            "backbone": "PyTorch/cuDNN, channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam", "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
+            "backbone": "PyTorch/cuDNN (benchmark=%d), channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam" % int(args.train_cudnn_benchmark), "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}
 
 
