@@ -391,7 +391,7 @@ struct BwdParams {
 template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(BwdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int B = p.B;
     const DomainInfo dom = make_domain(B, p.n, p.K);
     const int M = dom.M;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) mmd_fwd_kernel(MmdParams p) {
 template <bool kSmem>
 __global__ void __launch_bounds__(kEpiThreads, 1) mmd_bwd_kernel(MmdParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const DomainInfo dom = make_domain(p.B, p.n, p.K);
     const int M = dom.M;
     const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, p.B, M);

@@ -25,9 +25,35 @@ def _prep(x, wavelet, J):
     return x.contiguous(), nmaps, H, W, WAVELETS[wavelet], int(J)
 
 
+_WS_CACHE = {}
+
+
 def _ws(lib, x, nmaps, H, W, J):
+    """Scratch for one call.  One grow-only buffer per (device, stream): every launch that touches it is ordered on that
+    stream, so consecutive calls can share it (a fresh 28 MB torch.empty per call is most of the host time otherwise)."""
     nbytes = lib.wtpse_wavelet_workspace_bytes(nmaps, H, W, J)
-    return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device), nbytes
+    key = (x.device.index, torch.cuda.current_stream(x.device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+        _WS_CACHE[key] = buf
+    return buf, nbytes
+
+
+class _on_device:
+    """torch.cuda.device(dev) without the context-manager cost when dev is already current (the usual case)."""
+
+    def __init__(self, device):
+        self.ctx = None if torch.cuda.current_device() == device.index else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 class _Dwt(torch.autograd.Function):
@@ -35,7 +61,7 @@ class _Dwt(torch.autograd.Function):
     def forward(ctx, x, wavelet, J, inverse):
         x, nmaps, H, W, wid, J = _prep(x, wavelet, J)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             out = torch.empty_like(x)
             ws, nbytes = _ws(lib, x, nmaps, H, W, J)
             if inverse:
@@ -73,7 +99,7 @@ class _WaveletLoss(torch.autograd.Function):
         x, nmaps, H, W, wid, J = _prep(x, wavelet, J)
         w = _weights(weights, J)
         lib = _lib.load()
-        with torch.cuda.device(x.device):
+        with _on_device(x.device):
             gcoef = torch.empty_like(x)
             loss = torch.empty((), dtype=torch.float32, device=x.device)
             ws, nbytes = _ws(lib, x, nmaps, H, W, J)
@@ -91,7 +117,7 @@ class _WaveletLoss(torch.autograd.Function):
         if gout is None:
             return None, None, None, None
         lib = _lib.load()
-        with torch.cuda.device(gcoef.device):
+        with _on_device(gcoef.device):
             dx = torch.empty_like(gcoef)
             ws, nbytes = _ws(lib, gcoef, nmaps, H, W, J)
             p_g, keep = _grad_ptr(gout, gcoef)
@@ -111,7 +137,7 @@ def _weights(weights, J):
 
 def _resident_call(x, nmaps, H, W, wid, J, weights, upstream, want_grad):
     lib = _lib.load()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         loss = torch.empty((), dtype=torch.float32, device=x.device)
         grad = torch.empty_like(x) if want_grad else None
         ws, nbytes = _ws(lib, x, nmaps, H, W, J)
@@ -124,8 +150,8 @@ def _resident_call(x, nmaps, H, W, wid, J, weights, upstream, want_grad):
 
 
 class _WaveletLossResident(torch.autograd.Function):
-    """Cluster-resident path: ONE kernel reads every map once, keeps it in the distributed shared memory of a
-    thread-block cluster through all J levels and writes dloss/dx (for upstream = 1) in the same pass.  The backward
+    """Fused plans (wtpse_wavelet_loss_resident: cluster-resident maps, or streamed levels + a resident stage): the
+    forward call already writes dloss/dx for upstream = 1 next to the loss, no coefficient buffer in HBM.  The backward
     then only rescales that buffer -- on the device, and only if the upstream gradient is not exactly 1."""
 
     @staticmethod
@@ -151,7 +177,7 @@ class _WaveletLossResident(torch.autograd.Function):
             _, grad = _resident_call(x, nmaps, H, W, wid, J, weights, gout, True)
             return grad, None, None, None
         lib = _lib.load()
-        with torch.cuda.device(grad.device):
+        with _on_device(grad.device):
             p_g, keep = _grad_ptr(gout, grad)
             _lib.check(lib.wtpse_scale_unless_one(_ptr(grad), grad.numel(), p_g, _stream_ptr(grad.device)))
             del keep
