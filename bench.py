@@ -191,6 +191,28 @@ def time_cpu(B, H, W, n, K, budget_s, max_iters):
             "sample": "%dx16x%dx%d fp32 (n=%d,K=%d) fwd+bwd, best of %d after 1 warm-up" % (B, H, W, n, K, len(times))}
 
 
+def time_gpu_eager(z, n, K, iters=10):
+    """The reference's operator sequence (oracle/whitening_torch.py: bmm + ATen element-wise + the O(K^2) MMD loop, i.e.
+    what the unmodified reference launches on a GPU) in PyTorch eager on the same device and the same resident input.
+    A reported baseline beside cpu_baseline -- test infrastructure, never the product path."""
+    import torch
+    from oracle import whitening_torch as wt
+
+    for _ in range(2):
+        wt.fwd_bwd(z, n, K)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(iters):
+        ins, dom, _ = wt.fwd_bwd(z, n, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / iters
+    return {"value": z.shape[0] * z.shape[2] * z.shape[3] / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms, "iters": iters,
+            "kind": "port: reference operator sequence in PyTorch eager (CUDA), same GPU, same device-resident input",
+            "losses": [float(ins), float(dom)]}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path on the host cores, same metric/config."""
     rank = int(os.environ.get("RANK", "0"))
@@ -386,8 +408,15 @@ def run_ours(args):
         roofline["step_frac"] = 192.0 * pix / (ms_step * 1e-3) / 1e9 / peak    # whole fwd+bwd step vs 192 B/pix
 
     cpu = None
+    gpu_eager = None
     if not args.no_cpu_baseline and world == 1:
         cpu = time_cpu(6, H, W, 2, 3, args.cpu_seconds, 40)
+        try:
+            gpu_eager = time_gpu_eager(zs[(args.steps - 1) & 1], n, K)         # the input whose losses the line reports
+            gpu_eager["losses_match_ours"] = bool(abs(gpu_eager["losses"][0] - losses[0]) <= 1e-5 * abs(losses[0]) and
+                                                  abs(gpu_eager["losses"][1] - losses[1]) <= 1e-4)
+        except Exception as exc:                          # e.g. out of memory on a smaller device: report, do not hide
+            gpu_eager = {"unavailable": str(exc).splitlines()[0][:160]}
 
     line = {
         "metric": "shape-loss fwd+bwd Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
@@ -398,7 +427,7 @@ def run_ours(args):
                    "per_gpu_batch": B, "l2": "inputs (%.0f MB, two alternating buffers) larger than L2" % (nbytes / 1e6),
                    "sharding": "independent [K x n] batches per rank, no data-path collective"},
         "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
-        "clocks": clocks, "losses": losses, "train_step": train,
+        "gpu_eager_baseline": gpu_eager, "clocks": clocks, "losses": losses, "train_step": train,
     }
     print(json.dumps(line))
     if world > 1:
