@@ -83,3 +83,33 @@ def test_product_never_imports_oracle():
         src = open(os.path.join(ROOT, f)).read()
         # bench.py may use the oracle only in its CPU legs
         assert "from oracle" in src and "def cpu_step_fn" in src
+
+
+def test_wavelet_planner_host_logic():
+    """Track W planner (pure host code in the library, no GPU needed): which shapes get a fused plan and with what cluster
+    size for the resident stage.  512^2 db2 J=4 streams one level (256^2 band, cluster of 2), 1024^2 two levels, Haar never
+    needs a cluster, shapes whose widths are neither divisible by 2^(J+1) nor tileable have no fused plan."""
+    import wtpse_b200 as wb
+
+    lib = wb._lib.load()
+    plan = lib.wtpse_wavelet_resident_cluster
+    try:
+        assert plan(512, 512, 1, 4) == 2
+        assert plan(1024, 1024, 1, 5) == 2
+        assert plan(2048, 2048, 1, 4) == 2
+        assert plan(1024, 1024, 1, 2) == 1              # both levels streamed, nothing resident
+        assert plan(256, 256, 0, 3) == 1 and plan(1024, 1024, 0, 2) == 1 and plan(512, 512, 0, 4) == 1
+        assert plan(48, 64, 1, 4) == 1                  # whole map in one CTA
+        assert plan(64, 96, 1, 5) == 0 and plan(64, 96, 0, 5) == 0
+        assert plan(24, 24, 0, 4) == 0 and plan(0, 64, 0, 1) == 0 and plan(64, 64, 2, 1) == 0 and plan(64, 64, 0, 0) == 0
+        lib.wtpse_debug_set_wavelet_peel_max(1)
+        assert plan(1024, 1024, 1, 5) == 8              # one streamed level: 512^2 bands need a cluster of 8
+        lib.wtpse_debug_set_wavelet_peel_max(8)
+        lib.wtpse_debug_set_wavelet_resident(0)
+        assert plan(512, 512, 1, 4) == 0
+    finally:
+        lib.wtpse_debug_set_wavelet_resident(1)
+        lib.wtpse_debug_set_wavelet_peel_max(8)
+    # workspace covers the low-low bands and sign planes of every streamed level
+    n = 64 * 512 * 512
+    assert lib.wtpse_wavelet_workspace_bytes(64, 512, 512, 4) >= 4 * (n // 4 + n // 16) + n // 4 + n // 16
