@@ -569,6 +569,22 @@ def run_wavelet(args):
 
     ms_autograd, loss_ag = timed(step_autograd)
     ms, loss = timed(step_abi)
+
+    # the plain transform pair (W1 / W2): coefficients in Mallat layout and back, through the C ABI
+    coef = torch.empty(B, C, H, W, device=dev)
+    back = torch.empty(B, C, H, W, device=dev)
+
+    def step_fwd(i):
+        wb._lib.check(lib.wtpse_dwt2d_forward(_ptr(xs[i % 4]), nmaps, H, W, wid, J, _ptr(coef), _ptr(ws), nbytes, st))
+        return coef
+
+    def step_inv(i):
+        wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(coef), nmaps, H, W, wid, J, _ptr(back), None, _ptr(ws), nbytes, st))
+        return back
+
+    ms_fwd, _ = timed(step_fwd)
+    ms_inv, _ = timed(step_inv)
+    recon_err = float((back - xs[(args.steps - 1) % 4].detach()).abs().max())
     assert abs(float(loss) - float(loss_ag)) <= 1e-6 * abs(float(loss_ag)), (float(loss), float(loss_ag))
     elems = B * C * H * W
     peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
@@ -593,6 +609,8 @@ def run_wavelet(args):
                    "path": ("fused plan (wavelet-split=%d), resident stage in clusters of %d CTAs" % (args.wavelet_split, cs)) if cs else "one kernel per level",
                    "timed_through": "C ABI, preallocated outputs"},
         "autograd_ms_per_step": ms_autograd,
+        "transform": {"dwt2d_ms": ms_fwd, "idwt2d_ms": ms_inv, "max_abs_reconstruction_error": recon_err,
+                      "frac_of_8B_per_element_roofline": [8.0 * B * C * H * W / (t * 1e-3) / 1e9 / (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_PEAK_GBS) for t in (ms_fwd, ms_inv)]},
         "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "per": "GPU",
                      "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": traffic,
                      "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},
