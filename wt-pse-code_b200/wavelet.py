@@ -40,6 +40,11 @@ def _ws(lib, x, nmaps, H, W, J):
     return buf, nbytes
 
 
+def clear_workspace_cache():
+    """Drops the cached scratch buffers (one per device and stream that has run a wavelet call)."""
+    _WS_CACHE.clear()
+
+
 class _on_device:
     """torch.cuda.device(dev) without the context-manager cost when dev is already current (the usual case)."""
 
