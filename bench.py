@@ -40,6 +40,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--train-reference-work", type=int, default=1,
+                    help="also time the iteration with the reference's dead teacher backward kept (train_step.with_teacher_backward)")
+    ap.add_argument("--train-fuse-relu", type=int, default=0, help="train step with the fused DeepWT tail (SURVEY 8(f).1)")
+    ap.add_argument("--train-fuse-compare", type=int, default=1, help="also time the train step with the other --train-fuse-relu setting")
     ap.add_argument("--train-cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the train-step backbone")
     ap.add_argument("--wavelet-name", default="db2", choices=["haar", "db2"])
     ap.add_argument("--wavelet-levels", type=int, default=4)
@@ -211,6 +215,50 @@ def time_gpu_eager(z, n, K, iters=10):
     return {"value": z.shape[0] * z.shape[2] * z.shape[3] / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms, "iters": iters,
             "kind": "port: reference operator sequence in PyTorch eager (CUDA), same GPU, same device-resident input",
             "losses": [float(ins), float(dom)]}
+
+
+def time_relu_fusion(z, n, K, peak, iters=10):
+    """embedding + the ReLU that follows it (DeepWT tail), forward and backward with an upstream gradient
+    on relu(z).  `unfused` = ATen relu / threshold_backward / gradient add around the plain loss kernels; `fused` =
+    wtpse_whitening_relu_forward/backward.  Device-resident, same input as the headline step."""
+    import torch
+
+    import wtpse_b200 as wb
+
+    zz = z.detach().clone().requires_grad_(True)
+    g = torch.randn_like(zz)
+    one = torch.ones((), device=z.device)
+    pix = z.shape[0] * z.shape[2] * z.shape[3]
+
+    def unfused():
+        zz.grad = None
+        ins, dom = wb.whitening_folded(zz, n, K)
+        r = torch.relu(zz)
+        torch.autograd.backward([ins, dom, r], [one, one, g])
+
+    def fused():
+        zz.grad = None
+        r, ins, dom = wb.relu_whitening_folded(zz, n, K)
+        torch.autograd.backward([r, ins, dom], [g, one, one])
+
+    out = {}
+    for name, fn, bytes_per_pix in (("unfused", unfused, 704), ("fused", fused, 320)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(iters):
+            fn()
+        ev1.record()
+        torch.cuda.synchronize()
+        us = ev0.elapsed_time(ev1) / iters * 1e3
+        out[name] = {"us_per_step": us, "algorithmic_bytes_per_pix": bytes_per_pix,
+                     "hbm_frac": bytes_per_pix * pix / (us * 1e-6) / 1e9 / peak}
+    out["what"] = ("relu(z) + whitening loss fwd, and bwd with an upstream gradient on relu(z); unfused: 64 + 128 fwd, "
+                   "128 + 192 + 192 bwd B/pix; fused: 128 fwd, 192 bwd")
+    out["speedup"] = out["unfused"]["us_per_step"] / out["fused"]["us_per_step"]
+    return out
 
 
 def run_reference_arm(args):
@@ -418,6 +466,13 @@ def run_ours(args):
         except Exception as exc:                          # e.g. out of memory on a smaller device: report, do not hide
             gpu_eager = {"unavailable": str(exc).splitlines()[0][:160]}
 
+    relu_fusion = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            relu_fusion = time_relu_fusion(zs[0], n, K, peak)
+        except Exception as exc:
+            relu_fusion = {"unavailable": str(exc).splitlines()[0][:160]}
+
     line = {
         "metric": "shape-loss fwd+bwd Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -428,6 +483,7 @@ def run_ours(args):
                    "sharding": "independent [K x n] batches per rank, no data-path collective"},
         "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager, "clocks": clocks, "losses": losses, "train_step": train,
+        "relu_fusion": relu_fusion,
     }
     print(json.dumps(line))
     if world > 1:
@@ -438,7 +494,35 @@ def time_train_step(args, dev, rank, world, barrier):
     """BASELINE configs[2]/[3]: full WT-PSE iteration (4 network updates: reference U-Net backbone in PyTorch/cuDNN
     + the CUDA shape-loss path) on synthetic fundus-shaped batches, data-parallel over the ranks with one bucketed
     NCCL all-reduce per backward.  Reported as images/s over all ranks; loader time (device-side generator +
-    bit-exact label kernel) is inside the timed region."""
+    bit-exact label kernel) is inside the timed region.
+
+    `value` skips the reference's dead teacher backward in the two shape updates (its gradients are zeroed unread,
+    Trainer.py:768; weights and losses unchanged, tests/test_gpu_update.py); `with_teacher_backward` is the same
+    iteration doing exactly the reference's work."""
+    import gc
+
+    import torch
+
+    res = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=False, steps=args.train_steps,
+                              fuse_relu=bool(args.train_fuse_relu))
+    res["fused_deepwt_tail"] = bool(args.train_fuse_relu)
+    res["dead_teacher_backward"] = "skipped (SURVEY 8(f).3); weights, losses and BatchNorm statistics unchanged"
+    if args.train_reference_work:
+        gc.collect()
+        torch.cuda.empty_cache()
+        ref = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=True, steps=max(2, args.train_steps // 2))
+        res["with_teacher_backward"] = {k: ref[k] for k in ("value", "unit", "ms_per_step", "steps", "launch_mode")}
+    if args.train_fuse_compare:
+        gc.collect()
+        torch.cuda.empty_cache()
+        alt = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=False, steps=max(2, args.train_steps // 2),
+                                  fuse_relu=not args.train_fuse_relu)
+        key = "with_fused_deepwt_tail" if not args.train_fuse_relu else "without_fused_deepwt_tail"
+        res[key] = {k: alt[k] for k in ("value", "unit", "ms_per_step", "steps", "launch_mode", "our_kernels_per_iteration")}
+    return res
+
+
+def _time_train_variant(args, dev, rank, world, barrier, teacher_backward, steps, fuse_relu=False):
     import torch
     import torch.distributed as dist
 
@@ -448,7 +532,8 @@ def time_train_step(args, dev, rank, world, barrier):
     torch.backends.cudnn.benchmark = bool(args.train_cudnn_benchmark)
     n_per_domain, used = wb.dp.per_rank_batch(args.train_batch * world, world, 3)
     S = args.train_size
-    ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0)
+    ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0, teacher_backward=teacher_backward,
+                      fuse_relu=fuse_relu)
     lib = wb._lib.load()
 
     mode = "eager"
@@ -475,7 +560,7 @@ def time_train_step(args, dev, rank, world, barrier):
     lib.wtpse_profile_reset()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    for it in range(args.train_steps):
+    for it in range(steps):
         out = one(3 + it)
     ev1.record()
     barrier()
@@ -483,9 +568,9 @@ def time_train_step(args, dev, rank, world, barrier):
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.train_steps
+    ms = float(t.item()) / steps
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
-            "steps": args.train_steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
+            "steps": steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
             "global_batch_used": world * used, "our_kernels_per_iteration": kernels_per_iteration,
             "backbone": "PyTorch/cuDNN (benchmark=%d), channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam" % int(args.train_cudnn_benchmark), "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}

@@ -80,6 +80,25 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
                              float margin, float* dz,
                              void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/*
+ * Producer fusion with the DeepWT tail.  In DeepWT.forward (algorithms.py:1099-1113) each embedding
+ * that feeds the loss is followed immediately by `F.relu(z_instance)` (:1105, :1112).  These two entry points do both
+ * in the passes the loss makes anyway:
+ *   forward : everything wtpse_whitening_forward does, and relu_out = relu(z)  (same shape as z; must not alias it)
+ *   backward: dz = (S_b + S_b^T) z_b / (P-1) + [z > 0] * grad_relu              (grad_relu: upstream gradient of relu_out)
+ * i.e. the ReLU forward, its backward (ATen threshold_backward: passes where z > 0 or z is NaN) and the sum autograd
+ * forms of the two gradients reaching z.  HBM traffic for embedding + activation: 128 + 192 B/pixel instead of
+ * (64 + 128) + (128 + 192 + 192).  relu_out / grad_relu need the same 16-byte alignment as z for the TMA path.
+ */
+int wtpse_whitening_relu_forward(const float* z, float* relu_out, int B, int C, int64_t P,
+                                 int n_per_domain, int n_domains, float margin, float eps,
+                                 float* losses, float* gram, float* rowstat,
+                                 void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
+                                  const float* g_off, const float* g_diag, const float* g_dom,
+                                  int B, int C, int64_t P, int n_per_domain, int n_domains, float* dz,
+                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

@@ -105,6 +105,40 @@ def test_reparameterisation_equals_torch_normal():
     assert torch.equal(ours, ref) and torch.equal(g_ours[0], mu.grad) and torch.allclose(g_ours[1], logvar.grad, rtol=1e-6, atol=0)
 
 
+def test_skipping_the_dead_teacher_backward_changes_nothing_the_trainer_keeps():
+    """ShapeVariationalDist_x.teacher_grad=False (what TrainStep uses): same five losses, same student gradients, same
+    teacher BatchNorm statistics; only the teacher gradients the trainer zeroes anyway (Trainer.py:768) are not produced."""
+    import copy
+
+    from wtpse_b200 import segmentation as seg
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(5)
+    main0 = seg.WT_PSE(3, 1, HP, dev, True, per_domain_batch=2, source_domain_num=3).to(dev).train()
+    shape0 = seg.ShapeVariationalDist_x(HP, dev, 1, number_source_domain=3, batch_size=2).to(dev).train()
+    assert shape0.teacher_grad is True                                  # the class default is the reference's behaviour
+    x = torch.randn(6, 3, 64, 48, device=dev)
+    mask = (torch.rand(6, 1, 64, 48, device=dev) > 0.5).float()
+    res = []
+    for teacher_grad in (True, False):
+        main, shape = copy.deepcopy(main0), copy.deepcopy(shape0)
+        shape.teacher_grad = teacher_grad
+        torch.manual_seed(17)
+        out = shape.update(main, x, mask, step=0, plot_show=0, two_stage_inputs=x, two_step=True)
+        (out[0] + out[1] + out[4]).backward()
+        res.append(([float(v) for v in out], torch.cat([p.grad.reshape(-1) for p in shape.parameters()]),
+                    main.prior_dist.down1.bn1.running_mean.clone(),
+                    [p.grad for p in main.parameters()]))
+    assert res[0][0] == res[1][0]
+    assert torch.allclose(res[0][1], res[1][1], rtol=1e-5, atol=1e-9)
+    assert torch.equal(res[0][2], res[1][2]) and not torch.equal(res[0][2], main0.prior_dist.down1.bn1.running_mean)
+    assert any(g is not None for g in res[0][3]) and all(g is None for g in res[1][3])
+    import wtpse_b200 as wb
+    ts = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=0)
+    assert ts.model_shape.teacher_grad is False and ts.model_shape_oc.teacher_grad is False
+    assert wb.TrainStep(n_per_domain=2, device=dev, teacher_backward=True).model_shape.teacher_grad is True
+
+
 def test_train_step_runs_and_learns():
     import wtpse_b200 as wb
 

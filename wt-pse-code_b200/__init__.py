@@ -5,7 +5,8 @@ Import as ``wtpse_b200`` (alias package at the repo root).  The arithmetic lives
 side.  There is no CPU or eager-PyTorch fallback: calls raise if the library is missing.
 """
 from . import _build, _lib  # noqa: F401
-from .functional import HostPlan, gram_matrix, kd_mse, whitening_folded, whitening_terms  # noqa: F401
+from .functional import (HostPlan, gram_matrix, kd_mse, relu_whitening_folded, relu_whitening_terms,  # noqa: F401
+                         whitening_folded, whitening_terms)
 from .mmd import mmd_penalty  # noqa: F401
 from .elementwise import attention_fuse, od_roi, prepare_batch  # noqa: F401
 from .wavelet import dwt2d, idwt2d, wavelet_shape_loss  # noqa: F401
@@ -14,5 +15,5 @@ from . import dp, segmentation, synthetic, train_step  # noqa: F401
 from .segmentation import ShapeVariationalDist_x, WT_PSE  # noqa: F401
 from .train_step import TrainStep  # noqa: F401
 
-__all__ = ["whitening_terms", "whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin",
+__all__ = ["whitening_terms", "whitening_folded", "relu_whitening_terms", "relu_whitening_folded", "gram_matrix", "kd_mse", "mmd_penalty", "HostPlan", "dropin",
            "prepare_batch", "od_roi", "attention_fuse", "WT_PSE", "ShapeVariationalDist_x", "TrainStep"]

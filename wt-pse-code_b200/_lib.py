@@ -25,6 +25,12 @@ EXPORTS = {
     "wtpse_whitening_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                             _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p,
                                             _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_whitening_relu_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                                _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                _c.c_size_t, _c.c_void_p]),
+    "wtpse_whitening_relu_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                                 _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                                 _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
     "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_size_t, _c.c_void_p]),

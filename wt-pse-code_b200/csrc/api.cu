@@ -97,18 +97,18 @@ size_t wtpse_whitening_workspace_bytes(int B, int64_t P) {
     return carve(nullptr, B, P, sm_count_cached()).total;
 }
 
-int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_domain, int n_domains, float margin,
-                            float eps, float* losses, float* gram, float* rowstat, void* workspace,
-                            size_t workspace_bytes, wtpse_stream_t stream) {
+static int whitening_forward_impl(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
+                                  float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                                  size_t workspace_bytes, wtpse_stream_t stream) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
     if (!losses || !gram || !rowstat || !workspace) return fail(WTPSE_ERR_INVALID, "null output/workspace pointer");
     const int sms = sm_count_cached();
     const WhitenWorkspace w = carve(workspace, B, P, sms);
     if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const GramPlan g = plan_gram(z, B, P, sms);
+    const GramPlan g = plan_gram(z, B, P, sms, relu_out);
     cudaError_t e;
-    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, w.slot_count, B, P, g, s); }
+    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out); }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
     if (g_two_stage_epilogue) {
         LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
@@ -124,11 +124,26 @@ int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_d
     return WTPSE_OK;
 }
 
-int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* g_off,
-                             const float* g_diag, const float* g_dom, int B, int C, int64_t P, int n_per_domain,
-                             int n_domains, float margin, float* dz, void* workspace, size_t workspace_bytes,
-                             wtpse_stream_t stream) {
-    (void)margin;  // already folded into rowstat by the forward
+int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_domain, int n_domains, float margin,
+                            float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                            size_t workspace_bytes, wtpse_stream_t stream) {
+    return whitening_forward_impl(z, nullptr, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
+                                  workspace_bytes, stream);
+}
+
+int wtpse_whitening_relu_forward(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
+                                 float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                                 size_t workspace_bytes, wtpse_stream_t stream) {
+    if (!relu_out) return fail(WTPSE_ERR_INVALID, "null relu_out pointer");
+    if (relu_out == z) return fail(WTPSE_ERR_INVALID, "relu_out must not alias z (the backward pass re-reads z)");
+    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
+                                  workspace_bytes, stream);
+}
+
+static int whitening_backward_impl(const float* z, const float* grelu, const float* gram, const float* rowstat,
+                                   const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
+                                   int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
+                                   wtpse_stream_t stream) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
     if (!gram || !rowstat || !dz || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
     const int sms = sm_count_cached();
@@ -139,7 +154,7 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
     // g_backward_mode: 0 = per-sample M_b kernel + round-robin apply chained by programmatic dependent launch (default),
     //                  1 = M_b derived inside the apply kernel (one launch, contiguous tile ranges),
     //                  2 = single-CTA epilogue + apply (also the fallback for very many MMD samples)
-    if (g_backward_mode == 1 && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
+    if (g_backward_mode == 1 && !grelu && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
         LaunchScope scope(kKernApply, s);
         e = launch_apply_fused(z, gram, rowstat, g_off, g_diag, g_dom, dz, B, P, n_per_domain, n_domains, sms, s);
     } else if (g_backward_mode != 2 && mmat_multi_cta_ok(B, n_per_domain, n_domains)) {
@@ -147,14 +162,32 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
         e = launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s);
         if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
         profile_count_kernel(kKernMmat);
-        e = launch_apply(z, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/true);
+        e = launch_apply(z, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/true, grelu);
     } else {
         { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s); }
         if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
-        { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s); }
+        { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s, false, grelu); }
     }
     if (e != cudaSuccess) return cuda_fail(e, "apply launch");
     return WTPSE_OK;
+}
+
+int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* g_off,
+                             const float* g_diag, const float* g_dom, int B, int C, int64_t P, int n_per_domain,
+                             int n_domains, float margin, float* dz, void* workspace, size_t workspace_bytes,
+                             wtpse_stream_t stream) {
+    (void)margin;  // already folded into rowstat by the forward
+    return whitening_backward_impl(z, nullptr, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
+                                   workspace, workspace_bytes, stream);
+}
+
+int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
+                                  const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
+                                  int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
+                                  wtpse_stream_t stream) {
+    if (!grad_relu) return fail(WTPSE_ERR_INVALID, "null grad_relu pointer (use wtpse_whitening_backward)");
+    return whitening_backward_impl(z, grad_relu, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
+                                   workspace, workspace_bytes, stream);
 }
 
 void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }

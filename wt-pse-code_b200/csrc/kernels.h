@@ -16,10 +16,10 @@ struct GramPlan {
     int variant;                 // 0: one thread per pixel quad (whitening_gram.cu), 1: two threads per quad (..._split.cu)
 };
 
-GramPlan plan_gram(const float* z, int B, long long P, int sm_count);
+GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float* relu_out = nullptr);
 size_t gram_partial_floats(int B, long long P, int sm_count);
 cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
-                        cudaStream_t stream);
+                        cudaStream_t stream, float* relu_out = nullptr);   // relu_out: also write relu(z) (8(f).1)
 
 // epilogues (single CTA).  `scratch` is the global fallback for their working set (epilogue_scratch_bytes).
 size_t epilogue_scratch_bytes(int B, int K);
@@ -60,8 +60,9 @@ cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domai
                        void* scratch, cudaStream_t stream);
 
 // backward apply: dz_b = M_b z_b
+// grelu != nullptr: dz_b = M_b z_b + [z_b > 0] * grelu_b (ReLU backward + gradient sum fused)
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
-                         cudaStream_t stream, bool programmatic_dependent = false);
+                         cudaStream_t stream, bool programmatic_dependent = false, const float* grelu = nullptr);
 
 // fused backward: every CTA derives M_b for its own samples (no separate epilogue launch)
 bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains);

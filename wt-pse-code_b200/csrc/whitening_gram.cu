@@ -84,9 +84,20 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4
     }
 }
 
+// ReLU of the DeepWT tail (algorithms.py:1105,1112: `F.relu(z_instance)` right after the embedding that feeds the loss).
+// `x < 0 ? 0 : x` keeps NaN, like ATen's clamp_min.
+__device__ __forceinline__ float4 relu4(const float4& v) {
+    return make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y, v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
+}
+
+// kRelu: the same pass also writes relu(z) (SURVEY 8(f).1 -- the activation that follows the embedding no longer
+// re-reads z); the consumers store the 4 pixels x 16 channels they hold anyway, one coalesced 512 B row piece per
+// warp and channel.  Default-policy stores: the next convolution reads relu(z) right away.
+template <bool kRelu>
 __global__ void __launch_bounds__(kThreads, 1)
-gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
-                long long tiles_per_sample, long long T, int nslots, int group, int hint) {
+gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial,
+                int* __restrict__ slot_count, long long P, long long tiles_per_sample, long long T, int nslots, int group,
+                int hint) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
@@ -162,6 +173,11 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
                 float4 x[kC];
 #pragma unroll
                 for (int c = 0; c < kC; ++c) x[c] = *reinterpret_cast<const float4*>(src + c * kTilePx);
+                if (kRelu) {
+                    float* dst = relu_out + (b * kC) * P + px0 + 4 * tid;
+#pragma unroll
+                    for (int c = 0; c < kC; ++c) *reinterpret_cast<float4*>(dst + c * P) = relu4(x[c]);
+                }
                 gram_accumulate(acc, x);
             }
             __syncwarp();
@@ -181,9 +197,10 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ partial, int* _
 // Fallback for inputs the bulk copies cannot take (P % 4 != 0 or a base pointer that is not 16-byte
 // aligned): same arithmetic, plain coalesced scalar loads, one pixel per thread per step.
 // grid = (nslots, B); block = 256.
+template <bool kRelu>
 __global__ void __launch_bounds__(kConsumers)
-gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, int* __restrict__ slot_count, long long P,
-                    int nslots) {
+gram_generic_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial,
+                    int* __restrict__ slot_count, long long P, int nslots) {
     __shared__ float red[kConsumerWarps * kTri];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long b = blockIdx.y;
@@ -200,6 +217,10 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, in
         float x[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) x[c] = __ldg(zb + c * P + p);
+        if (kRelu) {
+#pragma unroll
+            for (int c = 0; c < kC; ++c) relu_out[(b * kC + c) * P + p] = x[c] < 0.f ? 0.f : x[c];
+        }
 #pragma unroll
         for (int i = 0; i < kC; ++i)
 #pragma unroll
@@ -217,12 +238,12 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ partial, in
 int g_gram_group = 1;
 int g_gram_variant = 0;
 
-GramPlan plan_gram(const float* z, int B, long long P, int sm_count) {
+GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float* relu_out) {
     GramPlan g;
-    g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0);
+    g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(relu_out) & 15u) == 0);
     g.round_robin = false;
     g.group = 1;
-    g.variant = g_gram_variant;
+    g.variant = relu_out ? 0 : g_gram_variant;      // the fused ReLU write exists for the one-thread-per-quad kernel only
     if (g.tma) {
         const long long tile_px = g.variant == 1 ? gram_split_tile_px() : kTilePx;
         g.tiles_per_sample = (P + tile_px - 1) / tile_px;
@@ -268,11 +289,12 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
     return size_t(B) * size_t(slots) * kTri;
 }
 
-cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
-                        cudaStream_t stream) {
-    if (g.tma && g.variant == 1) return launch_gram_split(z, partial, slot_count, P, g, stream);
+namespace {
+template <bool kRelu>
+cudaError_t launch_gram_t(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P,
+                          const GramPlan& g, cudaStream_t stream) {
     if (g.tma) {
-        cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+        cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<kRelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(unsigned(g.G));
@@ -284,12 +306,22 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, gram_tma_kernel, z, partial, slot_count, (long long)P, g.tiles_per_sample, g.T, g.nslots,
-                                  g.group, g_l2_evict_first);
+        return cudaLaunchKernelEx(&cfg, gram_tma_kernel<kRelu>, z, relu_out, partial, slot_count, (long long)P,
+                                  g.tiles_per_sample, g.T, g.nslots, g.group, g_l2_evict_first);
     } else {
-        gram_generic_kernel<<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, partial, slot_count, P, g.nslots);
+        gram_generic_kernel<kRelu><<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, relu_out, partial,
+                                                                                                   slot_count, P, g.nslots);
     }
     return cudaGetLastError();
+}
+}  // namespace
+
+// relu_out != nullptr: fused ReLU write (plan_gram must have been made with the same relu_out, see its alignment rule)
+cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                        cudaStream_t stream, float* relu_out) {
+    if (relu_out) return launch_gram_t<true>(z, relu_out, partial, slot_count, B, P, g, stream);
+    if (g.tma && g.variant == 1) return launch_gram_split(z, partial, slot_count, P, g, stream);
+    return launch_gram_t<false>(z, nullptr, partial, slot_count, B, P, g, stream);
 }
 
 }  // namespace wtpse

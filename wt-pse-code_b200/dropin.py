@@ -25,14 +25,25 @@ def _domain_cfg(obj):
     return int(op.batch_size), int(op.domain_num)
 
 
+def _fused(z, arity):
+    from .segmentation import fused_terms
+    return fused_terms(z, arity)
+
+
 def wt_pse_compute_whitening_loss(self, z):
     """Replacement for WT_PSE.compute_whitening_loss (algorithms.py:1277-1309)."""
+    pre = _fused(z, 2)                 # attached by the fused DeepWT tail (bind(..., fuse_relu=True)), if that is on
+    if pre is not None:
+        return pre
     n, K = _domain_cfg(self)
     return F.whitening_folded(z, n, K, float(self.margin), float(self.eps))
 
 
 def shape_compute_whitening_loss(self, z):
     """Replacement for ShapeVariationalDist_x.compute_whitening_loss (shape_networks.py:561-594)."""
+    pre = _fused(z, 3)
+    if pre is not None:
+        return pre
     n, K = _domain_cfg(self)          # K is the literal 3 of shape_networks.py:448
     return F.whitening_terms(z, n, K, float(self.margin), float(self.eps))
 
@@ -74,9 +85,17 @@ def uninstall(saved):
         setattr(cls, name, fn)
 
 
-def bind(obj):
-    """Rebind on ONE instance (e.g. only the OD model) instead of the class."""
+def bind(obj, fuse_relu=False):
+    """Rebind on ONE instance (e.g. only the OD model) instead of the class.
+
+    fuse_relu=True additionally rebinds ``obj.wt_model.forward`` (DeepWT.forward, algorithms.py:1091-1117 /
+    shape_networks.py:215-239) to the fused tail: Gram + ReLU in one pass over each embedding, and one backward pass
+    (SURVEY.md 8(f).1).  Same outputs, same gradients; no parameters or buffers change."""
     name = type(obj).__name__
+    if fuse_relu and name in ("WT_PSE", "ShapeVariationalDist_x"):
+        from . import segmentation as seg
+        seg.enable_relu_fusion(obj, True)
+        obj.wt_model.forward = types.MethodType(seg.deepwt_forward, obj.wt_model)
     if name == "WT_PSE":
         obj.compute_whitening_loss = types.MethodType(wt_pse_compute_whitening_loss, obj)
     elif name == "ShapeVariationalDist_x":

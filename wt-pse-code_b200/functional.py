@@ -103,6 +103,88 @@ class _WhiteningLoss(torch.autograd.Function):
         return dz, None, None, None, None, None
 
 
+class _ReluWhiteningLoss(torch.autograd.Function):
+    """relu(z) and the loss terms of z in one pass each way (include/wtpse_b200.h
+    wtpse_whitening_relu_forward/backward).  Outputs: (relu(z), L_off, L_diag, L_dom) or, with fold=True,
+    (relu(z), L_off + L_diag, L_dom)."""
+
+    @staticmethod
+    def forward(ctx, z, n_per_domain, n_domains, margin, eps, fold):
+        _require_cuda_f32(z, "z")
+        if z.dim() != 4:
+            raise ValueError("z must be B x C x H x W, got shape %s" % (tuple(z.shape),))
+        B, C, H, W = z.shape
+        if C != CHANNELS:
+            raise ValueError("whitening loss is defined for C == 16 feature maps (self.dim), got C == %d" % C)
+        z = z.contiguous()
+        P = H * W
+        lib = _lib.load()
+        with torch.cuda.device(z.device):
+            ws_bytes = lib.wtpse_whitening_workspace_bytes(B, P)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+            losses = torch.empty(4, dtype=torch.float32, device=z.device)
+            gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
+            rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+            relu_out = torch.empty_like(z)
+            _lib.check(lib.wtpse_whitening_relu_forward(_ptr(z), _ptr(relu_out), B, C, P, int(n_per_domain), int(n_domains),
+                                                        float(margin), float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat),
+                                                        _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+        ctx.save_for_backward(z, gram, rowstat)
+        ctx.cfg = (int(n_per_domain), int(n_domains), bool(fold), ws_bytes)
+        if fold:
+            return relu_out, _scalar_alias(losses, 3), _scalar_alias(losses, 2)
+        return relu_out, _scalar_alias(losses, 0), _scalar_alias(losses, 1), _scalar_alias(losses, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_relu, *grads):
+        z, gram, rowstat = ctx.saved_tensors
+        n, K, fold, ws_bytes = ctx.cfg
+        if fold:
+            g_ins, g_dom = grads
+            g_off, g_diag = g_ins, g_ins
+        else:
+            g_off, g_diag, g_dom = grads
+        none = (None,) * 6
+        if not ctx.needs_input_grad[0]:
+            return none
+        no_loss_grad = g_off is None and g_diag is None and g_dom is None
+        if g_relu is None and no_loss_grad:
+            return none
+        B, C, H, W = z.shape
+        lib = _lib.load()
+        with torch.cuda.device(z.device):
+            dz = torch.empty_like(z)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
+            p_off, k0 = _grad_ptr(g_off, z)
+            p_diag, k1 = _grad_ptr(g_diag, z)
+            p_dom, k2 = _grad_ptr(g_dom, z)
+            if g_relu is None:                       # only the loss was used downstream
+                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
+                                                        n, K, 0.0, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            else:
+                # loss unused (e.g. the teacher pass of the shape update): all-NULL upstream scalars make M_b = 0 and the
+                # same kernel degenerates to the ReLU backward
+                _require_cuda_f32(g_relu, "grad of relu(z)")
+                g_relu = g_relu.contiguous()
+                _lib.check(lib.wtpse_whitening_relu_backward(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), p_off, p_diag,
+                                                             p_dom, B, C, H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes,
+                                                             _stream_ptr(z.device)))
+            del k0, k1, k2
+        return (dz,) + none[1:]
+
+
+def relu_whitening_terms(z, n_per_domain, n_domains, margin=0.0, eps=1e-5):
+    """(relu(z), L_off, L_diag, L_dom): the DeepWT tail `F.relu(z)` (algorithms.py:1105,1112) fused with
+    ShapeVariationalDist_x.compute_whitening_loss(z)."""
+    return _ReluWhiteningLoss.apply(z, n_per_domain, n_domains, margin, eps, False)
+
+
+def relu_whitening_folded(z, n_per_domain, n_domains, margin=0.0, eps=1e-5):
+    """(relu(z), L_off + L_diag, L_dom): the same for WT_PSE.compute_whitening_loss(z)."""
+    return _ReluWhiteningLoss.apply(z, n_per_domain, n_domains, margin, eps, True)
+
+
 def whitening_terms(z, n_per_domain, n_domains, margin=0.0, eps=1e-5):
     """(L_off, L_diag, L_dom): the three-value form ShapeVariationalDist_x.compute_whitening_loss returns."""
     return _WhiteningLoss.apply(z, n_per_domain, n_domains, margin, eps, False)

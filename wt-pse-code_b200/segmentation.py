@@ -124,16 +124,61 @@ class DeepWT(nn.Module):
     def __init__(self, input_channel, out_channel, whitening=True):
         super().__init__()
         self.whitening = whitening
+        self.fused_loss = None            # see enable_relu_fusion / deepwt_forward
+        self.out_memory_format = None
         if whitening:
             self.DoubleConv = _DoubleConvWT(input_channel, out_channel)
             self.DoubleConv2 = _DoubleConvWT(out_channel, out_channel)
 
     def forward(self, x):
-        if not self.whitening:
-            return [x]
-        z0 = self.DoubleConv(x)
+        return deepwt_forward(self, x)
+
+
+_LOSS_TAG = "_wtpse_loss"
+
+
+def deepwt_forward(self, x):
+    """DeepWT.forward (algorithms.py:1091-1117, shape_networks.py:215-239), also bindable on the reference's own DeepWT
+    instances (dropin.bind(..., fuse_relu=True)).
+
+    With ``self.fused_loss`` set by the owning network each embedding z_k and the ``F.relu(z_k)`` that
+    follows it take ONE pass over z_k forward (Gram + ReLU write, wtpse_whitening_relu_forward) and ONE backward
+    (M_b z + ReLU backward + the sum of both gradients, wtpse_whitening_relu_backward).  The loss terms are attached to
+    the returned z_k; the owner's compute_whitening_loss(z_k) picks them up instead of reading z_k again.  Values and
+    gradients are those of the unfused sequence (tests/test_gpu_fusion.py)."""
+    if not self.whitening:
+        return [x]
+    cfg = getattr(self, "fused_loss", None)
+    z0 = self.DoubleConv(x)
+    if cfg is None or not (torch.is_grad_enabled() and z0.requires_grad and z0.is_cuda):
         z1 = self.DoubleConv2(F.relu(z0))
         return [z0, z1, F.relu(z1)]
+    fn = wf.relu_whitening_folded if cfg["fold"] else wf.relu_whitening_terms
+    args = (cfg["n_per_domain"], cfg["n_domains"], cfg["margin"], cfg["eps"])
+    r0, *terms0 = fn(z0, *args)
+    z1 = self.DoubleConv2(r0)
+    r1, *terms1 = fn(z1, *args)
+    setattr(z0, _LOSS_TAG, tuple(terms0))
+    setattr(z1, _LOSS_TAG, tuple(terms1))
+    fmt = getattr(self, "out_memory_format", None)
+    if fmt is not None:
+        r1 = r1.contiguous(memory_format=fmt)
+    return [z0, z1, r1]
+
+
+def enable_relu_fusion(owner, on=True):
+    """Turn the DeepWT-tail fusion on/off for a WT_PSE or ShapeVariationalDist_x (ours or the reference's)."""
+    fold = type(owner).__name__ == "WT_PSE"           # two-value form (algorithms.py:1301) vs three values
+    owner.wt_model.fused_loss = None if not on else {
+        "fold": fold, "n_per_domain": int(owner.mmd_operator.batch_size), "n_domains": int(owner.mmd_operator.domain_num),
+        "margin": float(owner.margin), "eps": float(owner.eps)}
+    return owner
+
+
+def fused_terms(z, arity):
+    """Loss terms deepwt_forward attached to an embedding, or None."""
+    t = getattr(z, _LOSS_TAG, None)
+    return t if t is not None and len(t) == arity else None
 
 
 def _head(cin, mid, cout):
@@ -231,6 +276,9 @@ class WT_PSE(_UNetTrunk):
     # -- hot path ---------------------------------------------------------------------------------
     def compute_whitening_loss(self, z):
         """(instance_loss, domain_loss) -- algorithms.py:1277-1309, one CUDA forward + one fused backward."""
+        pre = fused_terms(z, 2)
+        if pre is not None:
+            return pre
         return wf.whitening_folded(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
                                    float(self.eps))
 
@@ -298,6 +346,11 @@ class ShapeVariationalDist_x(_UNetTrunk):
         self.mmd_operator = _MmdConfig(domain_num=3, batch_size=batch_size)      # literal 3, shape_networks.py:448
         self.mu_prior = _head(2 * n, 8, n_classes)
         self.logvar_prior = _head(2 * n, 8, n_classes)
+        # True = the reference's behaviour: the KD loss back-propagates into the teacher (`main_network`), whose
+        # gradients the trainer throws away at its next zero_grad (shape_networks.py:524, Trainer.py:768).  False runs
+        # the teacher forward (BatchNorm statistics still update) without recording it: every student gradient and
+        # every weight after the optimizer steps is unchanged, one U-Net backward per update is saved.
+        self.teacher_grad = True
 
     def unet_extractor(self, inputs):
         return self._trunk(inputs if self.wt else self.inc(inputs))
@@ -327,6 +380,9 @@ class ShapeVariationalDist_x(_UNetTrunk):
 
     def compute_whitening_loss(self, z):
         """(off_diagonal_loss, diagonal_loss, domain_loss) -- shape_networks.py:561-594."""
+        pre = fused_terms(z, 3)
+        if pre is not None:
+            return pre
         return wf.whitening_terms(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
                                   float(self.eps))
 
@@ -337,11 +393,12 @@ class ShapeVariationalDist_x(_UNetTrunk):
         if not self.hparams["whitening"]:
             return 0, 0, 0, 0, 0
         x = two_stage_inputs if two_step else inputs
-        teacher_feats = main_network.wt_model(x)
-        student_feats = self.wt_model(x)
         # teacher: features + mask (its mean is NOT detached: gradients reach main_network and are discarded
         # by the caller's zero_grad, shape_networks.py:524); student: features only
-        _z_post, z_post_mu = main_network.prior_dist.sample_forward(teacher_feats[-1], mask, training=True)
+        with torch.set_grad_enabled(self.teacher_grad and torch.is_grad_enabled()):
+            teacher_feats = main_network.wt_model(x)
+            _z_post, z_post_mu = main_network.prior_dist.sample_forward(teacher_feats[-1], mask, training=True)
+        student_feats = self.wt_model(x)
         _z_pre, z_pre_mu = self.sample_forward(student_feats[-1], training=True)
         kd_loss = self.wasser_distance(z_post_mu, z_pre_mu)
         # (the two attention_layer forwards at shape_networks.py:531-535 have no effect on any output)

@@ -26,7 +26,7 @@ DEFAULT_HPARAMS = {   # hparams_registry.py:75-93
 
 class TrainStep:
     def __init__(self, n_per_domain, n_domains=3, device="cuda", hparams=None, lr=5e-4, seed=0, process_group=None,
-                 channels_last=True, fused_adam=True):
+                 channels_last=True, fused_adam=True, teacher_backward=False, fuse_relu=False):
         self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
         self.device = torch.device(device)
         torch.manual_seed(seed)                                   # identical initial weights on every rank
@@ -37,6 +37,10 @@ class TrainStep:
         self.model, self.model_shape = mk(False).to(self.device), sh().to(self.device)
         self.model_oc, self.model_shape_oc = mk(True).to(self.device), sh().to(self.device)
         self.nets = (self.model, self.model_shape, self.model_oc, self.model_shape_oc)
+        # The reference back-propagates the KD loss into the teacher and discards the result at the next zero_grad
+        # (SURVEY appendix A.3 item 6).  teacher_backward=False skips that dead backward pass; weights and losses of
+        # all four networks are unchanged (tests/test_gpu_update.py).  True reproduces the reference's work exactly.
+        self.model_shape.teacher_grad = self.model_shape_oc.teacher_grad = bool(teacher_backward)
         for m in self.nets:
             m.train()
             if channels_last:
@@ -44,6 +48,13 @@ class TrainStep:
                 # 512x512); with channels-last weights every conv/BN of the backbone takes the NHWC kernels.
                 # The loss kernels keep the reference's NCHW layout (`z.contiguous()`, algorithms.py:1280).
                 m.to(memory_format=torch.channels_last)
+            if fuse_relu:
+                # Gram + ReLU in one pass over each embedding.  The loss kernels read NCHW, so the four
+                # 16-channel DeepWT convolutions (no BatchNorm) stay NCHW and only relu(z1) is converted for the U-Nets.
+                seg.enable_relu_fusion(m, True)
+                if channels_last:
+                    m.wt_model.to(memory_format=torch.contiguous_format)
+                    m.wt_model.out_memory_format = torch.channels_last
         self.buckets = [FlatGradBucket(m, process_group) for m in self.nets]
         fused = bool(fused_adam) and self.device.type == "cuda"       # one multi-tensor kernel per optimizer step
         self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused, capturable=fused)
