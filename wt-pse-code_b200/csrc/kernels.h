@@ -64,6 +64,11 @@ cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domai
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
                          cudaStream_t stream, bool programmatic_dependent = false, const float* grelu = nullptr);
 
+// whitening_apply_relu.cu: the TMA path of the grelu variant (z and grelu both staged by the producer warp)
+bool apply_relu_tma_ok(const float* z, const float* grelu, const float* dz, long long P);
+cudaError_t launch_apply_relu(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P,
+                              int sm_count, cudaStream_t stream, bool programmatic_dependent);
+
 // fused backward: every CTA derives M_b for its own samples (no separate epilogue launch)
 bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains);
 cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,

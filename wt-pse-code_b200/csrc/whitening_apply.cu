@@ -50,21 +50,10 @@ struct FusedArgs {
     int l2_hint;            // 1: TMA loads carry an L2 evict-first policy (z is read once)
 };
 
-__device__ __forceinline__ float4 ld_stream(const float* p) {
-    float4 v;
-    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
-// (ReLU backward below is ATen's threshold_backward: the gradient passes unless the input is <= 0, so NaN passes.)
-// kReluGrad: dz = M_b z + [z > 0] * grelu -- the backward of the ReLU that follows the embedding and
-// the sum autograd would do of the two gradients reaching z, in the pass that writes dz anyway (192 B/pixel instead
-// of 128 + 192 + 192).  grelu is read straight from global memory with streaming 128-bit loads issued before the
-// wait on the z tile, so they are in flight while the ring fills.
-template <bool kFused, bool kReluGrad>
+template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
-apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, const float* __restrict__ grelu,
-                 float* __restrict__ dz, long long P, long long tiles_per_sample, long long T, FusedArgs fa) {
+apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, float* __restrict__ dz, long long P,
+                 long long tiles_per_sample, long long T, FusedArgs fa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* msh = stage_buf + size_t(kStages) * kStageFloats;
@@ -191,14 +180,8 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, co
             named_bar_sync(1, kConsumers);
             cur_b = b;
         }
-        const bool active = 4LL * tid < rem;
-        float4 gr[kReluGrad ? kC : 1];
-        if (kReluGrad && active) {
-            const float* gsrc = grelu + (b * kC) * P + px0 + 4 * tid;
-#pragma unroll
-            for (int i = 0; i < kC; ++i) gr[i] = ld_stream(gsrc + i * P);
-        }
         mbar_wait(&full[stage], phase);
+        const bool active = 4LL * tid < rem;
         float4 out[kC];
         if (active) {
 #pragma unroll
@@ -220,20 +203,6 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, co
                     out[i].z = fmaf(m.z, x[2].z, out[i].z); out[i].w = fmaf(m.z, x[2].w, out[i].w);
                     out[i].x = fmaf(m.w, x[3].x, out[i].x); out[i].y = fmaf(m.w, x[3].y, out[i].y);
                     out[i].z = fmaf(m.w, x[3].z, out[i].z); out[i].w = fmaf(m.w, x[3].w, out[i].w);
-                }
-                if (kReluGrad) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) gr[4 * jq + r] = make_float4(x[r].x <= 0.f ? 0.f : gr[4 * jq + r].x,
-                                                                             x[r].y <= 0.f ? 0.f : gr[4 * jq + r].y,
-                                                                             x[r].z <= 0.f ? 0.f : gr[4 * jq + r].z,
-                                                                             x[r].w <= 0.f ? 0.f : gr[4 * jq + r].w);
-                }
-            }
-            if (kReluGrad) {
-                // added after the matrix product: the sum has the rounding of autograd's `dz_loss + dz_relu`
-#pragma unroll
-                for (int i = 0; i < kC; ++i) {
-                    out[i].x += gr[i].x; out[i].y += gr[i].y; out[i].z += gr[i].z; out[i].w += gr[i].w;
                 }
             }
         }
@@ -296,8 +265,10 @@ bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_p
 
 cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
                          cudaStream_t stream, bool programmatic_dependent, const float* grelu) {
-    if (tma_ok(z, dz, P) && (reinterpret_cast<uintptr_t>(grelu) & 15u) == 0) {
-        auto kern = grelu ? apply_tma_kernel<false, true> : apply_tma_kernel<false, false>;
+    if (grelu && apply_relu_tma_ok(z, grelu, dz, P))
+        return launch_apply_relu(z, grelu, mmat, dz, B, P, sm_count, stream, programmatic_dependent);
+    if (!grelu && tma_ok(z, dz, P)) {
+        auto kern = apply_tma_kernel<false>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemPlain));
         if (e != cudaSuccess) return e;
         const long long tps = (P + kTilePx - 1) / kTilePx;
@@ -316,7 +287,7 @@ cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, lo
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = programmatic_dependent ? 1 : 0;
-        return cudaLaunchKernelEx(&cfg, kern, z, mmat, grelu, dz, P, tps, T, fa);
+        return cudaLaunchKernelEx(&cfg, kern, z, mmat, dz, P, tps, T, fa);
     } else {
         apply_generic_kernel<<<dim3(unsigned((P + 255) / 256), unsigned(B)), 256, 0, stream>>>(z, mmat, grelu, dz, P);
     }
@@ -326,13 +297,13 @@ cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, lo
 cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,
                                const float* g_diag, const float* g_dom, float* dz, int B, long long P, int n_per_domain,
                                int n_domains, int sm_count, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemFused));
+    cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemFused));
     if (e != cudaSuccess) return e;
     const long long tps = (P + kTilePx - 1) / kTilePx;
     const long long T = tps * B;
     const long long G = T < sm_count ? T : sm_count;
     FusedArgs fa{gram, rowstat, g_off, g_diag, g_dom, B, n_per_domain, n_domains, 0, g_l2_evict_first};
-    apply_tma_kernel<true, false><<<dim3(unsigned(G)), kThreads, kSmemFused, stream>>>(z, nullptr, nullptr, dz, P, tps, T, fa);
+    apply_tma_kernel<true><<<dim3(unsigned(G)), kThreads, kSmemFused, stream>>>(z, nullptr, dz, P, tps, T, fa);
     return cudaGetLastError();
 }
 

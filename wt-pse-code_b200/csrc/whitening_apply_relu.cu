@@ -1,0 +1,177 @@
+// Backward of the fused DeepWT tail:  dz_b = M_b z_b + [z_b > 0] * grelu_b.
+//
+// In DeepWT.forward (algorithms.py:1099-1113) every embedding z that feeds the whitening loss is followed by
+// F.relu(z).  Autograd then makes three passes for dz: the loss adjoint (whitening_apply.cu: read z, write),
+// the ReLU backward (read grelu, read relu(z), write) and the sum of the two (read, read, write) -- 512 B per
+// pixel.  Here it is one pass: read z, read grelu, write dz = 192 B per pixel.
+//
+// Same structure as apply_tma_kernel (persistent CTAs, tiles dealt round-robin, M_b from whiten_mmat_kernel via
+// programmatic dependent launch), but BOTH streams are staged by the producer warp with 1-D TMA bulk copies:
+// a stage holds 16 channel rows of 896 pixels of z and of grelu (112 KB), two stages fill the shared memory.
+// (Reading grelu with per-thread 128-bit global loads instead -- no lead time, 8 warps per SM -- reached 0.78 of
+// the HBM roofline: 315 us at 32x16x512x512 against 246 us for the bytes.)  7 consumer warps + the producer warp
+// = 256 threads, so each thread may hold 255 registers: 64 outputs + 64 masked gradients.
+//
+// Rounding: the masked gradient is added AFTER the 16-term matrix product, so dz is bit-identical to autograd's
+// `dz_loss + dz_relu` (tests/test_gpu_fusion.py).  ReLU backward is ATen's threshold_backward: the gradient
+// passes unless z <= 0 (so it passes for NaN).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wtpse {
+
+namespace {
+
+constexpr int kConsumers = 224;
+constexpr int kConsumerWarps = kConsumers / 32;
+constexpr int kThreads = kConsumers + 32;
+constexpr int kTilePx = kConsumers * 4;            // 896 pixels
+constexpr int kStages = 2;
+constexpr int kRowsFloats = kC * kTilePx;          // one tensor's share of a stage: 56 KB
+constexpr int kStageFloats = 2 * kRowsFloats;      // z rows, then grelu rows
+constexpr size_t kSmemBytes = size_t(kStages) * kStageFloats * sizeof(float) + 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+
+__device__ __forceinline__ void st_stream4(float* p, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ grelu, const float* __restrict__ mmat,
+                      float* __restrict__ dz, long long P, long long tiles_per_sample, long long T) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* stage_buf = reinterpret_cast<float*>(smem_raw);
+    float* msh = stage_buf + size_t(kStages) * kStageFloats;
+    uint64_t* full = reinterpret_cast<uint64_t*>(msh + 256);
+    uint64_t* empty = full + kStages;
+
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long G = gridDim.x, k = blockIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerWarps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // producer: z and grelu were written by kernels that completed before whiten_mmat_kernel started, so they
+        // are streamed without waiting for it
+        if (lane == 0) {
+            const uint64_t policy = make_evict_first_policy();      // both inputs are read exactly once
+            int stage = 0;
+            uint32_t phase = 0;
+            for (long long t = k; t < T; t += G) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                const long long b = t / tiles_per_sample;
+                const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+                const long long rem = P - px0;
+                const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
+                const uint32_t bytes = npx * 4u;
+                mbar_arrive_expect_tx(&full[stage], bytes * 2 * kC);
+                const long long off = (b * kC) * P + px0;
+                float* dst = stage_buf + size_t(stage) * kStageFloats;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) tma_load_1d_hint(dst + c * kTilePx, z + off + c * P, bytes, &full[stage], policy);
+#pragma unroll
+                for (int c = 0; c < kC; ++c)
+                    tma_load_1d_hint(dst + kRowsFloats + c * kTilePx, grelu + off + c * P, bytes, &full[stage], policy);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+
+    int stage = 0;
+    uint32_t phase = 0;
+    long long cur_b = -1;
+    for (long long t = k; t < T; t += G) {
+        const long long b = t / tiles_per_sample;
+        const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+        const long long rem = P - px0;
+        if (b != cur_b) {
+            named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use
+            if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
+            for (int e = tid; e < 256; e += kConsumers) msh[e] = __ldg(mmat + b * 256 + e);
+            named_bar_sync(1, kConsumers);
+            cur_b = b;
+        }
+        mbar_wait(&full[stage], phase);
+        const bool active = 4LL * tid < rem;
+        float4 out[kC];
+        if (active) {
+            float4 gm[kC];
+#pragma unroll
+            for (int i = 0; i < kC; ++i) out[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float* src = stage_buf + size_t(stage) * kStageFloats + 4 * tid;
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq) {
+                float4 x[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) x[r] = *reinterpret_cast<const float4*>(src + (4 * jq + r) * kTilePx);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const float4 g = *reinterpret_cast<const float4*>(src + kRowsFloats + (4 * jq + r) * kTilePx);
+                    gm[4 * jq + r] = make_float4(x[r].x <= 0.f ? 0.f : g.x, x[r].y <= 0.f ? 0.f : g.y,
+                                                 x[r].z <= 0.f ? 0.f : g.z, x[r].w <= 0.f ? 0.f : g.w);
+                }
+#pragma unroll
+                for (int i = 0; i < kC; ++i) {
+                    const float4 m = *reinterpret_cast<const float4*>(msh + i * kC + 4 * jq);
+                    out[i].x = fmaf(m.x, x[0].x, out[i].x); out[i].y = fmaf(m.x, x[0].y, out[i].y);
+                    out[i].z = fmaf(m.x, x[0].z, out[i].z); out[i].w = fmaf(m.x, x[0].w, out[i].w);
+                    out[i].x = fmaf(m.y, x[1].x, out[i].x); out[i].y = fmaf(m.y, x[1].y, out[i].y);
+                    out[i].z = fmaf(m.y, x[1].z, out[i].z); out[i].w = fmaf(m.y, x[1].w, out[i].w);
+                    out[i].x = fmaf(m.z, x[2].x, out[i].x); out[i].y = fmaf(m.z, x[2].y, out[i].y);
+                    out[i].z = fmaf(m.z, x[2].z, out[i].z); out[i].w = fmaf(m.z, x[2].w, out[i].w);
+                    out[i].x = fmaf(m.w, x[3].x, out[i].x); out[i].y = fmaf(m.w, x[3].y, out[i].y);
+                    out[i].z = fmaf(m.w, x[3].z, out[i].z); out[i].w = fmaf(m.w, x[3].w, out[i].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kC; ++i) {
+                out[i].x += gm[i].x; out[i].y += gm[i].y; out[i].z += gm[i].z; out[i].w += gm[i].w;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (active) {
+            float* dst = dz + (b * kC) * P + px0 + 4 * tid;
+#pragma unroll
+            for (int i = 0; i < kC; ++i) st_stream4(dst + i * P, out[i]);
+        }
+    }
+}
+
+}  // namespace
+
+bool apply_relu_tma_ok(const float* z, const float* grelu, const float* dz, long long P) {
+    return (P % 4 == 0) && (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(grelu) | reinterpret_cast<uintptr_t>(dz)) & 15u) == 0);
+}
+
+cudaError_t launch_apply_relu(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P,
+                              int sm_count, cudaStream_t stream, bool programmatic_dependent) {
+    cudaError_t e = cudaFuncSetAttribute(apply_relu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
+    if (e != cudaSuccess) return e;
+    const long long tps = (P + kTilePx - 1) / kTilePx;
+    const long long T = tps * B;
+    const long long G = T < sm_count ? T : sm_count;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(G));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = programmatic_dependent ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, apply_relu_tma_kernel, z, grelu, mmat, dz, P, tps, T);
+}
+
+}  // namespace wtpse
