@@ -114,3 +114,46 @@ def test_dropin_install_rebinds_the_reference_classes():
         wb.dropin.uninstall(saved)
     after = ref_main.compute_whitening_loss(z)
     assert float(before[0]) == float(after[0]) and float(before[1]) == float(after[1])
+
+
+def test_conv_bias_folding_keeps_outputs_gradients_and_running_statistics():
+    """segmentation._conv_bn(fold=True) -- what TrainStep runs -- against the plain conv(+bias) -> BatchNorm sequence of the
+    reference (algorithms.py:877-962): same activations, input/weight/BN gradients and BatchNorm buffers up to fp32 rounding;
+    the conv biases in front of a BatchNorm only ever see rounding noise as their gradient (in both modes)."""
+    import copy
+
+    from wtpse_b200 import segmentation as seg
+
+    torch.manual_seed(0)
+    cases = [(seg.ConvD(8, 16), False), (seg.ConvD(8, 16, first=True), False), (seg.ConvU(16), True), (seg._DoubleConv(8, 16), False)]
+    for m0, is_up in cases:
+        m0.train()
+        for p in m0.parameters():
+            p.data.normal_(0, 0.5)
+        x = torch.randn(4, 32 if is_up else 8, 16, 16)
+        skip = torch.randn(4, 8, 32, 32)
+        res = []
+        for fold in (False, True):
+            m = seg.set_conv_bias_folding(copy.deepcopy(m0), fold)
+            xx = x.clone().requires_grad_()
+            for _ in range(2):                                     # two updates of the running statistics
+                y = m(xx, skip) if is_up else m(xx)
+            m.zero_grad()
+            xx.grad = None
+            (y * torch.linspace(0, 1, y.numel()).view_as(y)).sum().backward()
+            res.append((y.detach(), xx.grad, dict((n, p.grad.clone()) for n, p in m.named_parameters()),
+                        dict((n, b.clone()) for n, b in m.named_buffers())))
+        a, b = res
+        conv_biases = {name + ".bias" for name, mod in m0.named_modules() if isinstance(mod, torch.nn.Conv2d)}
+        assert float((a[0] - b[0]).abs().max()) <= 1e-5 * float(a[0].abs().max())
+        assert float((a[1] - b[1]).abs().max()) <= 1e-5 * float(a[1].abs().max())
+        for n in a[2]:
+            if n in conv_biases:
+                scale = max(float(g.abs().max()) for k, g in a[2].items() if k.endswith("weight"))
+                assert float(a[2][n].abs().max()) <= 1e-4 * scale and float(b[2][n].abs().max()) <= 1e-4 * scale   # noise only
+            else:
+                assert float((a[2][n] - b[2][n]).abs().max()) <= 1e-5 * max(float(a[2][n].abs().max()), 1.0), n
+        for n in a[3]:
+            assert torch.allclose(a[3][n].float(), b[3][n].float(), rtol=1e-5, atol=1e-6), n
+            if n.endswith("num_batches_tracked"):
+                assert int(b[3][n]) == 2
