@@ -99,6 +99,16 @@ int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const 
                                   int B, int C, int64_t P, int n_per_domain, int n_domains, float* dz,
                                   void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/*
+ * Decoder up-sampling of the U-Net stages: F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)
+ * (algorithms.py:947, ConvU.forward) on a CHANNELS-LAST tensor, and its adjoint (the backward pass).
+ *   adjoint == 0: in [N][H][W][C] -> out [N][2H][2W][C]
+ *   adjoint != 0: in [N][2H][2W][C] (gradient of the output) -> out [N][H][W][C] (gradient of the input)
+ * H and W are the LOW-resolution sizes in both directions; C % 4 == 0; 16-byte aligned pointers.  Deterministic (the
+ * adjoint gathers, no atomics).
+ */
+int wtpse_upsample2x_nhwc(const float* in, float* out, int64_t N, int H, int W, int C, int adjoint, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

@@ -112,3 +112,27 @@ def test_attention_fuse_forward_backward(B, Ce, H, W):
     assert rel_err(zp.grad.cpu().numpy(), z64.grad.cpu().numpy()) < TOL
     assert abs(float(conv.weight.grad) - float(w64.grad)) <= TOL * abs(float(w64.grad))
     assert abs(float(conv.bias.grad) - float(b64.grad)) <= TOL * abs(float(b64.grad))
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 1, 1), (3, 4, 5, 7), (2, 32, 16, 24), (1, 256, 8, 8), (15, 32, 64, 64)])
+def test_upsample2x_matches_aten_bilinear_forward_and_backward(shape):
+    """ConvU's F.interpolate(scale_factor=2, bilinear, align_corners=False) (algorithms.py:947) on channels-last tensors."""
+    import torch.nn.functional as F
+
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape[0], shape[1], 2 * shape[2], 2 * shape[3], generator=g).to(dev)
+    xa = x.clone().requires_grad_()
+    xb = x.clone().requires_grad_()
+    ya = F.interpolate(xa, scale_factor=2, mode="bilinear", align_corners=False)
+    yb = wb.upsample2x(xb)
+    assert yb.shape == ya.shape and yb.is_contiguous(memory_format=torch.channels_last)
+    assert float((ya - yb).abs().max()) <= 1e-6 * max(float(ya.abs().max()), 1.0)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert float((xa.grad - xb.grad).abs().max()) <= 2e-6 * max(float(xa.grad.abs().max()), 1.0)
+    with pytest.raises(ValueError):
+        wb.upsample2x(torch.randn(2, 6, 4, 4, device=dev))               # C % 4 != 0 / not channels-last

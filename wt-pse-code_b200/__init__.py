@@ -8,7 +8,7 @@ from . import _build, _lib  # noqa: F401
 from .functional import (HostPlan, gram_matrix, kd_mse, relu_whitening_folded, relu_whitening_terms,  # noqa: F401
                          whitening_folded, whitening_terms)
 from .mmd import mmd_penalty  # noqa: F401
-from .elementwise import attention_fuse, od_roi, prepare_batch  # noqa: F401
+from .elementwise import attention_fuse, od_roi, prepare_batch, upsample2x  # noqa: F401
 from .wavelet import dwt2d, idwt2d, wavelet_shape_loss  # noqa: F401
 from . import dropin  # noqa: F401
 from . import dp, segmentation, synthetic, train_step  # noqa: F401

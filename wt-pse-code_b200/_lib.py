@@ -31,6 +31,7 @@ EXPORTS = {
     "wtpse_whitening_relu_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                  _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
                                                  _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_upsample2x_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
     "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_size_t, _c.c_void_p]),

@@ -329,6 +329,17 @@ int wtpse_attention_fuse_backward(const float* grad_fuse, const float* emb, cons
     return WTPSE_OK;
 }
 
+int wtpse_upsample2x_nhwc(const float* in, float* out, int64_t N, int H, int W, int C, int adjoint, wtpse_stream_t stream) {
+    if (!in || !out) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 4) != 0) return fail(WTPSE_ERR_INVALID, "need N, H, W >= 1 and C a positive multiple of 4 (got C=%d)", C);
+    if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernUpsample, s); e = launch_upsample2x_nhwc(in, out, N, H, W, C, adjoint != 0, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "upsample launch");
+    return WTPSE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Track W: wavelet transform + L1 detail loss (parity unpinned, see include/wtpse_b200.h)
 // ---------------------------------------------------------------------------------------------

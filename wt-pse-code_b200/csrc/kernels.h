@@ -96,6 +96,10 @@ cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, c
                             int B, int Ce, long long P, float* d_emb, float* d_zp, float* d_wb, double* partial, int sm_count,
                             cudaStream_t stream);
 
+// bilinear x2 up-sampling, channels-last (upsample.cu); adjoint = its backward.  H, W are the LOW-resolution sizes.
+cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int H, int W, int C, bool adjoint, int sm_count,
+                                   cudaStream_t stream);
+
 // Track W (wavelet.cu)
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);

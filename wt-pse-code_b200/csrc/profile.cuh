@@ -22,6 +22,7 @@ enum KernelId {
     kKernWaveletBwd,
     kKernGramReduce,      // counted only: timed inside the kKernEpilogueFwd scope
     kKernMmat,            // counted only: timed inside the kKernApply scope
+    kKernUpsample,
     kKernCount
 };
 

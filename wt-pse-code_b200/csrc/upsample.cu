@@ -1,0 +1,138 @@
+// Bilinear x2 up-sampling of the decoder stages, channels-last, forward and adjoint.
+//
+// ConvU.forward (algorithms.py:947: `F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)`) runs 8
+// times per U-Net pass; ATen's NHWC kernel reaches ~0.6 TB/s on it (1.04 ms for 15x32x256x256 -> 512x512, 26 ms of
+// the 242 ms train iteration forward + backward).  The operation is a fixed 2-tap filter per axis:
+//     out[2k]   = 0.25 in[k-1] + 0.75 in[k]      (out[0]    = in[0])
+//     out[2k+1] = 0.75 in[k]   + 0.25 in[k+1]    (out[2n-1] = in[n-1])
+// evaluated exactly in ATen's order, h0*(w0*a + w1*b) + h1*(w0*c + w1*d) with (lambda0, lambda1) = (0.75, 0.25) or
+// (0.25, 0.75) and clamped neighbours, so results agree with F.interpolate to the last bit or two.
+//
+// Layout: x [N][H][W][C] (channels-last memory of an N x C x H x W tensor), C % 4 == 0; a thread owns one 128-bit
+// channel quad of one INPUT pixel: forward reads its 3x3 neighbourhood (L1/L2 hits) and writes the 2x2 output block;
+// the adjoint gathers the 4x4 output-gradient neighbourhood and writes one quad (no atomics, deterministic).
+// HBM-bound: forward 4 + 16 B per input element, backward 16 + 4.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wtpse {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __forceinline__ float4 lerp2(float h0, float h1, float w0, float w1, const float4& a, const float4& b,
+                                        const float4& c, const float4& d) {
+    float4 r;
+    r.x = h0 * (w0 * a.x + w1 * b.x) + h1 * (w0 * c.x + w1 * d.x);
+    r.y = h0 * (w0 * a.y + w1 * b.y) + h1 * (w0 * c.y + w1 * d.y);
+    r.z = h0 * (w0 * a.z + w1 * b.z) + h1 * (w0 * c.z + w1 * d.z);
+    r.w = h0 * (w0 * a.w + w1 * b.w) + h1 * (w0 * c.w + w1 * d.w);
+    return r;
+}
+
+__global__ void __launch_bounds__(kThreads)
+upsample2x_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long N, int H, int W, int C4) {
+    const long long total = N * H * W * C4;
+    const long long C = 4LL * C4;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const int c = int(idx % C4);
+        long long r = idx / C4;
+        const int j = int(r % W); r /= W;
+        const int i = int(r % H);
+        const long long n = r / H;
+        const int im = i > 0 ? i - 1 : 0, ip = i < H - 1 ? i + 1 : H - 1;
+        const int jm = j > 0 ? j - 1 : 0, jp = j < W - 1 ? j + 1 : W - 1;
+        const float* base = x + n * H * W * C + 4 * c;
+        auto at = [&](int ii, int jj) { return ld4(base + ((long long)ii * W + jj) * C); };
+        const float4 a00 = at(im, jm), a01 = at(im, j), a02 = at(im, jp);
+        const float4 a10 = at(i, jm), a11 = at(i, j), a12 = at(i, jp);
+        const float4 a20 = at(ip, jm), a21 = at(ip, j), a22 = at(ip, jp);
+        // even output row/col 2k: source k - 0.25 -> (k-1, k) with lambda (0.25, 0.75); at k == 0 the source clamps to 0:
+        // (0, 1) with lambda (1, 0).  odd 2k+1: source k + 0.25 -> (k, k+1 clamped) with lambda (0.75, 0.25).
+        const float he0 = i > 0 ? 0.25f : 1.0f, he1 = i > 0 ? 0.75f : 0.0f;
+        const float we0 = j > 0 ? 0.25f : 1.0f, we1 = j > 0 ? 0.75f : 0.0f;
+        // operands of the even position at the border: (in[0], in[1]) -- in[1] is `ip` / `jp`
+        const float4 e_r0c0 = i > 0 ? (j > 0 ? a00 : a01) : (j > 0 ? a10 : a11);      // (row0, col0) of the even/even stencil
+        const float4 e_r0c1 = i > 0 ? (j > 0 ? a01 : a02) : (j > 0 ? a11 : a12);
+        const float4 e_r1c0 = i > 0 ? (j > 0 ? a10 : a11) : (j > 0 ? a20 : a21);
+        const float4 e_r1c1 = i > 0 ? (j > 0 ? a11 : a12) : (j > 0 ? a21 : a22);
+        // even row, odd col: rows as above, cols (j, jp) with (0.75, 0.25)
+        const float4 eo_r0c0 = i > 0 ? a01 : a11, eo_r0c1 = i > 0 ? a02 : a12;
+        const float4 eo_r1c0 = i > 0 ? a11 : a21, eo_r1c1 = i > 0 ? a12 : a22;
+        // odd row: rows (i, ip) with (0.75, 0.25)
+        const float4 oe_r0c0 = j > 0 ? a10 : a11, oe_r0c1 = j > 0 ? a11 : a12;
+        const float4 oe_r1c0 = j > 0 ? a20 : a21, oe_r1c1 = j > 0 ? a21 : a22;
+        float* out = y + ((n * 2 * H + 2 * i) * 2 * W + 2 * j) * C + 4 * c;
+        const long long row = 2LL * W * C;
+        *reinterpret_cast<float4*>(out) = lerp2(he0, he1, we0, we1, e_r0c0, e_r0c1, e_r1c0, e_r1c1);
+        *reinterpret_cast<float4*>(out + C) = lerp2(he0, he1, 0.75f, 0.25f, eo_r0c0, eo_r0c1, eo_r1c0, eo_r1c1);
+        *reinterpret_cast<float4*>(out + row) = lerp2(0.75f, 0.25f, we0, we1, oe_r0c0, oe_r0c1, oe_r1c0, oe_r1c1);
+        *reinterpret_cast<float4*>(out + row + C) = lerp2(0.75f, 0.25f, 0.75f, 0.25f, a11, a12, a21, a22);
+    }
+}
+
+// 1-D adjoint weights: input k receives from outputs 2k-1 (0.25), 2k (0.75, or 1 at k == 0), 2k+1 (0.75, or 1 at k == n-1:
+// there in[n-1] is both operands), 2k+2 (0.25); out-of-range outputs contribute nothing.
+__device__ __forceinline__ void adjoint_taps(int k, int n, float (&w)[4]) {
+    w[0] = k > 0 ? 0.25f : 0.f;
+    w[1] = k > 0 ? 0.75f : 1.0f;
+    w[2] = k < n - 1 ? 0.75f : 1.0f;
+    w[3] = k < n - 1 ? 0.25f : 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads)
+upsample2x_nhwc_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, long long N, int H, int W, int C4) {
+    const long long total = N * H * W * C4;
+    const long long C = 4LL * C4;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const int c = int(idx % C4);
+        long long r = idx / C4;
+        const int j = int(r % W); r /= W;
+        const int i = int(r % H);
+        const long long n = r / H;
+        float wr[4], wc[4];
+        adjoint_taps(i, H, wr);
+        adjoint_taps(j, W, wc);
+        const float* base = gy + n * 4 * H * W * C + 4 * c;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int oi = 2 * i - 1 + p;
+            if (oi < 0 || oi >= 2 * H) continue;
+            float4 rowacc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int oj = 2 * j - 1 + q;
+                if (oj < 0 || oj >= 2 * W) continue;
+                const float4 g = ld4(base + ((long long)oi * 2 * W + oj) * C);
+                rowacc.x = fmaf(wc[q], g.x, rowacc.x); rowacc.y = fmaf(wc[q], g.y, rowacc.y);
+                rowacc.z = fmaf(wc[q], g.z, rowacc.z); rowacc.w = fmaf(wc[q], g.w, rowacc.w);
+            }
+            acc.x = fmaf(wr[p], rowacc.x, acc.x); acc.y = fmaf(wr[p], rowacc.y, acc.y);
+            acc.z = fmaf(wr[p], rowacc.z, acc.z); acc.w = fmaf(wr[p], rowacc.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(gx + ((n * H + i) * W + j) * C + 4 * c) = acc;
+    }
+}
+
+int grid_for(long long items, int sm_count) {
+    long long b = (items + kThreads - 1) / kThreads;
+    const long long cap = 16LL * sm_count;
+    if (b > cap) b = cap;
+    return int(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int H, int W, int C, bool adjoint, int sm_count,
+                                   cudaStream_t stream) {
+    const long long items = N * H * W * (C / 4);
+    if (adjoint) upsample2x_nhwc_bwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, out, N, H, W, C / 4);
+    else upsample2x_nhwc_fwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, out, N, H, W, C / 4);
+    return cudaGetLastError();
+}
+
+}  // namespace wtpse

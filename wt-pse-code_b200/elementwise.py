@@ -3,6 +3,7 @@
   prepare_batch    custom_transforms.py:466-499 + :581-599  (uint8 image / raw mask -> fp32 image, OD/OC labels)
   od_roi           Trainer.py:842-853, 865-867              (threshold, in-place image += 1, ROI image, pos weight)
   attention_fuse   algorithms.py:1243-1249                  (sigmoid(conv1x1(z_post)) gate on the embedding), autograd
+  upsample2x       algorithms.py:947                        (bilinear x2 of the decoder stages, channels-last), autograd
 """
 import torch
 from torch.autograd.function import once_differentiable
@@ -126,3 +127,42 @@ class _AttentionFuse(torch.autograd.Function):
 def attention_fuse(embedding, z_posterior, weight, bias, coef, threshold=0.75):
     """(fuse_embedding, z_posterior_attention_mask) of algorithms.py:1243-1249."""
     return _AttentionFuse.apply(embedding, z_posterior, weight, bias, coef, threshold)
+
+
+def upsample2x_supported(x):
+    """True if `x` can take the channels-last x2 kernel: CUDA float32, 4-D, C % 4 == 0, dense channels-last memory."""
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0
+            and x.numel() > 0 and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _upsample2x_call(t, N, H, W, C, adjoint):
+    """H, W: low-resolution sizes.  Returns a channels-last N x C x (2H | H) x (2W | W) tensor."""
+    lib = _lib.load()
+    oh, ow = (H, W) if adjoint else (2 * H, 2 * W)
+    with torch.cuda.device(t.device):
+        out = torch.empty((N, C, oh, ow), dtype=torch.float32, device=t.device, memory_format=torch.channels_last)
+        _lib.check(lib.wtpse_upsample2x_nhwc(_ptr(t), _ptr(out), N, H, W, C, 1 if adjoint else 0, _stream_ptr(t.device)))
+    return out
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        if not upsample2x_supported(x):
+            raise ValueError("upsample2x needs a CUDA float32 channels-last N x C x H x W tensor with C % 4 == 0")
+        N, C, H, W = x.shape
+        ctx.dims = (N, C, H, W)
+        return _upsample2x_call(x, N, H, W, C, False)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        N, C, H, W = ctx.dims
+        g = g.contiguous(memory_format=torch.channels_last)
+        return _upsample2x_call(g, N, H, W, C, True)
+
+
+def upsample2x(x):
+    """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) for a channels-last tensor
+    (ConvU.forward, algorithms.py:947), forward and backward as one-pass CUDA kernels."""
+    return _Upsample2x.apply(x)

@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as wf
-from .elementwise import attention_fuse
+from .elementwise import attention_fuse, upsample2x, upsample2x_supported
 
 BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
 
@@ -63,6 +63,14 @@ def _conv_bn(conv, bn, x, fold):
     bn.running_mean.copy_(shifted_mean + b)
     bn.num_batches_tracked.add_(1)
     return out
+
+
+def set_cuda_upsample(module, on=True):
+    """Decoder stages below `module` up-sample with the channels-last CUDA kernel when their input allows it."""
+    for m in module.modules():
+        if hasattr(m, "cuda_upsample"):
+            m.cuda_upsample = bool(on)
+    return module
 
 
 def set_conv_bias_folding(module, on=True):
@@ -104,11 +112,15 @@ class ConvU(nn.Module):
         self.conv2, self.bn2 = nn.Conv2d(planes, planes // 2, 1), _norm(planes // 2)
         self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
         self.fold_bias = False
+        self.cuda_upsample = False        # TrainStep: channels-last x2 kernel instead of ATen's (elementwise.upsample2x)
 
     def forward(self, x, skip):
         if not self.first:
             x = F.relu(_conv_bn(self.conv1, self.bn1, x, self.fold_bias), inplace=True)
-        x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        if self.cuda_upsample and upsample2x_supported(x):
+            x = upsample2x(x)
+        else:
+            x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
         x = F.relu(_conv_bn(self.conv2, self.bn2, x, self.fold_bias), inplace=True)
         x = torch.cat([skip, x], 1)
         return F.relu(_conv_bn(self.conv3, self.bn3, x, self.fold_bias), inplace=True)
