@@ -109,6 +109,13 @@ int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const 
  */
 int wtpse_upsample2x_nhwc(const float* in, float* out, int64_t N, int H, int W, int C, int adjoint, wtpse_stream_t stream);
 
+/*
+ * Convolution bias (+ ReLU) pass of the backbone blocks that have no BatchNorm (DoubleConvWT algorithms.py:416-428, the
+ * 1x1 heads :1019-1030, :1176-1183): y[p][c] = act(y[p][c] + bias[c]) IN PLACE on a channels-last activation of npix
+ * pixels x C channels; relu != 0 applies max(., 0) with NaN propagating (ATen's clamp_min).  C % 4 == 0, 16-byte aligned.
+ */
+int wtpse_bias_act_nhwc(float* y, const float* bias, int64_t npix, int C, int relu, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

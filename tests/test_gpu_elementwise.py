@@ -136,3 +136,34 @@ def test_upsample2x_matches_aten_bilinear_forward_and_backward(shape):
     assert float((xa.grad - xb.grad).abs().max()) <= 2e-6 * max(float(xa.grad.abs().max()), 1.0)
     with pytest.raises(ValueError):
         wb.upsample2x(torch.randn(2, 6, 4, 4, device=dev))               # C % 4 != 0 / not channels-last
+
+
+def test_conv_bias_act_matches_the_plain_sequential():
+    """_ConvActSeq.fast_bias (TrainStep): DoubleConvWT (algorithms.py:416-428) and the 1x1 heads (:1019-1030) with the bias
+    (+ ReLU) pass as one in-place kernel: same outputs (bit-exact: the same fp32 add and max) and the same gradients."""
+    import copy
+
+    from wtpse_b200 import segmentation as seg
+
+    dev = torch.device("cuda:0")
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(2)
+        for make, cin in ((lambda: seg._DoubleConvWT(4, 16), 4), (lambda: seg._head(32, 8, 1), 32)):
+            m0 = make().to(dev).to(memory_format=torch.channels_last)
+            x = torch.randn(3, cin, 24, 20, device=dev).contiguous(memory_format=torch.channels_last)
+            res = []
+            for fast in (False, True):
+                m = seg.set_fast_bias(copy.deepcopy(m0), fast)
+                xx = x.clone().requires_grad_()
+                y = m(xx)
+                (y * torch.linspace(-1, 1, y.numel(), device=dev).view_as(y)).sum().backward()
+                res.append((y.detach(), xx.grad, [p.grad.clone() for p in m.parameters()]))
+            assert torch.equal(res[0][0], res[1][0])
+            assert float((res[0][1] - res[1][1]).abs().max()) <= 1e-5 * float(res[0][1].abs().max())
+            for a, b in zip(res[0][2], res[1][2]):
+                assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-6)
+        assert list(seg._head(32, 8, 1).state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias"]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

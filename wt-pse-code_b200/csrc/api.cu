@@ -340,6 +340,17 @@ int wtpse_upsample2x_nhwc(const float* in, float* out, int64_t N, int H, int W, 
     return WTPSE_OK;
 }
 
+int wtpse_bias_act_nhwc(float* y, const float* bias, int64_t npix, int C, int relu, wtpse_stream_t stream) {
+    if (!y || !bias) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (npix <= 0 || C <= 0 || (C % 4) != 0) return fail(WTPSE_ERR_INVALID, "need npix >= 1 and C a positive multiple of 4 (got C=%d)", C);
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15u) return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernUpsample, s); e = launch_bias_act_nhwc(y, bias, npix, C, relu != 0, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "bias_act launch");
+    return WTPSE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Track W: wavelet transform + L1 detail loss (parity unpinned, see include/wtpse_b200.h)
 // ---------------------------------------------------------------------------------------------

@@ -100,6 +100,9 @@ cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, c
 cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int H, int W, int C, bool adjoint, int sm_count,
                                    cudaStream_t stream);
 
+// y = act(y + bias[c]) in place on a channels-last tensor of npix pixels x C channels (upsample.cu)
+cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, int C, bool relu, int sm_count, cudaStream_t stream);
+
 // Track W (wavelet.cu)
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);

@@ -25,7 +25,7 @@ constexpr size_t kMaxPairs = 1 << 16;
 const char* kNames[kKernCount] = {"gram_tma_kernel", "whiten_epilogue_fwd_kernel", "whiten_epilogue_bwd_kernel",
                                   "apply_tma_kernel", "mmd_fwd_kernel", "mmd_bwd_kernel", "mse_fwd_kernels",
                                   "mse_bwd_kernel", "fuse_kernels", "label_kernels", "wavelet_fwd_kernels",
-                                  "wavelet_bwd_kernels", "gram_reduce_kernel", "whiten_mmat_kernel", "upsample2x_kernels"};
+                                  "wavelet_bwd_kernels", "gram_reduce_kernel", "whiten_mmat_kernel", "backbone_elementwise_kernels"};
 
 thread_local Pair t_open = {nullptr, nullptr, -1};
 

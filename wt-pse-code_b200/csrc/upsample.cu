@@ -1,4 +1,5 @@
-// Bilinear x2 up-sampling of the decoder stages, channels-last, forward and adjoint.
+// Channels-last element-wise kernels of the U-Net backbone's train step: bilinear x2 up-sampling of the decoder stages
+// (forward and adjoint) and the convolution bias (+ ReLU) pass.
 //
 // ConvU.forward (algorithms.py:947: `F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)`) runs 8
 // times per U-Net pass; ATen's NHWC kernel reaches ~0.6 TB/s on it (1.04 ms for 15x32x256x256 -> 512x512, 26 ms of
@@ -118,6 +119,24 @@ upsample2x_nhwc_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx,
     }
 }
 
+// y[n][h][w][c] = act(y + bias[c]) in place, channels-last, C % 4 == 0: the bias add ATen runs as a separate broadcast
+// `add_` after a cuDNN convolution (non-vectorised for channels-last operands: ~3 TB/s of traffic), merged with the
+// ReLU that follows it in the 1x1 heads and the DeepWT blocks (algorithms.py:416-428, 1019-1030): one pass instead of two.
+__global__ void __launch_bounds__(kThreads)
+bias_act_nhwc_kernel(float* __restrict__ y, const float* __restrict__ bias, long long npix, int C4, int relu) {
+    const long long total = npix * C4;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const int c = int(idx % C4);
+        const float4 b = ld4(bias + 4 * c);
+        float4 v = reinterpret_cast<float4*>(y)[idx];
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (relu) {          // ATen's relu is clamp_min(0): NaN propagates
+            v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y; v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
+        }
+        reinterpret_cast<float4*>(y)[idx] = v;
+    }
+}
+
 int grid_for(long long items, int sm_count) {
     long long b = (items + kThreads - 1) / kThreads;
     const long long cap = 16LL * sm_count;
@@ -132,6 +151,11 @@ cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int
     const long long items = N * H * W * (C / 4);
     if (adjoint) upsample2x_nhwc_bwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, out, N, H, W, C / 4);
     else upsample2x_nhwc_fwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, out, N, H, W, C / 4);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, int C, bool relu, int sm_count, cudaStream_t stream) {
+    bias_act_nhwc_kernel<<<grid_for(npix * (C / 4), sm_count), kThreads, 0, stream>>>(y, bias, npix, C / 4, relu ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -4,6 +4,7 @@
   od_roi           Trainer.py:842-853, 865-867              (threshold, in-place image += 1, ROI image, pos weight)
   attention_fuse   algorithms.py:1243-1249                  (sigmoid(conv1x1(z_post)) gate on the embedding), autograd
   upsample2x       algorithms.py:947                        (bilinear x2 of the decoder stages, channels-last), autograd
+  conv_bias_act    algorithms.py:416-428, 1019-1030         (convolution bias + ReLU in one in-place pass, channels-last), autograd
 """
 import torch
 from torch.autograd.function import once_differentiable
@@ -166,3 +167,42 @@ def upsample2x(x):
     """F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False) for a channels-last tensor
     (ConvU.forward, algorithms.py:947), forward and backward as one-pass CUDA kernels."""
     return _Upsample2x.apply(x)
+
+
+class _BiasAct(torch.autograd.Function):
+    """y (a bias-free convolution output, dense channels-last) -> act(y + bias), in place."""
+
+    @staticmethod
+    def forward(ctx, y, bias, relu):
+        N, C, H, W = y.shape
+        lib = _lib.load()
+        with torch.cuda.device(y.device):
+            _lib.check(lib.wtpse_bias_act_nhwc(_ptr(y), _ptr(bias), N * H * W, C, 1 if relu else 0, _stream_ptr(y.device)))
+        ctx.mark_dirty(y)
+        ctx.relu = bool(relu)
+        if relu:
+            ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            g = torch.ops.aten.threshold_backward(g, out, 0)          # what ReluBackward0 runs
+        return g, (g.sum((0, 2, 3)) if ctx.needs_input_grad[1] else None), None
+
+
+def conv_bias_act(conv, x, relu):
+    """relu(conv(x)) or conv(x) for an nn.Conv2d with a bias: cuDNN convolution without the bias, then ONE in-place pass
+    for bias (+ ReLU) instead of ATen's broadcast `add_` followed by a separate `relu_`.  Falls back to the plain
+    operators when the output is not a dense channels-last CUDA float32 tensor with C % 4 == 0."""
+    F = torch.nn.functional
+    if (conv.bias is None or not x.is_cuda or x.dtype != torch.float32 or conv.out_channels % 4 != 0
+            or conv.bias.data_ptr() % 16 != 0):
+        y = conv(x)
+        return F.relu(y, inplace=True) if relu else y
+    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if not (y.is_contiguous(memory_format=torch.channels_last) and y.data_ptr() % 16 == 0):
+        y = y + conv.bias.view(1, -1, 1, 1)
+        return F.relu(y, inplace=True) if relu else y
+    return _BiasAct.apply(y, conv.bias, relu)

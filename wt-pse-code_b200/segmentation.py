@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as wf
-from .elementwise import attention_fuse, upsample2x, upsample2x_supported
+from .elementwise import attention_fuse, conv_bias_act, upsample2x, upsample2x_supported
 
 BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
 
@@ -63,6 +63,36 @@ def _conv_bn(conv, bn, x, fold):
     bn.running_mean.copy_(shifted_mean + b)
     bn.num_batches_tracked.add_(1)
     return out
+
+
+class _ConvActSeq(nn.Sequential):
+    """nn.Sequential of Conv2d / ReLU layers (same state-dict keys).  With ``fast_bias`` (TrainStep) every convolution
+    runs without its bias and one in-place kernel applies bias (+ the ReLU that follows it): elementwise.conv_bias_act."""
+
+    fast_bias = False
+
+    def forward(self, x):
+        if not self.fast_bias:
+            return super().forward(x)
+        mods = list(self)
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Conv2d):
+                relu = i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU)
+                x = conv_bias_act(m, x, relu)
+                i += 2 if relu else 1
+            else:
+                x = m(x)
+                i += 1
+        return x
+
+
+def set_fast_bias(module, on=True):
+    for m in module.modules():
+        if isinstance(m, _ConvActSeq):
+            m.fast_bias = bool(on)
+    return module
 
 
 def set_cuda_upsample(module, on=True):
@@ -166,8 +196,8 @@ class _DoubleConvWT(nn.Module):
 
     def __init__(self, cin, cout):
         super().__init__()
-        self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(inplace=True),
-                                         nn.Conv2d(cout, cout, 3, padding=1))
+        self.double_conv = _ConvActSeq(nn.Conv2d(cin, cout, 3, padding=1), nn.ReLU(inplace=True),
+                                       nn.Conv2d(cout, cout, 3, padding=1))
 
     def forward(self, x):
         return self.double_conv(x)
@@ -239,7 +269,7 @@ def fused_terms(z, arity):
 
 
 def _head(cin, mid, cout):
-    return nn.Sequential(nn.Conv2d(cin, cin, 1), nn.ReLU(), nn.Conv2d(cin, mid, 1), nn.ReLU(), nn.Conv2d(mid, cout, 1))
+    return _ConvActSeq(nn.Conv2d(cin, cin, 1), nn.ReLU(), nn.Conv2d(cin, mid, 1), nn.ReLU(), nn.Conv2d(mid, cout, 1))
 
 
 class ShapeVariationalDist_y_x(_UNetTrunk):
@@ -252,7 +282,7 @@ class ShapeVariationalDist_y_x(_UNetTrunk):
         n = BASE_WIDTH
         if self.wt:
             self.inc = _DoubleConv(n_channels, n)
-            self.fusion = nn.Sequential(nn.Conv2d(2 * n, n, 1), nn.ReLU())
+            self.fusion = _ConvActSeq(nn.Conv2d(2 * n, n, 1), nn.ReLU())
         else:
             self.inc = _DoubleConv(n_channels + 1, n)
         self._build_trunk(n)
@@ -322,7 +352,7 @@ class WT_PSE(_UNetTrunk):
                                                        prior=True, number_source_domain=source_domain_num)
             if self.cat_shape:
                 fuse_dim = feature_dim + 1
-        self.mu = nn.Sequential(nn.Conv2d(2 * n, 2 * n, 1), nn.ReLU(), nn.Conv2d(2 * n, feature_dim, 1))
+        self.mu = _ConvActSeq(nn.Conv2d(2 * n, 2 * n, 1), nn.ReLU(), nn.Conv2d(2 * n, feature_dim, 1))
         self.outc = nn.Sequential(nn.Conv2d(fuse_dim, n_classes, 1))
         self.attention_layer = attention_layer(1, 1)
 
