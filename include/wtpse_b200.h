@@ -116,6 +116,15 @@ int wtpse_upsample2x_nhwc(const float* in, float* out, int64_t N, int H, int W, 
  */
 int wtpse_bias_act_nhwc(float* y, const float* bias, int64_t npix, int C, int relu, wtpse_stream_t stream);
 
+/*
+ * Bias gradient of a backbone convolution: out[c] = sum over the npix pixels of g[p][c] (`grad.sum((0, 2, 3))`, what
+ * aten::convolution_backward reduces for Conv2d.bias) on a channels-last gradient.  C a power of two in [4, 1024];
+ * two deterministic stages, no atomics.
+ */
+size_t wtpse_channel_sum_workspace_bytes(int64_t npix, int C);
+int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out,
+                           void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

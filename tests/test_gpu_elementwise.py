@@ -167,3 +167,17 @@ def test_conv_bias_act_matches_the_plain_sequential():
         assert list(seg._head(32, 8, 1).state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias"]
     finally:
         torch.backends.cudnn.allow_tf32 = old
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 1, 1), (2, 8, 5, 7), (3, 16, 33, 17), (15, 32, 64, 64), (2, 256, 9, 9), (1, 1024, 3, 2)])
+def test_channel_sum_matches_aten(shape):
+    from wtpse_b200.elementwise import channel_sum
+
+    dev = torch.device("cuda:0")
+    g = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape))).to(dev).contiguous(memory_format=torch.channels_last)
+    got, want = channel_sum(g), g.double().sum((0, 2, 3))
+    assert got.shape == (shape[1],) and got.dtype == torch.float32
+    assert float((got.double() - want).abs().max()) <= 1e-5 * max(float(g.double().abs().sum((0, 2, 3)).max()), 1.0)
+    assert torch.equal(channel_sum(g), got)                                  # deterministic
+    odd = torch.randn(2, 6, 4, 4, device=dev)
+    assert torch.allclose(channel_sum(odd), odd.sum((0, 2, 3)))             # ATen route for other shapes/layouts

@@ -33,6 +33,8 @@ EXPORTS = {
                                                  _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_upsample2x_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "wtpse_bias_act_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p]),
+    "wtpse_channel_sum_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int]),
+    "wtpse_channel_sum_nhwc": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
     "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_size_t, _c.c_void_p]),

@@ -351,6 +351,24 @@ int wtpse_bias_act_nhwc(float* y, const float* bias, int64_t npix, int C, int re
     return WTPSE_OK;
 }
 
+size_t wtpse_channel_sum_workspace_bytes(int64_t npix, int C) {
+    if (npix <= 0 || !channel_sum_supported(C)) return 0;
+    return align_up(size_t(channel_sum_blocks(npix, C, sm_count_cached())) * C * sizeof(float), 256);
+}
+
+int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out, void* workspace, size_t workspace_bytes,
+                           wtpse_stream_t stream) {
+    if (!g || !out || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (npix <= 0 || !channel_sum_supported(C)) return fail(WTPSE_ERR_INVALID, "need npix >= 1 and C in {4, 8, 16, ..., 1024} (got C=%d)", C);
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(workspace)) & 15u) return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (workspace_bytes < wtpse_channel_sum_workspace_bytes(npix, C)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernUpsample, s); e = launch_channel_sum_nhwc(g, npix, C, out, static_cast<float*>(workspace), sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "channel_sum launch");
+    return WTPSE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Track W: wavelet transform + L1 detail loss (parity unpinned, see include/wtpse_b200.h)
 // ---------------------------------------------------------------------------------------------

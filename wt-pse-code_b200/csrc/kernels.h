@@ -103,6 +103,12 @@ cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int
 // y = act(y + bias[c]) in place on a channels-last tensor of npix pixels x C channels (upsample.cu)
 cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, int C, bool relu, int sm_count, cudaStream_t stream);
 
+// out[c] = sum_p g[p][c] on a channels-last tensor (a convolution's bias gradient); partial: channel_sum_blocks * C floats
+int channel_sum_blocks(long long npix, int C, int sm_count);
+bool channel_sum_supported(int C);
+cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float* out, float* partial, int sm_count,
+                                    cudaStream_t stream);
+
 // Track W (wavelet.cu)
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);

@@ -137,6 +137,56 @@ bias_act_nhwc_kernel(float* __restrict__ y, const float* __restrict__ bias, long
     }
 }
 
+// out[c] = sum over pixels of g[p][c] (channels-last): the bias gradient of a convolution, `g.sum((0, 2, 3))`.
+// Two deterministic stages: every CTA sums a contiguous pixel range per channel (thread t owns channel quad t % C4,
+// 128-bit loads, fixed-order shared-memory tree), then one CTA adds the per-CTA partials in index order.
+__global__ void __launch_bounds__(kThreads)
+channel_sum_partial_kernel(const float* __restrict__ g, long long npix, int C4, float* __restrict__ partial) {
+    __shared__ float4 red[kThreads];
+    const int tid = threadIdx.x;
+    const int lanes = kThreads / C4;                 // pixels in flight per CTA iteration (C4 divides 256)
+    const int q = tid % C4, r = tid / C4;
+    const long long per = (npix + gridDim.x - 1) / gridDim.x;
+    const long long p0 = (long long)blockIdx.x * per;
+    const long long p1 = p0 + per < npix ? p0 + per : npix;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    long long p = p0 + r;
+    for (; p + lanes < p1; p += 2 * lanes) {        // two independent accumulators: two loads in flight
+        const float4 v0 = ld4(g + (p * C4 + q) * 4), v1 = ld4(g + ((p + lanes) * C4 + q) * 4);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+    }
+    if (p < p1) {
+        const float4 v0 = ld4(g + (p * C4 + q) * 4);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    }
+    red[tid] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    __syncthreads();
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+        if (r < s) {
+            const float4 o = red[tid + s * C4];
+            float4 m = red[tid];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[tid] = m;
+        }
+        __syncthreads();
+    }
+    if (r == 0) reinterpret_cast<float4*>(partial)[(long long)blockIdx.x * C4 + q] = red[tid];
+}
+
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int b = 0;
+    for (; b + 3 < nblocks; b += 4) {
+        s0 += partial[(long long)b * C + c]; s1 += partial[(long long)(b + 1) * C + c];
+        s2 += partial[(long long)(b + 2) * C + c]; s3 += partial[(long long)(b + 3) * C + c];
+    }
+    for (; b < nblocks; ++b) s0 += partial[(long long)b * C + c];
+    out[c] = (s0 + s1) + (s2 + s3);
+}
+
 int grid_for(long long items, int sm_count) {
     long long b = (items + kThreads - 1) / kThreads;
     const long long cap = 16LL * sm_count;
@@ -156,6 +206,24 @@ cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int
 
 cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, int C, bool relu, int sm_count, cudaStream_t stream) {
     bias_act_nhwc_kernel<<<grid_for(npix * (C / 4), sm_count), kThreads, 0, stream>>>(y, bias, npix, C / 4, relu ? 1 : 0);
+    return cudaGetLastError();
+}
+
+int channel_sum_blocks(long long npix, int C, int sm_count) {
+    const long long lanes = kThreads / (C / 4);
+    long long b = (npix + lanes - 1) / lanes;        // at least one pixel per thread row
+    const long long cap = 2LL * sm_count;
+    if (b > cap) b = cap;
+    return int(b < 1 ? 1 : b);
+}
+
+bool channel_sum_supported(int C) { return C >= 4 && C <= 4 * kThreads && (C % 4) == 0 && (kThreads % (C / 4)) == 0; }
+
+cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float* out, float* partial, int sm_count,
+                                    cudaStream_t stream) {
+    const int blocks = channel_sum_blocks(npix, C, sm_count);
+    channel_sum_partial_kernel<<<blocks, kThreads, 0, stream>>>(g, npix, C / 4, partial);
+    channel_sum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, blocks, C, out);
     return cudaGetLastError();
 }
 

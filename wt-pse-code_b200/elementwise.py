@@ -169,6 +169,23 @@ def upsample2x(x):
     return _Upsample2x.apply(x)
 
 
+def channel_sum(g):
+    """g.sum((0, 2, 3)) -- a convolution's bias gradient.  Dense channels-last CUDA float32 gradients with a power-of-two
+    channel count take the two-stage CUDA reduction; anything else goes to ATen (this is the backbone, not the loss path)."""
+    C = g.shape[1] if g.dim() == 4 else 0
+    if not (g.is_cuda and g.dtype == torch.float32 and g.dim() == 4 and 4 <= C <= 1024 and (C & (C - 1)) == 0
+            and g.is_contiguous(memory_format=torch.channels_last) and g.data_ptr() % 16 == 0):
+        return g.sum((0, 2, 3))
+    N, _, H, W = g.shape
+    lib = _lib.load()
+    with torch.cuda.device(g.device):
+        ws_bytes = lib.wtpse_channel_sum_workspace_bytes(N * H * W, C)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+        out = torch.empty(C, dtype=torch.float32, device=g.device)
+        _lib.check(lib.wtpse_channel_sum_nhwc(_ptr(g), N * H * W, C, _ptr(out), _ptr(ws), ws_bytes, _stream_ptr(g.device)))
+    return out
+
+
 class _BiasAct(torch.autograd.Function):
     """y (a bias-free convolution output, dense channels-last) -> act(y + bias), in place."""
 
@@ -189,7 +206,7 @@ class _BiasAct(torch.autograd.Function):
         if ctx.relu:
             (out,) = ctx.saved_tensors
             g = torch.ops.aten.threshold_backward(g, out, 0)          # what ReluBackward0 runs
-        return g, (g.sum((0, 2, 3)) if ctx.needs_input_grad[1] else None), None
+        return g, (channel_sum(g) if ctx.needs_input_grad[1] else None), None
 
 
 def conv_bias_act(conv, x, relu):

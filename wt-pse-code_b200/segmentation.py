@@ -24,7 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as wf
-from .elementwise import attention_fuse, conv_bias_act, upsample2x, upsample2x_supported
+from .elementwise import attention_fuse, channel_sum, conv_bias_act, upsample2x, upsample2x_supported
 
 BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
 
@@ -43,7 +43,7 @@ class _PhantomBias(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g, (g.sum((0, 2, 3)) if ctx.needs_input_grad[1] else None)
+        return g, (channel_sum(g) if ctx.needs_input_grad[1] else None)
 
 
 def _conv_bn(conv, bn, x, fold):
