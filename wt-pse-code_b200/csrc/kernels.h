@@ -96,11 +96,11 @@ cudaError_t launch_fuse_bwd(const float* g, const float* emb, const float* zp, c
                             int B, int Ce, long long P, float* d_emb, float* d_zp, float* d_wb, double* partial, int sm_count,
                             cudaStream_t stream);
 
-// bilinear x2 up-sampling, channels-last (upsample.cu); adjoint = its backward.  H, W are the LOW-resolution sizes.
+// bilinear x2 up-sampling, channels-last (backbone_elementwise.cu); adjoint = its backward.  H, W are the LOW-resolution sizes.
 cudaError_t launch_upsample2x_nhwc(const float* in, float* out, long long N, int H, int W, int C, bool adjoint, int sm_count,
                                    cudaStream_t stream);
 
-// y = act(y + bias[c]) in place on a channels-last tensor of npix pixels x C channels (upsample.cu)
+// y = act(y + bias[c]) in place on a channels-last tensor of npix pixels x C channels (backbone_elementwise.cu)
 cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, int C, bool relu, int sm_count, cudaStream_t stream);
 
 // out[c] = sum_p g[p][c] on a channels-last tensor (a convolution's bias gradient); partial: channel_sum_blocks * C floats
