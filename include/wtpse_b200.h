@@ -125,6 +125,25 @@ size_t wtpse_channel_sum_workspace_bytes(int64_t npix, int C);
 int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out,
                            void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/*
+ * Training-mode nn.BatchNorm2d followed (relu != 0) by ReLU, on a channels-last activation of npix pixels x C channels
+ * -- the conv -> bn -> relu stages of ConvD / ConvU / DoubleConv (algorithms.py:877-962, 398-413).
+ *   forward : batch mean / biased variance per channel, y = relu?((x - mean) * gamma / sqrt(var + eps) + beta);
+ *             running_mean = (1 - momentum) * running_mean + momentum * (mean + mean_shift)   (mean_shift NULL == 0: the bias of
+ *             the preceding convolution when its add was folded away), running_var likewise with the UNBIASED variance
+ *             (torch.nn.BatchNorm2d semantics; either may be NULL);  save_stats[3][C] = mean, invstd, gamma * invstd.
+ *   backward: dx, dgamma, dbeta of that composite given dy (gradient of y); the ReLU mask is recomputed from x.
+ * C a power of two in [4, 1024]; gamma and beta required; all pointers 16-byte aligned; deterministic (no atomics).
+ */
+size_t wtpse_batchnorm_workspace_bytes(int64_t npix, int C);
+int wtpse_batchnorm_relu_forward(const float* x, int64_t npix, int C, const float* gamma, const float* beta,
+                                 const float* mean_shift, float eps, float momentum, int relu,
+                                 float* running_mean, float* running_var, float* y, float* save_stats,
+                                 void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+int wtpse_batchnorm_relu_backward(const float* x, const float* dy, int64_t npix, int C, const float* gamma, const float* beta,
+                                  const float* save_stats, int relu, float* dx, float* dgamma, float* dbeta,
+                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

@@ -181,3 +181,50 @@ def test_channel_sum_matches_aten(shape):
     assert torch.equal(channel_sum(g), got)                                  # deterministic
     odd = torch.randn(2, 6, 4, 4, device=dev)
     assert torch.allclose(channel_sum(odd), odd.sum((0, 2, 3)))             # ATen route for other shapes/layouts
+
+
+@pytest.mark.parametrize("shape,relu,offset", [((2, 4, 3, 5), True, 0.0), ((3, 16, 33, 17), True, 0.5), ((15, 32, 64, 64), False, 0.0),
+                                                ((4, 256, 8, 8), True, -1.0), ((2, 64, 40, 24), True, 50.0), ((1, 1024, 2, 2), False, 0.0)])
+def test_batch_norm_act_matches_torch(shape, relu, offset):
+    """Training BatchNorm2d (+ ReLU) kernels against torch in float64: output, running statistics (incl. the folded-bias
+    shift of the running mean), dx / dgamma / dbeta.  offset = 50 with std 0.1: the shifted-data variance must not cancel."""
+    import torch.nn.functional as F
+
+    from wtpse_b200.elementwise import batch_norm_act, batch_norm_act_supported
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(sum(shape))
+    N, C, H, W = shape
+    std = 0.1 if offset == 50.0 else 1.0
+    x = (std * torch.randn(*shape, generator=gen) + offset + torch.randn(1, C, 1, 1, generator=gen) * std).to(dev)
+    x = x.contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(*shape, generator=gen).to(dev).contiguous(memory_format=torch.channels_last)
+    bn = torch.nn.BatchNorm2d(C).to(dev).train()
+    bn.weight.data.uniform_(0.5, 1.5, generator=None)
+    bn.bias.data.normal_(0, 0.3)
+    bn.running_mean.normal_(0, 1)
+    bn.running_var.uniform_(0.5, 2.0)
+    shift = torch.randn(C, device=dev)
+    ref_rm = (0.9 * bn.running_mean.double() + 0.1 * (x.double().mean((0, 2, 3)) + shift.double()))
+    ref_rv = (0.9 * bn.running_var.double() + 0.1 * x.double().var((0, 2, 3), unbiased=True)) if N * H * W > 1 else None
+    assert batch_norm_act_supported(x, bn)
+
+    xd = x.double().requires_grad_()
+    wd, bd = bn.weight.detach().double().requires_grad_(), bn.bias.detach().double().requires_grad_()
+    yd = F.batch_norm(xd, None, None, wd, bd, True, 0.1, bn.eps)
+    yd = torch.relu(yd) if relu else yd
+    yd.backward(gy.double())
+
+    xa = x.clone().requires_grad_()
+    ya = batch_norm_act(xa, bn, relu, shift)
+    ya.backward(gy)
+    assert ya.is_contiguous(memory_format=torch.channels_last) and int(bn.num_batches_tracked) == 1
+    tol = 2e-5 if offset != 50.0 else 2e-3          # fp32 input resolution relative to std is 50/0.1 times coarser there
+    assert float((ya.double() - yd).abs().max()) <= tol * max(float(yd.abs().max()), 1.0)
+    assert float((bn.running_mean.double() - ref_rm).abs().max()) <= 1e-5 * max(float(ref_rm.abs().max()), 1.0)
+    if ref_rv is not None:
+        assert float((bn.running_var.double() - ref_rv).abs().max()) <= 1e-4 * float(ref_rv.abs().max())
+    # gradients: a ReLU mask may flip where |y| is at rounding level, so compare norms of the difference
+    for got, want in ((xa.grad, xd.grad), (bn.weight.grad, wd.grad), (bn.bias.grad, bd.grad)):
+        err = float((got.double() - want).norm() / max(float(want.norm()), 1e-12))
+        assert err <= (5e-4 if offset != 50.0 else 2e-2), err

@@ -369,6 +369,54 @@ int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out, void
     return WTPSE_OK;
 }
 
+size_t wtpse_batchnorm_workspace_bytes(int64_t npix, int C) {
+    if (npix <= 0 || !batchnorm_supported(C)) return 0;
+    return align_up(batchnorm_workspace_floats(npix, C, sm_count_cached()) * sizeof(float), 256);
+}
+
+static int check_bn(const void* x, int64_t npix, int C, const void* gamma, const void* beta, const void* ws, size_t ws_bytes) {
+    if (!x || !gamma || !beta || !ws) return fail(WTPSE_ERR_INVALID, "null pointer (affine BatchNorm only)");
+    if (npix <= 0 || !batchnorm_supported(C)) return fail(WTPSE_ERR_INVALID, "need npix >= 1 and C a power of two in [4, 1024] (got C=%d)", C);
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta) | reinterpret_cast<uintptr_t>(ws)) & 15u)
+        return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (ws_bytes < wtpse_batchnorm_workspace_bytes(npix, C)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    return WTPSE_OK;
+}
+
+int wtpse_batchnorm_relu_forward(const float* x, int64_t npix, int C, const float* gamma, const float* beta, const float* mean_shift,
+                                 float eps, float momentum, int relu, float* running_mean, float* running_var, float* y,
+                                 float* save_stats, void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_bn(x, npix, C, gamma, beta, workspace, workspace_bytes)) return rc;
+    if (!y || !save_stats) return fail(WTPSE_ERR_INVALID, "null output pointer");
+    if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(save_stats)) & 15u) return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    {
+        LaunchScope scope(kKernUpsample, s);
+        e = launch_batchnorm_fwd(x, npix, C, gamma, beta, mean_shift, eps, momentum, relu != 0, running_mean, running_var, y, save_stats,
+                                 save_stats + C, save_stats + 2 * C, static_cast<float*>(workspace), sm_count_cached(), s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "batchnorm forward launch");
+    return WTPSE_OK;
+}
+
+int wtpse_batchnorm_relu_backward(const float* x, const float* dy, int64_t npix, int C, const float* gamma, const float* beta,
+                                  const float* save_stats, int relu, float* dx, float* dgamma, float* dbeta, void* workspace,
+                                  size_t workspace_bytes, wtpse_stream_t stream) {
+    if (int rc = check_bn(x, npix, C, gamma, beta, workspace, workspace_bytes)) return rc;
+    if (!dy || !save_stats || !dx) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(save_stats)) & 15u) return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    {
+        LaunchScope scope(kKernUpsample, s);
+        e = launch_batchnorm_bwd(x, dy, npix, C, gamma, beta, save_stats, save_stats + C, save_stats + 2 * C, relu != 0, dx, dgamma, dbeta,
+                                 static_cast<float*>(workspace), sm_count_cached(), s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "batchnorm backward launch");
+    return WTPSE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Track W: wavelet transform + L1 detail loss (parity unpinned, see include/wtpse_b200.h)
 // ---------------------------------------------------------------------------------------------

@@ -109,6 +109,17 @@ bool channel_sum_supported(int C);
 cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float* out, float* partial, int sm_count,
                                     cudaStream_t stream);
 
+// training-mode BatchNorm2d (+ ReLU), channels-last (batchnorm.cu)
+bool batchnorm_supported(int C);
+size_t batchnorm_workspace_floats(long long npix, int C, int sm_count);
+cudaError_t launch_batchnorm_fwd(const float* x, long long npix, int C, const float* gamma, const float* beta,
+                                 const float* mean_shift, float eps, float momentum, bool relu, float* running_mean,
+                                 float* running_var, float* y, float* save_mean, float* save_invstd, float* save_scale,
+                                 float* workspace, int sm_count, cudaStream_t stream);
+cudaError_t launch_batchnorm_bwd(const float* x, const float* dy, long long npix, int C, const float* gamma, const float* beta,
+                                 const float* save_mean, const float* save_invstd, const float* save_scale, bool relu, float* dx,
+                                 float* dgamma, float* dbeta, float* workspace, int sm_count, cudaStream_t stream);
+
 // Track W (wavelet.cu)
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);

@@ -5,6 +5,7 @@
   attention_fuse   algorithms.py:1243-1249                  (sigmoid(conv1x1(z_post)) gate on the embedding), autograd
   upsample2x       algorithms.py:947                        (bilinear x2 of the decoder stages, channels-last), autograd
   conv_bias_act    algorithms.py:416-428, 1019-1030         (convolution bias + ReLU in one in-place pass, channels-last), autograd
+  batch_norm_act   algorithms.py:877-962, 398-413           (training BatchNorm2d + ReLU, channels-last), autograd
 """
 import torch
 from torch.autograd.function import once_differentiable
@@ -223,3 +224,60 @@ def conv_bias_act(conv, x, relu):
         y = y + conv.bias.view(1, -1, 1, 1)
         return F.relu(y, inplace=True) if relu else y
     return _BiasAct.apply(y, conv.bias, relu)
+
+
+def batch_norm_act_supported(x, bn):
+    """Can `bn` (training mode, affine, with running statistics) run on `x` through the channels-last CUDA kernels?"""
+    C = x.shape[1] if x.dim() == 4 else 0
+    return (bn.training and bn.affine and bn.track_running_stats and bn.momentum is not None and x.is_cuda
+            and x.dtype == torch.float32 and x.dim() == 4 and 4 <= C <= 1024 and (C & (C - 1)) == 0 and x.numel() > 0
+            and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0
+            and bn.weight.dtype == torch.float32 and bn.weight.data_ptr() % 16 == 0 and bn.bias.data_ptr() % 16 == 0)
+
+
+class _BatchNormAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, mean_shift, momentum, eps, relu):
+        N, C, H, W = x.shape
+        npix = N * H * W
+        lib = _lib.load()
+        dev = x.device
+        with torch.cuda.device(dev):
+            y = torch.empty_like(x)                                   # preserves the channels-last layout
+            stats = torch.empty(3, C, dtype=torch.float32, device=dev)
+            ws_bytes = lib.wtpse_batchnorm_workspace_bytes(npix, C)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.wtpse_batchnorm_relu_forward(_ptr(x), npix, C, _ptr(weight), _ptr(bias), _ptr(mean_shift), float(eps),
+                                                        float(momentum), 1 if relu else 0, _ptr(running_mean), _ptr(running_var),
+                                                        _ptr(y), _ptr(stats), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.relu, ctx.ws_bytes = bool(relu), ws_bytes
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight, bias, stats = ctx.saved_tensors
+        N, C, H, W = x.shape
+        g = g.contiguous(memory_format=torch.channels_last)
+        lib = _lib.load()
+        dev = x.device
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            dwb = torch.empty(2, C, dtype=torch.float32, device=dev)
+            ws = torch.empty(ctx.ws_bytes, dtype=torch.uint8, device=dev)
+            _lib.check(lib.wtpse_batchnorm_relu_backward(_ptr(x), _ptr(g), N * H * W, C, _ptr(weight), _ptr(bias), _ptr(stats),
+                                                         1 if ctx.relu else 0, _ptr(dx), _ptr(dwb[0]), _ptr(dwb[1]), _ptr(ws),
+                                                         ctx.ws_bytes, _stream_ptr(dev)))
+        return dx, dwb[0], dwb[1], None, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, relu, mean_shift=None):
+    """relu?(bn(x)) for a training-mode nn.BatchNorm2d on a channels-last tensor (check batch_norm_act_supported first).
+    Updates bn.running_mean / running_var / num_batches_tracked like the module; `mean_shift` (a [C] tensor) is added to the
+    mean the running mean tracks -- the bias of the preceding convolution when its add was folded away."""
+    if mean_shift is not None:
+        mean_shift = mean_shift.detach()
+    y = _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, mean_shift, bn.momentum, bn.eps, relu)
+    bn.num_batches_tracked.add_(1)
+    return y

@@ -24,7 +24,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as wf
-from .elementwise import attention_fuse, channel_sum, conv_bias_act, upsample2x, upsample2x_supported
+from .elementwise import (attention_fuse, batch_norm_act, batch_norm_act_supported, channel_sum, conv_bias_act, upsample2x,
+                          upsample2x_supported)
 
 BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
 
@@ -46,23 +47,42 @@ class _PhantomBias(torch.autograd.Function):
         return g, (channel_sum(g) if ctx.needs_input_grad[1] else None)
 
 
-def _conv_bn(conv, bn, x, fold):
-    """bn(conv(x)) in training mode.  With fold=True the convolution's bias add -- a separate pass over the activation in
-    ATen (`add_` with a broadcast [1, C, 1, 1] operand: 25 ms of the 242 ms iteration at 15 x 512 x 512) -- is not
-    executed: batch norm subtracts the batch mean, so bn(y + b) == bn(y) up to rounding.  What the bias does change is
-    kept: the running mean tracks mean(y) + b (shifted by -b before and +b after the update), and the bias still gets
-    the gradient sum autograd would give it (rounding noise, as in the reference)."""
-    if not (fold and bn.training and conv.bias is not None and bn.running_mean is not None and bn.momentum is not None):
-        return bn(conv(x))
-    y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
-    if conv.bias.requires_grad and torch.is_grad_enabled():
-        y = _PhantomBias.apply(y, conv.bias)
-    b = conv.bias.detach()
-    shifted_mean = bn.running_mean - b              # a temporary: batch_norm saves its running-mean argument for backward
-    out = F.batch_norm(y, shifted_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
-    bn.running_mean.copy_(shifted_mean + b)
-    bn.num_batches_tracked.add_(1)
-    return out
+def _conv_bn(conv, bn, x, fold, relu=False, cuda_bn=False):
+    """relu?(bn(conv(x))) in training mode.
+
+    fold=True: the convolution's bias add -- a separate pass over the activation in ATen (`add_` with a broadcast
+    [1, C, 1, 1] operand: 25 ms of the 242 ms iteration at 15 x 512 x 512) -- is not executed: batch norm subtracts the
+    batch mean, so bn(y + b) == bn(y) up to rounding.  What the bias does change is kept: the running mean tracks
+    mean(y) + b, and the bias still gets the gradient sum autograd would give it (rounding noise, as in the reference).
+
+    cuda_bn=True: batch norm and the ReLU run as the channels-last CUDA kernels (elementwise.batch_norm_act) when the
+    convolution output allows it; otherwise cuDNN's batch norm and ATen's in-place ReLU."""
+    foldable = fold and bn.training and conv.bias is not None and bn.running_mean is not None and bn.momentum is not None
+    if foldable:
+        y = F.conv2d(x, conv.weight, None, conv.stride, conv.padding, conv.dilation, conv.groups)
+        if conv.bias.requires_grad and torch.is_grad_enabled():
+            y = _PhantomBias.apply(y, conv.bias)
+    else:
+        y = conv(x)
+    if cuda_bn and batch_norm_act_supported(y, bn):
+        return batch_norm_act(y, bn, relu, conv.bias if foldable else None)
+    if foldable:
+        b = conv.bias.detach()
+        shifted_mean = bn.running_mean - b              # a temporary: batch_norm saves its running-mean argument for backward
+        out = F.batch_norm(y, shifted_mean, bn.running_var, bn.weight, bn.bias, True, bn.momentum, bn.eps)
+        bn.running_mean.copy_(shifted_mean + b)
+        bn.num_batches_tracked.add_(1)
+    else:
+        out = bn(y)
+    return F.relu(out, inplace=True) if relu else out
+
+
+def set_cuda_batchnorm(module, on=True):
+    """conv -> BatchNorm -> ReLU stages below `module` use the channels-last CUDA batch-norm kernels (TrainStep)."""
+    for m in module.modules():
+        if hasattr(m, "cuda_bn"):
+            m.cuda_bn = bool(on)
+    return module
 
 
 class _ConvActSeq(nn.Sequential):
@@ -121,13 +141,14 @@ class ConvD(nn.Module):
         self.conv2, self.bn2 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
         self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
         self.fold_bias = False
+        self.cuda_bn = False
 
     def forward(self, x):
         if not self.first:
             x = F.max_pool2d(x, 2)
-        x = _conv_bn(self.conv1, self.bn1, x, self.fold_bias)                      # no activation after the first conv
-        x = F.relu(_conv_bn(self.conv2, self.bn2, x, self.fold_bias), inplace=True)
-        return F.relu(_conv_bn(self.conv3, self.bn3, x, self.fold_bias), inplace=True)
+        x = _conv_bn(self.conv1, self.bn1, x, self.fold_bias, False, self.cuda_bn)      # no activation after the first conv
+        x = _conv_bn(self.conv2, self.bn2, x, self.fold_bias, True, self.cuda_bn)
+        return _conv_bn(self.conv3, self.bn3, x, self.fold_bias, True, self.cuda_bn)
 
 
 class ConvU(nn.Module):
@@ -142,18 +163,19 @@ class ConvU(nn.Module):
         self.conv2, self.bn2 = nn.Conv2d(planes, planes // 2, 1), _norm(planes // 2)
         self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
         self.fold_bias = False
+        self.cuda_bn = False
         self.cuda_upsample = False        # TrainStep: channels-last x2 kernel instead of ATen's (elementwise.upsample2x)
 
     def forward(self, x, skip):
         if not self.first:
-            x = F.relu(_conv_bn(self.conv1, self.bn1, x, self.fold_bias), inplace=True)
+            x = _conv_bn(self.conv1, self.bn1, x, self.fold_bias, True, self.cuda_bn)
         if self.cuda_upsample and upsample2x_supported(x):
             x = upsample2x(x)
         else:
             x = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
-        x = F.relu(_conv_bn(self.conv2, self.bn2, x, self.fold_bias), inplace=True)
+        x = _conv_bn(self.conv2, self.bn2, x, self.fold_bias, True, self.cuda_bn)
         x = torch.cat([skip, x], 1)
-        return F.relu(_conv_bn(self.conv3, self.bn3, x, self.fold_bias), inplace=True)
+        return _conv_bn(self.conv3, self.bn3, x, self.fold_bias, True, self.cuda_bn)
 
 
 class _UNetTrunk(nn.Module):
@@ -184,11 +206,12 @@ class _DoubleConv(nn.Module):
         self.double_conv = nn.Sequential(nn.Conv2d(cin, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True),
                                          nn.Conv2d(cout, cout, 3, padding=1), nn.BatchNorm2d(cout), nn.ReLU(inplace=True))
         self.fold_bias = False
+        self.cuda_bn = False
 
     def forward(self, x):
         dc = self.double_conv
-        x = F.relu(_conv_bn(dc[0], dc[1], x, self.fold_bias), inplace=True)
-        return F.relu(_conv_bn(dc[3], dc[4], x, self.fold_bias), inplace=True)
+        x = _conv_bn(dc[0], dc[1], x, self.fold_bias, True, self.cuda_bn)
+        return _conv_bn(dc[3], dc[4], x, self.fold_bias, True, self.cuda_bn)
 
 
 class _DoubleConvWT(nn.Module):
