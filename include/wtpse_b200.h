@@ -144,6 +144,16 @@ int wtpse_batchnorm_relu_backward(const float* x, const float* dy, int64_t npix,
                                   const float* save_stats, int relu, float* dx, float* dgamma, float* dbeta,
                                   void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
+/*
+ * Encoder down-sampling: F.max_pool2d(x, 2) (ConvD.forward, algorithms.py:897) on a channels-last tensor whose H and W are even.
+ *   backward == 0: in [N][2Ho][2Wo][C] -> out [N][Ho][Wo][C], argmax[N*Ho*Wo*C] = position 0..3 inside the 2x2 window
+ *                  (row-major; ATen's selection rule: first maximum, NaN wins)
+ *   backward != 0: in = gradient of the pooled output, out = gradient of the input (every element written once)
+ * C % 4 == 0; float pointers 16-byte aligned.
+ */
+int wtpse_maxpool2_nhwc(const float* in, float* out, unsigned char* argmax, int64_t N, int Ho, int Wo, int C, int backward,
+                        wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

@@ -228,3 +228,23 @@ def test_batch_norm_act_matches_torch(shape, relu, offset):
     for got, want in ((xa.grad, xd.grad), (bn.weight.grad, wd.grad), (bn.bias.grad, bd.grad)):
         err = float((got.double() - want).norm() / max(float(want.norm()), 1e-12))
         assert err <= (5e-4 if offset != 50.0 else 2e-2), err
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 2, 2), (2, 8, 6, 10), (15, 16, 64, 64), (3, 128, 16, 8)])
+def test_max_pool2_matches_aten(shape):
+    import torch.nn.functional as F
+
+    from wtpse_b200.elementwise import max_pool2
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=gen).to(dev)
+    x[0, 0, 0, :2] = 1.5                                                      # a tie inside one window: first maximum wins
+    x = x.contiguous(memory_format=torch.channels_last)
+    gy = torch.randn(shape[0], shape[1], shape[2] // 2, shape[3] // 2, generator=gen).to(dev)
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    ya, yb = F.max_pool2d(xa, 2), max_pool2(xb)
+    assert torch.equal(ya, yb) and yb.is_contiguous(memory_format=torch.channels_last)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert torch.equal(xa.grad, xb.grad)

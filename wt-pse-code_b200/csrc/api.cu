@@ -369,6 +369,19 @@ int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out, void
     return WTPSE_OK;
 }
 
+int wtpse_maxpool2_nhwc(const float* in, float* out, unsigned char* argmax, int64_t N, int Ho, int Wo, int C, int backward,
+                        wtpse_stream_t stream) {
+    if (!in || !out || !argmax) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (N <= 0 || Ho <= 0 || Wo <= 0 || C <= 0 || (C % 4) != 0) return fail(WTPSE_ERR_INVALID, "need N, Ho, Wo >= 1 and C a positive multiple of 4 (got C=%d)", C);
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) || (reinterpret_cast<uintptr_t>(argmax) & 3u))
+        return fail(WTPSE_ERR_INVALID, "float pointers must be 16-byte aligned, argmax 4-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernUpsample, s); e = launch_maxpool2_nhwc(in, out, argmax, N, Ho, Wo, C, backward != 0, sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "maxpool launch");
+    return WTPSE_OK;
+}
+
 size_t wtpse_batchnorm_workspace_bytes(int64_t npix, int C) {
     if (npix <= 0 || !batchnorm_supported(C)) return 0;
     return align_up(batchnorm_workspace_floats(npix, C, sm_count_cached()) * sizeof(float), 256);

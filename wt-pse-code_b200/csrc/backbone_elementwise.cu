@@ -13,6 +13,8 @@
 // channel quad of one INPUT pixel: forward reads its 3x3 neighbourhood (L1/L2 hits) and writes the 2x2 output block;
 // the adjoint gathers the 4x4 output-gradient neighbourhood and writes one quad (no atomics, deterministic).
 // HBM-bound: forward 4 + 16 B per input element, backward 16 + 4.
+#include <math.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -149,17 +151,22 @@ channel_sum_partial_kernel(const float* __restrict__ g, long long npix, int C4, 
     const long long per = (npix + gridDim.x - 1) / gridDim.x;
     const long long p0 = (long long)blockIdx.x * per;
     const long long p1 = p0 + per < npix ? p0 + per : npix;
-    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
     long long p = p0 + r;
-    for (; p + lanes < p1; p += 2 * lanes) {        // two independent accumulators: two loads in flight
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {    // four independent accumulators: four 128-bit loads in flight
         const float4 v0 = ld4(g + (p * C4 + q) * 4), v1 = ld4(g + ((p + lanes) * C4 + q) * 4);
+        const float4 v2 = ld4(g + ((p + 2 * lanes) * C4 + q) * 4), v3 = ld4(g + ((p + 3 * lanes) * C4 + q) * 4);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
     }
-    if (p < p1) {
+    for (; p < p1; p += lanes) {
         const float4 v0 = ld4(g + (p * C4 + q) * 4);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
     }
+    a0.x += a2.x; a0.y += a2.y; a0.z += a2.z; a0.w += a2.w;
+    a1.x += a3.x; a1.y += a3.y; a1.z += a3.z; a1.w += a3.w;
     red[tid] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
     __syncthreads();
     for (int s = lanes >> 1; s > 0; s >>= 1) {
@@ -174,17 +181,69 @@ channel_sum_partial_kernel(const float* __restrict__ g, long long npix, int C4, 
     if (r == 0) reinterpret_cast<float4*>(partial)[(long long)blockIdx.x * C4 + q] = red[tid];
 }
 
+// one warp per channel: lanes stride over the per-CTA partials, fixed-order butterfly
 __global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= C) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int b = 0;
-    for (; b + 3 < nblocks; b += 4) {
-        s0 += partial[(long long)b * C + c]; s1 += partial[(long long)(b + 1) * C + c];
-        s2 += partial[(long long)(b + 2) * C + c]; s3 += partial[(long long)(b + 3) * C + c];
+    float s = 0.f;
+    for (int b = lane; b < nblocks; b += 32) s += partial[(long long)b * C + c];
+    s = warp_sum(s);
+    if (lane == 0) out[c] = s;
+}
+
+// 2x2 / stride-2 max pooling of the encoder stages (F.max_pool2d(x, 2), algorithms.py:897), channels-last.  The argmax
+// is kept as one byte per output element (ATen keeps an int64: 8 B) and the backward writes every input element
+// exactly once (the windows do not overlap), so it needs no zero-fill and no atomics.  Selection rule as ATen's:
+// scan the window row-major, take v if v > current or v is NaN.
+__global__ void __launch_bounds__(kThreads)
+maxpool2_nhwc_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, unsigned char* __restrict__ arg, long long N, int Ho,
+                         int Wo, int C4) {
+    const long long total = N * Ho * Wo * C4;
+    const long long C = 4LL * C4;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const int c = int(idx % C4);
+        long long r = idx / C4;
+        const int j = int(r % Wo); r /= Wo;
+        const int i = int(r % Ho);
+        const long long n = r / Ho;
+        const float* base = x + ((n * 2 * Ho + 2 * i) * 2 * Wo + 2 * j) * C + 4 * c;
+        const long long row = 2LL * Wo * C;
+        const float4 v[4] = {ld4(base), ld4(base + C), ld4(base + row), ld4(base + row + C)};
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        unsigned char a[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float e[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+            for (int l = 0; l < 4; ++l)
+                if (e[l] > m[l] || e[l] != e[l]) { m[l] = e[l]; a[l] = (unsigned char)k; }
+        }
+        reinterpret_cast<float4*>(y)[idx] = make_float4(m[0], m[1], m[2], m[3]);
+        reinterpret_cast<uchar4*>(arg)[idx] = make_uchar4(a[0], a[1], a[2], a[3]);
     }
-    for (; b < nblocks; ++b) s0 += partial[(long long)b * C + c];
-    out[c] = (s0 + s1) + (s2 + s3);
+}
+
+__global__ void __launch_bounds__(kThreads)
+maxpool2_nhwc_bwd_kernel(const float* __restrict__ gy, const unsigned char* __restrict__ arg, float* __restrict__ gx, long long N,
+                         int Ho, int Wo, int C4) {
+    const long long total = N * Ho * Wo * C4;
+    const long long C = 4LL * C4;
+    for (long long idx = (long long)blockIdx.x * kThreads + threadIdx.x; idx < total; idx += (long long)gridDim.x * kThreads) {
+        const int c = int(idx % C4);
+        long long r = idx / C4;
+        const int j = int(r % Wo); r /= Wo;
+        const int i = int(r % Ho);
+        const long long n = r / Ho;
+        const float4 g = ld4(gy + idx * 4);
+        const uchar4 a = reinterpret_cast<const uchar4*>(arg)[idx];
+        float* base = gx + ((n * 2 * Ho + 2 * i) * 2 * Wo + 2 * j) * C + 4 * c;
+        const long long row = 2LL * Wo * C;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 o = make_float4(a.x == k ? g.x : 0.f, a.y == k ? g.y : 0.f, a.z == k ? g.z : 0.f, a.w == k ? g.w : 0.f);
+            *reinterpret_cast<float4*>(base + (k >> 1) * row + (k & 1) * C) = o;
+        }
+    }
 }
 
 int grid_for(long long items, int sm_count) {
@@ -209,10 +268,19 @@ cudaError_t launch_bias_act_nhwc(float* y, const float* bias, long long npix, in
     return cudaGetLastError();
 }
 
+// Ho, Wo: pooled sizes; the input is N x 2Ho x 2Wo x C.  backward: in = gy, out = gx.
+cudaError_t launch_maxpool2_nhwc(const float* in, float* out, unsigned char* arg, long long N, int Ho, int Wo, int C, bool backward,
+                                 int sm_count, cudaStream_t stream) {
+    const long long items = N * Ho * Wo * (C / 4);
+    if (backward) maxpool2_nhwc_bwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, arg, out, N, Ho, Wo, C / 4);
+    else maxpool2_nhwc_fwd_kernel<<<grid_for(items, sm_count), kThreads, 0, stream>>>(in, out, arg, N, Ho, Wo, C / 4);
+    return cudaGetLastError();
+}
+
 int channel_sum_blocks(long long npix, int C, int sm_count) {
     const long long lanes = kThreads / (C / 4);
-    long long b = (npix + lanes - 1) / lanes;        // at least one pixel per thread row
-    const long long cap = 2LL * sm_count;
+    long long b = (npix + 4 * lanes - 1) / (4 * lanes);        // about four pixels per thread row at least
+    const long long cap = 4LL * sm_count;
     if (b > cap) b = cap;
     return int(b < 1 ? 1 : b);
 }
@@ -223,7 +291,7 @@ cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float
                                     cudaStream_t stream) {
     const int blocks = channel_sum_blocks(npix, C, sm_count);
     channel_sum_partial_kernel<<<blocks, kThreads, 0, stream>>>(g, npix, C / 4, partial);
-    channel_sum_final_kernel<<<(C + 127) / 128, 128, 0, stream>>>(partial, blocks, C, out);
+    channel_sum_final_kernel<<<(C + 3) / 4, 128, 0, stream>>>(partial, blocks, C, out);
     return cudaGetLastError();
 }
 

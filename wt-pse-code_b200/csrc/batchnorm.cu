@@ -83,12 +83,18 @@ bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, lon
             fma4(s2, d, d);
         }
     };
+    // four independent pixel rows per iteration: four 128-bit loads (eight in the backward) in flight per thread
+    float4 c1 = a1, c2 = a1, d1 = a1, d2 = a1;
     long long p = p0 + r;
-    for (; p + lanes < p1; p += 2 * lanes) {
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
         step(p, a1, a2);
         step(p + lanes, b1, b2);
+        step(p + 2 * lanes, c1, c2);
+        step(p + 3 * lanes, d1, d2);
     }
-    if (p < p1) step(p, a1, a2);
+    for (; p < p1; p += lanes) step(p, a1, a2);
+    acc4(b1, d1); acc4(b2, d2);
+    acc4(a1, c1); acc4(a2, c2);
     acc4(a1, b1);
     acc4(a2, b2);
     const float4 t1 = quad_tree(a1, red, tid, C4, lanes, r);
@@ -197,7 +203,7 @@ bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, l
 int stat_blocks(long long npix, int C, int sm_count) {
     const long long lanes = kThreads / (C / 4);
     long long b = (npix + 4 * lanes - 1) / (4 * lanes);          // at least ~4 pixels per thread row
-    const long long cap = 2LL * sm_count;
+    const long long cap = 4LL * sm_count;                          // 4 resident CTAs per SM, 4 loads per thread in flight
     if (b > cap) b = cap;
     return int(b < 1 ? 1 : b);
 }

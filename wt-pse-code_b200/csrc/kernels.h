@@ -109,6 +109,10 @@ bool channel_sum_supported(int C);
 cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float* out, float* partial, int sm_count,
                                     cudaStream_t stream);
 
+// 2x2 stride-2 max pooling, channels-last; arg: one byte per pooled element (position inside the window)
+cudaError_t launch_maxpool2_nhwc(const float* in, float* out, unsigned char* arg, long long N, int Ho, int Wo, int C, bool backward,
+                                 int sm_count, cudaStream_t stream);
+
 // training-mode BatchNorm2d (+ ReLU), channels-last (batchnorm.cu)
 bool batchnorm_supported(int C);
 size_t batchnorm_workspace_floats(long long npix, int C, int sm_count);

@@ -6,6 +6,7 @@
   upsample2x       algorithms.py:947                        (bilinear x2 of the decoder stages, channels-last), autograd
   conv_bias_act    algorithms.py:416-428, 1019-1030         (convolution bias + ReLU in one in-place pass, channels-last), autograd
   batch_norm_act   algorithms.py:877-962, 398-413           (training BatchNorm2d + ReLU, channels-last), autograd
+  max_pool2        algorithms.py:897                        (F.max_pool2d(x, 2) of the encoder stages, channels-last), autograd
 """
 import torch
 from torch.autograd.function import once_differentiable
@@ -281,3 +282,42 @@ def batch_norm_act(x, bn, relu, mean_shift=None):
     y = _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, mean_shift, bn.momentum, bn.eps, relu)
     bn.num_batches_tracked.add_(1)
     return y
+
+
+def max_pool2_supported(x):
+    return (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] % 4 == 0
+            and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and x.numel() > 0
+            and x.is_contiguous(memory_format=torch.channels_last) and x.data_ptr() % 16 == 0)
+
+
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        if not max_pool2_supported(x):
+            raise ValueError("max_pool2 needs a CUDA float32 channels-last N x C x H x W tensor with C % 4 == 0 and even H, W")
+        N, C, H, W = x.shape
+        lib = _lib.load()
+        with torch.cuda.device(x.device):
+            y = torch.empty((N, C, H // 2, W // 2), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+            arg = torch.empty(y.numel(), dtype=torch.uint8, device=x.device)
+            _lib.check(lib.wtpse_maxpool2_nhwc(_ptr(x), _ptr(y), _ptr(arg), N, H // 2, W // 2, C, 0, _stream_ptr(x.device)))
+        ctx.save_for_backward(arg)
+        ctx.dims = (N, C, H, W)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (arg,) = ctx.saved_tensors
+        N, C, H, W = ctx.dims
+        g = g.contiguous(memory_format=torch.channels_last)
+        lib = _lib.load()
+        with torch.cuda.device(g.device):
+            gx = torch.empty((N, C, H, W), dtype=torch.float32, device=g.device, memory_format=torch.channels_last)
+            _lib.check(lib.wtpse_maxpool2_nhwc(_ptr(g), _ptr(gx), _ptr(arg), N, H // 2, W // 2, C, 1, _stream_ptr(g.device)))
+        return gx
+
+
+def max_pool2(x):
+    """F.max_pool2d(x, 2) for a channels-last tensor with even H, W (ConvD.forward, algorithms.py:897)."""
+    return _MaxPool2.apply(x)

@@ -24,8 +24,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as wf
-from .elementwise import (attention_fuse, batch_norm_act, batch_norm_act_supported, channel_sum, conv_bias_act, upsample2x,
-                          upsample2x_supported)
+from .elementwise import (attention_fuse, batch_norm_act, batch_norm_act_supported, channel_sum, conv_bias_act, max_pool2,
+                          max_pool2_supported, upsample2x, upsample2x_supported)
 
 BASE_WIDTH = 16      # `n = 16` in algorithms.py:1159 / shape_networks.py:428; also the whitening loss' channel count
 
@@ -75,6 +75,14 @@ def _conv_bn(conv, bn, x, fold, relu=False, cuda_bn=False):
     else:
         out = bn(y)
     return F.relu(out, inplace=True) if relu else out
+
+
+def set_cuda_pool(module, on=True):
+    """Encoder stages below `module` pool with the channels-last 2x2 CUDA kernels when their input allows it (TrainStep)."""
+    for m in module.modules():
+        if hasattr(m, "cuda_pool"):
+            m.cuda_pool = bool(on)
+    return module
 
 
 def set_cuda_batchnorm(module, on=True):
@@ -142,10 +150,11 @@ class ConvD(nn.Module):
         self.conv3, self.bn3 = nn.Conv2d(planes, planes, 3, padding=1), _norm(planes)
         self.fold_bias = False
         self.cuda_bn = False
+        self.cuda_pool = False
 
     def forward(self, x):
         if not self.first:
-            x = F.max_pool2d(x, 2)
+            x = max_pool2(x) if (self.cuda_pool and max_pool2_supported(x)) else F.max_pool2d(x, 2)
         x = _conv_bn(self.conv1, self.bn1, x, self.fold_bias, False, self.cuda_bn)      # no activation after the first conv
         x = _conv_bn(self.conv2, self.bn2, x, self.fold_bias, True, self.cuda_bn)
         return _conv_bn(self.conv3, self.bn3, x, self.fold_bias, True, self.cuda_bn)

@@ -27,7 +27,8 @@ DEFAULT_HPARAMS = {   # hparams_registry.py:75-93
 class TrainStep:
     def __init__(self, n_per_domain, n_domains=3, device="cuda", hparams=None, lr=5e-4, seed=0, process_group=None,
                  channels_last=True, fused_adam=True, teacher_backward=False, fuse_relu=False,
-                 fold_conv_bias=True, cuda_upsample=True, fast_bias=True, cuda_batchnorm=True):
+                 fold_conv_bias=True, cuda_upsample=True, fast_bias=True, cuda_batchnorm=True,
+                 cuda_pool=True):
         self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
         self.device = torch.device(device)
         torch.manual_seed(seed)                                   # identical initial weights on every rank
@@ -50,6 +51,7 @@ class TrainStep:
             seg.set_cuda_upsample(m, cuda_upsample and channels_last)     # ATen's NHWC bilinear kernel: 26 ms of 242
             seg.set_fast_bias(m, fast_bias and channels_last)             # bias (+ ReLU) of the convs without BatchNorm
             seg.set_cuda_batchnorm(m, cuda_batchnorm and channels_last)   # BatchNorm + ReLU, forward and backward
+            seg.set_cuda_pool(m, cuda_pool and channels_last)             # 2x2 max pooling with a one-byte argmax
             if channels_last:
                 # cuDNN's NCHW BatchNorm runs one CTA per channel (16-256 CTAs on 148 SMs: 55 % of the step at
                 # 512x512); with channels-last weights every conv/BN of the backbone takes the NHWC kernels.
