@@ -154,6 +154,22 @@ int wtpse_batchnorm_relu_backward(const float* x, const float* dy, int64_t npix,
 int wtpse_maxpool2_nhwc(const float* in, float* out, unsigned char* argmax, int64_t N, int Ho, int Wo, int C, int backward,
                         wtpse_stream_t stream);
 
+/*
+ * Channels-last variants: z, relu_out, grad_relu and dz are [B][P][16] -- the memory of channels-last B x 16 x H x W
+ * tensors (what a channels-last backbone hands over), so no layout conversion is needed around the loss.  Same
+ * arithmetic and outputs as the NCHW entry points (summation order differs, results agree to fp32 rounding).
+ * relu_out / grad_relu may be NULL: then these are plain wtpse_whitening_forward / _backward; non-NULL: the fused
+ * DeepWT tail of wtpse_whitening_relu_forward / _backward.  All tensor pointers 16-byte aligned.
+ */
+int wtpse_whitening_forward_cl(const float* z, float* relu_out, int B, int C, int64_t P,
+                               int n_per_domain, int n_domains, float margin, float eps,
+                               float* losses, float* gram, float* rowstat,
+                               void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+int wtpse_whitening_backward_cl(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
+                                const float* g_off, const float* g_diag, const float* g_dom,
+                                int B, int C, int64_t P, int n_per_domain, int n_domains, float* dz,
+                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
 size_t wtpse_mmd_workspace_bytes(int B);

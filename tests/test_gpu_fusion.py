@@ -152,3 +152,51 @@ def test_train_step_with_fused_tail_runs_channels_last_and_captures():
     ts.capture(image.clone(), od, oc, warmup=1)
     out = ts.replay(image.clone(), od, oc)
     assert all(np.isfinite(float(v)) for v in out.values())
+
+
+@pytest.mark.parametrize("B,H,W,n,K", [(6, 64, 64, 2, 3), (8, 256, 256, 2, 3), (5, 37, 29, 2, 2), (3, 30, 30, 1, 3), (30, 48, 40, 10, 3),
+                                       (2, 300, 280, 1, 2), (1, 8, 8, 1, 1)])
+def test_channels_last_loss_kernels_match_the_nchw_ones(B, H, W, n, K):
+    """wtpse_whitening_forward_cl / _backward_cl (plain and fused with the DeepWT-tail ReLU) on channels-last tensors against
+    the NCHW kernels on the same values: losses to fp32 rounding (the summation order differs), relu bit-exact, dz to 1e-5."""
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda:0")
+    z0 = _z(B, H, W, 21, dev)
+    g_relu = torch.randn(B, 16, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    ones = [torch.ones((), device=dev)] * 3
+
+    def run(z, fused):
+        z = z.requires_grad_()
+        if fused:
+            r, off, diag, dom = wb.relu_whitening_terms(z, n, K)
+            torch.autograd.backward([off, diag, dom, r], ones + [g_relu])
+        else:
+            r = None
+            off, diag, dom = wb.whitening_terms(z, n, K)
+            torch.autograd.backward([off, diag, dom], ones)
+        return r, (float(off), float(diag), float(dom)), z.grad
+
+    for fused in (False, True):
+        r_a, l_a, dz_a = run(z0.clone(), fused)
+        z_cl = z0.clone().contiguous(memory_format=torch.channels_last)
+        r_b, l_b, dz_b = run(z_cl, fused)
+        assert dz_b.is_contiguous(memory_format=torch.channels_last)
+        for a, b in zip(l_a, l_b):
+            assert abs(a - b) <= 1e-5 * max(abs(a), 1e-3) or (a != a and b != b), (l_a, l_b)
+        assert float((dz_a - dz_b).abs().max()) <= 1e-5 * float(dz_a.abs().max())
+        if fused:
+            assert torch.equal(r_a, r_b) and r_b.is_contiguous(memory_format=torch.channels_last)
+
+
+def test_train_step_fused_tail_channels_last_matches_unfused():
+    import wtpse_b200 as wb
+
+    dev = torch.device("cuda:0")
+    a = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=0, fuse_relu=True)
+    b = wb.TrainStep(n_per_domain=2, n_domains=3, device=dev, seed=0, fuse_relu=False)
+    assert a.model.wt_model.DoubleConv.double_conv[0].weight.is_contiguous(memory_format=torch.channels_last)
+    image, od, oc = wb.synthetic.fundus_batch(2, 3, 64, 64, dev, seed=9)
+    oa, ob = a.step(image.clone(), od, oc), b.step(image.clone(), od, oc)
+    for k in ("ins_wt", "dom_wt"):          # sub-step 1's whitening losses see only the initial weights (no RNG)
+        assert abs(float(oa[k]) - float(ob[k])) <= 2e-5 * max(abs(float(ob[k])), 1e-3), (k, float(oa[k]), float(ob[k]))

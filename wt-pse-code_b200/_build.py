@@ -6,7 +6,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwtpse_b200.so")
-SOURCES = ["api.cu", "whitening_gram.cu", "whitening_gram_split.cu", "whitening_epilogue.cu", "whitening_apply.cu", "whitening_apply_relu.cu", "mse.cu", "profile.cu", "elementwise.cu", "backbone_elementwise.cu", "batchnorm.cu",
+SOURCES = ["api.cu", "whitening_gram.cu", "whitening_gram_split.cu", "whitening_epilogue.cu", "whitening_apply.cu", "whitening_apply_relu.cu", "whitening_apply_cl.cu", "mse.cu", "profile.cu", "elementwise.cu", "backbone_elementwise.cu", "batchnorm.cu",
            "wavelet.cu", "wavelet_resident.cu", "wavelet_stream.cu", "wavelet_tiles.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

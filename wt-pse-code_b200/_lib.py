@@ -42,6 +42,12 @@ EXPORTS = {
     "wtpse_batchnorm_relu_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                  _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_maxpool2_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "wtpse_whitening_forward_cl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                              _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                              _c.c_size_t, _c.c_void_p]),
+    "wtpse_whitening_backward_cl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                               _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                               _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
     "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_size_t, _c.c_void_p]),

@@ -99,18 +99,24 @@ size_t wtpse_whitening_workspace_bytes(int B, int64_t P) {
 
 static int whitening_forward_impl(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
                                   float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
-                                  size_t workspace_bytes, wtpse_stream_t stream) {
+                                  size_t workspace_bytes, wtpse_stream_t stream, bool channels_last = false) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
     if (!losses || !gram || !rowstat || !workspace) return fail(WTPSE_ERR_INVALID, "null output/workspace pointer");
     const int sms = sm_count_cached();
     const WhitenWorkspace w = carve(workspace, B, P, sms);
     if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const GramPlan g = plan_gram(z, B, P, sms, relu_out);
+    if (channels_last && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(relu_out)) & 15u))
+        return fail(WTPSE_ERR_INVALID, "channels-last tensors must be 16-byte aligned");
+    const GramPlan g = channels_last ? plan_gram_cl(B, P, sms) : plan_gram(z, B, P, sms, relu_out);
     cudaError_t e;
-    { LaunchScope scope(kKernGram, s); e = launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out); }
+    {
+        LaunchScope scope(kKernGram, s);
+        e = channels_last ? launch_gram_cl(z, relu_out, w.partial, w.slot_count, B, P, g, s)
+                          : launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out);
+    }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
-    if (g_two_stage_epilogue) {
+    if (g_two_stage_epilogue || channels_last) {
         LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
         e = launch_gram_reduce(w.partial, w.slot_count, g, B, P, n_per_domain, n_domains, margin, eps, gram, rowstat, w.vd, w.statd, s);
         if (e != cudaSuccess) return cuda_fail(e, "gram reduce launch");
@@ -143,7 +149,7 @@ int wtpse_whitening_relu_forward(const float* z, float* relu_out, int B, int C, 
 static int whitening_backward_impl(const float* z, const float* grelu, const float* gram, const float* rowstat,
                                    const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
                                    int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
-                                   wtpse_stream_t stream) {
+                                   wtpse_stream_t stream, bool channels_last = false) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
     if (!gram || !rowstat || !dz || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
     const int sms = sm_count_cached();
@@ -154,7 +160,17 @@ static int whitening_backward_impl(const float* z, const float* grelu, const flo
     // g_backward_mode: 0 = per-sample M_b kernel + round-robin apply chained by programmatic dependent launch (default),
     //                  1 = M_b derived inside the apply kernel (one launch, contiguous tile ranges),
     //                  2 = single-CTA epilogue + apply (also the fallback for very many MMD samples)
-    if (g_backward_mode == 1 && !grelu && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
+    if (channels_last) {
+        if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(grelu) | reinterpret_cast<uintptr_t>(dz)) & 15u)
+            return fail(WTPSE_ERR_INVALID, "channels-last tensors must be 16-byte aligned");
+        const bool multi = mmat_multi_cta_ok(B, n_per_domain, n_domains);
+        LaunchScope scope(kKernApply, s);
+        e = multi ? launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s)
+                  : launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s);
+        if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
+        profile_count_kernel(kKernMmat);
+        e = launch_apply_cl(z, grelu, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/multi);
+    } else if (g_backward_mode == 1 && !grelu && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
         LaunchScope scope(kKernApply, s);
         e = launch_apply_fused(z, gram, rowstat, g_off, g_diag, g_dom, dz, B, P, n_per_domain, n_domains, sms, s);
     } else if (g_backward_mode != 2 && mmat_multi_cta_ok(B, n_per_domain, n_domains)) {
@@ -179,6 +195,22 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
     (void)margin;  // already folded into rowstat by the forward
     return whitening_backward_impl(z, nullptr, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
                                    workspace, workspace_bytes, stream);
+}
+
+int wtpse_whitening_forward_cl(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
+                               float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                               size_t workspace_bytes, wtpse_stream_t stream) {
+    if (relu_out && relu_out == z) return fail(WTPSE_ERR_INVALID, "relu_out must not alias z (the backward pass re-reads z)");
+    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
+                                  workspace_bytes, stream, /*channels_last=*/true);
+}
+
+int wtpse_whitening_backward_cl(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
+                                const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
+                                int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
+                                wtpse_stream_t stream) {
+    return whitening_backward_impl(z, grad_relu, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
+                                   workspace, workspace_bytes, stream, /*channels_last=*/true);
 }
 
 int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const float* gram, const float* rowstat,

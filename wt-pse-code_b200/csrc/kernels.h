@@ -14,10 +14,18 @@ struct GramPlan {
     bool round_robin;            // group > 1
     int group;                   // CTAs per group: the group owns a contiguous tile range and deals it round-robin
     int variant;                 // 0: one thread per pixel quad (whitening_gram.cu), 1: two threads per quad (..._split.cu)
+    long long item_px;           // channels-last schedule only: pixels per work item
 };
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float* relu_out = nullptr);
 size_t gram_partial_floats(int B, long long P, int sm_count);
+// channels-last input ([B][P][16]); relu_out (nullable, same layout): also write relu(z)
+GramPlan plan_gram_cl(int B, long long P, int sm_count);
+cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                           cudaStream_t stream);
+// channels-last backward: dz = M_b z (+ [z > 0] * grelu), all [B][P][16]
+cudaError_t launch_apply_cl(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P, int sm_count,
+                            cudaStream_t stream, bool programmatic_dependent);
 cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
                         cudaStream_t stream, float* relu_out = nullptr);   // relu_out: also write relu(z) (8(f).1)
 

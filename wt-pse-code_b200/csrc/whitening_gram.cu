@@ -44,8 +44,9 @@ __device__ __forceinline__ void halve(float (&a)[kTri], int lane, int mask) {
     }
 }
 
-// Reduce the 136 per-thread sums over the consumer threads and store them to `out[136]`.
-__device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int warp, int lane, int tid, float* out) {
+// Reduce the 136 per-thread sums over the kWarps consumer warps and store them to `out[136]`.
+template <int kWarps>
+__device__ __forceinline__ void flush_gram_t(float (&acc)[kTri], float* red, int warp, int lane, int tid, float* out) {
     halve<68>(acc, lane, 16);
     halve<34>(acc, lane, 8);
     halve<17>(acc, lane, 4);
@@ -59,14 +60,18 @@ __device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int w
 #pragma unroll
         for (int k = 0; k < 17; ++k) red[warp * kTri + base + k] = acc[k];
     }
-    named_bar_sync(1, kConsumers);
+    named_bar_sync(1, kWarps * 32);
     if (tid < kTri) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) s += red[w * kTri + tid];
+        for (int w = 0; w < kWarps; ++w) s += red[w * kTri + tid];
         out[tid] = s;
     }
-    named_bar_sync(1, kConsumers);
+    named_bar_sync(1, kWarps * 32);
+}
+
+__device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int warp, int lane, int tid, float* out) {
+    flush_gram_t<kConsumerWarps>(acc, red, warp, lane, tid, out);
 }
 
 __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4 (&x)[kC]) {
@@ -230,6 +235,76 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ relu_out, f
     if (slot == 0 && tid == 0) slot_count[b] = nslots;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Channels-last input: z is [B][P][16] (the memory of a channels-last B x 16 x H x W tensor, what a channels-last
+// backbone produces).  A pixel's 16 channels are 64 contiguous bytes, so every thread reads its own pixel with four
+// 128-bit loads (a warp covers 2 KB contiguous) and no shared-memory staging is needed; a 4-deep register ring keeps
+// three pixels per thread in flight (148 SMs x 256 threads x 192 B = 7.3 MB).  Work items of `item_px` pixels of one
+// sample are dealt round-robin to the persistent CTAs; each item ends with one cross-thread flush into its own slot,
+// so the slot reduction that follows is the same fixed-order sum as for the NCHW kernels.
+constexpr int kClThreads = 256;
+constexpr int kClWarps = kClThreads / 32;
+
+__device__ __forceinline__ void gram_accumulate1(float (&acc)[kTri], const float (&x)[kC]) {
+#pragma unroll
+    for (int i = 0; i < kC; ++i)
+#pragma unroll
+        for (int j = i; j < kC; ++j) acc[tri_idx(i, j)] = fmaf(x[i], x[j], acc[tri_idx(i, j)]);
+}
+
+template <bool kRelu>
+__global__ void __launch_bounds__(kClThreads, 1)
+gram_cl_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial, int* __restrict__ slot_count,
+               long long P, int B, int nslots, long long item_px) {
+    __shared__ float red[kClWarps * kTri];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const long long items = (long long)B * nslots;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long b = item / nslots;
+        const int slot = int(item - b * nslots);
+        const long long p0 = slot * item_px;
+        const long long p1 = p0 + item_px < P ? p0 + item_px : P;
+        const float* base = z + b * P * kC;
+        float acc[kTri];
+#pragma unroll
+        for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+        float4 r0[4], r1[4], r2[4], r3[4];
+        auto ld = [&](float4 (&r)[4], long long p) {
+            if (p < p1) {
+                const float4* s = reinterpret_cast<const float4*>(base + p * kC);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r[q] = __ldg(s + q);
+            }
+        };
+        auto use = [&](const float4 (&r)[4], long long p) {
+            if (p < p1) {
+                if (kRelu) {
+                    float4* d = reinterpret_cast<float4*>(relu_out + (b * P + p) * kC);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) d[q] = relu4(r[q]);
+                }
+                const float x[kC] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w,
+                                     r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
+                gram_accumulate1(acc, x);
+            }
+        };
+        long long p = p0 + tid;
+        ld(r0, p);
+        ld(r1, p + kClThreads);
+        ld(r2, p + 2 * kClThreads);
+        for (; p < p1; p += 4 * kClThreads) {
+            ld(r3, p + 3 * kClThreads); use(r0, p);
+            ld(r0, p + 4 * kClThreads); use(r1, p + kClThreads);
+            ld(r1, p + 5 * kClThreads); use(r2, p + 2 * kClThreads);
+            ld(r2, p + 6 * kClThreads); use(r3, p + 3 * kClThreads);
+        }
+        flush_gram_t<kClWarps>(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+        if (tid == 0 && slot == 0) slot_count[b] = nslots;
+    }
+}
 }  // namespace
 
 // Gram tile schedule: CTAs per group (see TileWalk).  1 = one contiguous range per CTA, 0 = pure round-robin.
@@ -240,6 +315,7 @@ int g_gram_variant = 0;
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float* relu_out) {
     GramPlan g;
+    g.item_px = 0;
     g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(relu_out) & 15u) == 0);
     g.round_robin = false;
     g.group = 1;
@@ -275,6 +351,35 @@ GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float
     return g;
 }
 
+// Channels-last schedule: items of >= 8192 pixels, at most 256 slots per sample (gram_partial_floats covers that).
+GramPlan plan_gram_cl(int B, long long P, int sm_count) {
+    GramPlan g{};
+    g.tma = false;
+    long long item_px = 8192;
+    if ((P + item_px - 1) / item_px > 256) item_px = (P + 255) / 256;
+    g.item_px = item_px;
+    g.nslots = int((P + item_px - 1) / item_px);
+    const long long items = (long long)B * g.nslots;
+    g.G = items < sm_count ? items : sm_count;
+    g.group = 1;
+    return g;
+}
+
+cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                           cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(g.G));
+    cfg.blockDim = dim3(kClThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (relu_out) return cudaLaunchKernelEx(&cfg, gram_cl_kernel<true>, z, relu_out, partial, slot_count, P, B, g.nslots, g.item_px);
+    return cudaLaunchKernelEx(&cfg, gram_cl_kernel<false>, z, relu_out, partial, slot_count, P, B, g.nslots, g.item_px);
+}
+
 size_t gram_partial_floats(int B, long long P, int sm_count) {
     // upper bound over both paths: nslots <= sm_count + 1 for the persistent path and <= 2*sm_count for the generic one
     const long long tps = (P + 640 - 1) / 640;      // smallest tile of the two variants
@@ -286,6 +391,9 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
     if (slots_gen < 1) slots_gen = 1;
     long long slots = slots_tma > slots_gen ? slots_tma : slots_gen;
     if (2 * G > slots) slots = 2 * G;      // grouped / round-robin schedules: at most (#groups touching a sample) * g <= 2G slots
+    long long slots_cl = (P + 8191) / 8192;   // channels-last schedule (plan_gram_cl)
+    if (slots_cl > 256) slots_cl = 256;
+    if (slots_cl > slots) slots = slots_cl;
     return size_t(B) * size_t(slots) * kTri;
 }
 

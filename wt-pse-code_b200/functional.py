@@ -48,6 +48,15 @@ def _grad_ptr(g, like):
     return ctypes.c_void_p(g.data_ptr()), g      # keep the tensor alive until the launch is enqueued
 
 
+def _as_loss_input(z):
+    """(tensor the kernels read, channels_last flag).  A dense channels-last z (what a channels-last backbone produces) is
+    read in place by the *_cl entry points; anything else is made NCHW-contiguous, the reference's layout
+    (`z.contiguous().view`, algorithms.py:1280)."""
+    if z.dim() == 4 and not z.is_contiguous() and z.is_contiguous(memory_format=torch.channels_last) and z.data_ptr() % 16 == 0:
+        return z, True
+    return z.contiguous(), False
+
+
 class _WhiteningLoss(torch.autograd.Function):
     """(L_off, L_diag, L_dom) or, with fold=True, (L_off + L_diag, L_dom)."""
 
@@ -59,7 +68,7 @@ class _WhiteningLoss(torch.autograd.Function):
         B, C, H, W = z.shape
         if C != CHANNELS:
             raise ValueError("whitening loss is defined for C == 16 feature maps (self.dim), got C == %d" % C)
-        z = z.contiguous()
+        z, cl = _as_loss_input(z)
         P = H * W
         lib = _lib.load()
         with torch.cuda.device(z.device):
@@ -68,10 +77,16 @@ class _WhiteningLoss(torch.autograd.Function):
             losses = torch.empty(4, dtype=torch.float32, device=z.device)
             gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
             rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
-            _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, P, int(n_per_domain), int(n_domains), float(margin),
-                                                   float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
-                                                   _stream_ptr(z.device)))
+            if cl:
+                _lib.check(lib.wtpse_whitening_forward_cl(_ptr(z), None, B, C, P, int(n_per_domain), int(n_domains), float(margin),
+                                                          float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
+                                                          _stream_ptr(z.device)))
+            else:
+                _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, P, int(n_per_domain), int(n_domains), float(margin),
+                                                       float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
+                                                       _stream_ptr(z.device)))
         ctx.save_for_backward(z, gram, rowstat)
+        ctx.cl = cl
         ctx.cfg = (int(n_per_domain), int(n_domains), float(margin), bool(fold), ws_bytes)
         if fold:
             return _scalar_alias(losses, 3), _scalar_alias(losses, 2)
@@ -97,8 +112,12 @@ class _WhiteningLoss(torch.autograd.Function):
             p_off, k0 = _grad_ptr(g_off, z)
             p_diag, k1 = _grad_ptr(g_diag, z)
             p_dom, k2 = _grad_ptr(g_dom, z)
-            _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
-                                                    n, K, margin, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            if ctx.cl:            # dz = empty_like(z) keeps the channels-last layout
+                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), None, _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C,
+                                                           H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            else:
+                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
+                                                        n, K, margin, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
             del k0, k1, k2
         return dz, None, None, None, None, None
 
@@ -116,7 +135,7 @@ class _ReluWhiteningLoss(torch.autograd.Function):
         B, C, H, W = z.shape
         if C != CHANNELS:
             raise ValueError("whitening loss is defined for C == 16 feature maps (self.dim), got C == %d" % C)
-        z = z.contiguous()
+        z, cl = _as_loss_input(z)
         P = H * W
         lib = _lib.load()
         with torch.cuda.device(z.device):
@@ -125,11 +144,12 @@ class _ReluWhiteningLoss(torch.autograd.Function):
             losses = torch.empty(4, dtype=torch.float32, device=z.device)
             gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
             rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
-            relu_out = torch.empty_like(z)
-            _lib.check(lib.wtpse_whitening_relu_forward(_ptr(z), _ptr(relu_out), B, C, P, int(n_per_domain), int(n_domains),
-                                                        float(margin), float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat),
-                                                        _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            relu_out = torch.empty_like(z)                      # same layout as z
+            fwd = lib.wtpse_whitening_forward_cl if cl else lib.wtpse_whitening_relu_forward
+            _lib.check(fwd(_ptr(z), _ptr(relu_out), B, C, P, int(n_per_domain), int(n_domains), float(margin), float(eps),
+                           _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
         ctx.save_for_backward(z, gram, rowstat)
+        ctx.cl = cl
         ctx.cfg = (int(n_per_domain), int(n_domains), bool(fold), ws_bytes)
         if fold:
             return relu_out, _scalar_alias(losses, 3), _scalar_alias(losses, 2)
@@ -159,7 +179,13 @@ class _ReluWhiteningLoss(torch.autograd.Function):
             p_off, k0 = _grad_ptr(g_off, z)
             p_diag, k1 = _grad_ptr(g_diag, z)
             p_dom, k2 = _grad_ptr(g_dom, z)
-            if g_relu is None:                       # only the loss was used downstream
+            if ctx.cl:
+                if g_relu is not None:
+                    _require_cuda_f32(g_relu, "grad of relu(z)")
+                    g_relu = g_relu.contiguous(memory_format=torch.channels_last)
+                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom,
+                                                           B, C, H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+            elif g_relu is None:                     # only the loss was used downstream
                 _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
                                                         n, K, 0.0, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
             else:

@@ -58,12 +58,9 @@ class TrainStep:
                 # The loss kernels keep the reference's NCHW layout (`z.contiguous()`, algorithms.py:1280).
                 m.to(memory_format=torch.channels_last)
             if fuse_relu:
-                # Gram + ReLU in one pass over each embedding.  The loss kernels read NCHW, so the four
-                # 16-channel DeepWT convolutions (no BatchNorm) stay NCHW and only relu(z1) is converted for the U-Nets.
+                # Gram + ReLU in one pass over each embedding (the *_cl kernels read the channels-last
+                # embeddings in place, so there is no layout conversion around the loss either way)
                 seg.enable_relu_fusion(m, True)
-                if channels_last:
-                    m.wt_model.to(memory_format=torch.contiguous_format)
-                    m.wt_model.out_memory_format = torch.channels_last
         self.buckets = [FlatGradBucket(m, process_group) for m in self.nets]
         fused = bool(fused_adam) and self.device.type == "cuda"       # one multi-tensor kernel per optimizer step
         self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused, capturable=fused)
