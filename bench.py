@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--train-reference-work", type=int, default=1,
                     help="also time the iteration with the reference's dead teacher backward kept (train_step.with_teacher_backward)")
-    ap.add_argument("--train-fuse-relu", type=int, default=0, help="train step with the fused DeepWT tail (SURVEY 8(f).1)")
+    ap.add_argument("--train-fuse-relu", type=int, default=1, help="train step with the fused DeepWT tail (SURVEY 8(f).1)")
     ap.add_argument("--train-fuse-compare", type=int, default=1, help="also time the train step with the other --train-fuse-relu setting")
     ap.add_argument("--train-cudnn-benchmark", type=int, default=1, help="torch.backends.cudnn.benchmark for the train-step backbone")
     ap.add_argument("--wavelet-name", default="db2", choices=["haar", "db2"])
@@ -241,8 +241,22 @@ def time_relu_fusion(z, n, K, peak, iters=10):
         r, ins, dom = wb.relu_whitening_folded(zz, n, K)
         torch.autograd.backward([r, ins, dom], [g, one, one])
 
+    zc = z.detach().clone().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gc_ = g.contiguous(memory_format=torch.channels_last)
+
+    def fused_cl():                                   # the same pair on channels-last tensors (wtpse_whitening_*_cl)
+        zc.grad = None
+        r, ins, dom = wb.relu_whitening_folded(zc, n, K)
+        torch.autograd.backward([r, ins, dom], [gc_, one, one])
+
+    def plain_cl():                                   # plain loss fwd+bwd on a channels-last z: 192 B/pix, no conversion
+        zc.grad = None
+        ins, dom = wb.whitening_folded(zc, n, K)
+        torch.autograd.backward([ins, dom], [one, one])
+
     out = {}
-    for name, fn, bytes_per_pix in (("unfused", unfused, 704), ("fused", fused, 320)):
+    for name, fn, bytes_per_pix in (("unfused", unfused, 704), ("fused", fused, 320), ("fused_channels_last", fused_cl, 320),
+                                    ("plain_loss_channels_last", plain_cl, 192)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

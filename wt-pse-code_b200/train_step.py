@@ -26,7 +26,7 @@ DEFAULT_HPARAMS = {   # hparams_registry.py:75-93
 
 class TrainStep:
     def __init__(self, n_per_domain, n_domains=3, device="cuda", hparams=None, lr=5e-4, seed=0, process_group=None,
-                 channels_last=True, fused_adam=True, teacher_backward=False, fuse_relu=False,
+                 channels_last=True, fused_adam=True, teacher_backward=False, fuse_relu=True,
                  fold_conv_bias=True, cuda_upsample=True, fast_bias=True, cuda_batchnorm=True,
                  cuda_pool=True):
         self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
