@@ -175,7 +175,7 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
                 // launched as a programmatic dependent of whiten_mmat_kernel: z is streaming already, the
                 // matrices are only needed here (no-op when there is no programmatic dependency)
                 if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");
-                msh[tid] = __ldg(mmat + b * 256 + tid);
+                msh[tid] = __ldcg(mmat + b * 256 + tid);   // coherent load: an invariant (.nc) one may be hoisted above the wait
             }
             named_bar_sync(1, kConsumers);
             cur_b = b;

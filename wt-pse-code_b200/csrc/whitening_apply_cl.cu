@@ -67,7 +67,7 @@ apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, co
         if (b != cur_b) {
             __syncthreads();                                  // previous matrix no longer in use
             if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
-            msh[tid] = __ldg(mmat + b * 256 + tid);
+            msh[tid] = __ldcg(mmat + b * 256 + tid);   // coherent load: an invariant (.nc) one may be hoisted above the wait
             __syncthreads();
             cur_b = b;
         }

@@ -96,7 +96,7 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
         if (b != cur_b) {
             named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use
             if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
-            for (int e = tid; e < 256; e += kConsumers) msh[e] = __ldg(mmat + b * 256 + e);
+            for (int e = tid; e < 256; e += kConsumers) msh[e] = __ldcg(mmat + b * 256 + e);   // coherent: .nc loads may be hoisted above the wait
             named_bar_sync(1, kConsumers);
             cur_b = b;
         }

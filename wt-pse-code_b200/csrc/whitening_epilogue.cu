@@ -27,6 +27,10 @@
 //         precision even when the domains are statistically identical (SURVEY.md section 7's
 //         3.8e-3 fp32-vs-fp64 gap of the reference does not arise).  Only the handful of final
 //         block sums run in float64.
+//   * everything these kernels read from global memory is loaded with ld.global.cg (__ldcg), never the read-only
+//     (.nc / __ldg) path: they are chained by programmatic dependent launch, their inputs are written by the kernel
+//     in front while they are already resident, and ptxas hoists invariant loads above griddepcontrol.wait
+//     (seen in SASS: LDG.E.CONSTANT in front of ACQBULK) -- a race that showed up as one flaky gradient test;
 //   * dependent loads are issued in batches (speculative slot loads, 8-deep gathers) so a phase pays one
 //     L2/DRAM round trip, not one per element;
 //   * pairwise distances: one LANE per unordered pair a < c (the matrix is symmetric), LDS.128 on rows
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int idx = base + u * kEpiThreads + tid;
-                    v[u] = idx < n4 ? __ldg(src4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[u] = idx < n4 ? __ldcg(src4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
                 }
             }
         }
-        for (int idx = tid; idx < 2 * B; idx += kEpiThreads) mem.stat[idx] = __ldg(p.statd + idx);
+        for (int idx = tid; idx < 2 * B; idx += kEpiThreads) mem.stat[idx] = __ldcg(p.statd + idx);
     } else
     for (int b = warp; b < B; b += kEpiWarps) {
         const float* src = p.partial + ((long long)b * p.nslots) * kTri;
@@ -203,11 +207,11 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
         for (int q = 0; q < 5; ++q) {
             const int e = lane + 32 * q;
             const bool ok = e < kTri;
-            v0[q] = ok ? __ldg(src + e) : 0.f;
-            v1[q] = (ok && p.nslots > 1) ? __ldg(src + kTri + e) : 0.f;
-            v2[q] = (ok && p.nslots > 2) ? __ldg(src + 2 * kTri + e) : 0.f;
+            v0[q] = ok ? __ldcg(src + e) : 0.f;
+            v1[q] = (ok && p.nslots > 1) ? __ldcg(src + kTri + e) : 0.f;
+            v2[q] = (ok && p.nslots > 2) ? __ldcg(src + 2 * kTri + e) : 0.f;
         }
-        const int cnt = __ldg(p.slot_count + b);
+        const int cnt = __ldcg(p.slot_count + b);
         float off = 0.f, dg = 0.f;
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_fwd_kernel(Fwd
                 float s = v0[q];
                 if (cnt > 1) s += v1[q];
                 if (cnt > 2) s += v2[q];
-                for (int sl = 3; sl < cnt; ++sl) s += __ldg(src + (long long)sl * kTri + e);
+                for (int sl = 3; sl < cnt; ++sl) s += __ldcg(src + (long long)sl * kTri + e);
                 const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
                 s = s / denom;                                   // .div(HW - 1), algorithms.py:1283
                 if (i == j) {
@@ -323,7 +327,7 @@ __global__ void __launch_bounds__(kReduceThreads) gram_reduce_kernel(ReduceParam
     // CTA k of the Gram kernel touched this sample iff its first tile at or after the sample start lies inside it
     const long long tb = (long long)b * p.tps, te = tb + p.tps;
     const int rb = int(tb % G);
-    const int cnt = p.slot_count ? __ldg(p.slot_count + b) : 0;
+    const int cnt = p.slot_count ? __ldcg(p.slot_count + b) : 0;
     const float* src = p.partial + ((long long)b * G) * kTri + e;
     float s = 0.f;
     for (int k = k0; k < k1; k += 8) {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(kReduceThreads) gram_reduce_kernel(ReduceParam
             const int kk = k + u;
             const int r = kk - rb + (kk < rb ? G : 0);
             const bool valid = p.slot_count ? (kk < cnt) : (tb + r < te);
-            v[u] = (kk < k1 && valid) ? __ldg(src + (long long)kk * kTri) : 0.f;
+            v[u] = (kk < k1 && valid) ? __ldcg(src + (long long)kk * kTri) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) s += v[u];
@@ -396,9 +400,9 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(Bwd
     const DomainInfo dom = make_domain(B, p.n, p.K);
     const int M = dom.M;
     const EpiMem mem = resolve_mem<kSmem>(smem_raw, p.scratch, B, M);
-    const float g_off = p.g_off ? __ldg(p.g_off) : 0.f;
-    const float g_diag = p.g_diag ? __ldg(p.g_diag) : 0.f;
-    const float g_dom = p.g_dom ? __ldg(p.g_dom) : 0.f;
+    const float g_off = p.g_off ? __ldcg(p.g_off) : 0.f;
+    const float g_diag = p.g_diag ? __ldcg(p.g_diag) : 0.f;
+    const float g_dom = p.g_dom ? __ldcg(p.g_dom) : 0.f;
     const bool need_dom = (M > 0) && (g_dom != 0.f);      // block-uniform
     __shared__ IndexTables tab;
     build_index_tables(tab, tid, kEpiThreads);
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(Bwd
         for (int idx = tid; idx < M * kOff; idx += kEpiThreads) {
             const int b = idx / kOff, o = idx - b * kOff;
             const int ij = tab.off[o];
-            mem.v[size_t(b) * kVStride + o] = __ldg(p.gram + b * 256 + (ij >> 4) * kC + (ij & 15));
+            mem.v[size_t(b) * kVStride + o] = __ldcg(p.gram + b * 256 + (ij >> 4) * kC + (ij & 15));
         }
         __syncthreads();
         WTPSE_STAMP(1);
@@ -433,10 +437,10 @@ __global__ void __launch_bounds__(kEpiThreads, 1) whiten_epilogue_bwd_kernel(Bwd
     for (int idx = tid; idx < B * kTri; idx += kEpiThreads) {
         const int b = idx / kTri, e = idx - b * kTri;
         const int ij = tab.tri[e], i = ij >> 4, j = ij & 15;
-        const float g = __ldg(p.gram + b * 256 + i * kC + j);
+        const float g = __ldcg(p.gram + b * 256 + i * kC + j);
         float dom_grad = 0.f;
         if (need_dom && b < M && i != j) dom_grad = g_dom * mmd_grad_entry(mem.v, mem.U + size_t(b) * M, M, b, off_idx(i, j));
-        const float m = backward_matrix_entry(i, j, g, __ldg(p.rowstat + b * 2 + 0), __ldg(p.rowstat + b * 2 + 1), w_off,
+        const float m = backward_matrix_entry(i, j, g, __ldcg(p.rowstat + b * 2 + 0), __ldcg(p.rowstat + b * 2 + 1), w_off,
                                               w_diag, dom_grad, denom);
         p.mmat[b * 256 + i * kC + j] = m;
         p.mmat[b * 256 + j * kC + i] = m;
@@ -464,9 +468,9 @@ __global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) 
     __shared__ IndexTables tab;
     build_index_tables(tab, tid, kMmatThreads);
     asm volatile("griddepcontrol.wait;" ::: "memory");             // inputs may come from the kernel right before us
-    const float g_off = p.g_off ? __ldg(p.g_off) : 0.f;
-    const float g_diag = p.g_diag ? __ldg(p.g_diag) : 0.f;
-    const float g_dom = p.g_dom ? __ldg(p.g_dom) : 0.f;
+    const float g_off = p.g_off ? __ldcg(p.g_off) : 0.f;
+    const float g_diag = p.g_diag ? __ldcg(p.g_diag) : 0.f;
+    const float g_dom = p.g_dom ? __ldcg(p.g_dom) : 0.f;
     const bool in_mmd = (M > 0) && (g_dom != 0.f) && (b < M);         // block-uniform
     __syncthreads();
     if (in_mmd) {
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) 
                 if (idx < M * kOff) {
                     const int c = idx / kOff, o = idx - c * kOff;
                     const int ij = tab.off[o];
-                    v[u] = __ldg(p.gram + c * 256 + (ij >> 4) * kC + (ij & 15));
+                    v[u] = __ldcg(p.gram + c * 256 + (ij >> 4) * kC + (ij & 15));
                 } else {
                     v[u] = 0.f;
                 }
@@ -506,10 +510,10 @@ __global__ void __launch_bounds__(kMmatThreads) whiten_mmat_kernel(BwdParams p) 
     const float w_diag = g_diag / (float(B) * float(kC));
     if (tid < kTri) {
         const int ij = tab.tri[tid], i = ij >> 4, j = ij & 15;
-        const float g = __ldg(p.gram + b * 256 + i * kC + j);
+        const float g = __ldcg(p.gram + b * 256 + i * kC + j);
         float dom_grad = 0.f;
         if (in_mmd && i != j) dom_grad = g_dom * mmd_grad_entry(vbuf, coefrow, M, b, off_idx(i, j));
-        const float m = backward_matrix_entry(i, j, g, __ldg(p.rowstat + b * 2 + 0), __ldg(p.rowstat + b * 2 + 1), w_off,
+        const float m = backward_matrix_entry(i, j, g, __ldcg(p.rowstat + b * 2 + 0), __ldcg(p.rowstat + b * 2 + 1), w_off,
                                               w_diag, dom_grad, denom);
         p.mmat[b * 256 + i * kC + j] = m;
         p.mmat[b * 256 + j * kC + i] = m;
@@ -530,7 +534,7 @@ struct MmdParams {
 __device__ __forceinline__ void mmd_stage_vectors(const MmdParams& p, const EpiMem& mem, int M, int tid) {
     for (int idx = tid; idx < M * kOff; idx += kEpiThreads) {
         const int b = idx / kOff, o = idx - b * kOff;
-        mem.v[size_t(b) * kVStride + o] = __ldg(p.v32 + idx);
+        mem.v[size_t(b) * kVStride + o] = __ldcg(p.v32 + idx);
     }
 }
 
@@ -576,7 +580,7 @@ __global__ void __launch_bounds__(kEpiThreads, 1) mmd_bwd_kernel(MmdParams p) {
     });
     for (int a = tid; a < M; a += kEpiThreads) coef[a * M + a] = 0.f;
     __syncthreads();
-    const float g = p.gout ? __ldg(p.gout) : 1.f;
+    const float g = p.gout ? __ldcg(p.gout) : 1.f;
     for (int idx = tid; idx < p.B * kOff; idx += kEpiThreads) {
         const int b = idx / kOff, o = idx - b * kOff;
         p.dv[idx] = (b < M) ? g * mmd_grad_entry(mem.v, mem.U + size_t(b) * M, M, b, o) : 0.f;
