@@ -2,12 +2,12 @@
 // [B][P][16] -- the memory of channels-last B x 16 x H x W tensors, so a channels-last backbone needs no layout
 // conversion around the loss.
 //
-// A pixel's 16 channels are 64 contiguous bytes: every thread loads its own pixel with four 128-bit loads (a warp
-// covers 2 KB contiguous) through a 4-deep register ring (three pixels per thread in flight), multiplies by M_b held in
-// shared memory (64 warp-uniform LDS.128 per pixel) and stores 64 contiguous bytes.  No shared-memory staging of the
-// streams: there is no reuse and the per-thread accesses are already contiguous.  Persistent CTAs, blocks of 1024
-// pixels dealt round-robin (adjacent CTAs stream adjacent memory).  Rounding as in the NCHW kernels: the
-// 16-term product is accumulated first, the masked ReLU gradient added last.
+// A pixel's 16 channels are 64 contiguous bytes: every thread loads its own pixels with four 128-bit loads each (a warp
+// covers 2 KB contiguous) through a two-deep register ring, multiplies by M_b held in shared memory (warp-uniform
+// LDS.128, amortised over the 2-4 pixels a thread owns) and stores 64 contiguous bytes per pixel.  No shared-memory
+// staging of the streams: there is no reuse and the per-thread accesses are already contiguous.  Persistent CTAs,
+// steps of 512 / 1024 pixels dealt round-robin (adjacent CTAs stream adjacent memory).  Rounding as in the NCHW
+// kernels: the 16-term product is accumulated first, the masked ReLU gradient added last.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,7 +16,6 @@ namespace wtpse {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kBlockSteps = 4;             // 4 x 256 pixels = 64 KB of each stream per schedule block
 
 __device__ __forceinline__ void st_cs4(float4* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -27,88 +26,101 @@ __device__ __forceinline__ float4 ld_cs4(const float4* p) {
     return v;
 }
 
+// kPx pixels per thread (tid, tid + 256, ...): one warp-uniform LDS.128 of M_b then feeds 4 * kPx FMAs.  With one pixel
+// per thread the kernel was bound by the shared-memory pipe (64 LDS.128 per pixel, ~4 cycles each: 427 us for the fused
+// variant at 32x16x512x512 = 0.58 of the HBM roofline).  Plain: 4 pixels per thread; fused (the ReLU gradient doubles
+// the staged registers): 2.  A two-deep register ring keeps the next step's loads (64 KB per SM) in flight.
 template <bool kReluGrad>
 __global__ void __launch_bounds__(kThreads, 1)
 apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, const float* __restrict__ mmat,
                 float* __restrict__ dz, long long P, long long steps_per_sample, long long total_steps) {
+    constexpr int kPx = kReluGrad ? 2 : 4;
+    constexpr int kStepPx = kPx * kThreads;
     __shared__ __align__(16) float msh[256];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
-    // A step = 256 consecutive pixels of one sample (one per thread).  Blocks of kBlockSteps consecutive steps (1024
-    // pixels, 64 KB per stream) are dealt round-robin to the CTAs, so the grid streams adjacent memory at any moment.
+    // A step = kStepPx consecutive pixels of one sample, dealt round-robin to the CTAs: the grid streams adjacent memory.
     const long long G = gridDim.x, bx = blockIdx.x;
-    const long long nblk = (total_steps + kBlockSteps - 1) / kBlockSteps;
-    const long long my_steps = (nblk > bx ? (nblk - bx + G - 1) / G : 0) * kBlockSteps;
-    auto global_step = [&](long long k) { return ((k / kBlockSteps) * G + bx) * kBlockSteps + (k % kBlockSteps); };
+    const long long my_steps = total_steps > bx ? (total_steps - bx + G - 1) / G : 0;
 
-    struct Px { float4 x[4]; float4 g[kReluGrad ? 4 : 1]; };
-    auto load_step = [&](Px& r, long long k) {
+    struct Stage { float4 x[kPx][4]; float4 g[kReluGrad ? kPx : 1][4]; };
+    auto load_step = [&](Stage& r, long long k) {
         if (k >= my_steps) return;
-        const long long s = global_step(k);
-        if (s >= total_steps) return;
+        const long long s = k * G + bx;
         const long long b = s / steps_per_sample;
-        const long long p = (s - b * steps_per_sample) * kThreads + tid;
-        if (p >= P) return;
-        const float4* src = reinterpret_cast<const float4*>(z + (b * P + p) * kC);
+        const long long p0 = (s - b * steps_per_sample) * kStepPx + tid;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) r.x[q] = ld_cs4(src + q);
-        if (kReluGrad) {
-            const float4* gs = reinterpret_cast<const float4*>(grelu + (b * P + p) * kC);
+        for (int u = 0; u < kPx; ++u) {
+            const long long p = p0 + u * kThreads;
+            if (p < P) {
+                const float4* src = reinterpret_cast<const float4*>(z + (b * P + p) * kC);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) r.g[q] = ld_cs4(gs + q);
+                for (int q = 0; q < 4; ++q) r.x[u][q] = ld_cs4(src + q);
+                if (kReluGrad) {
+                    const float4* gs = reinterpret_cast<const float4*>(grelu + (b * P + p) * kC);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) r.g[u][q] = ld_cs4(gs + q);
+                }
+            }
         }
     };
     long long cur_b = -1;
-    auto use_step = [&](const Px& r, long long k) {
+    auto use_step = [&](const Stage& r, long long k) {
         if (k >= my_steps) return;                            // every condition up to the barrier is uniform over the CTA
-        const long long s = global_step(k);
-        if (s >= total_steps) return;
+        const long long s = k * G + bx;
         const long long b = s / steps_per_sample;
         if (b != cur_b) {
             __syncthreads();                                  // previous matrix no longer in use
             if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
-            msh[tid] = __ldcg(mmat + b * 256 + tid);   // coherent load: an invariant (.nc) one may be hoisted above the wait
+            msh[tid] = __ldcg(mmat + b * 256 + tid);         // coherent load: an invariant (.nc) one may be hoisted above the wait
             __syncthreads();
             cur_b = b;
         }
-        const long long p = (s - b * steps_per_sample) * kThreads + tid;
-        if (p >= P) return;
-        const float x[kC] = {r.x[0].x, r.x[0].y, r.x[0].z, r.x[0].w, r.x[1].x, r.x[1].y, r.x[1].z, r.x[1].w,
-                             r.x[2].x, r.x[2].y, r.x[2].z, r.x[2].w, r.x[3].x, r.x[3].y, r.x[3].z, r.x[3].w};
-        float out[kC];
+        const long long p0 = (s - b * steps_per_sample) * kStepPx + tid;
+        float4 out[kPx][4];
+#pragma unroll
+        for (int u = 0; u < kPx; ++u)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[u][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // out[u][i] = sum_j M[i][j] x[u][j]; per (i, jq) one LDS.128 of M feeds 4 FMAs per pixel
 #pragma unroll
         for (int i = 0; i < kC; ++i) {
-            float a = 0.f;
 #pragma unroll
             for (int jq = 0; jq < 4; ++jq) {
                 const float4 m = *reinterpret_cast<const float4*>(msh + i * kC + 4 * jq);
-                a = fmaf(m.x, x[4 * jq + 0], a);
-                a = fmaf(m.y, x[4 * jq + 1], a);
-                a = fmaf(m.z, x[4 * jq + 2], a);
-                a = fmaf(m.w, x[4 * jq + 3], a);
+#pragma unroll
+                for (int u = 0; u < kPx; ++u) {
+                    float& o = (i & 3) == 0 ? out[u][i >> 2].x : (i & 3) == 1 ? out[u][i >> 2].y : (i & 3) == 2 ? out[u][i >> 2].z : out[u][i >> 2].w;
+                    o = fmaf(m.x, r.x[u][jq].x, o);
+                    o = fmaf(m.y, r.x[u][jq].y, o);
+                    o = fmaf(m.z, r.x[u][jq].z, o);
+                    o = fmaf(m.w, r.x[u][jq].w, o);
+                }
             }
-            out[i] = a;
         }
-        if (kReluGrad) {
-            const float g[kC] = {r.g[0].x, r.g[0].y, r.g[0].z, r.g[0].w, r.g[1].x, r.g[1].y, r.g[1].z, r.g[1].w,
-                                 r.g[2].x, r.g[2].y, r.g[2].z, r.g[2].w, r.g[3].x, r.g[3].y, r.g[3].z, r.g[3].w};
 #pragma unroll
-            for (int i = 0; i < kC; ++i) out[i] += x[i] <= 0.f ? 0.f : g[i];
+        for (int u = 0; u < kPx; ++u) {
+            const long long p = p0 + u * kThreads;
+            if (p >= P) continue;
+            float4* d = reinterpret_cast<float4*>(dz + (b * P + p) * kC);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 o = out[u][q];
+                if (kReluGrad) {                               // added last: the rounding of autograd's dz_loss + dz_relu
+                    const float4 xv = r.x[u][q], gv = r.g[u][q];
+                    o.x += xv.x <= 0.f ? 0.f : gv.x; o.y += xv.y <= 0.f ? 0.f : gv.y;
+                    o.z += xv.z <= 0.f ? 0.f : gv.z; o.w += xv.w <= 0.f ? 0.f : gv.w;
+                }
+                st_cs4(d + q, o);
+            }
         }
-        float4* d = reinterpret_cast<float4*>(dz + (b * P + p) * kC);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) st_cs4(d + q, make_float4(out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]));
     };
 
-    Px r0, r1, r2, r3;
+    Stage r0, r1;
     load_step(r0, 0);
-    load_step(r1, 1);
-    load_step(r2, 2);
-    for (long long k = 0; k < my_steps; k += 4) {
-        load_step(r3, k + 3); use_step(r0, k);
-        load_step(r0, k + 4); use_step(r1, k + 1);
-        load_step(r1, k + 5); use_step(r2, k + 2);
-        load_step(r2, k + 6); use_step(r3, k + 3);
+    for (long long k = 0; k < my_steps; k += 2) {
+        load_step(r1, k + 1); use_step(r0, k);
+        load_step(r0, k + 2); use_step(r1, k + 1);
     }
 }
 
@@ -116,10 +128,10 @@ apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, co
 
 cudaError_t launch_apply_cl(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P, int sm_count,
                             cudaStream_t stream, bool programmatic_dependent) {
-    const long long sps = (P + kThreads - 1) / kThreads;       // steps per sample
+    const long long step_px = (grelu ? 2 : 4) * kThreads;      // kPx * kThreads of the instantiation launched below
+    const long long sps = (P + step_px - 1) / step_px;         // steps per sample
     const long long total = sps * B;
-    const long long nblk = (total + kBlockSteps - 1) / kBlockSteps;
-    const long long G = nblk < sm_count ? nblk : sm_count;
+    const long long G = total < sm_count ? total : sm_count;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(G));
     cfg.blockDim = dim3(kThreads);
