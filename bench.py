@@ -282,6 +282,11 @@ def run_reference_arm(args):
         return
     import torch
 
+    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread this process may run on
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     H = args.size
     n, K = 2, 3
     B = n * K                                   # bounded sample: 6 of the workload's samples per step
