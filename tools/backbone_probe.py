@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import wtpse_b200 as wb
-from wtpse_b200.elementwise import batch_norm_act, channel_sum
+from wtpse_b200.elementwise import batch_norm_act, channel_sum, max_pool2
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -23,5 +23,8 @@ for C, S in ((16, 512), (32, 512), (32, 256), (64, 128), (128, 64), (256, 32)):
     if S < 512:
         u = wb.upsample2x(x)
         u.backward(torch.randn_like(u))
+    if S > 32:
+        m = max_pool2(x)
+        m.backward(torch.randn_like(m))
 torch.cuda.synchronize()
 print("ok")

@@ -140,28 +140,28 @@ bias_act_nhwc_kernel(float* __restrict__ y, const float* __restrict__ bias, long
 }
 
 // out[c] = sum over pixels of g[p][c] (channels-last): the bias gradient of a convolution, `g.sum((0, 2, 3))`.
-// Two deterministic stages: every CTA sums a contiguous pixel range per channel (thread t owns channel quad t % C4,
-// 128-bit loads, fixed-order shared-memory tree), then one CTA adds the per-CTA partials in index order.
+// Two deterministic stages: every CTA sums a fixed grid-strided set of pixels per channel (thread t owns channel quad
+// t % C4, 128-bit loads, fixed-order shared-memory tree), then one warp per channel adds the per-CTA partials.
 __global__ void __launch_bounds__(kThreads)
 channel_sum_partial_kernel(const float* __restrict__ g, long long npix, int C4, float* __restrict__ partial) {
     __shared__ float4 red[kThreads];
     const int tid = threadIdx.x;
     const int lanes = kThreads / C4;                 // pixels in flight per CTA iteration (C4 divides 256)
     const int q = tid % C4, r = tid / C4;
-    const long long per = (npix + gridDim.x - 1) / gridDim.x;
-    const long long p0 = (long long)blockIdx.x * per;
-    const long long p1 = p0 + per < npix ? p0 + per : npix;
+    // grid-stride over pixel rows: the whole grid reads one contiguous window at a time (DRAM locality)
+    const long long stride = (long long)gridDim.x * lanes;
+    const long long p1 = npix;
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    long long p = p0 + r;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {    // four independent accumulators: four 128-bit loads in flight
-        const float4 v0 = ld4(g + (p * C4 + q) * 4), v1 = ld4(g + ((p + lanes) * C4 + q) * 4);
-        const float4 v2 = ld4(g + ((p + 2 * lanes) * C4 + q) * 4), v3 = ld4(g + ((p + 3 * lanes) * C4 + q) * 4);
+    long long p = (long long)blockIdx.x * lanes + r;
+    for (; p + 3 * stride < p1; p += 4 * stride) {    // four independent accumulators: four 128-bit loads in flight
+        const float4 v0 = ld4(g + (p * C4 + q) * 4), v1 = ld4(g + ((p + stride) * C4 + q) * 4);
+        const float4 v2 = ld4(g + ((p + 2 * stride) * C4 + q) * 4), v3 = ld4(g + ((p + 3 * stride) * C4 + q) * 4);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
         a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
         a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
     }
-    for (; p < p1; p += lanes) {
+    for (; p < p1; p += stride) {
         const float4 v0 = ld4(g + (p * C4 + q) * 4);
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
     }

@@ -59,9 +59,10 @@ bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, lon
     const int tid = threadIdx.x;
     const int lanes = kThreads / C4;
     const int q = tid % C4, r = tid / C4;
-    const long long per = (npix + gridDim.x - 1) / gridDim.x;
-    const long long p0 = (long long)blockIdx.x * per;
-    const long long p1 = p0 + per < npix ? p0 + per : npix;
+    // grid-stride over pixel rows: at any moment the whole grid reads one contiguous window per stream (contiguous
+    // per-CTA ranges made 2 x 592 scattered streams: 142 us instead of 94 us for the backward sums at 15x16x512x512)
+    const long long stride = (long long)gridDim.x * lanes;
+    const long long p1 = npix;
     // forward: the shift K = first pixel of the channel; backward: the batch mean
     const float4 ctr = kBackward ? ldg4(mean + 4 * q) : ldg4(x + 4 * q);
     float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), bt = sc;
@@ -85,14 +86,14 @@ bn_partial_kernel(const float* __restrict__ x, const float* __restrict__ dy, lon
     };
     // four independent pixel rows per iteration: four 128-bit loads (eight in the backward) in flight per thread
     float4 c1 = a1, c2 = a1, d1 = a1, d2 = a1;
-    long long p = p0 + r;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    long long p = (long long)blockIdx.x * lanes + r;
+    for (; p + 3 * stride < p1; p += 4 * stride) {
         step(p, a1, a2);
-        step(p + lanes, b1, b2);
-        step(p + 2 * lanes, c1, c2);
-        step(p + 3 * lanes, d1, d2);
+        step(p + stride, b1, b2);
+        step(p + 2 * stride, c1, c2);
+        step(p + 3 * stride, d1, d2);
     }
-    for (; p < p1; p += lanes) step(p, a1, a2);
+    for (; p < p1; p += stride) step(p, a1, a2);
     acc4(b1, d1); acc4(b2, d2);
     acc4(a1, c1); acc4(a2, c2);
     acc4(a1, b1);
