@@ -244,7 +244,6 @@ class DeepWT(nn.Module):
         super().__init__()
         self.whitening = whitening
         self.fused_loss = None            # see enable_relu_fusion / deepwt_forward
-        self.out_memory_format = None
         if whitening:
             self.DoubleConv = _DoubleConvWT(input_channel, out_channel)
             self.DoubleConv2 = _DoubleConvWT(out_channel, out_channel)
@@ -279,9 +278,6 @@ def deepwt_forward(self, x):
     r1, *terms1 = fn(z1, *args)
     setattr(z0, _LOSS_TAG, tuple(terms0))
     setattr(z1, _LOSS_TAG, tuple(terms1))
-    fmt = getattr(self, "out_memory_format", None)
-    if fmt is not None:
-        r1 = r1.contiguous(memory_format=fmt)
     return [z0, z1, r1]
 
 
