@@ -157,3 +157,61 @@ def test_conv_bias_folding_keeps_outputs_gradients_and_running_statistics():
             assert torch.allclose(a[3][n].float(), b[3][n].float(), rtol=1e-5, atol=1e-6), n
             if n.endswith("num_batches_tracked"):
                 assert int(b[3][n]) == 2
+
+
+def test_host_side_switches_of_the_train_step_kernels():
+    """Host logic around the backbone / fusion kernels that needs no GPU: layout dispatch of the loss input, the
+    per-network fusion config, the flag setters, state-dict keys of the Sequential subclass, ATen fall-backs."""
+    from wtpse_b200 import elementwise as ew
+    from wtpse_b200 import functional as wf
+    from wtpse_b200 import segmentation as seg
+
+    # loss input: dense channels-last -> read in place by the *_cl entry points; everything else -> NCHW contiguous
+    z = torch.randn(2, 16, 6, 5)
+    t, cl = wf._as_loss_input(z)
+    assert not cl and t.is_contiguous()
+    t, cl = wf._as_loss_input(z.contiguous(memory_format=torch.channels_last))
+    assert cl and t.is_contiguous(memory_format=torch.channels_last)
+    t, cl = wf._as_loss_input(z.contiguous(memory_format=torch.channels_last)[:, :, ::2])       # strided view: copy
+    assert not cl and t.is_contiguous()
+    t, cl = wf._as_loss_input(torch.randn(2, 16, 1, 1))                                          # ambiguous strides: NCHW
+    assert not cl
+
+    hp = dict(HP)
+    main = seg.WT_PSE(3, 1, hp, "cpu", True, per_domain_batch=4, source_domain_num=2)
+    shape = seg.ShapeVariationalDist_x(hp, "cpu", 1, number_source_domain=2, batch_size=4)
+    assert main.wt_model.fused_loss is None and shape.teacher_grad is True
+    seg.enable_relu_fusion(main)
+    seg.enable_relu_fusion(shape)
+    assert main.wt_model.fused_loss == {"fold": True, "n_per_domain": 4, "n_domains": 2, "margin": 0.0, "eps": 1e-5}
+    assert shape.wt_model.fused_loss["fold"] is False and shape.wt_model.fused_loss["n_domains"] == 3     # literal 3
+    seg.enable_relu_fusion(main, False)
+    assert main.wt_model.fused_loss is None
+    assert seg.fused_terms(z, 2) is None                        # no tag -> compute_whitening_loss runs the kernels
+
+    for setter, attr in ((seg.set_conv_bias_folding, "fold_bias"), (seg.set_cuda_batchnorm, "cuda_bn"),
+                         (seg.set_cuda_pool, "cuda_pool"), (seg.set_cuda_upsample, "cuda_upsample")):
+        setter(main, True)
+        mods = [m for m in main.modules() if hasattr(m, attr)]
+        assert mods and all(getattr(m, attr) for m in mods)
+        setter(main, False)
+        assert not any(getattr(m, attr) for m in mods)
+    seg.set_fast_bias(main, True)
+    assert all(m.fast_bias for m in main.modules() if isinstance(m, seg._ConvActSeq))
+    seg.set_fast_bias(main, False)
+
+    head = seg._head(32, 8, 1)
+    assert isinstance(head, torch.nn.Sequential) and list(head.state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias"]
+    x = torch.randn(2, 32, 5, 5)
+    want = head(x)
+    head.fast_bias = True                                       # CPU input: conv_bias_act takes the plain operators
+    assert torch.allclose(head(x), want)
+
+    g = torch.randn(3, 8, 4, 4)
+    assert torch.allclose(ew.channel_sum(g), g.sum((0, 2, 3)))  # ATen route off the GPU
+    bn = torch.nn.BatchNorm2d(8).train()
+    assert not ew.batch_norm_act_supported(g, bn) and not ew.upsample2x_supported(g) and not ew.max_pool2_supported(g)
+    with pytest.raises(ValueError):
+        ew.upsample2x(g)
+    with pytest.raises(ValueError):
+        ew.max_pool2(g)
