@@ -122,6 +122,10 @@ int wtpse_bias_act_nhwc(float* y, const float* bias, int64_t npix, int C, int re
  * two deterministic stages, no atomics.
  */
 size_t wtpse_channel_sum_workspace_bytes(int64_t npix, int C);
+/* Backward of wtpse_bias_act_nhwc(relu = 1) in one pass: gx = [out > 0] * g (ATen threshold_backward on the saved output; passes
+ * where out is NaN) and bias_grad[c] = sum_p gx[p][c].  Workspace as for wtpse_channel_sum_nhwc; gx may alias g. */
+int wtpse_relu_backward_channel_sum_nhwc(const float* g, const float* out, int64_t npix, int C, float* gx, float* bias_grad,
+                                         void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out,
                            void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 

@@ -48,6 +48,8 @@ EXPORTS = {
     "wtpse_whitening_backward_cl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
                                                _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "wtpse_relu_backward_channel_sum_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                                        _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
     "wtpse_mmd_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                      _c.c_size_t, _c.c_void_p]),

@@ -401,6 +401,20 @@ int wtpse_channel_sum_nhwc(const float* g, int64_t npix, int C, float* out, void
     return WTPSE_OK;
 }
 
+int wtpse_relu_backward_channel_sum_nhwc(const float* g, const float* out, int64_t npix, int C, float* gx, float* bias_grad,
+                                         void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
+    if (!g || !out || !gx || !bias_grad || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
+    if (npix <= 0 || !channel_sum_supported(C)) return fail(WTPSE_ERR_INVALID, "need npix >= 1 and C a power of two in [4, 1024] (got C=%d)", C);
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gx) | reinterpret_cast<uintptr_t>(workspace)) & 15u)
+        return fail(WTPSE_ERR_INVALID, "pointers must be 16-byte aligned");
+    if (workspace_bytes < wtpse_channel_sum_workspace_bytes(npix, C)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    { LaunchScope scope(kKernUpsample, s); e = launch_relu_bwd_channel_sum_nhwc(g, out, gx, npix, C, bias_grad, static_cast<float*>(workspace), sm_count_cached(), s); }
+    if (e != cudaSuccess) return cuda_fail(e, "relu_backward_channel_sum launch");
+    return WTPSE_OK;
+}
+
 int wtpse_maxpool2_nhwc(const float* in, float* out, unsigned char* argmax, int64_t N, int Ho, int Wo, int C, int backward,
                         wtpse_stream_t stream) {
     if (!in || !out || !argmax) return fail(WTPSE_ERR_INVALID, "null pointer");

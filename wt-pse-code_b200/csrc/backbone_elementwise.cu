@@ -181,6 +181,46 @@ channel_sum_partial_kernel(const float* __restrict__ g, long long npix, int C4, 
     if (r == 0) reinterpret_cast<float4*>(partial)[(long long)blockIdx.x * C4 + q] = red[tid];
 }
 
+// Backward of bias + ReLU in one pass: gx = [out > 0] * g (ATen's threshold_backward on the saved output) and the
+// per-CTA channel sums of gx (the bias gradient) -- instead of threshold_backward followed by a second read for the sum.
+// Same schedule and reduction order as channel_sum_partial_kernel.
+__global__ void __launch_bounds__(kThreads)
+relu_bwd_channel_sum_kernel(const float* __restrict__ g, const float* __restrict__ out, float* __restrict__ gx, long long npix, int C4,
+                            float* __restrict__ partial) {
+    __shared__ float4 red[kThreads];
+    const int tid = threadIdx.x;
+    const int lanes = kThreads / C4;
+    const int q = tid % C4, r = tid / C4;
+    const long long stride = (long long)gridDim.x * lanes;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    auto step = [&](long long p, float4& a) {
+        const long long e = (p * C4 + q) * 4;
+        float4 v = ld4(g + e);
+        const float4 o = ld4(out + e);
+        v.x = o.x <= 0.f ? 0.f : v.x; v.y = o.y <= 0.f ? 0.f : v.y; v.z = o.z <= 0.f ? 0.f : v.z; v.w = o.w <= 0.f ? 0.f : v.w;
+        *reinterpret_cast<float4*>(gx + e) = v;
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    };
+    long long p = (long long)blockIdx.x * lanes + r;
+    for (; p + stride < npix; p += 2 * stride) {
+        step(p, a0);
+        step(p + stride, a1);
+    }
+    if (p < npix) step(p, a0);
+    red[tid] = make_float4(a0.x + a1.x, a0.y + a1.y, a0.z + a1.z, a0.w + a1.w);
+    __syncthreads();
+    for (int s = lanes >> 1; s > 0; s >>= 1) {
+        if (r < s) {
+            const float4 o = red[tid + s * C4];
+            float4 m = red[tid];
+            m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+            red[tid] = m;
+        }
+        __syncthreads();
+    }
+    if (r == 0) reinterpret_cast<float4*>(partial)[(long long)blockIdx.x * C4 + q] = red[tid];
+}
+
 // one warp per channel: lanes stride over the per-CTA partials, fixed-order butterfly
 __global__ void channel_sum_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -292,6 +332,14 @@ cudaError_t launch_channel_sum_nhwc(const float* g, long long npix, int C, float
     const int blocks = channel_sum_blocks(npix, C, sm_count);
     channel_sum_partial_kernel<<<blocks, kThreads, 0, stream>>>(g, npix, C / 4, partial);
     channel_sum_final_kernel<<<(C + 3) / 4, 128, 0, stream>>>(partial, blocks, C, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relu_bwd_channel_sum_nhwc(const float* g, const float* out, float* gx, long long npix, int C, float* bias_grad,
+                                             float* partial, int sm_count, cudaStream_t stream) {
+    const int blocks = channel_sum_blocks(npix, C, sm_count);
+    relu_bwd_channel_sum_kernel<<<blocks, kThreads, 0, stream>>>(g, out, gx, npix, C / 4, partial);
+    channel_sum_final_kernel<<<(C + 3) / 4, 128, 0, stream>>>(partial, blocks, C, bias_grad);
     return cudaGetLastError();
 }
 

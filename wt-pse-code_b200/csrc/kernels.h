@@ -132,6 +132,10 @@ cudaError_t launch_batchnorm_bwd(const float* x, const float* dy, long long npix
                                  const float* save_mean, const float* save_invstd, const float* save_scale, bool relu, float* dx,
                                  float* dgamma, float* dbeta, float* workspace, int sm_count, cudaStream_t stream);
 
+// gx = [out > 0] * g and bias_grad[c] = sum_p gx[p][c] in one pass (backward of bias + ReLU); partial as for channel_sum
+cudaError_t launch_relu_bwd_channel_sum_nhwc(const float* g, const float* out, float* gx, long long npix, int C, float* bias_grad,
+                                             float* partial, int sm_count, cudaStream_t stream);
+
 // Track W (wavelet.cu)
 size_t wavelet_scratch_floats(long long nmaps, int H, int W);
 size_t wavelet_partial_doubles(long long nmaps, int H, int W, int J);

@@ -207,6 +207,20 @@ class _BiasAct(torch.autograd.Function):
     def backward(ctx, g):
         if ctx.relu:
             (out,) = ctx.saved_tensors
+            C = out.shape[1]
+            if (ctx.needs_input_grad[1] and g.dtype == torch.float32 and (C & (C - 1)) == 0 and 4 <= C <= 1024
+                    and g.is_contiguous(memory_format=torch.channels_last) and g.data_ptr() % 16 == 0):
+                # ReLU backward and the bias gradient in one pass over g and the saved output
+                N, _, H, W = out.shape
+                lib = _lib.load()
+                with torch.cuda.device(g.device):
+                    gx = torch.empty_like(out)
+                    gb = torch.empty(C, dtype=torch.float32, device=g.device)
+                    ws_bytes = lib.wtpse_channel_sum_workspace_bytes(N * H * W, C)
+                    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=g.device)
+                    _lib.check(lib.wtpse_relu_backward_channel_sum_nhwc(_ptr(g), _ptr(out), N * H * W, C, _ptr(gx), _ptr(gb),
+                                                                        _ptr(ws), ws_bytes, _stream_ptr(g.device)))
+                return gx, gb, None
             g = torch.ops.aten.threshold_backward(g, out, 0)          # what ReluBackward0 runs
         return g, (channel_sum(g) if ctx.needs_input_grad[1] else None), None
 
