@@ -13,7 +13,11 @@ z = 32 x 16 x 512 x 512 fp32 feature maps, 3 domains x 10 samples.  1 pix = one 
           H2D, forward, backward, D2H of dz and of the losses, every step
   roofline  the dominant kernel (apply_tma_kernel, backward) -- algorithmic bytes / its CUDA-event duration
             measured inside the timed region, against MEASURED_PEAKS.json
-  cpu_baseline  the oracle's PyTorch-CPU port of the reference path on this box's host cores (bounded sample)
+  cpu_baseline  the reference's own CPU path (the unmodified algorithms.py from oracle/_ref, `kind: "reference"`; the
+          oracle's operator-sequence port only if that copy is missing) on this box's host cores, SAME workload
+  configs   the other BASELINE configs mapped onto Track R (8x16x256x256, 64x16x1024x1024) -- device-resident fwd+bwd
+  wavelet   BASELINE configs as literally written (Track W, parity unpinned): Haar J=3 8x2x256^2, db2 J=4 32x2x512^2,
+          Haar + db2 J=1..5 at 64x2x1024^2
 
 N > 1 (torchrun, one rank per GPU): the path shards over whole [K domains x n] batches with no data-path
 collective; every rank processes its own batch -> "scaling": "weak".
@@ -32,6 +36,47 @@ if ROOT not in sys.path:
 WORKLOAD = dict(B=32, C=16, H=512, W=512, n_per_domain=10, n_domains=3, margin=0.0, eps=1e-5)
 ALGO_BYTES_PER_PIX = {"gram_tma_kernel": 64, "apply_tma_kernel": 128}   # fwd read z; bwd read z + write dz
 FALLBACK_PEAK_GBS = 6650.0                                               # B200_PROFILING.md fallback
+METRIC = "shape-loss fwd+bwd Mpix/s"
+
+
+def workload_config(B, H, W, n, K):
+    """`config` of the JSON line -- built by ONE function so that both arms (ours / --impl reference) print the same dict."""
+    return {"workload": "whitening+MMD shape loss fwd+bwd (WT_PSE.compute_whitening_loss), z=%dx16x%dx%d fp32, "
+                        "n=%d K=%d per GPU [BASELINE configs[1] mapped per SURVEY 8(d)]" % (B, H, W, n, K),
+            "per_gpu_batch": B,
+            "l2": "inputs (%.0f MB, two alternating buffers) larger than L2" % (B * 16 * H * W * 4 / 1e6),
+            "sharding": "independent [K x n] batches per rank, no data-path collective"}
+
+
+def workload_dims(args):
+    B, H = args.batch, args.size
+    n = max(1, B // 3) if B != WORKLOAD["B"] else WORKLOAD["n_per_domain"]
+    return B, H, H, n, WORKLOAD["n_domains"]
+
+
+def kernel_source_hash():
+    """sha256 over the CUDA sources the loaded library was built from (the GPU box has no .git): profiles/traffic.json
+    records the hash its ncu capture was taken at, so a stale `roofline.traffic` is flagged instead of silently reused."""
+    import hashlib
+
+    csrc = os.path.join(ROOT, "wt-pse-code_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h")):
+            h.update(name.encode())
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def traffic_entry(key):
+    """(bytes per launch or None, stale flag, capture hash) from profiles/traffic.json."""
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tpath):
+        return None, None, None
+    t = json.load(open(tpath))
+    cap = t.get("kernel_source_hash")
+    return t.get(key), (cap != kernel_source_hash()), cap
 
 
 def parse_args():
@@ -71,6 +116,9 @@ def parse_args():
     ap.add_argument("--debug-l2-hint", type=int, default=-1)
     ap.add_argument("--debug-gram-variant", type=int, default=-1)
     ap.add_argument("--debug-two-stage-epilogue", type=int, default=1)
+    ap.add_argument("--extra-configs", type=int, default=1, help="also time the other BASELINE configs (Track R 256^2 / 1024^2, Track W) at N=1")
+    ap.add_argument("--numa-affinity", type=int, default=1, help="bind each rank to the CPUs NVML reports as local to its GPU before allocating pinned buffers")
+    ap.add_argument("--train-reference-eager", type=int, default=1, help="also time the UNMODIFIED reference classes' iteration (oracle/_ref) on the same GPU")
     ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
 
@@ -154,67 +202,106 @@ def physical_gpu_index(local_rank):
 # CPU legs (oracle port, or the real reference when its tree is on this box)
 # -------------------------------------------------------------------------------------------------
 def cpu_step_fn(n, K):
-    """Returns (callable(z) -> None doing one fwd+bwd, kind)."""
+    """Returns (callable(z) -> None doing one fwd+bwd on HOST tensors, kind, context manager to run it under)."""
+    import contextlib
+
     import torch
     from oracle import ref_shim
 
-    if ref_shim.available() and not torch.cuda.is_available():
-        # build container: the unmodified reference through the import shim
+    if ref_shim.available():
+        # the unmodified reference (oracle/_ref: byte-for-byte copy, sha256-checked; /root/reference in the build
+        # container); its hard-coded .cuda() calls are neutralised for the CPU leg (ref_shim.cpu_only)
         alg, _, _ = ref_shim.load()
         hp = dict(ref_shim.DEFAULT_HPARAMS)
-        torch.manual_seed(0)
-        model = alg.WT_PSE(3, 1, hp, "cpu", False, per_domain_batch=n, source_domain_num=K)
+        with ref_shim.cpu_only():
+            torch.manual_seed(0)
+            model = alg.WT_PSE(3, 1, hp, "cpu", False, per_domain_batch=n, source_domain_num=K)
 
         def step(z):
             z = z.detach().requires_grad_(True)
-            ins, dom = model.compute_whitening_loss(z)
+            ins, dom = model.compute_whitening_loss(z)          # algorithms.py:1277-1309, as published
             (ins + dom).backward()
-        return step, "reference"
+            return float(ins.detach()), float(dom.detach())
+        return step, "reference", ref_shim.cpu_only
     from oracle import whitening_torch as wt
 
     def step(z):
-        wt.fwd_bwd(z, n, K)
-    return step, "port"
+        ins, dom, _ = wt.fwd_bwd(z, n, K)
+        return float(ins.detach()), float(dom.detach())
+    return step, "port", contextlib.nullcontext
 
 
-def time_cpu(B, H, W, n, K, budget_s, max_iters):
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def time_cpu(B, H, W, n, K, budget_s, max_iters, z=None):
+    """cpu_baseline: the SAME workload as the GPU arm on this box's host cores; bounded by time, not by shrinking it.
+    z: host copy of the very batch the GPU arm's reported losses come from (else a seeded host batch)."""
     import torch
 
-    step, kind = cpu_step_fn(n, K)
-    z = synth_batch(B, H, W, seed=7)
-    step(z)                                     # warm-up
-    times = []
-    t_start = time.perf_counter()
-    while len(times) < max_iters and (time.perf_counter() - t_start) < budget_s:
-        t0 = time.perf_counter()
-        step(z)
-        times.append(time.perf_counter() - t0)
+    old = torch.get_num_threads()
+    torch.set_num_threads(host_threads())          # torchrun exports OMP_NUM_THREADS=1
+    step, kind, ctx = cpu_step_fn(n, K)
+    if z is None:
+        z = synth_batch(B, H, W, seed=7)
+    with ctx():
+        step(z)                                     # warm-up
+        times = []
+        t_start = time.perf_counter()
+        while len(times) < max_iters and (len(times) < 2 or (time.perf_counter() - t_start) < budget_s):
+            t0 = time.perf_counter()
+            losses = step(z)
+            times.append(time.perf_counter() - t0)
     pix = B * H * W
-    return {"value": pix / min(times) / 1e6, "mean_value": pix / (sum(times) / len(times)) / 1e6, "unit": "Mpix/s",
-            "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind, "iters": len(times),
-            "sample": "%dx16x%dx%d fp32 (n=%d,K=%d) fwd+bwd, best of %d after 1 warm-up" % (B, H, W, n, K, len(times))}
+    out = {"value": pix / min(times) / 1e6, "mean_value": pix / (sum(times) / len(times)) / 1e6, "unit": "Mpix/s",
+           "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(), "kind": kind, "iters": len(times),
+           "losses": list(losses),
+           "sample": "%dx16x%dx%d fp32 (n=%d,K=%d) fwd+bwd -- the full workload, best of %d after 1 warm-up" % (B, H, W, n, K, len(times))}
+    torch.set_num_threads(old)
+    return out
 
 
 def time_gpu_eager(z, n, K, iters=10):
-    """The reference's operator sequence (oracle/whitening_torch.py: bmm + ATen element-wise + the O(K^2) MMD loop, i.e.
-    what the unmodified reference launches on a GPU) in PyTorch eager on the same device and the same resident input.
-    A reported baseline beside cpu_baseline -- test infrastructure, never the product path."""
+    """The reference's own eager-CUDA path on the same GPU and the same resident input: the unmodified
+    `algorithms.WT_PSE.compute_whitening_loss` (its hard-coded .cuda() copies and .item() sync included) when oracle/_ref
+    is present, else the oracle's operator-sequence port.  A reported baseline -- test infrastructure, never the product path."""
     import torch
-    from oracle import whitening_torch as wt
+    from oracle import ref_shim
 
+    if ref_shim.available():
+        alg, _, _ = ref_shim.load()
+        torch.manual_seed(0)
+        model = alg.WT_PSE(3, 1, dict(ref_shim.DEFAULT_HPARAMS), z.device, False, per_domain_batch=n, source_domain_num=K)
+        kind = "reference: unmodified algorithms.WT_PSE.compute_whitening_loss in PyTorch eager (CUDA), same GPU, same device-resident input"
+
+        def fwd_bwd():
+            zz = z.detach().requires_grad_(True)
+            ins, dom = model.compute_whitening_loss(zz)
+            (ins + dom).backward()
+            return ins, dom
+    else:
+        from oracle import whitening_torch as wt
+        kind = "port: reference operator sequence in PyTorch eager (CUDA), same GPU, same device-resident input"
+
+        def fwd_bwd():
+            ins, dom, _ = wt.fwd_bwd(z, n, K)
+            return ins, dom
     for _ in range(2):
-        wt.fwd_bwd(z, n, K)
+        fwd_bwd()
     torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(iters):
-        ins, dom, _ = wt.fwd_bwd(z, n, K)
+        ins, dom = fwd_bwd()
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1) / iters
     return {"value": z.shape[0] * z.shape[2] * z.shape[3] / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_step": ms, "iters": iters,
-            "kind": "port: reference operator sequence in PyTorch eager (CUDA), same GPU, same device-resident input",
-            "losses": [float(ins), float(dom)]}
+            "kind": kind, "losses": [float(ins.detach()), float(dom.detach())]}
 
 
 def time_relu_fusion(z, n, K, peak, iters=10):
@@ -276,42 +363,229 @@ def time_relu_fusion(z, n, K, peak, iters=10):
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores, same metric/config."""
+    """--impl reference: the reference's own CPU implementation of the path (oracle/_ref, unmodified) on all host cores,
+    SAME metric, SAME config, SAME workload as the GPU arm (32x16x512x512 is ~0.5 s per fwd+bwd on 8 cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import torch
 
-    # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host thread this process may run on
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, OSError):
-        torch.set_num_threads(max(1, os.cpu_count() or 1))
-    H = args.size
-    n, K = 2, 3
-    B = n * K                                   # bounded sample: 6 of the workload's samples per step
-    step, kind = cpu_step_fn(n, K)
-    z = synth_batch(B, H, H, seed=7)
-    for _ in range(max(1, min(args.warmup, 3))):
-        step(z)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step(z)
-    dt = time.perf_counter() - t0
-    pix = B * H * H
+    torch.set_num_threads(host_threads())         # torchrun exports OMP_NUM_THREADS=1
+    B, H, W, n, K = workload_dims(args)
+    step, kind, ctx = cpu_step_fn(n, K)
+    z = synth_batch(B, H, W, seed=7)
+    with ctx():
+        for _ in range(max(1, min(args.warmup, 2))):
+            step(z)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            losses = step(z)
+        dt = time.perf_counter() - t0
+    pix = B * H * W
     val = pix * args.steps / dt / 1e6
     line = {
-        "impl": "reference", "metric": "shape-loss fwd+bwd Mpix/s", "value": val, "unit": "Mpix/s",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "whitening+MMD shape loss fwd+bwd, %dx16x%dx%d fp32, n=%d K=%d (bounded sample of the "
-                               "32x16x512x512 workload, CPU)" % (B, H, H, n, K)},
+        "config": workload_config(B, H, W, n, K),
         "cpu_baseline": {"value": val, "unit": "Mpix/s", "cores": torch.get_num_threads(), "kind": kind,
-                         "sample": "%dx16x%dx%d per step, %d steps" % (B, H, H, args.steps)},
+                         "sample": "%dx16x%dx%d per step (the full workload), %d steps" % (B, H, W, args.steps)},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "losses": list(losses),
     }
     print(json.dumps(line))
+
+
+def pin_to_gpu_numa_node(gpu_index):
+    """Bind this rank's threads (and therefore the first-touch placement of the pinned host buffers it allocates next)
+    to the CPUs NVML reports as local to its GPU.  Returns a short description, or None when NVML cannot tell."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d CPUs local to GPU %d (NVML)" % (len(cpus), gpu_index)
+    except Exception:
+        return None
+
+
+def time_link(dev, h_src, h_dst, world, barrier, reps=4):
+    """Plain pinned cudaMemcpyAsync of one step's bytes: H2D alone, D2H alone, and both at once on two streams (what the
+    e2e pipeline can reach at best).  GB/s per rank; at N > 1 all ranks copy at the same time (min over ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    nbytes = h_src.numel() * h_src.element_size()
+    d_in = torch.empty(h_src.shape, device=dev)
+    d_out = torch.randn(h_dst.shape, device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(h2d, d2h):
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if h2d:
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(h_src, non_blocking=True)
+            if d2h:
+                with torch.cuda.stream(s_out):
+                    h_dst.copy_(d_out, non_blocking=True)
+        s_in.synchronize()
+        s_out.synchronize()
+        dt = time.perf_counter() - t0
+        return (int(h2d) + int(d2h)) * nbytes * reps / dt / 1e9
+
+    run(True, True)                                   # warm-up
+    res = {"h2d_gbs": run(True, False), "d2h_gbs": run(False, True), "bidir_gbs": run(True, True)}
+    if world > 1:
+        t = torch.tensor([res["h2d_gbs"], res["d2h_gbs"], res["bidir_gbs"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        res = {"h2d_gbs": float(t[0]), "d2h_gbs": float(t[1]), "bidir_gbs": float(t[2]),
+               "note": "all %d ranks copying at the same time, min over ranks" % world}
+    res["bytes_per_direction"] = nbytes
+    return res
+
+
+def time_track_r_configs(dev, peak, steps=20):
+    """BASELINE configs[0] and configs[4] mapped onto Track R: device-resident fwd+bwd of the whitening/MMD
+    loss at 8x16x256x256 (n=2, K=3: launch-bound, 100 MB -- no roofline claim) and 64x16x1024x1024 (n=21, K=3)."""
+    import torch
+
+    import wtpse_b200 as wb
+
+    out = {}
+    one = torch.ones((), device=dev)
+    for name, B, S, n in (("8x16x256x256", 8, 256, 2), ("64x16x1024x1024", 64, 1024, 21)):
+        nbuf = 2 if B * 16 * S * S * 4 > 130e6 else 8           # rotate through more than the 126 MB L2
+        zs = [synth_batch(B, S, S, seed=500 + i, device=dev).requires_grad_(True) for i in range(nbuf)]
+
+        def step(i):
+            z = zs[i % nbuf]
+            z.grad = None
+            ins, dom = wb.whitening_folded(z, n, 3, 0.0, 1e-5)
+            torch.autograd.backward([ins, dom], [one, one])
+            return ins, dom
+        for i in range(nbuf + 4):                                # every buffer's gradient block comes from the allocator cache
+            step(i)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            ins, dom = step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / steps
+        pix = B * S * S
+        frac = 192.0 * pix / (ms * 1e-3) / 1e9 / peak
+        out[name] = {"ms_per_step": ms, "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": steps, "n_per_domain": n,
+                     "step_frac": frac if S >= 512 else None,
+                     "note": None if S >= 512 else "launch-bound (100.7 MB per step = 15 us at the HBM peak): no roofline claim",
+                     "l2": "%d alternating inputs of %.0f MB" % (nbuf, B * 16 * S * S * 4 / 1e6),
+                     "losses": [float(ins.detach()), float(dom.detach())]}
+        del zs
+        torch.cuda.empty_cache()
+    return out
+
+
+def wavelet_case(dev, B, S, wv, J, steps=20, warmup=5, with_transform=False, debug=None):
+    """One Track-W measurement: wavelet shape loss fwd+bwd on B x 2 x S x S softmax maps through the C ABI with preallocated
+    outputs (the launches the autograd Function makes, without its Python bookkeeping).  PARITY UNPINNED."""
+    import torch
+
+    import wtpse_b200 as wb
+    from wtpse_b200 import wavelet as wvm
+    from wtpse_b200.functional import _ptr, _stream_ptr
+
+    lib = wb._lib.load()
+    C, H, W = 2, S, S
+    wid = {"haar": 0, "db2": 1}[wv]
+    cs = wvm.resident_cluster_size(H, W, wv, J)
+    nin = max(4, int(300e6 // (B * C * H * W * 4)) + 1)          # the rotation is larger than the 126 MB L2
+    nin = min(nin, 16)
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev, generator=gen), 1) for _ in range(nin)]
+    one = torch.ones((), device=dev)
+    nmaps = B * C
+    nbytes = lib.wtpse_wavelet_workspace_bytes(nmaps, H, W, J)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    loss_abi = torch.zeros((), device=dev)
+    grad = torch.empty(B, C, H, W, device=dev)
+    gcoef = None if cs else torch.empty(B, C, H, W, device=dev)
+    st = _stream_ptr(dev)
+
+    def step_abi(i):
+        x = xs[i % nin]
+        if cs:
+            wb._lib.check(lib.wtpse_wavelet_loss_resident(_ptr(x), nmaps, H, W, wid, J, None, None, _ptr(loss_abi), _ptr(grad),
+                                                          _ptr(ws), nbytes, st))
+            wb._lib.check(lib.wtpse_scale_unless_one(_ptr(grad), grad.numel(), _ptr(one), st))
+        else:
+            wb._lib.check(lib.wtpse_wavelet_loss_forward(_ptr(x), nmaps, H, W, wid, J, None, _ptr(loss_abi), _ptr(gcoef), _ptr(ws),
+                                                         nbytes, st))
+            wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(gcoef), nmaps, H, W, wid, J, _ptr(grad), _ptr(one), _ptr(ws), nbytes, st))
+        return loss_abi
+
+    def timed(step):
+        for i in range(max(warmup, 3)):
+            step(i)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            out = step(i)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1) / steps, out
+
+    ms, loss = timed(step_abi)
+    elems = B * C * H * W
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_PEAK_GBS
+    res = {"us_per_step": ms * 1e3, "value": B * H * W / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": steps,
+           "frac": 8.0 * elems / (ms * 1e-3) / 1e9 / peak, "loss": float(loss),
+           "path": ("fused plan, resident stage in clusters of %d CTAs" % cs) if cs else "one kernel per level",
+           "l2": "%d alternating inputs of %.0f MB" % (nin, elems * 4 / 1e6)}
+    if with_transform:
+        coef = torch.empty(B, C, H, W, device=dev)
+        back = torch.empty(B, C, H, W, device=dev)
+
+        def step_fwd(i):
+            wb._lib.check(lib.wtpse_dwt2d_forward(_ptr(xs[i % nin]), nmaps, H, W, wid, J, _ptr(coef), _ptr(ws), nbytes, st))
+            return coef
+
+        def step_inv(i):
+            wb._lib.check(lib.wtpse_dwt2d_inverse(_ptr(coef), nmaps, H, W, wid, J, _ptr(back), None, _ptr(ws), nbytes, st))
+            return back
+        ms_fwd, _ = timed(step_fwd)
+        ms_inv, _ = timed(step_inv)
+        res["transform"] = {"dwt2d_us": ms_fwd * 1e3, "idwt2d_us": ms_inv * 1e3,
+                            "max_abs_reconstruction_error": float((back - xs[(steps - 1) % nin]).abs().max()),
+                            "frac_of_8B_per_element_roofline": [8.0 * elems / (t * 1e-3) / 1e9 / peak for t in (ms_fwd, ms_inv)]}
+    return res
+
+
+def time_wavelet_configs(dev, peak):
+    """BASELINE configs[0], [1], [4] as literally written (Track W): the reference has no wavelet code, so every entry is
+    parity UNPINNED -- checked against this repository's own float64 specification only (oracle/wavelet_np.py)."""
+    out = {"parity": "unpinned", "metric": "wavelet shape-loss fwd+bwd, frac = 8 B/element (4N read + 4N gradient written) / time / HBM peak",
+           "peak_gbs": peak}
+    out["haar_J3_8x2x256x256"] = wavelet_case(dev, 8, 256, "haar", 3)
+    out["haar_J3_8x2x256x256"]["note"] = "4.2 MB per step: launch-bound, no roofline claim"
+    out["db2_J4_32x2x512x512"] = wavelet_case(dev, 32, 512, "db2", 4, with_transform=True)
+    sweep = {}
+    for wv in ("haar", "db2"):
+        for J in range(1, 6):
+            r = wavelet_case(dev, 64, 1024, wv, J, steps=10, warmup=3)
+            sweep["%s_J%d" % (wv, J)] = {"us_per_step": r["us_per_step"], "frac": r["frac"], "value": r["value"], "path": r["path"]}
+    out["sweep_64x2x1024x1024"] = sweep
+    return out
 
 
 # -------------------------------------------------------------------------------------------------
@@ -334,12 +608,11 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B, H, W = args.batch, args.size, args.size
-    n = max(1, B // 3) if B != WORKLOAD["B"] else WORKLOAD["n_per_domain"]
-    K = WORKLOAD["n_domains"]
+    B, H, W, n, K = workload_dims(args)
     margin, eps = WORKLOAD["margin"], WORKLOAD["eps"]
     pix = B * H * W
     lib = wb._lib.load()
+    affinity = pin_to_gpu_numa_node(physical_gpu_index(local_rank)) if args.numa_affinity else None
     lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
     lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
     if args.debug_gram_variant >= 0:
@@ -440,6 +713,13 @@ def run_ours(args):
            "d2h_bytes_per_step": nbytes + 16, "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
            "api": "wtpse_host_plan_submit/_wait (pinned host z -> H2D -> fwd -> bwd -> D2H dz + losses every step; "
                   "consecutive steps overlap their PCIe transfers)", "losses": e2e_losses}
+    # the e2e leg's own roofline: plain pinned cudaMemcpyAsync of the same bytes, H2D and D2H at once on two streams
+    link = time_link(dev, z_host[0], dz_host[0], world, barrier)
+    e2e_rate = (2 * nbytes + 16) / (e2e_s / e2e_steps) / 1e9               # GB/s per rank, both directions
+    e2e.update({"link_gbs": link["bidir_gbs"], "link_frac": e2e_rate / link["bidir_gbs"], "achieved_gbs": e2e_rate,
+                "link": link, "cpu_affinity": affinity,
+                "bound": "host link (PCIe): %.2f GB per step against %.2f ms of kernels" % ((2 * nbytes) / 1e9, ms_step)})
+    del z_host, dz_host
 
     train = None
     if args.train_steps > 0:
@@ -460,12 +740,12 @@ def run_ours(args):
     roofline = None
     if dom_name:
         achieved = ALGO_BYTES_PER_PIX[dom_name] * pix / (kern[dom_name]["avg_us"] * 1e-6) / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom_name)
+        traffic, stale, cap_hash = traffic_entry(dom_name)
         roofline = {"bound": "hbm", "kernel": dom_name, "event_stride": stride, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_stale": stale,
+                    "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch), "
+                                      "captured at kernel-source hash %s; this run's sources hash to %s" % (cap_hash, kernel_source_hash()),
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PIX[dom_name] * pix,
                     "kernel_avg_us": kern[dom_name]["avg_us"]}
         other = "gram_tma_kernel" if dom_name == "apply_tma_kernel" else "apply_tma_kernel"
@@ -477,7 +757,8 @@ def run_ours(args):
     cpu = None
     gpu_eager = None
     if not args.no_cpu_baseline and world == 1:
-        cpu = time_cpu(6, H, W, 2, 3, args.cpu_seconds, 40)
+        cpu = time_cpu(B, H, W, n, K, args.cpu_seconds, 40, z=zs[(args.steps - 1) & 1].detach().cpu())
+        cpu["losses_match_ours"] = bool(abs(cpu["losses"][0] - losses[0]) <= 1e-5 * abs(losses[0]) and abs(cpu["losses"][1] - losses[1]) <= 1e-5)
         try:
             gpu_eager = time_gpu_eager(zs[(args.steps - 1) & 1], n, K)         # the input whose losses the line reports
             gpu_eager["losses_match_ours"] = bool(abs(gpu_eager["losses"][0] - losses[0]) <= 1e-5 * abs(losses[0]) and
@@ -492,17 +773,28 @@ def run_ours(args):
         except Exception as exc:
             relu_fusion = {"unavailable": str(exc).splitlines()[0][:160]}
 
+    configs = wavelet = None
+    if world == 1 and args.extra_configs:
+        del zs
+        torch.cuda.empty_cache()
+        try:
+            configs = time_track_r_configs(dev, peak)
+        except Exception as exc:
+            configs = {"unavailable": str(exc).splitlines()[0][:160]}
+        torch.cuda.empty_cache()
+        try:
+            wavelet = time_wavelet_configs(dev, peak)
+        except Exception as exc:
+            wavelet = {"unavailable": str(exc).splitlines()[0][:160]}
+
     line = {
-        "metric": "shape-loss fwd+bwd Mpix/s", "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "whitening+MMD shape loss fwd+bwd (WT_PSE.compute_whitening_loss), z=%dx16x%dx%d fp32, "
-                               "n=%d K=%d per GPU [BASELINE configs[1] mapped per SURVEY 8(d)]" % (B, H, W, n, K),
-                   "per_gpu_batch": B, "l2": "inputs (%.0f MB, two alternating buffers) larger than L2" % (nbytes / 1e6),
-                   "sharding": "independent [K x n] batches per rank, no data-path collective"},
+        "config": workload_config(B, H, W, n, K),
         "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager, "clocks": clocks, "losses": losses, "train_step": train,
-        "relu_fusion": relu_fusion,
+        "relu_fusion": relu_fusion, "configs": configs, "wavelet": wavelet,
     }
     print(json.dumps(line))
     if world > 1:
@@ -538,6 +830,77 @@ def time_train_step(args, dev, rank, world, barrier):
                                   fuse_relu=not args.train_fuse_relu)
         key = "with_fused_deepwt_tail" if not args.train_fuse_relu else "without_fused_deepwt_tail"
         res[key] = {k: alt[k] for k in ("value", "unit", "ms_per_step", "steps", "launch_mode", "our_kernels_per_iteration")}
+    if args.train_reference_eager and world == 1:
+        gc.collect()
+        torch.cuda.empty_cache()
+        try:
+            res["reference_eager"] = time_reference_train(args, dev, rank)
+            res["speedup_vs_reference_eager"] = res["value"] / res["reference_eager"]["value"]
+            if "dropin_installed" in res["reference_eager"]:
+                res["reference_eager"]["dropin_installed"]["speedup"] = (res["reference_eager"]["dropin_installed"]["value"] /
+                                                                        res["reference_eager"]["value"])
+        except Exception as exc:
+            res["reference_eager"] = {"unavailable": str(exc).splitlines()[0][:200]}
+    return res
+
+
+def time_reference_train(args, dev, rank):
+    """The reference's OWN training iteration on the same GPU: the unmodified algorithms.WT_PSE / shape_networks.
+    ShapeVariationalDist_x classes (oracle/_ref) driven in Trainer.train_epoch's order with its per-loss .item() host
+    syncs (oracle/ref_iteration.py restates Trainer.py:762-925; Trainer.py itself needs packages this image lacks),
+    PyTorch eager, torch defaults (NCHW, cuDNN with TF32 convolutions allowed, cudnn.deterministic=True / benchmark=False
+    as utils.seed_initialization sets them), same synthetic batches, same batch arithmetic (15 of 16 images used).
+    Also timed: the same reference classes with wtpse_b200.dropin.install() underneath -- the drop-in as a user gets it."""
+    import torch
+
+    import wtpse_b200 as wb
+    from oracle import ref_iteration as ri
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        return {"unavailable": "oracle/_ref missing (run __graft_entry__.build() where /root/reference exists)"}
+    alg, sn, _ = ref_shim.load()
+    hp = dict(ref_shim.DEFAULT_HPARAMS)
+    n_per_domain, used = wb.dp.per_rank_batch(args.train_batch, 1, 3)
+    S = args.train_size
+    old = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False          # utils.py:58-65
+    steps = max(2, args.train_steps // 2)
+
+    def batch(it):
+        return wb.synthetic.fundus_batch(n_per_domain, 3, S, S, dev, seed=wb.dp.rank_batch_seed(1, rank, it))
+
+    def run(install):
+        nets, optims = ri.build_reference_models(alg, sn, hp, n_per_domain, 3, dev, seed=0)
+        saved = wb.dropin.install(alg, sn) if install else None
+        try:
+            for it in range(2):
+                ri.trainer_iteration(nets, optims, *batch(it), hp, epoch=0, host_syncs=True)
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for it in range(steps):
+                out = ri.trainer_iteration(nets, optims, *batch(3 + it), hp, epoch=0, host_syncs=True)
+            ev1.record()
+            torch.cuda.synchronize()
+        finally:
+            if saved:
+                wb.dropin.uninstall(saved)
+        ms = ev0.elapsed_time(ev1) / steps
+        del nets, optims
+        return {"value": used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms, "steps": steps,
+                "losses": {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.dim() == 0}}
+
+    try:
+        res = run(False)
+        res["kind"] = ("reference: unmodified algorithms.WT_PSE / shape_networks.ShapeVariationalDist_x (oracle/_ref), "
+                       "Trainer.train_epoch order with its .item() syncs, PyTorch eager CUDA, same GPU")
+        res["image_size"], res["per_gpu_batch_used"] = S, used
+        torch.cuda.empty_cache()
+        res["dropin_installed"] = run(True)
+        res["dropin_installed"]["what"] = "same reference classes and loop with wtpse_b200.dropin.install(algorithms, shape_networks)"
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = old
     return res
 
 

@@ -183,11 +183,16 @@ def test_host_side_switches_of_the_train_step_kernels():
     assert main.wt_model.fused_loss is None and shape.teacher_grad is True
     seg.enable_relu_fusion(main)
     seg.enable_relu_fusion(shape)
-    assert main.wt_model.fused_loss == {"fold": True, "n_per_domain": 4, "n_domains": 2, "margin": 0.0, "eps": 1e-5}
-    assert shape.wt_model.fused_loss["fold"] is False and shape.wt_model.fused_loss["n_domains"] == 3     # literal 3
+    assert seg.fused_config(main.wt_model) == {"fold": True, "n_per_domain": 4, "n_domains": 2, "margin": 0.0, "eps": 1e-5}
+    assert shape.wt_model.fused_loss["fold"] is False and seg.fused_config(shape.wt_model)["n_domains"] == 3     # literal 3
+    main.margin = 0.25                                          # read at call time, not snapshotted
+    assert seg.fused_config(main.wt_model)["margin"] == 0.25
+    main.margin = hp["margin"]
+    import copy
+    assert copy.deepcopy(main).wt_model._pending_terms == {}
     seg.enable_relu_fusion(main, False)
     assert main.wt_model.fused_loss is None
-    assert seg.fused_terms(z, 2) is None                        # no tag -> compute_whitening_loss runs the kernels
+    assert seg.fused_terms(main, z, 2) is None                        # no tag -> compute_whitening_loss runs the kernels
 
     for setter, attr in ((seg.set_conv_bias_folding, "fold_bias"), (seg.set_cuda_batchnorm, "cuda_bn"),
                          (seg.set_cuda_pool, "cuda_pool"), (seg.set_cuda_upsample, "cuda_upsample")):

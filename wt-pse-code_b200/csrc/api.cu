@@ -593,6 +593,8 @@ int wtpse_scale_unless_one(float* data, int64_t n, const float* scale, wtpse_str
 struct HostSlot {
     float *z, *dz, *gram, *rowstat, *losses, *gvec;
     void* ws;
+    float* pinned;            // [8] page-locked: losses (4) + upstream gradients (4); copies to/from it are truly asynchronous
+    float* user_losses;       // where the step's losses go once it has left the device (filled by drain_slot)
     cudaStream_t stream;
     cudaEvent_t done;
     bool pending;
@@ -608,13 +610,28 @@ struct wtpse_host_plan {
 
 static void free_slot(HostSlot& s) {
     cudaFree(s.z); cudaFree(s.dz); cudaFree(s.gram); cudaFree(s.rowstat); cudaFree(s.losses); cudaFree(s.gvec); cudaFree(s.ws);
+    if (s.pinned) cudaFreeHost(s.pinned);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
 }
 
+// Wait until the slot's step has left the device and hand its losses to the caller's buffer.
+static int drain_slot(HostSlot& s) {
+    if (!s.pending) return WTPSE_OK;
+    cudaError_t e = cudaEventSynchronize(s.done);
+    s.pending = false;
+    if (e != cudaSuccess) return cuda_fail(e, "slot synchronize");
+    if (s.user_losses) memcpy(s.user_losses, s.pinned, 4 * sizeof(float));
+    s.user_losses = nullptr;
+    return WTPSE_OK;
+}
+
 void wtpse_host_plan_destroy(wtpse_host_plan* p) {
     if (!p) return;
-    for (int i = 0; i < 2; ++i) free_slot(p->slot[i]);
+    for (int i = 0; i < 2; ++i) {
+        if (p->slot[i].pending && p->slot[i].done) cudaEventSynchronize(p->slot[i].done);
+        free_slot(p->slot[i]);
+    }
     delete p;
 }
 
@@ -634,6 +651,7 @@ int wtpse_host_plan_create(int B, int64_t P, wtpse_host_plan** out) {
             (e = cudaMalloc(&s.rowstat, size_t(B) * 2 * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&s.losses, 4 * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&s.gvec, 4 * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&s.ws, p->ws_bytes)) != cudaSuccess ||
+            (e = cudaMallocHost(&s.pinned, 8 * sizeof(float))) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) {
             wtpse_host_plan_destroy(p);
@@ -644,32 +662,42 @@ int wtpse_host_plan_create(int B, int64_t P, wtpse_host_plan** out) {
     return WTPSE_OK;
 }
 
+// Asynchronous: returns once the step is enqueued (all staging goes through the slot's page-locked buffer, so no copy
+// blocks the host).  `losses_host` and `dz_host` are complete after wtpse_host_plan_wait() -- or after the second-next
+// submit, which reuses the slot -- and must stay valid until then.
 int wtpse_host_plan_submit(wtpse_host_plan* p, const float* z_host, int n_per_domain, int n_domains, float margin, float eps,
                            const float grad_w[3], float losses_host[4], float* dz_host) {
     if (!p || !z_host || !losses_host) return fail(WTPSE_ERR_INVALID, "null pointer");
     HostSlot& s = p->slot[p->submitted & 1];
-    cudaError_t e;
-    if (s.pending) {                                   // the slot's previous step must have left the device
-        if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) return cuda_fail(e, "slot synchronize");
-        s.pending = false;
-    }
+    if (int rc = drain_slot(s)) return rc;             // the slot's previous step must have left the device
     const size_t nz = size_t(p->B) * WTPSE_CHANNELS * size_t(p->P) * sizeof(float);
-    if ((e = cudaMemcpyAsync(s.z, z_host, nz, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) return cuda_fail(e, "H2D copy");
-    int rc = wtpse_whitening_forward(s.z, p->B, WTPSE_CHANNELS, p->P, n_per_domain, n_domains, margin, eps, s.losses, s.gram,
-                                     s.rowstat, s.ws, p->ws_bytes, s.stream);
-    if (rc) return rc;
-    if ((e = cudaMemcpyAsync(losses_host, s.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess)
-        return cuda_fail(e, "D2H losses");
-    if (dz_host) {
-        const float g[4] = {grad_w ? grad_w[0] : 1.f, grad_w ? grad_w[1] : 1.f, grad_w ? grad_w[2] : 1.f, 0.f};
-        if ((e = cudaMemcpyAsync(s.gvec, g, sizeof(g), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess)   // pageable: staged now
-            return cuda_fail(e, "H2D grads");
-        rc = wtpse_whitening_backward(s.z, s.gram, s.rowstat, s.gvec, s.gvec + 1, s.gvec + 2, p->B, WTPSE_CHANNELS, p->P,
-                                      n_per_domain, n_domains, margin, s.dz, s.ws, p->ws_bytes, s.stream);
-        if (rc) return rc;
-        if ((e = cudaMemcpyAsync(dz_host, s.dz, nz, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) return cuda_fail(e, "D2H dz");
+    int rc = WTPSE_OK;
+    cudaError_t e = cudaSuccess;
+    bool enqueued = false;
+    do {
+        if ((e = cudaMemcpyAsync(s.z, z_host, nz, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
+        enqueued = true;
+        if ((rc = wtpse_whitening_forward(s.z, p->B, WTPSE_CHANNELS, p->P, n_per_domain, n_domains, margin, eps, s.losses, s.gram,
+                                          s.rowstat, s.ws, p->ws_bytes, s.stream))) break;
+        if ((e = cudaMemcpyAsync(s.pinned, s.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "D2H losses"); break; }
+        if (dz_host) {
+            s.pinned[4] = grad_w ? grad_w[0] : 1.f; s.pinned[5] = grad_w ? grad_w[1] : 1.f; s.pinned[6] = grad_w ? grad_w[2] : 1.f; s.pinned[7] = 0.f;
+            if ((e = cudaMemcpyAsync(s.gvec, s.pinned + 4, 4 * sizeof(float), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "H2D grads"); break; }
+            if ((rc = wtpse_whitening_backward(s.z, s.gram, s.rowstat, s.gvec, s.gvec + 1, s.gvec + 2, p->B, WTPSE_CHANNELS, p->P,
+                                               n_per_domain, n_domains, margin, s.dz, s.ws, p->ws_bytes, s.stream))) break;
+            if ((e = cudaMemcpyAsync(dz_host, s.dz, nz, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "D2H dz"); break; }
+        }
+    } while (false);
+    if (rc != WTPSE_OK) {
+        // work may already be in flight on the slot's stream: let it finish before anyone reuses the slot's buffers
+        if (enqueued) cudaStreamSynchronize(s.stream);
+        return rc;
     }
-    if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) return cuda_fail(e, "event record");
+    if ((e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) {
+        cudaStreamSynchronize(s.stream);
+        return cuda_fail(e, "event record");
+    }
+    s.user_losses = losses_host;
     s.pending = true;
     ++p->submitted;
     return WTPSE_OK;
@@ -677,14 +705,10 @@ int wtpse_host_plan_submit(wtpse_host_plan* p, const float* z_host, int n_per_do
 
 int wtpse_host_plan_wait(wtpse_host_plan* p) {
     if (!p) return fail(WTPSE_ERR_INVALID, "null pointer");
-    for (int i = 0; i < 2; ++i) {
-        HostSlot& s = p->slot[i];
-        if (!s.pending) continue;
-        cudaError_t e = cudaEventSynchronize(s.done);
-        if (e != cudaSuccess) return cuda_fail(e, "stream synchronize");
-        s.pending = false;
-    }
-    return WTPSE_OK;
+    int rc = WTPSE_OK;
+    for (int i = 0; i < 2; ++i)
+        if (int r = drain_slot(p->slot[i])) rc = r;
+    return rc;
 }
 
 int wtpse_host_plan_run(wtpse_host_plan* p, const float* z_host, int n_per_domain, int n_domains, float margin, float eps,

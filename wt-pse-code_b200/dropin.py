@@ -25,14 +25,14 @@ def _domain_cfg(obj):
     return int(op.batch_size), int(op.domain_num)
 
 
-def _fused(z, arity):
+def _fused(obj, z, arity):
     from .segmentation import fused_terms
-    return fused_terms(z, arity)
+    return fused_terms(obj, z, arity)
 
 
 def wt_pse_compute_whitening_loss(self, z):
     """Replacement for WT_PSE.compute_whitening_loss (algorithms.py:1277-1309)."""
-    pre = _fused(z, 2)                 # attached by the fused DeepWT tail (bind(..., fuse_relu=True)), if that is on
+    pre = _fused(self, z, 2)           # parked by the fused DeepWT tail (bind(..., fuse_relu=True)), if that is on
     if pre is not None:
         return pre
     n, K = _domain_cfg(self)
@@ -41,7 +41,7 @@ def wt_pse_compute_whitening_loss(self, z):
 
 def shape_compute_whitening_loss(self, z):
     """Replacement for ShapeVariationalDist_x.compute_whitening_loss (shape_networks.py:561-594)."""
-    pre = _fused(z, 3)
+    pre = _fused(self, z, 3)
     if pre is not None:
         return pre
     n, K = _domain_cfg(self)          # K is the literal 3 of shape_networks.py:448

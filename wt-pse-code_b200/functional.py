@@ -291,6 +291,7 @@ class HostPlan:
         self._lib = _lib.load()
         self._dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
         self._h = ctypes.c_void_p()
+        self._inflight = []           # (losses array, z_host, dz_host) of submitted steps: kept alive until wait()
         with torch.cuda.device(self._dev):
             _lib.check(self._lib.wtpse_host_plan_create(self.B, self.H * self.W, ctypes.byref(self._h)))
 
@@ -325,11 +326,14 @@ class HostPlan:
             _lib.check(self._lib.wtpse_host_plan_submit(self._h, ctypes.c_void_p(z_host.data_ptr()), int(n_per_domain),
                                                         int(n_domains), float(margin), float(eps), gw, out,
                                                         ctypes.c_void_p(dz_host.data_ptr()) if dz_host is not None else None))
+        self._inflight.append((out, z_host, dz_host))
+        del self._inflight[:-2]                       # the plan has two slots: older steps have left the device
         return out
 
     def wait(self):
         with torch.cuda.device(self._dev):
             _lib.check(self._lib.wtpse_host_plan_wait(self._h))
+        self._inflight.clear()
 
     def close(self):
         if self._h:

@@ -19,6 +19,8 @@ embeddings but divided by 3; the ``instance_wt_loss2`` overwrite-and-double in t
 network's MMD always using 3 domains; the teacher mean NOT detached in the KD loss; the
 ``normal(mu, std) * std + mu`` re-parameterisation.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -244,6 +246,7 @@ class DeepWT(nn.Module):
         super().__init__()
         self.whitening = whitening
         self.fused_loss = None            # see enable_relu_fusion / deepwt_forward
+        self._pending_terms = _PendingTerms()
         if whitening:
             self.DoubleConv = _DoubleConvWT(input_channel, out_channel)
             self.DoubleConv2 = _DoubleConvWT(out_channel, out_channel)
@@ -252,7 +255,29 @@ class DeepWT(nn.Module):
         return deepwt_forward(self, x)
 
 
-_LOSS_TAG = "_wtpse_loss"
+class _PendingTerms(dict):
+    """id(embedding) -> (weakref to it, its loss terms).  Never copied or pickled with the module: the terms are
+    non-leaf autograd tensors of ONE forward pass."""
+
+    def __deepcopy__(self, memo):
+        return _PendingTerms()
+
+    def __reduce__(self):
+        return (_PendingTerms, ())
+
+
+def fused_config(wt_model):
+    """The fused tail's loss configuration, read from the owning network AT CALL TIME (so later changes to
+    ``owner.margin`` / ``owner.mmd_operator`` are honoured), or None when the fusion is off."""
+    cfg = getattr(wt_model, "fused_loss", None)
+    if cfg is None:
+        return None
+    owner = cfg["owner"]()
+    if owner is None:
+        return None
+    op = owner.mmd_operator
+    return {"fold": cfg["fold"], "n_per_domain": int(op.batch_size), "n_domains": int(op.domain_num),
+            "margin": float(owner.margin), "eps": float(owner.eps)}
 
 
 def deepwt_forward(self, x):
@@ -261,14 +286,18 @@ def deepwt_forward(self, x):
 
     With ``self.fused_loss`` set by the owning network each embedding z_k and the ``F.relu(z_k)`` that
     follows it take ONE pass over z_k forward (Gram + ReLU write, wtpse_whitening_relu_forward) and ONE backward
-    (M_b z + ReLU backward + the sum of both gradients, wtpse_whitening_relu_backward).  The loss terms are attached to
-    the returned z_k; the owner's compute_whitening_loss(z_k) picks them up instead of reading z_k again.  Values and
-    gradients are those of the unfused sequence (tests/test_gpu_fusion.py)."""
+    (M_b z + ReLU backward + the sum of both gradients, wtpse_whitening_relu_backward).  The loss terms are parked in
+    ``self._pending_terms`` (keyed by the embedding's identity, overwritten by the next forward); the owner's
+    compute_whitening_loss(z_k) takes them from there instead of reading z_k again.  Nothing is attached to the tensors
+    themselves: an attribute on z_k holding scalars whose grad_fn saves z_k would be a reference cycle through the
+    autograd graph that Python's collector cannot see.  Values and gradients are those of the unfused sequence
+    (tests/test_gpu_fusion.py)."""
     if not self.whitening:
         return [x]
-    cfg = getattr(self, "fused_loss", None)
+    cfg = fused_config(self)
     z0 = self.DoubleConv(x)
     if cfg is None or not (torch.is_grad_enabled() and z0.requires_grad and z0.is_cuda):
+        self._pending_terms = _PendingTerms()
         z1 = self.DoubleConv2(F.relu(z0))
         return [z0, z1, F.relu(z1)]
     fn = wf.relu_whitening_folded if cfg["fold"] else wf.relu_whitening_terms
@@ -276,24 +305,29 @@ def deepwt_forward(self, x):
     r0, *terms0 = fn(z0, *args)
     z1 = self.DoubleConv2(r0)
     r1, *terms1 = fn(z1, *args)
-    setattr(z0, _LOSS_TAG, tuple(terms0))
-    setattr(z1, _LOSS_TAG, tuple(terms1))
+    self._pending_terms = _PendingTerms({id(z0): (weakref.ref(z0), tuple(terms0)), id(z1): (weakref.ref(z1), tuple(terms1))})
     return [z0, z1, r1]
 
 
 def enable_relu_fusion(owner, on=True):
     """Turn the DeepWT-tail fusion on/off for a WT_PSE or ShapeVariationalDist_x (ours or the reference's)."""
     fold = type(owner).__name__ == "WT_PSE"           # two-value form (algorithms.py:1301) vs three values
-    owner.wt_model.fused_loss = None if not on else {
-        "fold": fold, "n_per_domain": int(owner.mmd_operator.batch_size), "n_domains": int(owner.mmd_operator.domain_num),
-        "margin": float(owner.margin), "eps": float(owner.eps)}
+    owner.wt_model.fused_loss = None if not on else {"fold": fold, "owner": weakref.ref(owner)}
+    owner.wt_model._pending_terms = _PendingTerms()
     return owner
 
 
-def fused_terms(z, arity):
-    """Loss terms deepwt_forward attached to an embedding, or None."""
-    t = getattr(z, _LOSS_TAG, None)
-    return t if t is not None and len(t) == arity else None
+def fused_terms(owner, z, arity):
+    """Loss terms ``owner.wt_model``'s fused forward computed for the embedding z, or None.  Taken once: the entry is
+    removed, so nothing keeps the autograd graph alive after the caller drops its own references."""
+    table = getattr(getattr(owner, "wt_model", None), "_pending_terms", None)
+    if not table:
+        return None
+    hit = table.get(id(z))
+    if hit is None or hit[0]() is not z or len(hit[1]) != arity:
+        return None
+    del table[id(z)]
+    return hit[1]
 
 
 def _head(cin, mid, cout):
@@ -391,7 +425,7 @@ class WT_PSE(_UNetTrunk):
     # -- hot path ---------------------------------------------------------------------------------
     def compute_whitening_loss(self, z):
         """(instance_loss, domain_loss) -- algorithms.py:1277-1309, one CUDA forward + one fused backward."""
-        pre = fused_terms(z, 2)
+        pre = fused_terms(self, z, 2)
         if pre is not None:
             return pre
         return wf.whitening_folded(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
@@ -495,7 +529,7 @@ class ShapeVariationalDist_x(_UNetTrunk):
 
     def compute_whitening_loss(self, z):
         """(off_diagonal_loss, diagonal_loss, domain_loss) -- shape_networks.py:561-594."""
-        pre = fused_terms(z, 3)
+        pre = fused_terms(self, z, 3)
         if pre is not None:
             return pre
         return wf.whitening_terms(z, self.mmd_operator.batch_size, self.mmd_operator.domain_num, float(self.margin),
