@@ -110,12 +110,8 @@ def parse_args():
     ap.add_argument("--train-graph", type=int, default=1, help="replay the train iteration as a CUDA graph")
     ap.add_argument("--train-batch", type=int, default=16, help="nominal per-GPU batch (the reference uses 3 * (batch // 3))")
     ap.add_argument("--no-kernel-events", action="store_true", help="diagnostic: timed region without per-kernel CUDA events")
-    ap.add_argument("--debug-backward-mode", type=int, default=0)
-    ap.add_argument("--debug-round-robin", type=int, default=1)
-    ap.add_argument("--debug-gram-group", type=int, default=-1)
-    ap.add_argument("--debug-l2-hint", type=int, default=-1)
-    ap.add_argument("--debug-gram-variant", type=int, default=-1)
-    ap.add_argument("--debug-two-stage-epilogue", type=int, default=1)
+    ap.add_argument("--debug", action="append", default=[], metavar="NAME=VALUE",
+                    help="diagnostic switch of include/wtpse_b200_debug.h, e.g. --debug fused_tail=0 (repeatable)")
     ap.add_argument("--extra-configs", type=int, default=1, help="also time the other BASELINE configs (Track R 256^2 / 1024^2, Track W) at N=1")
     ap.add_argument("--numa-affinity", type=int, default=1, help="bind each rank to the CPUs NVML reports as local to its GPU before allocating pinned buffers")
     ap.add_argument("--train-reference-eager", type=int, default=1, help="also time the UNMODIFIED reference classes' iteration (oracle/_ref) on the same GPU")
@@ -613,15 +609,9 @@ def run_ours(args):
     pix = B * H * W
     lib = wb._lib.load()
     affinity = pin_to_gpu_numa_node(physical_gpu_index(local_rank)) if args.numa_affinity else None
-    lib.wtpse_debug_set_backward_mode(args.debug_backward_mode)
-    lib.wtpse_debug_set_apply_round_robin(args.debug_round_robin)
-    if args.debug_gram_variant >= 0:
-        lib.wtpse_debug_set_gram_variant(args.debug_gram_variant)
-    if args.debug_l2_hint >= 0:
-        lib.wtpse_debug_set_l2_hint(args.debug_l2_hint)
-    if args.debug_gram_group >= 0:
-        lib.wtpse_debug_set_gram_group(args.debug_gram_group)
-    lib.wtpse_debug_set_two_stage_epilogue(args.debug_two_stage_epilogue)
+    for item in args.debug:
+        name, _, val = item.partition("=")
+        wb._lib.debug_set(name, int(val))
 
     # two resident input batches, alternated, each 4x the 126 MB L2 -> no timed step finds its input in L2
     zs = [synth_batch(B, H, W, seed=1234 + 17 * rank + i, device=dev).requires_grad_(True) for i in range(2)]
@@ -980,11 +970,11 @@ def run_wavelet(args):
     from wtpse_b200.functional import _ptr, _stream_ptr
 
     lib = wb._lib.load()
-    lib.wtpse_debug_set_wavelet_resident(int(args.wavelet_resident))
-    lib.wtpse_debug_set_wavelet_split(int(args.wavelet_split))
-    lib.wtpse_debug_set_wavelet_cluster_max(int(args.wavelet_cluster_max))
-    lib.wtpse_debug_set_wavelet_tiles(int(args.wavelet_tiles))
-    lib.wtpse_debug_set_wavelet_peel_max(int(args.wavelet_peel_max))
+    wb._lib.debug_set("wavelet_resident", int(args.wavelet_resident))
+    wb._lib.debug_set("wavelet_split", int(args.wavelet_split))
+    wb._lib.debug_set("wavelet_cluster_max", int(args.wavelet_cluster_max))
+    wb._lib.debug_set("wavelet_tiles", int(args.wavelet_tiles))
+    wb._lib.debug_set("wavelet_peel_max", int(args.wavelet_peel_max))
     cs = wvm.resident_cluster_size(H, W, wv, J)
     xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev), 1).requires_grad_(True) for _ in range(4)]
     one = torch.ones((), device=dev)

@@ -18,7 +18,12 @@
  *   z       [B][16][P]      P = H*W
  *   gram    [B][16][16]     f_cor of algorithms.py:1283 (symmetric, eps on the diagonal)
  *   rowstat [B][2]          off_b (algorithms.py:1289) and diag_b (algorithms.py:1297), margin subtracted
+ *   domgrad [B][120]        d L_dom / d v_b over the upper-triangle entries in torch.triu_indices(16,16,1) order
+ *                           (algorithms.py:1305); rows of samples outside the MMD are not written and not read
  *   losses  [4]             L_off, L_diag, L_dom, L_off + L_diag
+ * gram, rowstat and domgrad are what the forward SAVES for the backward.
+ *
+ * Diagnostic switches and the launch accounting bench.py reads live in wtpse_b200_debug.h, not here.
  */
 #ifndef WTPSE_B200_H
 #define WTPSE_B200_H
@@ -36,7 +41,7 @@ extern "C" {
 #define WTPSE_ERR_WORKSPACE   3   /* workspace too small                             */
 
 #define WTPSE_CHANNELS        16
-#define WTPSE_ABI_VERSION     1
+#define WTPSE_ABI_VERSION     2
 
 typedef void* wtpse_stream_t;     /* cudaStream_t */
 
@@ -47,8 +52,17 @@ int         wtpse_sm_count(void);
 
 /* ---- whitening (Gram) loss: algorithms.py:1277-1309, shape_networks.py:561-594 ------------- */
 
-/* Bytes of scratch the forward/backward need for a [B][16][P] input (max of both). */
+/* Bytes of scratch the forward needs for a [B][16][P] input.  The backward needs none. */
 size_t wtpse_whitening_workspace_bytes(int B, int64_t P);
+/*
+ * The first wtpse_whitening_ticket_bytes(B) bytes of the forward's workspace are arrival tickets of the in-kernel
+ * tail (the CTA that arrives last finishes the sample / the batch: no second launch, no float atomics).  CONTRACT:
+ * they must be ZERO when a forward is enqueued, and every forward leaves them zero again when it completes -- so a
+ * workspace that is zeroed once (cudaMemset at allocation) and then reused by stream-ordered calls needs nothing
+ * more.  A caller that hands over fresh, uninitialised scratch every time clears that prefix with cudaMemsetAsync on
+ * the same stream first.  (The rest of the workspace needs no initialisation.)
+ */
+size_t wtpse_whitening_ticket_bytes(int B);
 
 /*
  * Forward.  Replaces the body of WT_PSE.compute_whitening_loss (algorithms.py:1280-1307) and of
@@ -62,23 +76,25 @@ size_t wtpse_whitening_workspace_bytes(int B, int64_t P);
  *             chunk yields NaN exactly like the reference's mean over an empty tensor);
  *             0 when n_domains <= 1.
  * NaN/Inf in z propagate to the losses (the caller's NaN guard is Trainer.py:799-800).
+ * ONE kernel launch for 16-byte-aligned z with P % 4 == 0 (anything else, and MMD batches beyond ~100 samples, take a
+ * chain of small kernels with the same results).
  */
 int wtpse_whitening_forward(const float* z, int B, int C, int64_t P,
                             int n_per_domain, int n_domains, float margin, float eps,
-                            float* losses, float* gram, float* rowstat,
+                            float* losses, float* gram, float* rowstat, float* domgrad,
                             void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 
 /*
  * Backward (what autograd derives from the statements above):
  *   dz_b = (S_b + S_b^T) z_b / (P-1)
  * g_off / g_diag / g_dom are DEVICE pointers to the upstream gradients of L_off / L_diag / L_dom
- * (NULL == 0), so no host synchronisation is needed between forward and backward.
+ * (NULL == 0), so no host synchronisation is needed between forward and backward.  ONE kernel launch, no workspace:
+ * the per-sample matrix is combined inside the kernel from gram, rowstat, domgrad and the three scalars.
  */
-int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat,
+int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* domgrad,
                              const float* g_off, const float* g_diag, const float* g_dom,
                              int B, int C, int64_t P, int n_per_domain, int n_domains,
-                             float margin, float* dz,
-                             void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+                             float* dz, wtpse_stream_t stream);
 
 /*
  * Producer fusion with the DeepWT tail.  In DeepWT.forward (algorithms.py:1099-1113) each embedding
@@ -92,12 +108,12 @@ int wtpse_whitening_backward(const float* z, const float* gram, const float* row
  */
 int wtpse_whitening_relu_forward(const float* z, float* relu_out, int B, int C, int64_t P,
                                  int n_per_domain, int n_domains, float margin, float eps,
-                                 float* losses, float* gram, float* rowstat,
+                                 float* losses, float* gram, float* rowstat, float* domgrad,
                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
-                                  const float* g_off, const float* g_diag, const float* g_dom,
+                                  const float* domgrad, const float* g_off, const float* g_diag, const float* g_dom,
                                   int B, int C, int64_t P, int n_per_domain, int n_domains, float* dz,
-                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+                                  wtpse_stream_t stream);
 
 /*
  * Decoder up-sampling of the U-Net stages: F.interpolate(x, scale_factor=2, mode='bilinear', align_corners=False)
@@ -167,12 +183,12 @@ int wtpse_maxpool2_nhwc(const float* in, float* out, unsigned char* argmax, int6
  */
 int wtpse_whitening_forward_cl(const float* z, float* relu_out, int B, int C, int64_t P,
                                int n_per_domain, int n_domains, float margin, float eps,
-                               float* losses, float* gram, float* rowstat,
+                               float* losses, float* gram, float* rowstat, float* domgrad,
                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
 int wtpse_whitening_backward_cl(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
-                                const float* g_off, const float* g_diag, const float* g_dom,
+                                const float* domgrad, const float* g_off, const float* g_diag, const float* g_dom,
                                 int B, int C, int64_t P, int n_per_domain, int n_domains, float* dz,
-                                void* workspace, size_t workspace_bytes, wtpse_stream_t stream);
+                                wtpse_stream_t stream);
 
 /* ---- standalone MMD: compute_MMD.forward, algorithms.py:102-121 / shape_networks.py:283-309 ---- */
 
@@ -303,47 +319,6 @@ int  wtpse_host_plan_submit(wtpse_host_plan* plan, const float* z_host,
                             int n_per_domain, int n_domains, float margin, float eps,
                             const float grad_w[3], float losses_host[4], float* dz_host);
 int  wtpse_host_plan_wait(wtpse_host_plan* plan);
-
-/* ---- launch accounting / in-step kernel timing (used by bench.py, not by the reference path) - */
-
-/* Every kernel launch made by this library is counted; with profiling enabled each launch is also
- * bracketed by CUDA events on its own stream.  Kernel ids: 0 .. wtpse_profile_kernel_count()-1. */
-void        wtpse_profile_enable(int on);
-void        wtpse_profile_reset(void);
-int         wtpse_profile_kernel_count(void);
-const char* wtpse_profile_kernel_name(int id);
-long long   wtpse_profile_launches(int id);            /* id < 0: all kernels */
-/* Sum of event-timed durations (ms) of kernel `id` since the last reset; synchronises those events. */
-int         wtpse_profile_read(int id, long long* timed_launches, double* total_ms);
-/* Diagnostics: a 16 x int64 DEVICE buffer that receives clock64() at the epilogue kernels' phase
- * boundaries ([0..7] forward, [8..15] backward); NULL (default) disables the stamps. */
-void        wtpse_debug_set_stamp_buffer(long long* device_buffer16);
-/* Diagnostics: launch each epilogue kernel n times back to back (warm instruction cache experiment). */
-void        wtpse_debug_set_epilogue_repeat(int n);
-/* Tests/diagnostics: backward variant. 0 (default) per-sample M_b kernel + round-robin apply chained by
- * programmatic dependent launch; 1 M_b derived inside the apply kernel; 2 single-CTA epilogue + apply. */
-void        wtpse_debug_set_backward_mode(int mode);
-/* Diagnostics: round-robin instead of contiguous tile schedule in the unfused apply kernel. */
-void        wtpse_debug_set_apply_round_robin(int chunk_tiles);
-/* Diagnostics: 0 makes wtpse_wavelet_resident_cluster report 0 for every shape (callers fall back to the per-level path). */
-void        wtpse_debug_set_wavelet_resident(int on);
-/* Diagnostics: fused-plan choice, -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed whenever possible. */
-void        wtpse_debug_set_wavelet_split(int mode);
-/* Diagnostics: level 1 of the streamed plan as persistent TMA pipelines (1, default) or with per-thread global loads (0). */
-void        wtpse_debug_set_wavelet_tiles(int on);
-/* Diagnostics: most levels the streamed plan may run global-to-global before the resident stage (default 8; 1 = level 1 only). */
-void        wtpse_debug_set_wavelet_peel_max(int levels);
-/* Diagnostics: largest cluster size the resident planner may pick (1..8, default 8). */
-void        wtpse_debug_set_wavelet_cluster_max(int cs);
-/* Diagnostics: L2 evict-first policy on the TMA loads of z in the Gram and apply kernels. */
-void        wtpse_debug_set_l2_hint(int on);
-/* Diagnostics: Gram tile schedule = CTAs per group (a group owns a contiguous tile range and deals it round-robin
- * to its members): 1 contiguous range per CTA, 0 pure round-robin, else a divisor of the grid size. */
-void        wtpse_debug_set_gram_group(int ctas_per_group);
-/* Diagnostics: Gram kernel variant, 0 one thread per pixel quad (255 registers, 8 warps/SM), 1 two threads per quad. */
-void        wtpse_debug_set_gram_variant(int variant);
-/* Diagnostics: forward epilogue as per-sample reduce kernel + single-CTA MMD (1, default) or one single-CTA kernel (0). */
-void        wtpse_debug_set_two_stage_epilogue(int on);
 
 #ifdef __cplusplus
 }

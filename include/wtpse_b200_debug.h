@@ -1,0 +1,43 @@
+/*
+ * wtpse_b200_debug.h -- diagnostics of libwtpse_b200.so.  NOT part of the product ABI (include/wtpse_b200.h): nothing
+ * in the reference-facing path (wt-pse-code_b200/functional.py, dropin.py, segmentation.py) calls these; bench.py, the
+ * probe tools and the tests that compare kernel variants do.
+ */
+#ifndef WTPSE_B200_DEBUG_H
+#define WTPSE_B200_DEBUG_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- launch accounting / in-step kernel timing -------------------------------------------------
+ * Every kernel launch made by the library is counted; with profiling enabled each launch is also
+ * bracketed by CUDA events on its own stream.  Kernel ids: 0 .. wtpse_profile_kernel_count()-1. */
+void        wtpse_profile_enable(int on);
+void        wtpse_profile_reset(void);
+int         wtpse_profile_kernel_count(void);
+const char* wtpse_profile_kernel_name(int id);
+long long   wtpse_profile_launches(int id);            /* id < 0: all kernels */
+/* Sum of event-timed durations (ms) of kernel `id` since the last reset; synchronises those events. */
+int         wtpse_profile_read(int id, long long* timed_launches, double* total_ms);
+
+/* ---- variant switches ------------------------------------------------------------------------
+ * Process-wide integers read when a call is enqueued (a test that flips one restores it).  The product path never
+ * touches them; every value of every switch produces the same results (the tests compare them).
+ *   "fused_tail"           1 (default) forward tail inside the Gram kernel (last-arriving CTA); 0 separate kernels
+ *   "apply_round_robin"    NCHW apply kernel: tiles dealt round-robin over the CTAs (1, default) or contiguous ranges (0)
+ *   "l2_hint"              L2 evict-first policy on the TMA loads of z (default 1)
+ *   "cl_tma"               channels-last kernels: tensor-map TMA pipelines (1, default) or per-thread loads (0)
+ *   "wavelet_resident"     0 makes wtpse_wavelet_resident_cluster report 0 for every shape (per-level kernels)
+ *   "wavelet_split"        fused-plan choice: -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed
+ *   "wavelet_tiles"        level 1 of the streamed plan as TMA pipelines (1, default) or per-thread loads (0)
+ *   "wavelet_peel_max"     most levels streamed before the resident stage (default 8)
+ *   "wavelet_cluster_max"  largest cluster size of the resident stage (1..8, default 8)
+ * Return WTPSE_OK, or WTPSE_ERR_INVALID for an unknown name. */
+int wtpse_debug_set(const char* name, int value);
+int wtpse_debug_get(const char* name, int* value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTPSE_B200_DEBUG_H */

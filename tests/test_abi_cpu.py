@@ -10,8 +10,8 @@ import torch
 from conftest import ROOT
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "wtpse_b200.h")).read()
+def _declared_symbols(header="wtpse_b200.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(wtpse_[a-z0-9_]+)\s*\(", text)))
 
@@ -23,11 +23,19 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert os.path.exists(path)
     lib = ctypes.CDLL(path)
     declared = _declared_symbols()
+    debug = _declared_symbols("wtpse_b200_debug.h")
     assert len(declared) >= 12
-    for name in declared:
+    # the product header carries no diagnostics: switches and launch accounting live in wtpse_b200_debug.h
+    assert not [n for n in declared if "debug" in n or "profile" in n] and len(debug) == 8
+    for name in declared + debug:
         assert hasattr(lib, name), "header declares %s but the library does not export it" % name
-    # and the ctypes binding covers exactly the header
-    assert sorted(wtpse_b200._lib.EXPORTS) == declared
+    # and the ctypes binding covers exactly the two headers
+    assert sorted(wtpse_b200._lib.EXPORTS) == sorted(declared + debug)
+    # ... which is everything the library exports
+    import subprocess
+    exported = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True).stdout
+    exported = sorted(set(re.findall(r"\b(wtpse_[a-z0-9_]+)\b", exported)))
+    assert exported == sorted(declared + debug), set(exported) ^ set(declared + debug)
 
 
 def test_library_is_sm100a_native():
@@ -42,7 +50,9 @@ def test_abi_version_and_sizes_without_gpu():
     import wtpse_b200
 
     lib = wtpse_b200._lib.load()
-    assert lib.wtpse_abi_version() == 1
+    assert lib.wtpse_abi_version() == 2
+    assert lib.wtpse_whitening_ticket_bytes(0) == 0 and lib.wtpse_whitening_ticket_bytes(32) >= 4 * 33
+    assert lib.wtpse_whitening_workspace_bytes(32, 512 * 512) > lib.wtpse_whitening_ticket_bytes(32)
     assert lib.wtpse_whitening_workspace_bytes(0, 100) == 0
     assert lib.wtpse_mse_workspace_bytes(0) == 0
 
@@ -102,14 +112,14 @@ def test_wavelet_planner_host_logic():
         assert plan(48, 64, 1, 4) == 1                  # whole map in one CTA
         assert plan(64, 96, 1, 5) == 0 and plan(64, 96, 0, 5) == 0
         assert plan(24, 24, 0, 4) == 0 and plan(0, 64, 0, 1) == 0 and plan(64, 64, 2, 1) == 0 and plan(64, 64, 0, 0) == 0
-        lib.wtpse_debug_set_wavelet_peel_max(1)
+        wb._lib.debug_set("wavelet_peel_max", 1)
         assert plan(1024, 1024, 1, 5) == 8              # one streamed level: 512^2 bands need a cluster of 8
-        lib.wtpse_debug_set_wavelet_peel_max(8)
-        lib.wtpse_debug_set_wavelet_resident(0)
+        wb._lib.debug_set("wavelet_peel_max", 8)
+        wb._lib.debug_set("wavelet_resident", 0)
         assert plan(512, 512, 1, 4) == 0
     finally:
-        lib.wtpse_debug_set_wavelet_resident(1)
-        lib.wtpse_debug_set_wavelet_peel_max(8)
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_peel_max", 8)
     # workspace covers the low-low bands and sign planes of every streamed level
     n = 64 * 512 * 512
     assert lib.wtpse_wavelet_workspace_bytes(64, 512, 512, 4) >= 4 * (n // 4 + n // 16) + n // 4 + n // 16

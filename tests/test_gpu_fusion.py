@@ -83,13 +83,13 @@ def test_fused_entry_points_reject_bad_arguments():
     dev = torch.device("cuda:0")
     z = _z(2, 8, 8, 1, dev)
     ws = torch.empty(lib.wtpse_whitening_workspace_bytes(2, 64), dtype=torch.uint8, device=dev)
-    out = torch.empty(4 + 2 * 256 + 4, device=dev)
+    out = torch.empty(4 + 2 * 256 + 4 + 2 * 120, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    rc = lib.wtpse_whitening_relu_forward(p(z), p(z), 2, 16, 64, 1, 2, 0.0, 1e-5, p(out), p(out[4:]), p(out[516:]), p(ws),
-                                          ws.numel(), None)
+    rc = lib.wtpse_whitening_relu_forward(p(z), p(z), 2, 16, 64, 1, 2, 0.0, 1e-5, p(out), p(out[4:]), p(out[516:]), p(out[520:]),
+                                          p(ws), ws.numel(), None)
     assert rc != 0 and b"alias" in lib.wtpse_last_error()
-    rc = lib.wtpse_whitening_relu_forward(p(z), None, 2, 16, 64, 1, 2, 0.0, 1e-5, p(out), p(out[4:]), p(out[516:]), p(ws),
-                                          ws.numel(), None)
+    rc = lib.wtpse_whitening_relu_forward(p(z), None, 2, 16, 64, 1, 2, 0.0, 1e-5, p(out), p(out[4:]), p(out[516:]), p(out[520:]),
+                                          p(ws), ws.numel(), None)
     assert rc != 0
     with pytest.raises(RuntimeError):
         wb.relu_whitening_folded(z.cpu(), 1, 2)                          # no CPU path

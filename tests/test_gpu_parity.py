@@ -281,58 +281,69 @@ def test_run_to_run_bit_reproducible():
         assert o[0] == outs[0][0] and o[1] == outs[0][1] and torch.equal(o[2], outs[0][2])
 
 
-def test_backward_variants_are_bitwise_identical():
-    """Per-sample M_b kernel + round-robin apply (default), M_b derived inside the apply kernel, and the single-CTA
-    epilogue + apply share their arithmetic (mmd_device.cuh): same bits."""
+def test_in_kernel_tail_is_bitwise_identical_to_the_separate_kernels():
+    """Forward tail inside the Gram kernel (last-arriving CTA: slot reduction, f_cor, instance terms, MMD, the backward's
+    MMD seed) vs the chain of stand-alone kernels (whitening_epilogue.cu): shared device code, same summation orders ->
+    the same bits in every output, and therefore in dz.  Also: the ticket area of the workspace is left zero."""
     import wtpse_b200 as wb
+    from wtpse_b200 import functional as wf
 
     lib = wb._lib.load()
-    for B, H, n in ((9, 96, 3), (32, 128, 10), (6, 32, 2)):
-        z = _synth(B, H, H, seed=B).to(_dev())
-        grads = []
-        for mode in (0, 1, 2):
-            lib.wtpse_debug_set_backward_mode(mode)
+    for B, H, W, n, K in ((9, 96, 96, 3, 3), (32, 128, 128, 10, 3), (6, 32, 20, 2, 3), (8, 64, 64, 2, 3), (3, 300, 300, 1, 3),
+                          (7, 40, 40, 3, 2), (5, 24, 24, 5, 1), (1, 64, 64, 1, 3)):
+        z = _synth(B, H, W, seed=B).to(_dev())
+        res = []
+        for fused in (1, 0, 1):
+            wb._lib.debug_set("fused_tail", fused)
             try:
                 zz = z.clone().requires_grad_(True)
-                off, diag, dom = wb.whitening_terms(zz, n, 3)
+                off, diag, dom = wb.whitening_terms(zz, n, K)
+                saved = [t.clone() for t in off.grad_fn.saved_tensors[1:]]          # gram, rowstat, domgrad
                 (0.7 * off + 1.9 * diag + 1.3 * dom).backward()
-                grads.append(zz.grad.clone())
+                res.append(([off.item(), diag.item(), dom.item()], saved, zz.grad.clone()))
             finally:
-                lib.wtpse_debug_set_backward_mode(0)
-        assert torch.equal(grads[0], grads[1]) and torch.equal(grads[0], grads[2])
+                wb._lib.debug_set("fused_tail", 1)
+        M = min(B, n * K) if K > 1 else 0
+        for other in res[1:]:
+            assert [repr(x) for x in res[0][0]] == [repr(x) for x in other[0]], (B, H, res[0][0], other[0])      # NaN-safe equality
+            assert torch.equal(res[0][1][0], other[1][0]) and torch.equal(res[0][1][1], other[1][1])
+            assert torch.equal(res[0][1][2][:M], other[1][2][:M])
+            assert torch.equal(res[0][2], other[2])
+        ws, _ = wf._workspace(lib, B, H * W, z.device)
+        nt = lib.wtpse_whitening_ticket_bytes(B)
+        assert nt >= 4 * (B + 1) and int(ws[:nt].count_nonzero()) == 0
 
 
-def test_forward_schedules_agree():
-    """Gram tile schedules (contiguous ranges, grouped, pure round-robin) x epilogue variants (per-sample reduce
-    kernel + single-CTA MMD, or one single-CTA kernel): same math, different summation order -> equal to fp32
-    rounding; each bit-reproducible run to run."""
+def test_dirty_tickets_are_the_callers_responsibility_and_clean_ones_stay_clean():
+    """The C-ABI contract of wtpse_whitening_ticket_bytes: many back-to-back forwards on one workspace that was zeroed
+    once give identical results (every call leaves the tickets zero)."""
+    import ctypes
+
     import wtpse_b200 as wb
+    from wtpse_b200.functional import _forward_outputs, _ptr, _stream_ptr
 
     lib = wb._lib.load()
-    for B, H, W, n in ((9, 96, 96, 3), (32, 128, 128, 10), (6, 32, 20, 2), (3, 300, 300, 1), (200, 16, 16, 66)):
-        z = _synth(B, H, W, seed=B + 1).to(_dev())
-        res = []
-        for grp, two_stage, variant in ((0, 1, 0), (1, 0, 0), (0, 1, 0), (4, 1, 0), (2, 0, 0), (37, 1, 0),
-                                        (1, 1, 1), (0, 1, 1), (4, 0, 1)):
-            lib.wtpse_debug_set_gram_group(grp)                  # 0 = pure round-robin, 1 = contiguous ranges
-            lib.wtpse_debug_set_two_stage_epilogue(two_stage)
-            lib.wtpse_debug_set_gram_variant(variant)            # 1 = two threads per pixel quad
-            try:
-                off, diag, dom = wb.whitening_terms(z, n, 3)
-                res.append((float(off), float(diag), float(dom), wb.gram_matrix(z).clone()))
-            finally:
-                lib.wtpse_debug_set_gram_group(1)
-                lib.wtpse_debug_set_two_stage_epilogue(1)
-                lib.wtpse_debug_set_gram_variant(0)
-        assert res[0][:3] == res[2][:3] and torch.equal(res[0][3], res[2][3])          # reproducible
-        for other in res[1:]:
-            for a, b in zip(res[0][:3], other[:3]):
-                assert _close(a, b, tol=2e-6, scale=1e-3)
-            assert rel_err(res[0][3].cpu().numpy(), other[3].cpu().numpy()) < 2e-6
+    dev = _dev()
+    B, H, n = 12, 64, 4
+    z = _synth(B, H, H, seed=5).to(dev)
+    nbytes = lib.wtpse_whitening_workspace_bytes(B, H * H)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev).random_(0, 255)              # garbage everywhere ...
+    ws[:lib.wtpse_whitening_ticket_bytes(B)] = 0                                          # ... except the ticket prefix
+    outs = []
+    for _ in range(5):
+        losses, (gram, rowstat, domgrad) = _forward_outputs(B, dev)
+        wb._lib.check(lib.wtpse_whitening_forward(_ptr(z), B, 16, H * H, n, 3, 0.0, 1e-5, _ptr(losses), _ptr(gram), _ptr(rowstat),
+                                                  _ptr(domgrad), _ptr(ws), nbytes, _stream_ptr(dev)))
+        outs.append((losses.clone(), gram.clone(), domgrad.clone()))
+    for o in outs[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(o, outs[0]))
+    ref = wb.whitening_terms(z, n, 3)
+    assert [float(x) for x in ref] == [float(x) for x in outs[0][0][:3]]
 
 
 def test_many_mmd_samples_fall_back_to_the_epilogue_kernel():
-    """More than 64 samples in the MMD do not fit beside the pipeline stages: two-kernel backward."""
+    """An MMD over ~100+ samples does not fit the last CTA's pipeline buffers: the forward tail runs as separate kernels
+    (the backward is one launch either way)."""
     import wtpse_b200 as wb
     from oracle import whitening_np as wnp
 

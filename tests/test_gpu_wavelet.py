@@ -95,15 +95,15 @@ def test_fused_plans_match_per_level_path(wavelet, shape, J):
         return float(loss), g1, xg.grad.clone(), float(wb.wavelet_shape_loss(x, wavelet, J, weights))
 
     try:
-        lib.wtpse_debug_set_wavelet_resident(0)
+        wb._lib.debug_set("wavelet_resident", 0)
         assert wv.resident_cluster_size(shape[-2], shape[-1], wavelet, J) == 0
         l_p, g_p, g2_p, lo_p = run()
         assert lo_p == l_p
-        lib.wtpse_debug_set_wavelet_resident(1)
+        wb._lib.debug_set("wavelet_resident", 1)
         for split, cmax, tiles in ((0, 8, 1), (1, 8, 1), (1, 2, 1), (1, 8, 0), (-1, 8, 1)):
-            lib.wtpse_debug_set_wavelet_split(split)
-            lib.wtpse_debug_set_wavelet_cluster_max(cmax)
-            lib.wtpse_debug_set_wavelet_tiles(tiles)
+            wb._lib.debug_set("wavelet_split", split)
+            wb._lib.debug_set("wavelet_cluster_max", cmax)
+            wb._lib.debug_set("wavelet_tiles", tiles)
             assert wv.resident_cluster_size(shape[-2], shape[-1], wavelet, J) > 0, (split, cmax)
             l_r, g_r, g2_r, lo_r = run()
             assert abs(l_r - l_p) <= 2e-6 * abs(l_p) and lo_r == l_r, (split, cmax)
@@ -111,10 +111,10 @@ def test_fused_plans_match_per_level_path(wavelet, shape, J):
             assert rel_err(g2_r.cpu().numpy(), g2_p.cpu().numpy()) < 2e-6, (split, cmax)
             assert rel_err(g2_r.cpu().numpy(), (g_r / 0.3 * 2.0).cpu().numpy()) < 2e-6, (split, cmax)
     finally:
-        lib.wtpse_debug_set_wavelet_resident(1)
-        lib.wtpse_debug_set_wavelet_split(-1)
-        lib.wtpse_debug_set_wavelet_cluster_max(8)
-        lib.wtpse_debug_set_wavelet_tiles(1)
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_split", -1)
+        wb._lib.debug_set("wavelet_cluster_max", 8)
+        wb._lib.debug_set("wavelet_tiles", 1)
 
 
 def test_fused_plan_covers_maps_too_large_for_a_cluster():
@@ -129,16 +129,16 @@ def test_fused_plan_covers_maps_too_large_for_a_cluster():
     res = []
     try:
         for resident, peel, cs in ((1, 8, 2), (1, 1, 8), (0, 8, 0)):
-            lib.wtpse_debug_set_wavelet_resident(resident)
-            lib.wtpse_debug_set_wavelet_peel_max(peel)
+            wb._lib.debug_set("wavelet_resident", resident)
+            wb._lib.debug_set("wavelet_peel_max", peel)
             assert wv.resident_cluster_size(1024, 1024, "db2", 5) == cs
             xg = x.clone().requires_grad_(True)
             loss = wb.wavelet_shape_loss(xg, "db2", 5)
             loss.backward()
             res.append((float(loss), xg.grad.clone()))
     finally:
-        lib.wtpse_debug_set_wavelet_resident(1)
-        lib.wtpse_debug_set_wavelet_peel_max(8)
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_peel_max", 8)
     for l, g in res[:2]:
         assert abs(l - res[2][0]) <= 2e-6 * abs(res[2][0])
         assert rel_err(g.cpu().numpy(), res[2][1].cpu().numpy()) < 2e-6
@@ -156,10 +156,10 @@ def test_streamed_plan_with_every_level_streamed(wavelet):
     x = torch.rand(1, 2, 1024, 1024, generator=torch.Generator().manual_seed(5)).to(_dev())
     res = []
     try:
-        lib.wtpse_debug_set_wavelet_split(1)            # Haar would otherwise take the single band kernel here
+        wb._lib.debug_set("wavelet_split", 1)            # Haar would otherwise take the single band kernel here
         for resident, peel, cs in ((1, 8, 1), (1, 1, 8), (0, 8, 0)):
-            lib.wtpse_debug_set_wavelet_resident(resident)
-            lib.wtpse_debug_set_wavelet_peel_max(peel)
+            wb._lib.debug_set("wavelet_resident", resident)
+            wb._lib.debug_set("wavelet_peel_max", peel)
             # Haar row bands are independent work items: the resident stage never needs a cluster
             assert wv.resident_cluster_size(1024, 1024, wavelet, 2) == (cs if wavelet == "db2" or cs == 0 else 1)
             xg = x.clone().requires_grad_(True)
@@ -167,9 +167,9 @@ def test_streamed_plan_with_every_level_streamed(wavelet):
             (0.5 * loss).backward()
             res.append((float(loss), xg.grad.clone()))
     finally:
-        lib.wtpse_debug_set_wavelet_resident(1)
-        lib.wtpse_debug_set_wavelet_peel_max(8)
-        lib.wtpse_debug_set_wavelet_split(-1)
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_peel_max", 8)
+        wb._lib.debug_set("wavelet_split", -1)
     for l, g in res[:2]:
         assert abs(l - res[2][0]) <= 2e-6 * abs(res[2][0])
         assert rel_err(g.cpu().numpy(), res[2][1].cpu().numpy()) < 2e-6
@@ -213,11 +213,11 @@ def test_fused_plans_random_shapes_and_determinism():
             l1, g1 = run()
             assert torch.equal(l0, l1) and torch.equal(g0, g1), (H, W, wavelet, J, nmaps)
         if fused_available:
-            lib.wtpse_debug_set_wavelet_resident(0)
+            wb._lib.debug_set("wavelet_resident", 0)
             try:
                 lp, gp = run()
             finally:
-                lib.wtpse_debug_set_wavelet_resident(1)
+                wb._lib.debug_set("wavelet_resident", 1)
             assert abs(float(l0) - float(lp)) <= 2e-6 * abs(float(lp)), (H, W, wavelet, J, nmaps)
             assert rel_err(g0.cpu().numpy(), gp.cpu().numpy()) < 2e-6, (H, W, wavelet, J, nmaps)
 

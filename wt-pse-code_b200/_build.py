@@ -6,7 +6,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libwtpse_b200.so")
-SOURCES = ["api.cu", "whitening_gram.cu", "whitening_gram_split.cu", "whitening_epilogue.cu", "whitening_apply.cu", "whitening_apply_relu.cu", "whitening_apply_cl.cu", "mse.cu", "profile.cu", "elementwise.cu", "backbone_elementwise.cu", "batchnorm.cu",
+SOURCES = ["api.cu", "whitening_gram.cu", "whitening_epilogue.cu", "whitening_apply.cu", "whitening_apply_relu.cu", "whitening_apply_cl.cu", "mse.cu", "profile.cu", "elementwise.cu", "backbone_elementwise.cu", "batchnorm.cu",
            "wavelet.cu", "wavelet_resident.cu", "wavelet_stream.cu", "wavelet_tiles.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -28,7 +28,7 @@ def needs_build():
         return True
     t = os.path.getmtime(LIB_PATH)
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(os.path.dirname(PKG_DIR), "include", "wtpse_b200.h"))
+    deps += [os.path.join(os.path.dirname(PKG_DIR), "include", h) for h in ("wtpse_b200.h", "wtpse_b200_debug.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 

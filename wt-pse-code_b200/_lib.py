@@ -11,7 +11,7 @@ _c = ctypes
 _LIB = None
 
 WTPSE_OK = 0
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = {
     # name: (restype, argtypes)
@@ -19,18 +19,23 @@ EXPORTS = {
     "wtpse_last_error": (_c.c_char_p, []),
     "wtpse_sm_count": (_c.c_int, []),
     "wtpse_whitening_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int64]),
+    "wtpse_whitening_ticket_bytes": (_c.c_size_t, [_c.c_int]),
+    # z, B, C, P, n, K, margin, eps, losses, gram, rowstat, domgrad, workspace, workspace_bytes, stream
     "wtpse_whitening_forward": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_float,
-                                           _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
-                                           _c.c_void_p]),
+                                           _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                           _c.c_size_t, _c.c_void_p]),
+    # z, gram, rowstat, domgrad, g_off, g_diag, g_dom, B, C, P, n, K, dz, stream
     "wtpse_whitening_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                            _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p,
-                                            _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                            _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p,
+                                            _c.c_void_p]),
+    # z, relu_out, B, C, P, n, K, margin, eps, losses, gram, rowstat, domgrad, workspace, workspace_bytes, stream
     "wtpse_whitening_relu_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
                                                 _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                                _c.c_size_t, _c.c_void_p]),
+                                                _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    # z, grad_relu, gram, rowstat, domgrad, g_off, g_diag, g_dom, B, C, P, n, K, dz, stream
     "wtpse_whitening_relu_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                                 _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
-                                                 _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                                 _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
+                                                 _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "wtpse_upsample2x_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "wtpse_bias_act_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p]),
     "wtpse_channel_sum_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int]),
@@ -44,10 +49,10 @@ EXPORTS = {
     "wtpse_maxpool2_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "wtpse_whitening_forward_cl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
                                               _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                              _c.c_size_t, _c.c_void_p]),
+                                              _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_whitening_backward_cl": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                               _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
-                                               _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                               _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
+                                               _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "wtpse_relu_backward_channel_sum_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p,
                                                         _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_mmd_workspace_bytes": (_c.c_size_t, [_c.c_int]),
@@ -86,24 +91,14 @@ EXPORTS = {
     "wtpse_profile_kernel_name": (_c.c_char_p, [_c.c_int]),
     "wtpse_profile_launches": (_c.c_longlong, [_c.c_int]),
     "wtpse_profile_read": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_longlong), _c.POINTER(_c.c_double)]),
-    "wtpse_debug_set_stamp_buffer": (None, [_c.c_void_p]),
-    "wtpse_debug_set_epilogue_repeat": (None, [_c.c_int]),
-    "wtpse_debug_set_backward_mode": (None, [_c.c_int]),
-    "wtpse_debug_set_apply_round_robin": (None, [_c.c_int]),
-    "wtpse_debug_set_l2_hint": (None, [_c.c_int]),
     "wtpse_wavelet_resident_cluster": (_c.c_int, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
     "wtpse_wavelet_loss_resident": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                                _c.POINTER(_c.c_float), _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                                _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "wtpse_scale_unless_one": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p]),
-    "wtpse_debug_set_wavelet_resident": (None, [_c.c_int]),
-    "wtpse_debug_set_wavelet_split": (None, [_c.c_int]),
-    "wtpse_debug_set_wavelet_tiles": (None, [_c.c_int]),
-    "wtpse_debug_set_wavelet_peel_max": (None, [_c.c_int]),
-    "wtpse_debug_set_wavelet_cluster_max": (None, [_c.c_int]),
-    "wtpse_debug_set_gram_group": (None, [_c.c_int]),
-    "wtpse_debug_set_gram_variant": (None, [_c.c_int]),
-    "wtpse_debug_set_two_stage_epilogue": (None, [_c.c_int]),
+    # include/wtpse_b200_debug.h (diagnostics: not part of the product ABI)
+    "wtpse_debug_set": (_c.c_int, [_c.c_char_p, _c.c_int]),
+    "wtpse_debug_get": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_int)]),
     "wtpse_host_plan_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     "wtpse_host_plan_destroy": (None, [_c.c_void_p]),
     "wtpse_host_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
@@ -141,6 +136,17 @@ def load():
         raise WtpseError("ABI mismatch: library %d, binding %d" % (lib.wtpse_abi_version(), ABI_VERSION))
     _LIB = lib
     return lib
+
+
+def debug_set(name, value):
+    """Diagnostic switch of include/wtpse_b200_debug.h (tests, bench.py, tools -- never the product path)."""
+    check(load().wtpse_debug_set(name.encode(), int(value)))
+
+
+def debug_get(name):
+    out = _c.c_int(0)
+    check(load().wtpse_debug_get(name.encode(), _c.byref(out)))
+    return out.value
 
 
 def check(rc):

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "../../include/wtpse_b200.h"
+#include "../../include/wtpse_b200_debug.h"
 #include "common.cuh"
 #include "kernels.h"
 #include "profile.cuh"
@@ -39,18 +40,20 @@ int sm_count_cached() {
     return cache[dev];
 }
 
-int g_two_stage_epilogue = 1;            // forward: per-sample reduce kernel (B CTAs) + single-CTA MMD; 0 = one single-CTA kernel
-int g_backward_mode = 0;                  // see wtpse_whitening_backward
+// Diagnostic switches (include/wtpse_b200_debug.h, wtpse_debug_set): process-wide, read when a call is enqueued.
+int g_tail_stamps = 0;                   // 1: the in-kernel tail records phase timestamps in the last 128 bytes of the workspace
+int g_fused_tail = 1;                     // 0: forward/backward as chains of separate kernels (the fallback path) for every shape
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct WhitenWorkspace {
+    int* ticket;             // [B + 1], FIRST in the workspace: zero on entry, zero on exit (wtpse_whitening_ticket_bytes)
     float* partial;
     int* slot_count;
-    float* mmat;
     float* vd;
     float* statd;
     void* scratch;
+    long long* stamps;       // 16 x int64, diagnostics only
     size_t total;
 };
 
@@ -63,14 +66,14 @@ WhitenWorkspace carve(void* base, int B, long long P, int sms) {
     size_t off = 0;
     const size_t partial_bytes = align_up(gram_partial_floats(B, P, sms) * sizeof(float), 256);
     const size_t count_bytes = align_up(size_t(B) * sizeof(int), 256);
-    const size_t mmat_bytes = align_up(size_t(B) * 256 * sizeof(float), 256);
     char* p = static_cast<char*>(base);
+    w.ticket = reinterpret_cast<int*>(p + off); off += align_up(size_t(B + 1) * sizeof(int), 256);
     w.partial = reinterpret_cast<float*>(p + off); off += partial_bytes;
     w.slot_count = reinterpret_cast<int*>(p + off); off += count_bytes;
-    w.mmat = reinterpret_cast<float*>(p + off); off += mmat_bytes;
     w.vd = reinterpret_cast<float*>(p + off); off += align_up(size_t(B) * 124 * sizeof(float), 256);
     w.statd = reinterpret_cast<float*>(p + off); off += align_up(size_t(B) * 2 * sizeof(float), 256);
     w.scratch = p + off; off += scratch_bytes_any_k(B);
+    w.stamps = reinterpret_cast<long long*>(p + off); off += 128;
     w.total = off;
     return w;
 }
@@ -97,144 +100,173 @@ size_t wtpse_whitening_workspace_bytes(int B, int64_t P) {
     return carve(nullptr, B, P, sm_count_cached()).total;
 }
 
+size_t wtpse_whitening_ticket_bytes(int B) {
+    if (B <= 0) return 0;
+    return align_up(size_t(B + 1) * sizeof(int), 256);
+}
+
+// One launch (Gram + in-kernel tail) when the batch's MMD fits the last CTA's pipeline buffers; otherwise the tail runs
+// as a chain of small kernels.  Either way the forward leaves the same outputs, `domgrad` included.
+static bool use_fused_tail(int B, int n, int K) { return g_fused_tail && gram_tail_fits(B, n, K); }
+
+static int forward_tail_kernels(const WhitenWorkspace& w, int nslots, int B, int64_t P, int n, int K, float margin, float eps,
+                                float* losses, float* gram, float* rowstat, float* domgrad, cudaStream_t s) {
+    cudaError_t e;
+    {
+        LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
+        e = launch_gram_reduce(w.partial, w.slot_count, nslots, B, P, n, K, margin, eps, gram, rowstat, w.vd, w.statd, s);
+        if (e != cudaSuccess) return cuda_fail(e, "gram reduce launch");
+        profile_count_kernel(kKernGramReduce);
+        e = launch_whiten_epilogue_fwd(B, P, n, K, losses, w.scratch, s, w.vd, w.statd);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "forward epilogue launch");
+    {
+        LaunchScope scope(kKernMmdBwd, s);            // the backward's MMD seed: d L_dom / d v_b
+        e = launch_mmd(w.vd, kVStride, nullptr, B, n, K, nullptr, domgrad, w.scratch, s);
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "MMD gradient launch");
+    return WTPSE_OK;
+}
+
 static int whitening_forward_impl(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
-                                  float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
-                                  size_t workspace_bytes, wtpse_stream_t stream, bool channels_last = false) {
+                                  float margin, float eps, float* losses, float* gram, float* rowstat, float* domgrad,
+                                  void* workspace, size_t workspace_bytes, wtpse_stream_t stream, bool channels_last = false) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
-    if (!losses || !gram || !rowstat || !workspace) return fail(WTPSE_ERR_INVALID, "null output/workspace pointer");
+    if (!losses || !gram || !rowstat || !domgrad || !workspace) return fail(WTPSE_ERR_INVALID, "null output/workspace pointer");
     const int sms = sm_count_cached();
     const WhitenWorkspace w = carve(workspace, B, P, sms);
     if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (channels_last && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(relu_out)) & 15u))
         return fail(WTPSE_ERR_INVALID, "channels-last tensors must be 16-byte aligned");
+    TailParams tp{};
+    tp.ticket = w.ticket; tp.partial = w.partial; tp.B = B; tp.P = P; tp.n = n_per_domain; tp.K = n_domains;
+    tp.margin = margin; tp.eps = eps; tp.gram = gram; tp.rowstat = rowstat; tp.vd = w.vd; tp.losses = losses; tp.domgrad = domgrad;
+    tp.stamps = g_tail_stamps ? w.stamps : nullptr;
+    const bool fused = use_fused_tail(B, n_per_domain, n_domains);
     const GramPlan g = channels_last ? plan_gram_cl(B, P, sms) : plan_gram(z, B, P, sms, relu_out);
+    tp.nslots = g.nslots;
+    const bool in_kernel = fused && !channels_last && g.tma;
     cudaError_t e;
     {
         LaunchScope scope(kKernGram, s);
         e = channels_last ? launch_gram_cl(z, relu_out, w.partial, w.slot_count, B, P, g, s)
-                          : launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out);
+                          : launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out, in_kernel ? &tp : nullptr);
     }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
-    if (g_two_stage_epilogue || channels_last) {
-        LaunchScope scope(kKernEpilogueFwd, s);       // per-sample reduce (B CTAs) + single-CTA MMD, chained programmatically
-        e = launch_gram_reduce(w.partial, w.slot_count, g, B, P, n_per_domain, n_domains, margin, eps, gram, rowstat, w.vd, w.statd, s);
-        if (e != cudaSuccess) return cuda_fail(e, "gram reduce launch");
-        profile_count_kernel(kKernGramReduce);
-        e = launch_whiten_epilogue_fwd(nullptr, nullptr, 0, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s, w.vd, w.statd, true);
-    } else {
-        LaunchScope scope(kKernEpilogueFwd, s);
-        e = launch_whiten_epilogue_fwd(w.partial, w.slot_count, g.nslots, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, w.scratch, s);
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "forward epilogue launch");
-    return WTPSE_OK;
+    if (in_kernel) return WTPSE_OK;
+    return forward_tail_kernels(w, g.nslots, B, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, domgrad, s);
 }
 
 int wtpse_whitening_forward(const float* z, int B, int C, int64_t P, int n_per_domain, int n_domains, float margin,
-                            float eps, float* losses, float* gram, float* rowstat, void* workspace,
+                            float eps, float* losses, float* gram, float* rowstat, float* domgrad, void* workspace,
                             size_t workspace_bytes, wtpse_stream_t stream) {
-    return whitening_forward_impl(z, nullptr, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
-                                  workspace_bytes, stream);
+    return whitening_forward_impl(z, nullptr, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, domgrad,
+                                  workspace, workspace_bytes, stream);
 }
 
 int wtpse_whitening_relu_forward(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
-                                 float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
-                                 size_t workspace_bytes, wtpse_stream_t stream) {
+                                 float margin, float eps, float* losses, float* gram, float* rowstat, float* domgrad,
+                                 void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
     if (!relu_out) return fail(WTPSE_ERR_INVALID, "null relu_out pointer");
     if (relu_out == z) return fail(WTPSE_ERR_INVALID, "relu_out must not alias z (the backward pass re-reads z)");
-    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
-                                  workspace_bytes, stream);
+    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, domgrad,
+                                  workspace, workspace_bytes, stream);
 }
 
 static int whitening_backward_impl(const float* z, const float* grelu, const float* gram, const float* rowstat,
-                                   const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
-                                   int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
-                                   wtpse_stream_t stream, bool channels_last = false) {
+                                   const float* domgrad, const float* g_off, const float* g_diag, const float* g_dom, int B,
+                                   int C, int64_t P, int n_per_domain, int n_domains, float* dz, wtpse_stream_t stream,
+                                   bool channels_last = false) {
     if (int rc = check_common(z, B, C, P, n_per_domain, n_domains)) return rc;
-    if (!gram || !rowstat || !dz || !workspace) return fail(WTPSE_ERR_INVALID, "null pointer");
-    const int sms = sm_count_cached();
-    const WhitenWorkspace w = carve(workspace, B, P, sms);
-    if (workspace_bytes < w.total) return fail(WTPSE_ERR_WORKSPACE, "workspace %zu < required %zu bytes", workspace_bytes, w.total);
+    if (!gram || !rowstat || !domgrad || !dz) return fail(WTPSE_ERR_INVALID, "null pointer");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (channels_last && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(grelu) | reinterpret_cast<uintptr_t>(dz)) & 15u))
+        return fail(WTPSE_ERR_INVALID, "channels-last tensors must be 16-byte aligned");
+    // ONE launch: every apply kernel derives M_b itself from (gram, rowstat, domgrad) and the upstream scalars
+    const SeedArgs seed{gram, rowstat, domgrad, g_off, g_diag, g_dom, B, n_per_domain, n_domains};
+    const int sms = sm_count_cached();
     cudaError_t e;
-    // g_backward_mode: 0 = per-sample M_b kernel + round-robin apply chained by programmatic dependent launch (default),
-    //                  1 = M_b derived inside the apply kernel (one launch, contiguous tile ranges),
-    //                  2 = single-CTA epilogue + apply (also the fallback for very many MMD samples)
-    if (channels_last) {
-        if ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(grelu) | reinterpret_cast<uintptr_t>(dz)) & 15u)
-            return fail(WTPSE_ERR_INVALID, "channels-last tensors must be 16-byte aligned");
-        const bool multi = mmat_multi_cta_ok(B, n_per_domain, n_domains);
+    {
         LaunchScope scope(kKernApply, s);
-        e = multi ? launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s)
-                  : launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s);
-        if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
-        profile_count_kernel(kKernMmat);
-        e = launch_apply_cl(z, grelu, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/multi);
-    } else if (g_backward_mode == 1 && !grelu && apply_can_fuse(z, dz, B, P, n_per_domain, n_domains)) {
-        LaunchScope scope(kKernApply, s);
-        e = launch_apply_fused(z, gram, rowstat, g_off, g_diag, g_dom, dz, B, P, n_per_domain, n_domains, sms, s);
-    } else if (g_backward_mode != 2 && mmat_multi_cta_ok(B, n_per_domain, n_domains)) {
-        LaunchScope scope(kKernApply, s);            // one scope: an event between the two would defeat the overlap
-        e = launch_whiten_mmat(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, s);
-        if (e != cudaSuccess) return cuda_fail(e, "backward matrix launch");
-        profile_count_kernel(kKernMmat);
-        e = launch_apply(z, w.mmat, dz, B, P, sms, s, /*programmatic_dependent=*/true, grelu);
-    } else {
-        { LaunchScope scope(kKernEpilogueBwd, s); e = launch_whiten_epilogue_bwd(gram, rowstat, g_off, g_diag, g_dom, B, P, n_per_domain, n_domains, w.mmat, w.scratch, s); }
-        if (e != cudaSuccess) return cuda_fail(e, "backward epilogue launch");
-        { LaunchScope scope(kKernApply, s); e = launch_apply(z, w.mmat, dz, B, P, sms, s, false, grelu); }
+        e = channels_last ? launch_apply_cl(z, grelu, seed, dz, B, P, sms, s) : launch_apply(z, seed, dz, B, P, sms, s, grelu);
     }
     if (e != cudaSuccess) return cuda_fail(e, "apply launch");
     return WTPSE_OK;
 }
 
-int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* g_off,
+int wtpse_whitening_backward(const float* z, const float* gram, const float* rowstat, const float* domgrad, const float* g_off,
                              const float* g_diag, const float* g_dom, int B, int C, int64_t P, int n_per_domain,
-                             int n_domains, float margin, float* dz, void* workspace, size_t workspace_bytes,
-                             wtpse_stream_t stream) {
-    (void)margin;  // already folded into rowstat by the forward
-    return whitening_backward_impl(z, nullptr, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
-                                   workspace, workspace_bytes, stream);
+                             int n_domains, float* dz, wtpse_stream_t stream) {
+    return whitening_backward_impl(z, nullptr, gram, rowstat, domgrad, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
+                                   stream);
 }
 
 int wtpse_whitening_forward_cl(const float* z, float* relu_out, int B, int C, int64_t P, int n_per_domain, int n_domains,
-                               float margin, float eps, float* losses, float* gram, float* rowstat, void* workspace,
-                               size_t workspace_bytes, wtpse_stream_t stream) {
+                               float margin, float eps, float* losses, float* gram, float* rowstat, float* domgrad,
+                               void* workspace, size_t workspace_bytes, wtpse_stream_t stream) {
     if (relu_out && relu_out == z) return fail(WTPSE_ERR_INVALID, "relu_out must not alias z (the backward pass re-reads z)");
-    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, workspace,
-                                  workspace_bytes, stream, /*channels_last=*/true);
+    return whitening_forward_impl(z, relu_out, B, C, P, n_per_domain, n_domains, margin, eps, losses, gram, rowstat, domgrad,
+                                  workspace, workspace_bytes, stream, /*channels_last=*/true);
 }
 
 int wtpse_whitening_backward_cl(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
-                                const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
-                                int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
-                                wtpse_stream_t stream) {
-    return whitening_backward_impl(z, grad_relu, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
-                                   workspace, workspace_bytes, stream, /*channels_last=*/true);
+                                const float* domgrad, const float* g_off, const float* g_diag, const float* g_dom, int B, int C,
+                                int64_t P, int n_per_domain, int n_domains, float* dz, wtpse_stream_t stream) {
+    return whitening_backward_impl(z, grad_relu, gram, rowstat, domgrad, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains,
+                                   dz, stream, /*channels_last=*/true);
 }
 
 int wtpse_whitening_relu_backward(const float* z, const float* grad_relu, const float* gram, const float* rowstat,
-                                  const float* g_off, const float* g_diag, const float* g_dom, int B, int C, int64_t P,
-                                  int n_per_domain, int n_domains, float* dz, void* workspace, size_t workspace_bytes,
-                                  wtpse_stream_t stream) {
+                                  const float* domgrad, const float* g_off, const float* g_diag, const float* g_dom, int B,
+                                  int C, int64_t P, int n_per_domain, int n_domains, float* dz, wtpse_stream_t stream) {
     if (!grad_relu) return fail(WTPSE_ERR_INVALID, "null grad_relu pointer (use wtpse_whitening_backward)");
-    return whitening_backward_impl(z, grad_relu, gram, rowstat, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains, dz,
-                                   workspace, workspace_bytes, stream);
+    return whitening_backward_impl(z, grad_relu, gram, rowstat, domgrad, g_off, g_diag, g_dom, B, C, P, n_per_domain, n_domains,
+                                   dz, stream);
 }
 
-void wtpse_debug_set_stamp_buffer(long long* device_buffer16) { g_epilogue_dbg = device_buffer16; }
-void wtpse_debug_set_epilogue_repeat(int n) { g_epilogue_repeat = n > 0 ? n : 1; }
-void wtpse_debug_set_backward_mode(int mode) { g_backward_mode = (mode >= 0 && mode <= 2) ? mode : 0; }
-void wtpse_debug_set_gram_variant(int v) { g_gram_variant = v == 1 ? 1 : 0; }
-void wtpse_debug_set_gram_group(int ctas_per_group) { g_gram_group = ctas_per_group >= 0 ? ctas_per_group : 1; }
-void wtpse_debug_set_two_stage_epilogue(int on) { g_two_stage_epilogue = on != 0; }
-void wtpse_debug_set_wavelet_resident(int on) { g_wavelet_resident = on != 0; }
-void wtpse_debug_set_wavelet_tiles(int on) { g_wavelet_tiles = on != 0; }
-void wtpse_debug_set_wavelet_peel_max(int k) { g_wavelet_peel_max = k < 1 ? 1 : k; }
-void wtpse_debug_set_wavelet_split(int mode) { g_wavelet_split = mode < 0 ? -1 : (mode ? 1 : 0); }
-void wtpse_debug_set_wavelet_cluster_max(int cs) { g_wavelet_cluster_max = cs < 1 ? 1 : (cs > 8 ? 8 : cs); }
-void wtpse_debug_set_l2_hint(int on) { g_l2_evict_first = on != 0; }
-void wtpse_debug_set_apply_round_robin(int chunk) { g_apply_round_robin = chunk > 0 ? chunk : 0; }
+// ---- diagnostic switches (include/wtpse_b200_debug.h; not part of the product ABI) -----------------------------------------
+namespace {
+struct Knob { const char* name; int* value; int lo, hi; };
+const Knob* knobs(int* count) {
+    static const Knob table[] = {
+        {"fused_tail", &g_fused_tail, 0, 1},
+        {"tail_stamps", &g_tail_stamps, 0, 1},                    // phase clocks of the in-kernel tail -> last 128 workspace bytes                      // 0: forward tail as separate kernels for every shape
+        {"apply_round_robin", &g_apply_round_robin, 0, 1},        // NCHW apply kernel: tiles dealt round-robin (1) or contiguous ranges (0)
+        {"l2_hint", &g_l2_evict_first, 0, 1},                     // L2 evict-first policy on the TMA loads of z
+        {"cl_tma", &g_cl_tma, 0, 1},                              // channels-last kernels: tensor-map TMA pipelines (1) or per-thread loads (0)
+        {"wavelet_resident", &g_wavelet_resident, 0, 1},
+        {"wavelet_tiles", &g_wavelet_tiles, 0, 1},
+        {"wavelet_peel_max", &g_wavelet_peel_max, 1, 16},
+        {"wavelet_split", &g_wavelet_split, -1, 1},
+        {"wavelet_cluster_max", &g_wavelet_cluster_max, 1, 8},
+    };
+    *count = int(sizeof(table) / sizeof(table[0]));
+    return table;
+}
+}  // namespace
+
+int wtpse_debug_set(const char* name, int value) {
+    int n = 0;
+    const Knob* t = knobs(&n);
+    for (int i = 0; i < n; ++i)
+        if (name && strcmp(name, t[i].name) == 0) {
+            *t[i].value = value < t[i].lo ? t[i].lo : (value > t[i].hi ? t[i].hi : value);
+            return WTPSE_OK;
+        }
+    return fail(WTPSE_ERR_INVALID, "unknown debug switch '%s'", name ? name : "(null)");
+}
+
+int wtpse_debug_get(const char* name, int* value) {
+    int n = 0;
+    const Knob* t = knobs(&n);
+    for (int i = 0; i < n; ++i)
+        if (name && value && strcmp(name, t[i].name) == 0) {
+            *value = *t[i].value;
+            return WTPSE_OK;
+        }
+    return fail(WTPSE_ERR_INVALID, "unknown debug switch '%s'", name ? name : "(null)");
+}
 
 size_t wtpse_mmd_workspace_bytes(int B) {
     if (B <= 0) return 0;
@@ -256,7 +288,7 @@ int wtpse_mmd_forward(const float* v, int B, int D, int n_per_domain, int n_doma
     if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    { LaunchScope scope(kKernMmdFwd, s); e = launch_mmd(v, nullptr, B, n_per_domain, n_domains, loss, nullptr, workspace, s); }
+    { LaunchScope scope(kKernMmdFwd, s); e = launch_mmd(v, kOff, nullptr, B, n_per_domain, n_domains, loss, nullptr, workspace, s); }
     if (e != cudaSuccess) return cuda_fail(e, "mmd forward launch");
     return WTPSE_OK;
 }
@@ -268,7 +300,7 @@ int wtpse_mmd_backward(const float* v, const float* gout, int B, int D, int n_pe
     if (workspace_bytes < wtpse_mmd_workspace_bytes(B)) return fail(WTPSE_ERR_WORKSPACE, "workspace too small");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    { LaunchScope scope(kKernMmdBwd, s); e = launch_mmd(v, gout, B, n_per_domain, n_domains, nullptr, dv, workspace, s); }
+    { LaunchScope scope(kKernMmdBwd, s); e = launch_mmd(v, kOff, gout, B, n_per_domain, n_domains, nullptr, dv, workspace, s); }
     if (e != cudaSuccess) return cuda_fail(e, "mmd backward launch");
     return WTPSE_OK;
 }
@@ -591,7 +623,7 @@ int wtpse_scale_unless_one(float* data, int64_t n, const float* scale, wtpse_str
 // step i (slot A) and the H2D of step i+1 (slot B) share the full-duplex PCIe link instead of queueing behind
 // each other -- the path is PCIe-bound (1.07 GB per step against 0.29 ms of kernels).
 struct HostSlot {
-    float *z, *dz, *gram, *rowstat, *losses, *gvec;
+    float *z, *dz, *gram, *rowstat, *domgrad, *losses, *gvec;
     void* ws;
     float* pinned;            // [8] page-locked: losses (4) + upstream gradients (4); copies to/from it are truly asynchronous
     float* user_losses;       // where the step's losses go once it has left the device (filled by drain_slot)
@@ -609,7 +641,7 @@ struct wtpse_host_plan {
 };
 
 static void free_slot(HostSlot& s) {
-    cudaFree(s.z); cudaFree(s.dz); cudaFree(s.gram); cudaFree(s.rowstat); cudaFree(s.losses); cudaFree(s.gvec); cudaFree(s.ws);
+    cudaFree(s.z); cudaFree(s.dz); cudaFree(s.gram); cudaFree(s.rowstat); cudaFree(s.domgrad); cudaFree(s.losses); cudaFree(s.gvec); cudaFree(s.ws);
     if (s.pinned) cudaFreeHost(s.pinned);
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.done) cudaEventDestroy(s.done);
@@ -649,8 +681,10 @@ int wtpse_host_plan_create(int B, int64_t P, wtpse_host_plan** out) {
         if ((e = cudaMalloc(&s.z, nz)) != cudaSuccess || (e = cudaMalloc(&s.dz, nz)) != cudaSuccess ||
             (e = cudaMalloc(&s.gram, size_t(B) * 256 * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&s.rowstat, size_t(B) * 2 * sizeof(float))) != cudaSuccess ||
+            (e = cudaMalloc(&s.domgrad, size_t(B) * 120 * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&s.losses, 4 * sizeof(float))) != cudaSuccess ||
             (e = cudaMalloc(&s.gvec, 4 * sizeof(float))) != cudaSuccess || (e = cudaMalloc(&s.ws, p->ws_bytes)) != cudaSuccess ||
+            (e = cudaMemset(s.ws, 0, wtpse_whitening_ticket_bytes(B))) != cudaSuccess ||        // the ticket contract: zero once
             (e = cudaMallocHost(&s.pinned, 8 * sizeof(float))) != cudaSuccess ||
             (e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) {
@@ -678,13 +712,13 @@ int wtpse_host_plan_submit(wtpse_host_plan* p, const float* z_host, int n_per_do
         if ((e = cudaMemcpyAsync(s.z, z_host, nz, cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "H2D copy"); break; }
         enqueued = true;
         if ((rc = wtpse_whitening_forward(s.z, p->B, WTPSE_CHANNELS, p->P, n_per_domain, n_domains, margin, eps, s.losses, s.gram,
-                                          s.rowstat, s.ws, p->ws_bytes, s.stream))) break;
+                                          s.rowstat, s.domgrad, s.ws, p->ws_bytes, s.stream))) break;
         if ((e = cudaMemcpyAsync(s.pinned, s.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "D2H losses"); break; }
         if (dz_host) {
             s.pinned[4] = grad_w ? grad_w[0] : 1.f; s.pinned[5] = grad_w ? grad_w[1] : 1.f; s.pinned[6] = grad_w ? grad_w[2] : 1.f; s.pinned[7] = 0.f;
             if ((e = cudaMemcpyAsync(s.gvec, s.pinned + 4, 4 * sizeof(float), cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "H2D grads"); break; }
-            if ((rc = wtpse_whitening_backward(s.z, s.gram, s.rowstat, s.gvec, s.gvec + 1, s.gvec + 2, p->B, WTPSE_CHANNELS, p->P,
-                                               n_per_domain, n_domains, margin, s.dz, s.ws, p->ws_bytes, s.stream))) break;
+            if ((rc = wtpse_whitening_backward(s.z, s.gram, s.rowstat, s.domgrad, s.gvec, s.gvec + 1, s.gvec + 2, p->B, WTPSE_CHANNELS,
+                                               p->P, n_per_domain, n_domains, s.dz, s.stream))) break;
             if ((e = cudaMemcpyAsync(dz_host, s.dz, nz, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess) { rc = cuda_fail(e, "D2H dz"); break; }
         }
     } while (false);

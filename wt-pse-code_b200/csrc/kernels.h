@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 
+#include "whitening_matrix.cuh"
+#include "whitening_tail.cuh"
+
 namespace wtpse {
 
 struct GramPlan {
@@ -11,9 +14,7 @@ struct GramPlan {
     long long T;                 // total tiles
     long long G;                 // grid (CTAs)
     int nslots;                  // partial slots per sample
-    bool round_robin;            // group > 1
-    int group;                   // CTAs per group: the group owns a contiguous tile range and deals it round-robin
-    int variant;                 // 0: one thread per pixel quad (whitening_gram.cu), 1: two threads per quad (..._split.cu)
+    int group;                   // always 1: one contiguous tile range per CTA (round-robin groups measured slower)
     long long item_px;           // channels-last schedule only: pixels per work item
 };
 
@@ -24,64 +25,42 @@ GramPlan plan_gram_cl(int B, long long P, int sm_count);
 cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
                            cudaStream_t stream);
 // channels-last backward: dz = M_b z (+ [z > 0] * grelu), all [B][P][16]
-cudaError_t launch_apply_cl(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P, int sm_count,
-                            cudaStream_t stream, bool programmatic_dependent);
+cudaError_t launch_apply_cl(const float* z, const float* grelu, const SeedArgs& seed, float* dz, int B, long long P,
+                            int sm_count, cudaStream_t stream);
+// relu_out: also write relu(z) (8(f).1); tail: run the rest of the forward inside the kernel (whitening_tail.cuh)
 cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
-                        cudaStream_t stream, float* relu_out = nullptr);   // relu_out: also write relu(z) (8(f).1)
+                        cudaStream_t stream, float* relu_out = nullptr, const TailParams* tail = nullptr);
+bool gram_tail_fits(int B, int n_per_domain, int n_domains);
 
-// epilogues (single CTA).  `scratch` is the global fallback for their working set (epilogue_scratch_bytes).
+// stand-alone forward tail (whitening_epilogue.cu): the fallback of the in-kernel tail.  `scratch` is the global fallback
+// for the single-CTA kernels' working set (epilogue_scratch_bytes).
 size_t epilogue_scratch_bytes(int B, int K);
-extern long long* g_epilogue_dbg;
-extern int g_epilogue_repeat;
 extern int g_apply_round_robin;
 extern int g_l2_evict_first;
+extern int g_cl_tma;
 
-// forward: partial slots -> gram, rowstat, losses
-cudaError_t launch_whiten_epilogue_fwd(const float* partial, const int* slot_count, int nslots, int B, long long P,
-                                       int n_per_domain, int n_domains, float margin, float eps, float* losses,
-                                       float* gram, float* rowstat, void* scratch, cudaStream_t stream,
-                                       const float* vd = nullptr, const float* statd = nullptr, bool pre_reduced = false);
-
-// forward stage 2a (round-robin Gram schedule): one CTA per sample reduces the per-CTA partials
-cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, const GramPlan& g, int B, long long P, int n_per_domain, int n_domains,
-                               float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
+// stage 2a: one CTA per sample reduces the per-CTA partials -> gram, rowstat, vd [B][124], statd [B][2]
+cudaError_t launch_gram_reduce(const float* partial, const int* slot_count, int nslots, int B, long long P, int n_per_domain,
+                               int n_domains, float margin, float eps, float* gram, float* rowstat, float* vd, float* statd,
                                cudaStream_t stream);
-extern int g_gram_group;
-extern int g_gram_variant;
-long long gram_split_tile_px();
-cudaError_t launch_gram_split(const float* z, float* partial, int* slot_count, long long P, const GramPlan& g,
-                              cudaStream_t stream);
+// stage 2b: ONE CTA, vd / statd -> losses
+cudaError_t launch_whiten_epilogue_fwd(int B, long long P, int n_per_domain, int n_domains, float* losses, void* scratch,
+                                       cudaStream_t stream, const float* vd, const float* statd);
 
-// backward: gram, rowstat, upstream grads -> M_b = (S_b + S_b^T)/(P-1), [B][16][16] floats
-cudaError_t launch_whiten_epilogue_bwd(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
-                                       const float* g_dom, int B, long long P, int n_per_domain, int n_domains,
-                                       float* mmat, void* scratch, cudaStream_t stream);
-
-// backward stage 1, one CTA per sample (triggers programmatic dependents immediately)
-bool mmat_multi_cta_ok(int B, int n_per_domain, int n_domains);
-cudaError_t launch_whiten_mmat(const float* gram, const float* rowstat, const float* g_off, const float* g_diag,
-                               const float* g_dom, int B, long long P, int n_per_domain, int n_domains, float* mmat,
-                               cudaStream_t stream);
-
-// standalone compute_MMD.forward / backward on v[B][120]; dv == nullptr selects the forward
-cudaError_t launch_mmd(const float* v, const float* gout, int B, int n_per_domain, int n_domains, float* loss, float* dv,
-                       void* scratch, cudaStream_t stream);
+// standalone compute_MMD.forward / backward on v[B][stride]; dv == nullptr selects the forward
+cudaError_t launch_mmd(const float* v, int stride, const float* gout, int B, int n_per_domain, int n_domains, float* loss,
+                       float* dv, void* scratch, cudaStream_t stream);
 
 // backward apply: dz_b = M_b z_b
 // grelu != nullptr: dz_b = M_b z_b + [z_b > 0] * grelu_b (ReLU backward + gradient sum fused)
-cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
-                         cudaStream_t stream, bool programmatic_dependent = false, const float* grelu = nullptr);
+// M_b is derived in the kernel from the forward's saved tensors and the upstream scalars (whitening_matrix.cuh)
+cudaError_t launch_apply(const float* z, const SeedArgs& seed, float* dz, int B, long long P, int sm_count,
+                         cudaStream_t stream, const float* grelu = nullptr);
 
 // whitening_apply_relu.cu: the TMA path of the grelu variant (z and grelu both staged by the producer warp)
 bool apply_relu_tma_ok(const float* z, const float* grelu, const float* dz, long long P);
-cudaError_t launch_apply_relu(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P,
-                              int sm_count, cudaStream_t stream, bool programmatic_dependent);
-
-// fused backward: every CTA derives M_b for its own samples (no separate epilogue launch)
-bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains);
-cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,
-                               const float* g_diag, const float* g_dom, float* dz, int B, long long P, int n_per_domain,
-                               int n_domains, int sm_count, cudaStream_t stream);
+cudaError_t launch_apply_relu(const float* z, const float* grelu, const SeedArgs& seed, float* dz, int B, long long P,
+                              int sm_count, cudaStream_t stream);
 
 // KD MSE
 size_t mse_partial_doubles(long long N, int sm_count);

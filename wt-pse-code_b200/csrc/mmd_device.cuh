@@ -88,6 +88,33 @@ __device__ __forceinline__ float mmd_grad_entry(const float* __restrict__ v, con
     return 2.0f * (a0 + a1);
 }
 
+// Four consecutive entries o = 4*q .. 4*q+3 of the same gradient row at once: one LDS.128 per sample instead of four
+// scalar loads.  Per entry the operations and their order are those of mmd_grad_entry (even samples into one
+// accumulator, odd ones into the other): identical bits.
+__device__ __forceinline__ float4 mmd_grad_entry4(const float* __restrict__ v, const float* __restrict__ coef_row, int M,
+                                                  int b, int q) {
+    const float4 vb = *reinterpret_cast<const float4*>(v + size_t(b) * kVStride + 4 * q);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    int c = 0;
+#pragma unroll 4
+    for (; c + 1 < M; c += 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v + size_t(c) * kVStride + 4 * q);
+        const float4 x1 = *reinterpret_cast<const float4*>(v + size_t(c + 1) * kVStride + 4 * q);
+        const float k0 = coef_row[c], k1 = coef_row[c + 1];
+        a0.x = fmaf(k0, vb.x - x0.x, a0.x); a0.y = fmaf(k0, vb.y - x0.y, a0.y);
+        a0.z = fmaf(k0, vb.z - x0.z, a0.z); a0.w = fmaf(k0, vb.w - x0.w, a0.w);
+        a1.x = fmaf(k1, vb.x - x1.x, a1.x); a1.y = fmaf(k1, vb.y - x1.y, a1.y);
+        a1.z = fmaf(k1, vb.z - x1.z, a1.z); a1.w = fmaf(k1, vb.w - x1.w, a1.w);
+    }
+    if (c < M) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v + size_t(c) * kVStride + 4 * q);
+        const float k0 = coef_row[c];
+        a0.x = fmaf(k0, vb.x - x0.x, a0.x); a0.y = fmaf(k0, vb.y - x0.y, a0.y);
+        a0.z = fmaf(k0, vb.z - x0.z, a0.z); a0.w = fmaf(k0, vb.w - x0.w, a0.w);
+    }
+    return make_float4(2.0f * (a0.x + a1.x), 2.0f * (a0.y + a1.y), 2.0f * (a0.z + a1.z), 2.0f * (a0.w + a1.w));
+}
+
 // distance row: D(b, c) = max(sum_e (v_b[e] - v_c[e])^2, 1e-30); rows are kVStride floats, 16-byte aligned
 __device__ __forceinline__ float mmd_distance(const float* __restrict__ vb, const float* __restrict__ vc) {
     const float4* x = reinterpret_cast<const float4*>(vb);
@@ -121,6 +148,106 @@ __device__ __forceinline__ float backward_matrix_entry(int i, int j, float g, fl
     const bool act = (off_b / float(kOff)) >= 0.f;
     const float s = (act ? w_off * sgn : 0.f) + dom_grad;
     return s / denom;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Working set of the MMD part (single CTA): v [M][124] f32 | U [M][M] f32 | stat [B][2] f32 | blk [K*K] f64.
+// Shared by the stand-alone epilogue kernels (whitening_epilogue.cu) and the in-kernel tail of the Gram kernels
+// (whitening_tail.cuh): one definition, identical bits.
+struct EpiMem {
+    float* v;
+    float* U;
+    float* stat;
+    double* blk;
+};
+
+__host__ __device__ inline size_t round4(size_t x) { return (x + 3) & ~size_t(3); }
+__host__ __device__ inline size_t epi_mem_bytes(int B, int M, int K) {
+    const size_t kk = size_t(K > 0 ? K : 1) * size_t(K > 0 ? K : 1);
+    return (round4(size_t(M) * kVStride) + round4(size_t(M) * M) + round4(size_t(B) * 2)) * sizeof(float) + kk * sizeof(double);
+}
+
+// kSmem is a template parameter so that the compiler sees shared-space pointers (LDS/STS) instead of
+// generic ones: generic accesses to shared memory go through the address-divergence unit and made
+// every phase of these kernels ~5x slower.
+template <bool kSmem>
+__device__ __forceinline__ EpiMem resolve_mem(void* smem, void* global, int B, int M) {
+    float* base = reinterpret_cast<float*>(kSmem ? smem : global);
+    EpiMem m;
+    m.v = base;
+    m.U = m.v + round4(size_t(M) * kVStride);
+    m.stat = m.U + round4(size_t(M) * M);
+    m.blk = reinterpret_cast<double*>(m.stat + round4(size_t(B) * 2));    // 16-byte aligned by construction
+    return m;
+}
+
+// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M, one LANE per pair (no shuffle chain);
+// emit(a, c, D) is expected to fill both (a, c) and (c, a).  Consecutive lanes share a and walk c, so the
+// v_a loads broadcast and the v_c loads hit distinct banks (row stride 124 floats).  nthreads cooperate.
+// (a, c) of flat index pidx into the strict upper triangle of an M x M matrix (row a starts at a*(2M-a-1)/2)
+__device__ __forceinline__ void upper_pair(int pidx, int M, int& a, int& c) {
+    const float t = float(2 * M - 1);
+    a = int((t - sqrtf(t * t - 8.0f * float(pidx))) * 0.5f);
+    while (a > 0 && a * (2 * M - a - 1) / 2 > pidx) --a;
+    while ((a + 1) * (2 * M - a - 2) / 2 <= pidx) ++a;
+    c = a + 1 + (pidx - a * (2 * M - a - 1) / 2);
+}
+
+// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M, one LANE per pair (no shuffle chain);
+// emit(a, c, D) is expected to fill both (a, c) and (c, a).  Consecutive lanes share a and walk c, so the
+// v_a loads broadcast and the v_c loads hit distinct banks (row stride 124 floats).  nthreads cooperate.
+// (Two pairs per lane and step, interleaved for twice the independent chains, measured no faster: 2.7 vs 2.6 us.)
+template <typename F>
+__device__ __forceinline__ void pairwise_upper_n(const float* __restrict__ v, int M, int tid, int nthreads, F&& emit) {
+    const int npairs = M * (M - 1) / 2;
+    for (int pidx = tid; pidx < npairs; pidx += nthreads) {
+        int a, c;
+        upper_pair(pidx, M, a, c);
+        emit(a, c, mmd_distance(v + size_t(a) * kVStride, v + size_t(c) * kVStride));
+    }
+}
+
+// per-domain-pair sums of u = E - 1: one warp per (k <= l) block.  Lane j sums column c0 + j (+ 32, ...) of the block top to
+// bottom in fp32 -- a fixed order with no index arithmetic in the loop -- and the lanes are combined in float64 (the
+// result does not depend on how many warps share the blocks).
+__device__ inline void domain_block_sums(const float* __restrict__ U, const DomainInfo& dom, double* __restrict__ blk,
+                                         int first_warp, int nwarps, int warp, int lane) {
+    const int K = dom.K;
+    for (int pr = warp - first_warp; pr < K * K; pr += nwarps) {
+        const int k = pr / K, l = pr - k * K;
+        if (l < k) continue;
+        const int a0 = chunk_lo(k, dom.n, dom.B), a1 = chunk_lo(k + 1, dom.n, dom.B);
+        const int c0 = chunk_lo(l, dom.n, dom.B), c1 = chunk_lo(l + 1, dom.n, dom.B);
+        float s = 0.f;
+        for (int c = c0 + lane; c < c1; c += 32)
+            for (int a = a0; a < a1; ++a) s += U[a * dom.M + c];
+        const double t = warp_sum(double(s));
+        if (lane == 0) blk[k * K + l] = t;
+    }
+}
+
+// L_dom = sum_{k<l} (Kxx + Kyy - 2Kxy) / (K(K-1)/2)   (algorithms.py:110-116, :82-88) from the u block sums;
+// executed by one warp, one lane per domain pair.  An empty chunk gives 0 * inf = NaN, as torch's
+// mean() over an empty tensor does.
+__device__ inline float mmd_from_blocks(const double* __restrict__ blk, const DomainInfo& dom, int lane) {
+    const int K = dom.K;
+    if (K <= 1) return 0.f;
+    const int npairs = K * (K - 1) / 2;
+    double acc = 0.0;
+    for (int pidx = lane; pidx < npairs; pidx += 32) {
+        int k = 0, r = pidx;
+        while (r >= K - 1 - k) { r -= K - 1 - k; ++k; }
+        const int l = k + 1 + r;
+        const float nk = float(dom.size(k)), nl = float(dom.size(l));
+        const double rkk = double(1.0f / (nk * nk)), rll = double(1.0f / (nl * nl)), rkl = double(1.0f / (nk * nl));
+        acc += blk[k * K + k] * rkk + blk[l * K + l] * rll - 2.0 * (blk[k * K + l] * rkl);
+    }
+    // butterfly over the lanes that hold a pair only (float64 adds have ~50 cycles of latency each: 2 levels for 3 domains
+    // instead of 5); lanes beyond hold 0
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1)
+        if (m < 2 * npairs) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+    return float(acc) / float(npairs);
 }
 
 }  // namespace wtpse

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../include/wtpse_b200.h"
+#include "../../include/wtpse_b200_debug.h"
 
 namespace wtpse {
 

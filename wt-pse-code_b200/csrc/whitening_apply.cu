@@ -10,17 +10,14 @@
 // adjacent 4 KB pieces of each of the 16 channel rows at the same time, which is worth 10 % of DRAM
 // throughput over giving every CTA its own contiguous range (2 368 scattered streams).
 //
-// Default path (apply_tma_kernel<false>): the matrices come from whiten_mmat_kernel (one CTA per sample,
-// whitening_epilogue.cu); this kernel is launched as its programmatic dependent, so z is already streaming
-// while the matrices are derived, and the consumers wait (griddepcontrol.wait) only before the first M_b read.
-//
-// Alternative (apply_tma_kernel<true>, wtpse_debug_set_backward_mode(1)): every CTA derives M_b itself for the
-// one or two samples of its CONTIGUOUS tile range -- one launch instead of two, but without the round-robin
-// schedule's DRAM locality (188 us vs 176 us for the pair at 32x16x512x512).  Same arithmetic (mmd_device.cuh),
-// bitwise-equal results (tests/test_gpu_parity.py).
+// The matrix M_b is derived in the kernel itself at every sample change from the forward's saved tensors and the three
+// upstream scalars (whitening_matrix.cuh): the backward is ONE launch, launched as a programmatic dependent of whatever
+// runs in front of it -- z is already streaming while that kernel finishes, and the consumers wait
+// (griddepcontrol.wait) only before the first matrix.
 #include "common.cuh"
 #include "kernels.h"
 #include "mmd_device.cuh"
+#include "whitening_matrix.cuh"
 
 namespace wtpse {
 
@@ -32,51 +29,57 @@ constexpr int kThreads = kConsumers + 32;
 constexpr int kTilePx = kConsumers * 4;
 constexpr int kStages = 3;
 constexpr int kStageFloats = kC * kTilePx;
-constexpr int kFusedMaxM = 64;     // MMD samples whose vectors fit beside the pipeline stages
 constexpr size_t kSmemPipe = size_t(kStages) * kStageFloats * sizeof(float);
-constexpr size_t kSmemPlain = kSmemPipe + 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
-constexpr size_t kSmemFused = kSmemPlain + (size_t(kFusedMaxM) * kVStride + kFusedMaxM) * sizeof(float) + sizeof(IndexTables) + 16;
+constexpr size_t kSmemPlain = kSmemPipe + 2 * 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
 
 __device__ __forceinline__ void st_stream(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-struct FusedArgs {
-    const float* gram;      // [B][16][16]
-    const float* rowstat;   // [B][2]
-    const float *g_off, *g_diag, *g_dom;
-    int B, n, K;
-    int round_robin;
-    int l2_hint;            // 1: TMA loads carry an L2 evict-first policy (z is read once)
+// Walks one CTA's tiles without a division per tile: round-robin (tile k, k + G, ...) or one contiguous range.
+struct TileIter {
+    long long t, tin, b;        // tile, tile index inside its sample, sample
+    long long step, tend, tps;
+    __device__ __forceinline__ void init(long long first, long long end, long long stride, long long tiles_per_sample) {
+        t = first; tend = end; step = stride; tps = tiles_per_sample;
+        b = first / tps;
+        tin = first - b * tps;
+    }
+    __device__ __forceinline__ bool valid() const { return t < tend; }
+    __device__ __forceinline__ void next() {
+        t += step;
+        tin += step;
+        while (tin >= tps) { tin -= tps; ++b; }
+    }
+    // sample of the first later tile that belongs to another sample (-1: none)
+    __device__ __forceinline__ long long next_sample() const {
+        TileIter it = *this;
+        for (it.next(); it.valid(); it.next())
+            if (it.b != b) return it.b;
+        return -1;
+    }
 };
 
-template <bool kFused>
 __global__ void __launch_bounds__(kThreads, 1)
-apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, float* __restrict__ dz, long long P,
-                 long long tiles_per_sample, long long T, FusedArgs fa) {
+apply_tma_kernel(const float* __restrict__ z, float* __restrict__ dz, long long P, long long tiles_per_sample, long long T,
+                 int round_robin, int l2_hint, SeedArgs sa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
-    float* msh = stage_buf + size_t(kStages) * kStageFloats;
-    uint64_t* full = reinterpret_cast<uint64_t*>(msh + 256);
+    float* msh2 = stage_buf + size_t(kStages) * kStageFloats;          // two matrices: the current sample's and the next one's
+    uint64_t* full = reinterpret_cast<uint64_t*>(msh2 + 512);
     uint64_t* empty = full + kStages;
-    float* vbuf = reinterpret_cast<float*>(empty + kStages);          // [kFusedMaxM][124]   (fused only)
-    float* coefrow = vbuf + size_t(kFusedMaxM) * kVStride;            // [kFusedMaxM]
-    IndexTables* tab = reinterpret_cast<IndexTables*>(coefrow + kFusedMaxM);
+    __shared__ IndexTables tab;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // e.g. the next Gram kernel: it waits for us itself
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
-    // tile schedule: one contiguous range per CTA, or blocks of tiles dealt round-robin over the grid (default: at any
-    // moment the CTAs then stream adjacent tiles of every channel row)
-    // round_robin = c > 0: blocks of c consecutive tiles dealt round-robin to the CTAs (block q -> CTA q % G)
-    const long long chunk = fa.round_robin;
-    const bool rr = chunk > 0;
-    const long long nblocks = rr ? (T + chunk - 1) / chunk : 0;
-    const long long my_blocks = rr ? (nblocks > k ? (nblocks - k + G - 1) / G : 0) : 0;
-    const long long t0 = rr ? 0 : part_begin(k, T, G);
-    const long long t1 = rr ? my_blocks * chunk : part_begin(k + 1, T, G);
-    auto tile_of = [=](long long j) -> long long { return rr ? ((j / chunk) * G + k) * chunk + (j % chunk) : j; };
+    // tile schedule: tiles dealt round-robin over the grid (default: at any moment the CTAs stream adjacent tiles of
+    // every channel row) or one contiguous range per CTA
+    TileIter it;
+    if (round_robin) it.init(k, T, G, tiles_per_sample);
+    else it.init(part_begin(k, T, G), part_begin(k + 1, T, G), 1, tiles_per_sample);
 
+    build_index_tables(tab, tid, kThreads);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -88,98 +91,57 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
     __syncthreads();
 
     if (warp == kConsumerWarps) {
+        // z was written before the forward pass ran: it is streamed without waiting for the kernel in front of us
         if (lane == 0) {
             const uint64_t policy = make_evict_first_policy();
-            const bool g_use_hint = fa.l2_hint != 0;
+            const bool g_use_hint = l2_hint != 0;
             int stage = 0;
             uint32_t phase = 0;
-            for (long long j = t0; j < t1; ++j) {
-                const long long t = tile_of(j);
-                if (t >= T) continue;
+            for (; it.valid(); it.next()) {
                 mbar_wait(&empty[stage], phase ^ 1);
-                const long long b = t / tiles_per_sample;
-                const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+                const long long px0 = it.tin * kTilePx;
                 const long long rem = P - px0;
                 const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
                 const uint32_t bytes = npx * 4u;
                 mbar_arrive_expect_tx(&full[stage], bytes * kC);
-                const float* src = z + (b * kC) * P + px0;
+                const float* src = z + (it.b * kC) * P + px0;
                 float* dst = stage_buf + size_t(stage) * kStageFloats;
 #pragma unroll
                 for (int c = 0; c < kC; ++c) {
-                        if (g_use_hint) tma_load_1d_hint(dst + c * kTilePx, src + c * P, bytes, &full[stage], policy);
-                        else tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
-                    }
+                    if (g_use_hint) tma_load_1d_hint(dst + c * kTilePx, src + c * P, bytes, &full[stage], policy);
+                    else tma_load_1d(dst + c * kTilePx, src + c * P, bytes, &full[stage]);
+                }
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
         }
         return;
     }
 
-    // ---- fused prologue: everything that does not depend on the sample ------------------------------
-    DomainInfo dom{0, 0, 0, 0};
-    float g_dom = 0.f, w_off = 0.f, w_diag = 0.f;
-    bool need_dom = false;
-    const float denom = float(P - 1);
-    if (kFused) {
-        dom = make_domain(fa.B, fa.n, fa.K);
-        const float g_off = fa.g_off ? __ldg(fa.g_off) : 0.f;
-        const float g_diag = fa.g_diag ? __ldg(fa.g_diag) : 0.f;
-        g_dom = fa.g_dom ? __ldg(fa.g_dom) : 0.f;
-        need_dom = (dom.M > 0) && (g_dom != 0.f);
-        w_off = g_off / (float(fa.B) * float(kOff));
-        w_diag = g_diag / (float(fa.B) * float(kC));
-        build_index_tables(*tab, tid, kConsumers);
-        named_bar_sync(1, kConsumers);
-        if (need_dom) {
-            for (int idx = tid; idx < dom.M * kOff; idx += kConsumers) {
-                const int b = idx / kOff, o = idx - b * kOff;
-                const int ij = tab->off[o];
-                vbuf[size_t(b) * kVStride + o] = __ldg(fa.gram + b * 256 + (ij >> 4) * kC + (ij & 15));
-            }
-        }
-    }
+    // Everything this kernel reads besides z (saved tensors, upstream scalars) and everything it writes may belong to
+    // the kernel in front of it: wait for that kernel here (no-op without a programmatic dependency).
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const SeedCtx sc = seed_context(sa, P);
 
-    int stage = 0;
+    int stage = 0, cur = 0;
     uint32_t phase = 0;
-    long long cur_b = -1;
-    for (long long j = t0; j < t1; ++j) {
-        const long long t = tile_of(j);
-        if (t >= T) continue;
-        const long long b = t / tiles_per_sample;
-        const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+    long long cur_b = it.valid() ? it.b : -1;
+    SeedRegs ahead = seed_load(sa, sc, tab, int(cur_b), tid);             // the first matrix pays its latency once
+    seed_store(ahead, sc, tab, msh2, tid);
+    ahead = seed_load(sa, sc, tab, it.valid() ? int(it.next_sample()) : -1, tid);   // in flight while the first sample is processed
+    named_bar_sync(1, kConsumers);
+    for (; it.valid(); it.next()) {
+        const long long b = it.b;
+        const long long px0 = it.tin * kTilePx;
         const long long rem = P - px0;
         if (b != cur_b) {
-            named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use; vbuf staged
-            if (kFused) {
-                const int bi = int(b);
-                const bool in_mmd = need_dom && bi < dom.M;
-                if (in_mmd) {
-                    for (int c = tid; c < dom.M; c += kConsumers) {
-                        const float D = mmd_distance(vbuf + size_t(bi) * kVStride, vbuf + size_t(c) * kVStride);
-                        coefrow[c] = mmd_coefficient(dom, bi, c, expf(-D));
-                    }
-                    named_bar_sync(1, kConsumers);
-                }
-                if (tid < kTri) {
-                    const int ij = tab->tri[tid], i = ij >> 4, j = ij & 15;
-                    const float g = __ldg(fa.gram + bi * 256 + i * kC + j);
-                    float dom_grad = 0.f;
-                    if (in_mmd && i != j) dom_grad = g_dom * mmd_grad_entry(vbuf, coefrow, dom.M, bi, off_idx(i, j));
-                    const float m = backward_matrix_entry(i, j, g, __ldg(fa.rowstat + bi * 2 + 0),
-                                                          __ldg(fa.rowstat + bi * 2 + 1), w_off, w_diag, dom_grad, denom);
-                    msh[i * kC + j] = m;
-                    msh[j * kC + i] = m;
-                }
-            } else {
-                // launched as a programmatic dependent of whiten_mmat_kernel: z is streaming already, the
-                // matrices are only needed here (no-op when there is no programmatic dependency)
-                if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");
-                msh[tid] = __ldcg(mmat + b * 256 + tid);   // coherent load: an invariant (.nc) one may be hoisted above the wait
-            }
-            named_bar_sync(1, kConsumers);
+            // the other buffer was last read two samples ago (a barrier has passed since): fill it from the registers
+            seed_store(ahead, sc, tab, msh2 + (cur ^ 1) * 256, tid);
+            cur ^= 1;
             cur_b = b;
+            ahead = seed_load(sa, sc, tab, int(it.next_sample()), tid);
+            named_bar_sync(1, kConsumers);
         }
+        const float* msh = msh2 + cur * 256;
         mbar_wait(&full[stage], phase);
         const bool active = 4LL * tid < rem;
         float4 out[kC];
@@ -220,11 +182,14 @@ apply_tma_kernel(const float* __restrict__ z, const float* __restrict__ mmat, fl
 // Fallback (P % 4 != 0 or unaligned pointers): one pixel per thread, scalar coalesced accesses.
 // grid = (ceil(P/256), B)
 __global__ void __launch_bounds__(256)
-apply_generic_kernel(const float* __restrict__ z, const float* __restrict__ mmat, const float* __restrict__ grelu,
-                     float* __restrict__ dz, long long P) {
+apply_generic_kernel(const float* __restrict__ z, const float* __restrict__ grelu, float* __restrict__ dz, long long P, SeedArgs sa) {
     __shared__ float msh[256];
+    __shared__ IndexTables tab;
     const long long b = blockIdx.y;
-    msh[threadIdx.x] = mmat[b * 256 + threadIdx.x];
+    build_index_tables(tab, threadIdx.x, 256);
+    __syncthreads();
+    const SeedCtx sc = seed_context(sa, P);
+    seed_matrix(sa, sc, tab, int(b), msh, threadIdx.x);
     __syncthreads();
     const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
     if (p >= P) return;
@@ -257,53 +222,29 @@ int g_apply_round_robin = 1;
 // Measured: step 281.5 -> 276 us, apply 174.9 -> 171.4 us, gram 104.2 -> 102.7 us.
 int g_l2_evict_first = 1;
 
-bool apply_can_fuse(const float* z, const float* dz, int B, long long P, int n_per_domain, int n_domains) {
-    long long m = n_domains > 1 ? (long long)n_per_domain * n_domains : 0;
-    if (m > B) m = B;
-    return tma_ok(z, dz, P) && m <= kFusedMaxM;
-}
-
-cudaError_t launch_apply(const float* z, const float* mmat, float* dz, int B, long long P, int sm_count,
-                         cudaStream_t stream, bool programmatic_dependent, const float* grelu) {
-    if (grelu && apply_relu_tma_ok(z, grelu, dz, P))
-        return launch_apply_relu(z, grelu, mmat, dz, B, P, sm_count, stream, programmatic_dependent);
+cudaError_t launch_apply(const float* z, const SeedArgs& seed, float* dz, int B, long long P, int sm_count, cudaStream_t stream,
+                         const float* grelu) {
+    if (grelu && apply_relu_tma_ok(z, grelu, dz, P)) return launch_apply_relu(z, grelu, seed, dz, B, P, sm_count, stream);
     if (!grelu && tma_ok(z, dz, P)) {
-        auto kern = apply_tma_kernel<false>;
+        auto kern = apply_tma_kernel;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemPlain));
         if (e != cudaSuccess) return e;
         const long long tps = (P + kTilePx - 1) / kTilePx;
         const long long T = tps * B;
         const long long G = T < sm_count ? T : sm_count;
-        FusedArgs fa{};
-        fa.round_robin = g_apply_round_robin;   // 0 = contiguous ranges, c > 0 = round-robin blocks of c tiles
-        fa.l2_hint = g_l2_evict_first;
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(unsigned(G));
         cfg.blockDim = dim3(kThreads);
         cfg.dynamicSmemBytes = kSmemPlain;
         cfg.stream = stream;
         cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue + z prefetch overlap the kernel in front
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = programmatic_dependent ? 1 : 0;
-        return cudaLaunchKernelEx(&cfg, kern, z, mmat, dz, P, tps, T, fa);
-    } else {
-        apply_generic_kernel<<<dim3(unsigned((P + 255) / 256), unsigned(B)), 256, 0, stream>>>(z, mmat, grelu, dz, P);
+        cfg.numAttrs = 1;
+                return cudaLaunchKernelEx(&cfg, kern, z, dz, P, tps, T, g_apply_round_robin, g_l2_evict_first, seed);
     }
-    return cudaGetLastError();
-}
-
-cudaError_t launch_apply_fused(const float* z, const float* gram, const float* rowstat, const float* g_off,
-                               const float* g_diag, const float* g_dom, float* dz, int B, long long P, int n_per_domain,
-                               int n_domains, int sm_count, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(apply_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemFused));
-    if (e != cudaSuccess) return e;
-    const long long tps = (P + kTilePx - 1) / kTilePx;
-    const long long T = tps * B;
-    const long long G = T < sm_count ? T : sm_count;
-    FusedArgs fa{gram, rowstat, g_off, g_diag, g_dom, B, n_per_domain, n_domains, 0, g_l2_evict_first};
-    apply_tma_kernel<true><<<dim3(unsigned(G)), kThreads, kSmemFused, stream>>>(z, nullptr, dz, P, tps, T, fa);
+    apply_generic_kernel<<<dim3(unsigned((P + 255) / 256), unsigned(B)), 256, 0, stream>>>(z, grelu, dz, P, seed);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@
 // kernels: the 16-term product is accumulated first, the masked ReLU gradient added last.
 #include "common.cuh"
 #include "kernels.h"
+#include "whitening_matrix.cuh"
 
 namespace wtpse {
 
@@ -32,13 +33,15 @@ __device__ __forceinline__ float4 ld_cs4(const float4* p) {
 // the staged registers): 2.  A two-deep register ring keeps the next step's loads (64 KB per SM) in flight.
 template <bool kReluGrad>
 __global__ void __launch_bounds__(kThreads, 1)
-apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, const float* __restrict__ mmat,
-                float* __restrict__ dz, long long P, long long steps_per_sample, long long total_steps) {
+apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, float* __restrict__ dz, long long P,
+                long long steps_per_sample, long long total_steps, SeedArgs sa) {
     constexpr int kPx = kReluGrad ? 2 : 4;
     constexpr int kStepPx = kPx * kThreads;
     __shared__ __align__(16) float msh[256];
+    __shared__ IndexTables tab;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x;
+    build_index_tables(tab, tid, kThreads);
     // A step = kStepPx consecutive pixels of one sample, dealt round-robin to the CTAs: the grid streams adjacent memory.
     const long long G = gridDim.x, bx = blockIdx.x;
     const long long my_steps = total_steps > bx ? (total_steps - bx + G - 1) / G : 0;
@@ -65,14 +68,14 @@ apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, co
         }
     };
     long long cur_b = -1;
+    SeedCtx sc{};
     auto use_step = [&](const Stage& r, long long k) {
         if (k >= my_steps) return;                            // every condition up to the barrier is uniform over the CTA
         const long long s = k * G + bx;
         const long long b = s / steps_per_sample;
         if (b != cur_b) {
             __syncthreads();                                  // previous matrix no longer in use
-            if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
-            msh[tid] = __ldcg(mmat + b * 256 + tid);         // coherent load: an invariant (.nc) one may be hoisted above the wait
+            seed_matrix(sa, sc, tab, int(b), msh, tid);
             __syncthreads();
             cur_b = b;
         }
@@ -117,7 +120,13 @@ apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, co
     };
 
     Stage r0, r1;
+    // z was written before the forward pass ran and may be prefetched at once; grelu, the saved tensors, the upstream
+    // scalars and dz may belong to the kernel in front of us (programmatic dependent launch): wait for it first.
+    if (kReluGrad) asm volatile("griddepcontrol.wait;" ::: "memory");
     load_step(r0, 0);
+    if (!kReluGrad) asm volatile("griddepcontrol.wait;" ::: "memory");
+    sc = seed_context(sa, P);
+    __syncthreads();                                          // index tables
     for (long long k = 0; k < my_steps; k += 2) {
         load_step(r1, k + 1); use_step(r0, k);
         load_step(r0, k + 2); use_step(r1, k + 1);
@@ -126,8 +135,8 @@ apply_cl_kernel(const float* __restrict__ z, const float* __restrict__ grelu, co
 
 }  // namespace
 
-cudaError_t launch_apply_cl(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P, int sm_count,
-                            cudaStream_t stream, bool programmatic_dependent) {
+cudaError_t launch_apply_cl(const float* z, const float* grelu, const SeedArgs& seed, float* dz, int B, long long P, int sm_count,
+                            cudaStream_t stream) {
     const long long step_px = (grelu ? 2 : 4) * kThreads;      // kPx * kThreads of the instantiation launched below
     const long long sps = (P + step_px - 1) / step_px;         // steps per sample
     const long long total = sps * B;
@@ -140,9 +149,9 @@ cudaError_t launch_apply_cl(const float* z, const float* grelu, const float* mma
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = programmatic_dependent ? 1 : 0;
-    if (grelu) return cudaLaunchKernelEx(&cfg, apply_cl_kernel<true>, z, grelu, mmat, dz, P, sps, total);
-    return cudaLaunchKernelEx(&cfg, apply_cl_kernel<false>, z, grelu, mmat, dz, P, sps, total);
+    cfg.numAttrs = 1;
+    if (grelu) return cudaLaunchKernelEx(&cfg, apply_cl_kernel<true>, z, grelu, dz, P, sps, total, seed);
+    return cudaLaunchKernelEx(&cfg, apply_cl_kernel<false>, z, grelu, dz, P, sps, total, seed);
 }
 
 }  // namespace wtpse

@@ -5,8 +5,8 @@
 // the ReLU backward (read grelu, read relu(z), write) and the sum of the two (read, read, write) -- 512 B per
 // pixel.  Here it is one pass: read z, read grelu, write dz = 192 B per pixel.
 //
-// Same structure as apply_tma_kernel (persistent CTAs, tiles dealt round-robin, M_b from whiten_mmat_kernel via
-// programmatic dependent launch), but BOTH streams are staged by the producer warp with 1-D TMA bulk copies:
+// Same structure as apply_tma_kernel (persistent CTAs, tiles dealt round-robin, M_b derived in the kernel from the
+// forward's seed: one launch), but BOTH streams are staged by the producer warp with 1-D TMA bulk copies:
 // a stage holds 16 channel rows of 896 pixels of z and of grelu (112 KB), two stages fill the shared memory.
 // (Reading grelu with per-thread 128-bit global loads instead -- no lead time, 8 warps per SM -- reached 0.78 of
 // the HBM roofline: 315 us at 32x16x512x512 against 246 us for the bytes.)  7 consumer warps + the producer warp
@@ -17,6 +17,7 @@
 // passes unless z <= 0 (so it passes for NaN).
 #include "common.cuh"
 #include "kernels.h"
+#include "whitening_matrix.cuh"
 
 namespace wtpse {
 
@@ -36,18 +37,20 @@ __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ grelu, const float* __restrict__ mmat,
-                      float* __restrict__ dz, long long P, long long tiles_per_sample, long long T) {
+apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ grelu, float* __restrict__ dz, long long P,
+                      long long tiles_per_sample, long long T, SeedArgs sa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* msh = stage_buf + size_t(kStages) * kStageFloats;
     uint64_t* full = reinterpret_cast<uint64_t*>(msh + 256);
     uint64_t* empty = full + kStages;
+    __shared__ IndexTables tab;
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
 
+    build_index_tables(tab, tid, kThreads);
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
@@ -59,21 +62,50 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
     __syncthreads();
 
     if (warp == kConsumerWarps) {
-        // producer: z and grelu were written by kernels that completed before whiten_mmat_kernel started, so they
-        // are streamed without waiting for it
+        // producer.  z was written before the forward pass ran and is streamed at once; grelu is the output of the kernel
+        // in FRONT of this one (the backward of whatever consumed relu(z)), and under programmatic dependent launch that
+        // kernel may still be running: the first grelu load is issued only after griddepcontrol.wait.  (The consumers'
+        // own wait does not cover the producer's loads.)
         if (lane == 0) {
             const uint64_t policy = make_evict_first_policy();      // both inputs are read exactly once
-            int stage = 0;
-            uint32_t phase = 0;
-            for (long long t = k; t < T; t += G) {
-                mbar_wait(&empty[stage], phase ^ 1);
+            auto tile_geom = [&](long long t, long long& off, uint32_t& bytes) {
                 const long long b = t / tiles_per_sample;
                 const long long px0 = (t - b * tiles_per_sample) * kTilePx;
                 const long long rem = P - px0;
                 const uint32_t npx = rem < kTilePx ? uint32_t(rem) : uint32_t(kTilePx);
-                const uint32_t bytes = npx * 4u;
+                bytes = npx * 4u;
+                off = (b * kC) * P + px0;
+            };
+            // the ring's first kStages tiles: z rows now, grelu rows after the wait
+            long long t = k;
+            int primed = 0;
+            for (; t < T && primed < kStages; t += G, ++primed) {
+                long long off; uint32_t bytes;
+                tile_geom(t, off, bytes);
+                mbar_arrive_expect_tx(&full[primed], bytes * 2 * kC);
+                float* dst = stage_buf + size_t(primed) * kStageFloats;
+#pragma unroll
+                for (int c = 0; c < kC; ++c) tma_load_1d_hint(dst + c * kTilePx, z + off + c * P, bytes, &full[primed], policy);
+            }
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            {
+                long long tt = k;
+                for (int q = 0; q < primed; ++q, tt += G) {
+                    long long off; uint32_t bytes;
+                    tile_geom(tt, off, bytes);
+                    float* dst = stage_buf + size_t(q) * kStageFloats;
+#pragma unroll
+                    for (int c = 0; c < kC; ++c)
+                        tma_load_1d_hint(dst + kRowsFloats + c * kTilePx, grelu + off + c * P, bytes, &full[q], policy);
+                }
+            }
+            int stage = primed == kStages ? 0 : primed;
+            uint32_t phase = primed == kStages ? 1 : 0;
+            for (; t < T; t += G) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                long long off; uint32_t bytes;
+                tile_geom(t, off, bytes);
                 mbar_arrive_expect_tx(&full[stage], bytes * 2 * kC);
-                const long long off = (b * kC) * P + px0;
                 float* dst = stage_buf + size_t(stage) * kStageFloats;
 #pragma unroll
                 for (int c = 0; c < kC; ++c) tma_load_1d_hint(dst + c * kTilePx, z + off + c * P, bytes, &full[stage], policy);
@@ -86,6 +118,9 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
         return;
     }
 
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // saved tensors, upstream scalars and dz may belong to the kernel in front
+    const SeedCtx sc = seed_context(sa, P);
+
     int stage = 0;
     uint32_t phase = 0;
     long long cur_b = -1;
@@ -95,8 +130,7 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
         const long long rem = P - px0;
         if (b != cur_b) {
             named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use
-            if (cur_b < 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // the matrices come from the primary kernel
-            for (int e = tid; e < 256; e += kConsumers) msh[e] = __ldcg(mmat + b * 256 + e);   // coherent: .nc loads may be hoisted above the wait
+            seed_matrix(sa, sc, tab, int(b), msh, tid);
             named_bar_sync(1, kConsumers);
             cur_b = b;
         }
@@ -154,8 +188,8 @@ bool apply_relu_tma_ok(const float* z, const float* grelu, const float* dz, long
     return (P % 4 == 0) && (((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(grelu) | reinterpret_cast<uintptr_t>(dz)) & 15u) == 0);
 }
 
-cudaError_t launch_apply_relu(const float* z, const float* grelu, const float* mmat, float* dz, int B, long long P,
-                              int sm_count, cudaStream_t stream, bool programmatic_dependent) {
+cudaError_t launch_apply_relu(const float* z, const float* grelu, const SeedArgs& seed, float* dz, int B, long long P,
+                              int sm_count, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(apply_relu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
     if (e != cudaSuccess) return e;
     const long long tps = (P + kTilePx - 1) / kTilePx;
@@ -170,8 +204,8 @@ cudaError_t launch_apply_relu(const float* z, const float* grelu, const float* m
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = programmatic_dependent ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, apply_relu_tma_kernel, z, grelu, mmat, dz, P, tps, T);
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, apply_relu_tma_kernel, z, grelu, dz, P, tps, T, seed);
 }
 
 }  // namespace wtpse

@@ -11,9 +11,12 @@
 //     LDS.128) and keep the 136 running sums in registers;
 //   * at a sample boundary the 136 sums are reduced across the warp with a halving butterfly
 //     (153 shuffles instead of 680), across warps through shared memory, and written to a
-//     per-(sample, slot) partial.  No float atomics: the epilogue sums slots in a fixed order.
+//     per-(sample, slot) partial.  No float atomics: the slots are summed in a fixed order;
+//   * the rest of the forward pass -- slot reduction, f_cor, instance terms, MMD, the backward's MMD seed -- runs
+//     inside this kernel too, in whichever CTA arrives last (whitening_tail.cuh): the forward is ONE launch.
 #include "common.cuh"
 #include "kernels.h"
+#include "whitening_tail.cuh"
 
 namespace wtpse {
 
@@ -101,18 +104,22 @@ __device__ __forceinline__ float4 relu4(const float4& v) {
 template <bool kRelu>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial,
-                int* __restrict__ slot_count, long long P, long long tiles_per_sample, long long T, int nslots, int group,
-                int hint) {
+                int* __restrict__ slot_count, long long P, long long tiles_per_sample, long long T, int nslots,
+                int hint, int fused_tail, TailParams tp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
     uint64_t* full = reinterpret_cast<uint64_t*>(red + kConsumerWarps * kTri);
     uint64_t* empty = full + kStages;
+    __shared__ IndexTables tab;
+    __shared__ float wred[16];
+    __shared__ int ticket_flag;
 
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the (tiny) dependents get resident early
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the dependents get resident early
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long G = gridDim.x, k = blockIdx.x;
-    const TileWalk walk(k, G, T, tiles_per_sample, group);
+    const TileWalk walk(k, G, T, tiles_per_sample, 1);
+    build_index_tables(tab, tid, kThreads);
 
     if (tid == 0) {
 #pragma unroll
@@ -159,6 +166,7 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
     }
 
     // ---------------- consumers ----------------
+    TailClock clk;
     float acc[kTri];
 #pragma unroll
     for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
@@ -191,9 +199,17 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
         }
         const long long first_grp = part_owner(b * tiles_per_sample, T, Gg);
         const long long slot = (grp - first_grp) * walk.g + walk.r;
+        clk.mark(0);
         flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
-        // the group that owns a sample's last tile knows how many slots that sample used
-        if (tid == 0 && walk.r == 0 && (b + 1) * tiles_per_sample <= walk.R1) slot_count[b] = int((grp - first_grp + 1) * walk.g);
+        clk.mark(1);
+        if (fused_tail) {
+            // every CTA whose range touches sample b stores exactly one partial for it
+            const int expected = int(part_owner((b + 1) * tiles_per_sample - 1, T, Gg) - first_grp + 1);
+            tail_after_flush<kConsumers>(tp, int(b), expected, tab, wred, &ticket_flag, stage_buf, tid, 1, clk);
+        } else if (tid == 0 && (b + 1) * tiles_per_sample <= walk.R1) {
+            // legacy tail (separate kernels): the CTA that owns a sample's last tile knows how many slots it used
+            slot_count[b] = int(grp - first_grp + 1);
+        }
 #pragma unroll
         for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
     }
@@ -307,35 +323,21 @@ gram_cl_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float*
 }
 }  // namespace
 
-// Gram tile schedule: CTAs per group (see TileWalk).  1 = one contiguous range per CTA, 0 = pure round-robin.
-// Round-robin gives DRAM the same ~10 % better locality it gives the apply kernel, but every CTA then touches every
-// sample and pays one 136-value cross-thread flush per sample (32 instead of 1-2): 123 us vs 104 us at 32x16x512x512.
-int g_gram_group = 1;
-int g_gram_variant = 0;
+int g_cl_tma = 1;        // channels-last kernels: tensor-map TMA pipelines (whitening_cl_tma.cu) or the per-thread kernels
 
 GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float* relu_out) {
-    GramPlan g;
-    g.item_px = 0;
+    GramPlan g{};
     g.tma = (P % 4 == 0) && ((reinterpret_cast<uintptr_t>(z) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(relu_out) & 15u) == 0);
-    g.round_robin = false;
     g.group = 1;
-    g.variant = relu_out ? 0 : g_gram_variant;      // the fused ReLU write exists for the one-thread-per-quad kernel only
     if (g.tma) {
-        const long long tile_px = g.variant == 1 ? gram_split_tile_px() : kTilePx;
-        g.tiles_per_sample = (P + tile_px - 1) / tile_px;
+        g.tiles_per_sample = (P + kTilePx - 1) / kTilePx;
         g.T = g.tiles_per_sample * B;
         g.G = g.T < sm_count ? g.T : sm_count;
-        long long grp = g_gram_group;
-        if (grp <= 0 || grp > g.G) grp = g.G;                    // 0 = pure round-robin
-        if (g.G % grp != 0) grp = 1;
-        g.group = int(grp);
-        g.round_robin = grp > 1;
-        const long long Gg = g.G / grp;
         int nslots = 1;
         for (int b = 0; b < B; ++b) {
-            const long long first = part_owner((long long)b * g.tiles_per_sample, g.T, Gg);
-            const long long last = part_owner((long long)(b + 1) * g.tiles_per_sample - 1, g.T, Gg);
-            if ((last - first + 1) * grp > nslots) nslots = int((last - first + 1) * grp);
+            const long long first = part_owner((long long)b * g.tiles_per_sample, g.T, g.G);
+            const long long last = part_owner((long long)(b + 1) * g.tiles_per_sample - 1, g.T, g.G);
+            if (last - first + 1 > nslots) nslots = int(last - first + 1);
         }
         g.nslots = nslots;
     } else {
@@ -344,11 +346,15 @@ GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float
         if (want > max_useful) want = max_useful;
         if (want < 1) want = 1;
         g.nslots = int(want);
-        g.tiles_per_sample = 0;
-        g.T = 0;
-        g.G = 0;
     }
     return g;
+}
+
+// The whole-batch phase of the in-kernel tail runs in the pipeline buffers of one CTA.
+bool gram_tail_fits(int B, int n_per_domain, int n_domains) {
+    long long m = n_domains > 1 ? (long long)n_per_domain * n_domains : 0;
+    if (m > B) m = B;
+    return tail_smem_bytes(B, int(m), n_domains) <= size_t(kStages) * kStageFloats * sizeof(float);
 }
 
 // Channels-last schedule: items of >= 8192 pixels, at most 256 slots per sample (gram_partial_floats covers that).
@@ -381,17 +387,17 @@ cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int*
 }
 
 size_t gram_partial_floats(int B, long long P, int sm_count) {
-    // upper bound over both paths: nslots <= sm_count + 1 for the persistent path and <= 2*sm_count for the generic one
-    const long long tps = (P + 640 - 1) / 640;      // smallest tile of the two variants
+    // upper bound over all paths: persistent TMA path <= ceil(tiles per sample / tiles per CTA) + 1, generic <= 2 * sm_count
+    const long long tps = (P + kTilePx - 1) / kTilePx;
     long long T = tps * B;
     long long G = T < sm_count ? T : sm_count;
-    long long per_cta = (T + G - 1) / G;
+    long long per_cta = T / G;                       // smallest range
+    if (per_cta < 1) per_cta = 1;
     long long slots_tma = (tps + per_cta - 1) / per_cta + 1;
     long long slots_gen = (2LL * sm_count + B - 1) / B;
     if (slots_gen < 1) slots_gen = 1;
     long long slots = slots_tma > slots_gen ? slots_tma : slots_gen;
-    if (2 * G > slots) slots = 2 * G;      // grouped / round-robin schedules: at most (#groups touching a sample) * g <= 2G slots
-    long long slots_cl = (P + 8191) / 8192;   // channels-last schedule (plan_gram_cl)
+    long long slots_cl = (P + 8191) / 8192;   // channels-last schedules (plan_gram_cl): items of >= 8192 pixels, <= 256 per sample
     if (slots_cl > 256) slots_cl = 256;
     if (slots_cl > slots) slots = slots_cl;
     return size_t(B) * size_t(slots) * kTri;
@@ -400,7 +406,7 @@ size_t gram_partial_floats(int B, long long P, int sm_count) {
 namespace {
 template <bool kRelu>
 cudaError_t launch_gram_t(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P,
-                          const GramPlan& g, cudaStream_t stream) {
+                          const GramPlan& g, cudaStream_t stream, const TailParams* tail) {
     if (g.tma) {
         cudaError_t e = cudaFuncSetAttribute(gram_tma_kernel<kRelu>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemBytes));
         if (e != cudaSuccess) return e;
@@ -414,8 +420,10 @@ cudaError_t launch_gram_t(const float* z, float* relu_out, float* partial, int* 
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
+        TailParams tp{};
+        if (tail) tp = *tail;
         return cudaLaunchKernelEx(&cfg, gram_tma_kernel<kRelu>, z, relu_out, partial, slot_count, (long long)P,
-                                  g.tiles_per_sample, g.T, g.nslots, g.group, g_l2_evict_first);
+                                  g.tiles_per_sample, g.T, g.nslots, g_l2_evict_first, tail ? 1 : 0, tp);
     } else {
         gram_generic_kernel<kRelu><<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, relu_out, partial,
                                                                                                    slot_count, P, g.nslots);
@@ -424,12 +432,13 @@ cudaError_t launch_gram_t(const float* z, float* relu_out, float* partial, int* 
 }
 }  // namespace
 
-// relu_out != nullptr: fused ReLU write (plan_gram must have been made with the same relu_out, see its alignment rule)
+// relu_out != nullptr: fused ReLU write (plan_gram must have been made with the same relu_out, see its alignment rule).
+// tail != nullptr (TMA plans only): the rest of the forward runs inside the kernel (whitening_tail.cuh).
 cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
-                        cudaStream_t stream, float* relu_out) {
-    if (relu_out) return launch_gram_t<true>(z, relu_out, partial, slot_count, B, P, g, stream);
-    if (g.tma && g.variant == 1) return launch_gram_split(z, partial, slot_count, P, g, stream);
-    return launch_gram_t<false>(z, nullptr, partial, slot_count, B, P, g, stream);
+                        cudaStream_t stream, float* relu_out, const TailParams* tail) {
+    if (tail && !g.tma) return cudaErrorInvalidValue;
+    if (relu_out) return launch_gram_t<true>(z, relu_out, partial, slot_count, B, P, g, stream, tail);
+    return launch_gram_t<false>(z, nullptr, partial, slot_count, B, P, g, stream, tail);
 }
 
 }  // namespace wtpse

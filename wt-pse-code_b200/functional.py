@@ -48,6 +48,33 @@ def _grad_ptr(g, like):
     return ctypes.c_void_p(g.data_ptr()), g      # keep the tensor alive until the launch is enqueued
 
 
+_WS_CACHE = {}
+
+
+def _workspace(lib, B, P, device):
+    """(buffer, bytes) of forward scratch for a [B][16][P] batch on the current stream of `device`.
+
+    The C ABI's ticket contract (include/wtpse_b200.h, wtpse_whitening_ticket_bytes): the first bytes of the forward's
+    workspace must be zero when a call is enqueued, and every call leaves them zero.  One grow-only buffer per (device,
+    stream), zeroed when it is created, satisfies that for free: all launches that touch it are ordered on that stream.
+    While a CUDA graph is being captured the buffer is a fresh `torch.zeros` instead (it then lives in the graph's own
+    memory pool and its memset is part of the graph), so captured and eager work never share tickets."""
+    nbytes = lib.wtpse_whitening_workspace_bytes(B, P)
+    if torch.cuda.is_current_stream_capturing():
+        return torch.zeros(nbytes, dtype=torch.uint8, device=device), nbytes
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf, nbytes
+
+
+def clear_workspace_cache():
+    """Drops the cached forward workspaces (one per device and stream that has run a whitening forward)."""
+    _WS_CACHE.clear()
+
+
 def _as_loss_input(z):
     """(tensor the kernels read, channels_last flag).  A dense channels-last z (what a channels-last backbone produces) is
     read in place by the *_cl entry points; anything else is made NCHW-contiguous, the reference's layout
@@ -55,6 +82,16 @@ def _as_loss_input(z):
     if z.dim() == 4 and not z.is_contiguous() and z.is_contiguous(memory_format=torch.channels_last) and z.data_ptr() % 16 == 0:
         return z, True
     return z.contiguous(), False
+
+
+def _forward_outputs(B, device):
+    """(losses [4], (gram [B][16][16], rowstat [B][2], domgrad [B][120])): the forward's outputs; the tuple is what it
+    saves for the backward (include/wtpse_b200.h)."""
+    losses = torch.empty(4, dtype=torch.float32, device=device)
+    gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=device)
+    rowstat = torch.empty(B, 2, dtype=torch.float32, device=device)
+    domgrad = torch.empty(B, 120, dtype=torch.float32, device=device)
+    return losses, (gram, rowstat, domgrad)
 
 
 class _WhiteningLoss(torch.autograd.Function):
@@ -72,22 +109,20 @@ class _WhiteningLoss(torch.autograd.Function):
         P = H * W
         lib = _lib.load()
         with torch.cuda.device(z.device):
-            ws_bytes = lib.wtpse_whitening_workspace_bytes(B, P)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-            losses = torch.empty(4, dtype=torch.float32, device=z.device)
-            gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
-            rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+            ws, ws_bytes = _workspace(lib, B, P, z.device)
+            losses, saved = _forward_outputs(B, z.device)
+            gram, rowstat, domgrad = saved
             if cl:
                 _lib.check(lib.wtpse_whitening_forward_cl(_ptr(z), None, B, C, P, int(n_per_domain), int(n_domains), float(margin),
-                                                          float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
-                                                          _stream_ptr(z.device)))
+                                                          float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(domgrad),
+                                                          _ptr(ws), ws_bytes, _stream_ptr(z.device)))
             else:
                 _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, P, int(n_per_domain), int(n_domains), float(margin),
-                                                       float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes,
-                                                       _stream_ptr(z.device)))
-        ctx.save_for_backward(z, gram, rowstat)
+                                                       float(eps), _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(domgrad),
+                                                       _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+        ctx.save_for_backward(z, gram, rowstat, domgrad)
         ctx.cl = cl
-        ctx.cfg = (int(n_per_domain), int(n_domains), float(margin), bool(fold), ws_bytes)
+        ctx.cfg = (int(n_per_domain), int(n_domains), bool(fold))
         if fold:
             return _scalar_alias(losses, 3), _scalar_alias(losses, 2)
         return _scalar_alias(losses, 0), _scalar_alias(losses, 1), _scalar_alias(losses, 2)
@@ -95,8 +130,8 @@ class _WhiteningLoss(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, *grads):
-        z, gram, rowstat = ctx.saved_tensors
-        n, K, margin, fold, ws_bytes = ctx.cfg
+        z, gram, rowstat, domgrad = ctx.saved_tensors
+        n, K, fold = ctx.cfg
         if fold:
             g_ins, g_dom = grads
             g_off, g_diag = g_ins, g_ins
@@ -108,16 +143,15 @@ class _WhiteningLoss(torch.autograd.Function):
         lib = _lib.load()
         with torch.cuda.device(z.device):
             dz = torch.empty_like(z)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
             p_off, k0 = _grad_ptr(g_off, z)
             p_diag, k1 = _grad_ptr(g_diag, z)
             p_dom, k2 = _grad_ptr(g_dom, z)
             if ctx.cl:            # dz = empty_like(z) keeps the channels-last layout
-                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), None, _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C,
-                                                           H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), None, _ptr(gram), _ptr(rowstat), _ptr(domgrad), p_off, p_diag,
+                                                           p_dom, B, C, H * W, n, K, _ptr(dz), _stream_ptr(z.device)))
             else:
-                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
-                                                        n, K, margin, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), _ptr(domgrad), p_off, p_diag, p_dom,
+                                                        B, C, H * W, n, K, _ptr(dz), _stream_ptr(z.device)))
             del k0, k1, k2
         return dz, None, None, None, None, None
 
@@ -139,18 +173,16 @@ class _ReluWhiteningLoss(torch.autograd.Function):
         P = H * W
         lib = _lib.load()
         with torch.cuda.device(z.device):
-            ws_bytes = lib.wtpse_whitening_workspace_bytes(B, P)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-            losses = torch.empty(4, dtype=torch.float32, device=z.device)
-            gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
-            rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+            ws, ws_bytes = _workspace(lib, B, P, z.device)
+            losses, saved = _forward_outputs(B, z.device)
+            gram, rowstat, domgrad = saved
             relu_out = torch.empty_like(z)                      # same layout as z
             fwd = lib.wtpse_whitening_forward_cl if cl else lib.wtpse_whitening_relu_forward
             _lib.check(fwd(_ptr(z), _ptr(relu_out), B, C, P, int(n_per_domain), int(n_domains), float(margin), float(eps),
-                           _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
-        ctx.save_for_backward(z, gram, rowstat)
+                           _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(domgrad), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+        ctx.save_for_backward(z, gram, rowstat, domgrad)
         ctx.cl = cl
-        ctx.cfg = (int(n_per_domain), int(n_domains), bool(fold), ws_bytes)
+        ctx.cfg = (int(n_per_domain), int(n_domains), bool(fold))
         if fold:
             return relu_out, _scalar_alias(losses, 3), _scalar_alias(losses, 2)
         return relu_out, _scalar_alias(losses, 0), _scalar_alias(losses, 1), _scalar_alias(losses, 2)
@@ -158,8 +190,8 @@ class _ReluWhiteningLoss(torch.autograd.Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, g_relu, *grads):
-        z, gram, rowstat = ctx.saved_tensors
-        n, K, fold, ws_bytes = ctx.cfg
+        z, gram, rowstat, domgrad = ctx.saved_tensors
+        n, K, fold = ctx.cfg
         if fold:
             g_ins, g_dom = grads
             g_off, g_diag = g_ins, g_ins
@@ -175,7 +207,6 @@ class _ReluWhiteningLoss(torch.autograd.Function):
         lib = _lib.load()
         with torch.cuda.device(z.device):
             dz = torch.empty_like(z)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
             p_off, k0 = _grad_ptr(g_off, z)
             p_diag, k1 = _grad_ptr(g_diag, z)
             p_dom, k2 = _grad_ptr(g_dom, z)
@@ -183,18 +214,18 @@ class _ReluWhiteningLoss(torch.autograd.Function):
                 if g_relu is not None:
                     _require_cuda_f32(g_relu, "grad of relu(z)")
                     g_relu = g_relu.contiguous(memory_format=torch.channels_last)
-                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom,
-                                                           B, C, H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+                _lib.check(lib.wtpse_whitening_backward_cl(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), _ptr(domgrad), p_off,
+                                                           p_diag, p_dom, B, C, H * W, n, K, _ptr(dz), _stream_ptr(z.device)))
             elif g_relu is None:                     # only the loss was used downstream
-                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), p_off, p_diag, p_dom, B, C, H * W,
-                                                        n, K, 0.0, _ptr(dz), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+                _lib.check(lib.wtpse_whitening_backward(_ptr(z), _ptr(gram), _ptr(rowstat), _ptr(domgrad), p_off, p_diag, p_dom,
+                                                        B, C, H * W, n, K, _ptr(dz), _stream_ptr(z.device)))
             else:
                 # loss unused (e.g. the teacher pass of the shape update): all-NULL upstream scalars make M_b = 0 and the
                 # same kernel degenerates to the ReLU backward
                 _require_cuda_f32(g_relu, "grad of relu(z)")
                 g_relu = g_relu.contiguous()
-                _lib.check(lib.wtpse_whitening_relu_backward(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), p_off, p_diag,
-                                                             p_dom, B, C, H * W, n, K, _ptr(dz), _ptr(ws), ws_bytes,
+                _lib.check(lib.wtpse_whitening_relu_backward(_ptr(z), _ptr(g_relu), _ptr(gram), _ptr(rowstat), _ptr(domgrad),
+                                                             p_off, p_diag, p_dom, B, C, H * W, n, K, _ptr(dz),
                                                              _stream_ptr(z.device)))
             del k0, k1, k2
         return (dz,) + none[1:]
@@ -228,13 +259,10 @@ def gram_matrix(z, eps=1e-5):
     z = z.contiguous()
     lib = _lib.load()
     with torch.cuda.device(z.device):
-        ws_bytes = lib.wtpse_whitening_workspace_bytes(B, H * W)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=z.device)
-        losses = torch.empty(4, dtype=torch.float32, device=z.device)
-        gram = torch.empty(B, CHANNELS, CHANNELS, dtype=torch.float32, device=z.device)
-        rowstat = torch.empty(B, 2, dtype=torch.float32, device=z.device)
+        ws, ws_bytes = _workspace(lib, B, H * W, z.device)
+        losses, (gram, rowstat, domgrad) = _forward_outputs(B, z.device)
         _lib.check(lib.wtpse_whitening_forward(_ptr(z), B, C, H * W, 0, 0, 0.0, float(eps), _ptr(losses), _ptr(gram),
-                                               _ptr(rowstat), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
+                                               _ptr(rowstat), _ptr(domgrad), _ptr(ws), ws_bytes, _stream_ptr(z.device)))
     return gram
 
 
