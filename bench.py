@@ -115,7 +115,7 @@ def parse_args():
     ap.add_argument("--extra-configs", type=int, default=1, help="also time the other BASELINE configs (Track R 256^2 / 1024^2, Track W) at N=1")
     ap.add_argument("--numa-affinity", type=int, default=1, help="bind each rank to the CPUs NVML reports as local to its GPU before allocating pinned buffers")
     ap.add_argument("--train-reference-eager", type=int, default=1, help="also time the UNMODIFIED reference classes' iteration (oracle/_ref) on the same GPU")
-    ap.add_argument("--event-stride", type=int, default=8, help="bracket kernels with CUDA events on every n-th timed step")
+    ap.add_argument("--event-stride", type=int, default=10, help="bracket kernels with CUDA events on every n-th timed step")
     return ap.parse_args()
 
 
@@ -352,6 +352,23 @@ def time_relu_fusion(z, n, K, peak, iters=10):
         us = ev0.elapsed_time(ev1) / iters * 1e3
         out[name] = {"us_per_step": us, "algorithmic_bytes_per_pix": bytes_per_pix,
                      "hbm_frac": bytes_per_pix * pix / (us * 1e-6) / 1e9 / peak}
+        # per-kernel durations (CUDA events around each launch; they serialise the launches, so these are measured
+        # outside the timed loop above)
+        lib = wb._lib.load()
+        lib.wtpse_profile_reset()
+        lib.wtpse_profile_enable(1)
+        for _ in range(3):
+            fn()
+        lib.wtpse_profile_enable(0)
+        torch.cuda.synchronize()
+        import ctypes
+        kern = {}
+        for kid in range(lib.wtpse_profile_kernel_count()):
+            cnt, ms = ctypes.c_longlong(0), ctypes.c_double(0.0)
+            wb._lib.check(lib.wtpse_profile_read(kid, ctypes.byref(cnt), ctypes.byref(ms)))
+            if cnt.value:
+                kern[lib.wtpse_profile_kernel_name(kid).decode()] = round(ms.value / cnt.value * 1e3, 1)
+        out[name]["kernel_us"] = kern
     out["what"] = ("relu(z) + whitening loss fwd, and bwd with an upstream gradient on relu(z); unfused: 64 + 128 fwd, "
                    "128 + 192 + 192 bwd B/pix; fused: 128 fwd, 192 bwd")
     out["speedup"] = out["unfused"]["us_per_step"] / out["fused"]["us_per_step"]

@@ -28,6 +28,8 @@ int         wtpse_profile_read(int id, long long* timed_launches, double* total_
  *   "apply_round_robin"    NCHW apply kernel: tiles dealt round-robin over the CTAs (1, default) or contiguous ranges (0)
  *   "l2_hint"              L2 evict-first policy on the TMA loads of z (default 1)
  *   "cl_tma"               channels-last kernels: tensor-map TMA pipelines (1, default) or per-thread loads (0)
+ *   "cl_tma_launches"      read-only counter of channels-last calls that took the TMA kernels (setting it resets it)
+ *   "tail_stamps"          1: the in-kernel tail writes 16 phase clocks into the last 128 bytes of the workspace
  *   "wavelet_resident"     0 makes wtpse_wavelet_resident_cluster report 0 for every shape (per-level kernels)
  *   "wavelet_split"        fused-plan choice: -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed
  *   "wavelet_tiles"        level 1 of the streamed plan as TMA pipelines (1, default) or per-thread loads (0)

@@ -180,13 +180,28 @@ def test_channels_last_loss_kernels_match_the_nchw_ones(B, H, W, n, K):
     for fused in (False, True):
         r_a, l_a, dz_a = run(z0.clone(), fused)
         z_cl = z0.clone().contiguous(memory_format=torch.channels_last)
+        wb._lib.debug_set("cl_tma_launches", 0)
         r_b, l_b, dz_b = run(z_cl, fused)
+        assert wb._lib.debug_get("cl_tma_launches") == 2          # forward + backward took the tensor-map TMA kernels
         assert dz_b.is_contiguous(memory_format=torch.channels_last)
         for a, b in zip(l_a, l_b):
             assert abs(a - b) <= 1e-5 * max(abs(a), 1e-3) or (a != a and b != b), (l_a, l_b)
         assert float((dz_a - dz_b).abs().max()) <= 1e-5 * float(dz_a.abs().max())
         if fused:
             assert torch.equal(r_a, r_b) and r_b.is_contiguous(memory_format=torch.channels_last)
+        # the per-thread channels-last kernels (the fallback for unaligned pointers): per pixel the same arithmetic in the
+        # same order -> relu and dz bit-identical; the Gram differs in summation order only
+        wb._lib.debug_set("cl_tma", 0)
+        try:
+            r_c, l_c, dz_c = run(z0.clone().contiguous(memory_format=torch.channels_last), fused)
+        finally:
+            wb._lib.debug_set("cl_tma", 1)
+        assert wb._lib.debug_get("cl_tma_launches") == 2
+        for a, b in zip(l_b, l_c):
+            assert abs(a - b) <= 1e-5 * max(abs(a), 1e-3) or (a != a and b != b), (l_b, l_c)
+        assert float((dz_b - dz_c).abs().max()) <= 1e-5 * float(dz_b.abs().max())
+        if fused:
+            assert torch.equal(r_b, r_c)
 
 
 def test_train_step_fused_tail_channels_last_matches_unfused():

@@ -41,6 +41,7 @@ int sm_count_cached() {
 }
 
 // Diagnostic switches (include/wtpse_b200_debug.h, wtpse_debug_set): process-wide, read when a call is enqueued.
+int g_cl_tma_launches = 0;               // read-only counter: channels-last calls that took the tensor-map TMA kernels
 int g_tail_stamps = 0;                   // 1: the in-kernel tail records phase timestamps in the last 128 bytes of the workspace
 int g_fused_tail = 1;                     // 0: forward/backward as chains of separate kernels (the fallback path) for every shape
 
@@ -144,14 +145,17 @@ static int whitening_forward_impl(const float* z, float* relu_out, int B, int C,
     tp.margin = margin; tp.eps = eps; tp.gram = gram; tp.rowstat = rowstat; tp.vd = w.vd; tp.losses = losses; tp.domgrad = domgrad;
     tp.stamps = g_tail_stamps ? w.stamps : nullptr;
     const bool fused = use_fused_tail(B, n_per_domain, n_domains);
-    const GramPlan g = channels_last ? plan_gram_cl(B, P, sms) : plan_gram(z, B, P, sms, relu_out);
+    const bool cl_tma = channels_last && cl_tma_ok(z, relu_out, nullptr, P);      // tensor-map TMA pipeline, else per-thread loads
+    const GramPlan g = cl_tma ? plan_gram_cl_tma(B, P, sms) : channels_last ? plan_gram_cl(B, P, sms) : plan_gram(z, B, P, sms, relu_out);
     tp.nslots = g.nslots;
-    const bool in_kernel = fused && !channels_last && g.tma;
+    const bool in_kernel = fused && g.tma && (!channels_last || gram_cl_tail_fits(B, n_per_domain, n_domains));
     cudaError_t e;
     {
         LaunchScope scope(kKernGram, s);
-        e = channels_last ? launch_gram_cl(z, relu_out, w.partial, w.slot_count, B, P, g, s)
-                          : launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out, in_kernel ? &tp : nullptr);
+        if (cl_tma) ++g_cl_tma_launches;
+        e = cl_tma         ? launch_gram_cl_tma(z, relu_out, w.partial, w.slot_count, B, P, g, s, in_kernel ? &tp : nullptr)
+            : channels_last ? launch_gram_cl(z, relu_out, w.partial, w.slot_count, B, P, g, s)
+                            : launch_gram(z, w.partial, w.slot_count, B, P, g, s, relu_out, in_kernel ? &tp : nullptr);
     }
     if (e != cudaSuccess) return cuda_fail(e, "gram launch");
     if (in_kernel) return WTPSE_OK;
@@ -189,7 +193,11 @@ static int whitening_backward_impl(const float* z, const float* grelu, const flo
     cudaError_t e;
     {
         LaunchScope scope(kKernApply, s);
-        e = channels_last ? launch_apply_cl(z, grelu, seed, dz, B, P, sms, s) : launch_apply(z, seed, dz, B, P, sms, s, grelu);
+        const bool cl_tma = channels_last && cl_tma_ok(z, grelu, dz, P);
+        if (cl_tma) ++g_cl_tma_launches;
+        e = !channels_last ? launch_apply(z, seed, dz, B, P, sms, s, grelu)
+            : cl_tma       ? launch_apply_cl_tma(z, grelu, seed, dz, B, P, sms, s)
+                           : launch_apply_cl(z, grelu, seed, dz, B, P, sms, s);
     }
     if (e != cudaSuccess) return cuda_fail(e, "apply launch");
     return WTPSE_OK;
@@ -234,7 +242,8 @@ const Knob* knobs(int* count) {
         {"tail_stamps", &g_tail_stamps, 0, 1},                    // phase clocks of the in-kernel tail -> last 128 workspace bytes                      // 0: forward tail as separate kernels for every shape
         {"apply_round_robin", &g_apply_round_robin, 0, 1},        // NCHW apply kernel: tiles dealt round-robin (1) or contiguous ranges (0)
         {"l2_hint", &g_l2_evict_first, 0, 1},                     // L2 evict-first policy on the TMA loads of z
-        {"cl_tma", &g_cl_tma, 0, 1},                              // channels-last kernels: tensor-map TMA pipelines (1) or per-thread loads (0)
+        {"cl_tma", &g_cl_tma, 0, 1},
+        {"cl_tma_launches", &g_cl_tma_launches, 0, 0},            // counter (setting it resets it to 0)                              // channels-last kernels: tensor-map TMA pipelines (1) or per-thread loads (0)
         {"wavelet_resident", &g_wavelet_resident, 0, 1},
         {"wavelet_tiles", &g_wavelet_tiles, 0, 1},
         {"wavelet_peel_max", &g_wavelet_peel_max, 1, 16},

@@ -156,4 +156,28 @@ struct TileWalk {
     }
 };
 
+// Walks one CTA's tiles without a division per tile: round-robin (tile k, k + G, ...) or one contiguous range.
+struct TileIter {
+    long long t, tin, b;        // tile, tile index inside its sample, sample
+    long long step, tend, tps;
+    __device__ __forceinline__ void init(long long first, long long end, long long stride, long long tiles_per_sample) {
+        t = first; tend = end; step = stride; tps = tiles_per_sample;
+        b = first / tps;
+        tin = first - b * tps;
+    }
+    __device__ __forceinline__ bool valid() const { return t < tend; }
+    __device__ __forceinline__ void next() {
+        t += step;
+        tin += step;
+        while (tin >= tps) { tin -= tps; ++b; }
+    }
+    // sample of the first later tile that belongs to another sample (-1: none)
+    __device__ __forceinline__ long long next_sample() const {
+        TileIter it = *this;
+        for (it.next(); it.valid(); it.next())
+            if (it.b != b) return it.b;
+        return -1;
+    }
+};
+
 }  // namespace wtpse

@@ -32,6 +32,15 @@ cudaError_t launch_gram(const float* z, float* partial, int* slot_count, int B, 
                         cudaStream_t stream, float* relu_out = nullptr, const TailParams* tail = nullptr);
 bool gram_tail_fits(int B, int n_per_domain, int n_domains);
 
+// channels-last kernels as tensor-map TMA pipelines (whitening_cl_tma.cu); cl_tma_ok: pointers (nullable) and size allow them
+bool cl_tma_ok(const float* a, const float* b, const float* c, long long P);
+GramPlan plan_gram_cl_tma(int B, long long P, int sm_count);
+bool gram_cl_tail_fits(int B, int n_per_domain, int n_domains);
+cudaError_t launch_gram_cl_tma(const float* z, float* relu_out, float* partial, int* slot_count, int B, long long P, const GramPlan& g,
+                               cudaStream_t stream, const TailParams* tail);
+cudaError_t launch_apply_cl_tma(const float* z, const float* grelu, const SeedArgs& seed, float* dz, int B, long long P, int sm_count,
+                                cudaStream_t stream);
+
 // stand-alone forward tail (whitening_epilogue.cu): the fallback of the in-kernel tail.  `scratch` is the global fallback
 // for the single-CTA kernels' working set (epilogue_scratch_bytes).
 size_t epilogue_scratch_bytes(int B, int K);

@@ -36,30 +36,6 @@ __device__ __forceinline__ void st_stream(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Walks one CTA's tiles without a division per tile: round-robin (tile k, k + G, ...) or one contiguous range.
-struct TileIter {
-    long long t, tin, b;        // tile, tile index inside its sample, sample
-    long long step, tend, tps;
-    __device__ __forceinline__ void init(long long first, long long end, long long stride, long long tiles_per_sample) {
-        t = first; tend = end; step = stride; tps = tiles_per_sample;
-        b = first / tps;
-        tin = first - b * tps;
-    }
-    __device__ __forceinline__ bool valid() const { return t < tend; }
-    __device__ __forceinline__ void next() {
-        t += step;
-        tin += step;
-        while (tin >= tps) { tin -= tps; ++b; }
-    }
-    // sample of the first later tile that belongs to another sample (-1: none)
-    __device__ __forceinline__ long long next_sample() const {
-        TileIter it = *this;
-        for (it.next(); it.valid(); it.next())
-            if (it.b != b) return it.b;
-        return -1;
-    }
-};
-
 __global__ void __launch_bounds__(kThreads, 1)
 apply_tma_kernel(const float* __restrict__ z, float* __restrict__ dz, long long P, long long tiles_per_sample, long long T,
                  int round_robin, int l2_hint, SeedArgs sa) {
@@ -120,14 +96,13 @@ apply_tma_kernel(const float* __restrict__ z, float* __restrict__ dz, long long 
     // Everything this kernel reads besides z (saved tensors, upstream scalars) and everything it writes may belong to
     // the kernel in front of it: wait for that kernel here (no-op without a programmatic dependency).
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const SeedCtx sc = seed_context(sa, P);
-
     int stage = 0, cur = 0;
     uint32_t phase = 0;
     long long cur_b = it.valid() ? it.b : -1;
-    SeedRegs ahead = seed_load(sa, sc, tab, int(cur_b), tid);             // the first matrix pays its latency once
+    SeedRegs ahead = seed_load(sa, tab, int(cur_b), tid);                 // the first matrix pays its latency once,
+    const SeedCtx sc = seed_context(sa, P);                               // together with the upstream scalars
     seed_store(ahead, sc, tab, msh2, tid);
-    ahead = seed_load(sa, sc, tab, it.valid() ? int(it.next_sample()) : -1, tid);   // in flight while the first sample is processed
+    ahead = seed_load(sa, tab, it.valid() ? int(it.next_sample()) : -1, tid);       // in flight while the first sample is processed
     named_bar_sync(1, kConsumers);
     for (; it.valid(); it.next()) {
         const long long b = it.b;
@@ -138,7 +113,7 @@ apply_tma_kernel(const float* __restrict__ z, float* __restrict__ dz, long long 
             seed_store(ahead, sc, tab, msh2 + (cur ^ 1) * 256, tid);
             cur ^= 1;
             cur_b = b;
-            ahead = seed_load(sa, sc, tab, int(it.next_sample()), tid);
+            ahead = seed_load(sa, tab, int(it.next_sample()), tid);
             named_bar_sync(1, kConsumers);
         }
         const float* msh = msh2 + cur * 256;

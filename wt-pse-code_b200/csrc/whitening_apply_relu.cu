@@ -30,7 +30,7 @@ constexpr int kTilePx = kConsumers * 4;            // 896 pixels
 constexpr int kStages = 2;
 constexpr int kRowsFloats = kC * kTilePx;          // one tensor's share of a stage: 56 KB
 constexpr int kStageFloats = 2 * kRowsFloats;      // z rows, then grelu rows
-constexpr size_t kSmemBytes = size_t(kStages) * kStageFloats * sizeof(float) + 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+constexpr size_t kSmemBytes = size_t(kStages) * kStageFloats * sizeof(float) + 2 * 256 * sizeof(float) + 2 * kStages * sizeof(uint64_t);
 
 __device__ __forceinline__ void st_stream4(float* p, const float4& v) {
     asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -41,8 +41,8 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
                       long long tiles_per_sample, long long T, SeedArgs sa) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
-    float* msh = stage_buf + size_t(kStages) * kStageFloats;
-    uint64_t* full = reinterpret_cast<uint64_t*>(msh + 256);
+    float* msh2 = stage_buf + size_t(kStages) * kStageFloats;          // two matrices: the current sample's and the next one's
+    uint64_t* full = reinterpret_cast<uint64_t*>(msh2 + 512);
     uint64_t* empty = full + kStages;
     __shared__ IndexTables tab;
 
@@ -119,21 +119,28 @@ apply_relu_tma_kernel(const float* __restrict__ z, const float* __restrict__ gre
     }
 
     asm volatile("griddepcontrol.wait;" ::: "memory");   // saved tensors, upstream scalars and dz may belong to the kernel in front
-    const SeedCtx sc = seed_context(sa, P);
-
-    int stage = 0;
+    TileIter it;
+    it.init(k, T, G, tiles_per_sample);                   // tiles dealt round-robin, as the producer walks them
+    int stage = 0, cur = 0;
     uint32_t phase = 0;
-    long long cur_b = -1;
-    for (long long t = k; t < T; t += G) {
-        const long long b = t / tiles_per_sample;
-        const long long px0 = (t - b * tiles_per_sample) * kTilePx;
+    long long cur_b = it.valid() ? it.b : -1;
+    SeedRegs ahead = seed_load(sa, tab, int(cur_b), tid);
+    const SeedCtx sc = seed_context(sa, P);
+    seed_store(ahead, sc, tab, msh2, tid);
+    ahead = seed_load(sa, tab, it.valid() ? int(it.next_sample()) : -1, tid);     // one sample ahead: no latency at a sample change
+    named_bar_sync(1, kConsumers);
+    for (; it.valid(); it.next()) {
+        const long long b = it.b;
+        const long long px0 = it.tin * kTilePx;
         const long long rem = P - px0;
         if (b != cur_b) {
-            named_bar_sync(1, kConsumers);          // previous sample's matrix no longer in use
-            seed_matrix(sa, sc, tab, int(b), msh, tid);
-            named_bar_sync(1, kConsumers);
+            seed_store(ahead, sc, tab, msh2 + (cur ^ 1) * 256, tid);      // the other buffer was last read two samples ago
+            cur ^= 1;
             cur_b = b;
+            ahead = seed_load(sa, tab, int(it.next_sample()), tid);
+            named_bar_sync(1, kConsumers);
         }
+        const float* msh = msh2 + cur * 256;
         mbar_wait(&full[stage], phase);
         const bool active = 4LL * tid < rem;
         float4 out[kC];

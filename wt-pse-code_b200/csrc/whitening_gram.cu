@@ -387,17 +387,22 @@ cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int*
 }
 
 size_t gram_partial_floats(int B, long long P, int sm_count) {
-    // upper bound over all paths: persistent TMA path <= ceil(tiles per sample / tiles per CTA) + 1, generic <= 2 * sm_count
-    const long long tps = (P + kTilePx - 1) / kTilePx;
-    long long T = tps * B;
-    long long G = T < sm_count ? T : sm_count;
-    long long per_cta = T / G;                       // smallest range
-    if (per_cta < 1) per_cta = 1;
-    long long slots_tma = (tps + per_cta - 1) / per_cta + 1;
+    // upper bound over all paths.  Persistent pipelines (contiguous ranges of `tile`-pixel tiles, NCHW: 896, channels-last
+    // TMA: 448): a sample spans at most ceil(tiles per sample / smallest range) + 1 CTAs.  Generic kernel: <= 2 * sm_count
+    // slots in total.  Per-thread channels-last kernel: items of >= 8192 pixels, <= 256 per sample.
+    long long slots = 1;
+    for (long long tile : {896LL, 448LL}) {
+        const long long tps = (P + tile - 1) / tile;
+        const long long T = tps * B;
+        const long long G = T < sm_count ? T : sm_count;
+        long long per_cta = T / G;
+        if (per_cta < 1) per_cta = 1;
+        const long long s = (tps + per_cta - 1) / per_cta + 1;
+        if (s > slots) slots = s;
+    }
     long long slots_gen = (2LL * sm_count + B - 1) / B;
-    if (slots_gen < 1) slots_gen = 1;
-    long long slots = slots_tma > slots_gen ? slots_tma : slots_gen;
-    long long slots_cl = (P + 8191) / 8192;   // channels-last schedules (plan_gram_cl): items of >= 8192 pixels, <= 256 per sample
+    if (slots_gen > slots) slots = slots_gen;
+    long long slots_cl = (P + 8191) / 8192;
     if (slots_cl > 256) slots_cl = 256;
     if (slots_cl > slots) slots = slots_cl;
     return size_t(B) * size_t(slots) * kTri;

@@ -43,14 +43,17 @@ struct SeedRegs {
     float g, off_b, diag_b, dom;
 };
 
-__device__ __forceinline__ SeedRegs seed_load(const SeedArgs& a, const SeedCtx& c, const IndexTables& tab, int b, int tid) {
+// (Does not depend on the upstream scalars: the kernel's first seed_load is issued together with their loads.)
+__device__ __forceinline__ SeedRegs seed_load(const SeedArgs& a, const IndexTables& tab, int b, int tid) {
     SeedRegs r{0.f, 0.f, 0.f, 0.f};
     if (tid >= kTri || b < 0 || b >= a.B) return r;
     const int ij = tab.tri[tid], i = ij >> 4, j = ij & 15;
+    const long long m = (long long)a.K * a.n;
+    const int M = a.K > 1 ? int(m < a.B ? m : a.B) : 0;
     r.g = __ldcg(a.gram + b * 256 + i * kC + j);
     r.off_b = __ldcg(a.rowstat + b * 2 + 0);
     r.diag_b = __ldcg(a.rowstat + b * 2 + 1);
-    if (c.need_dom && b < c.M && i != j) r.dom = __ldcg(a.domgrad + b * kOff + off_idx(i, j));
+    if (b < M && i != j) r.dom = __ldcg(a.domgrad + b * kOff + off_idx(i, j));
     return r;
 }
 
@@ -58,7 +61,7 @@ __device__ __forceinline__ SeedRegs seed_load(const SeedArgs& a, const SeedCtx& 
 __device__ __forceinline__ void seed_store(const SeedRegs& r, const SeedCtx& c, const IndexTables& tab, float* msh, int tid) {
     if (tid >= kTri) return;
     const int ij = tab.tri[tid], i = ij >> 4, j = ij & 15;
-    const float dom_grad = (r.dom != 0.f) ? c.g_dom * r.dom : 0.f;        // entries outside the MMD stay exactly 0
+    const float dom_grad = (c.need_dom && r.dom != 0.f) ? c.g_dom * r.dom : 0.f;   // no upstream gradient / outside the MMD: exactly 0
     const float m = backward_matrix_entry(i, j, r.g, r.off_b, r.diag_b, c.w_off, c.w_diag, dom_grad, c.denom);
     msh[i * kC + j] = m;
     msh[j * kC + i] = m;
@@ -66,7 +69,7 @@ __device__ __forceinline__ void seed_store(const SeedRegs& r, const SeedCtx& c, 
 
 // Threads tid < 136 fill msh[16][16] for sample b; the caller synchronises before and after.
 __device__ __forceinline__ void seed_matrix(const SeedArgs& a, const SeedCtx& c, const IndexTables& tab, int b, float* msh, int tid) {
-    seed_store(seed_load(a, c, tab, b, tid), c, tab, msh, tid);
+    seed_store(seed_load(a, tab, b, tid), c, tab, msh, tid);
 }
 
 }  // namespace wtpse
