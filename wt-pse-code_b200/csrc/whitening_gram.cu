@@ -4,14 +4,21 @@
 // are read once; 136 FMAs per pixel (symmetric half) run on the FP32 pipes underneath.
 //
 // Design (B200, 148 SMs, one persistent CTA per SM):
-//   * the B * ceil(P/896) pixel tiles are split into contiguous ranges, one per CTA;
-//   * a producer warp streams each tile -- 16 channel rows of 896 pixels, 56 KB -- into a 3-stage
+//   * the B * ceil(P/768) pixel tiles are split into contiguous ranges, one per CTA;
+//   * a producer warp streams each tile -- 16 channel rows of 768 pixels, 48 KB -- into a 4-stage
 //     shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier complete_tx);
-//   * 7 consumer warps read one float4 (4 pixels) per channel from shared memory (conflict-free
-//     LDS.128) and keep the 136 running sums in registers;
-//   * at a sample boundary the 136 sums are reduced across the warp with a halving butterfly
-//     (153 shuffles instead of 680), across warps through shared memory, and written to a
-//     per-(sample, slot) partial.  No float atomics: the slots are summed in a fixed order;
+//   * 6 consumer warps work as 3 PAIRS.  Both warps of a pair read the same 4 pixels per thread (conflict-free
+//     LDS.128) and each keeps HALF of the 136 running sums, as 68 packed (even pixel, odd pixel) accumulators fed by
+//     fma.rn.f32x2 (SASS FFMA2): 76 thread instructions per pixel instead of the 140 of one-thread-per-pixel-quad with
+//     scalar FMAs.  The scalar version left the kernel issue-bound (2 warps per scheduler at 0.49 IPC each way,
+//     tools/gram_lab.cu: 86.1 us alone, 0.952 of the HBM peak); this one runs at what the memory side delivers
+//     (82.4 us, 0.995).  Packing over PIXELS needs no operand shuffling: a 128-bit shared load leaves
+//     (px0, px1) and (px2, px3) in aligned register pairs.
+//   * which warp keeps what: the upper triangle in 4x4 channel blocks A B C D.  Even warp: AA AB BB AC AD (reads all
+//     16 channels), odd warp: CC CD DD BC BD (reads 12) -- 68 entries each;
+//   * at a sample boundary the sums are folded (even + odd pixel), reduced across the warp with a halving butterfly,
+//     across the three pairs through shared memory, and written to a per-(sample, slot) partial in packed
+//     upper-triangle order.  No float atomics: the slots are summed in a fixed order;
 //   * the rest of the forward pass -- slot reduction, f_cor, instance terms, MMD, the backward's MMD seed -- runs
 //     inside this kernel too, in whichever CTA arrives last (whitening_tail.cuh): the forward is ONE launch.
 #include "common.cuh"
@@ -22,19 +29,25 @@ namespace wtpse {
 
 namespace {
 
-// 7 consumer warps + 1 producer warp = 256 threads: the 136 accumulators + 64 staged inputs need 255 registers, so
-// 256 threads is the most an SM holds (a 9th warp pushes ptxas to 168 registers and spills).  Folding the producer
-// into a consumer warp (8 consumers, 1024-pixel tiles) was tried and is slower (110 vs 102 us): the issuing lane's
-// waits on the ring stall its warp and couple the look-ahead to the consumers' pace.
-constexpr int kConsumers = 224;
-constexpr int kConsumerWarps = kConsumers / 32;
+// 6 consumer warps + 1 producer warp: at most 2 warps per scheduler, so each thread may hold 255 registers (68 packed
+// accumulators = 136, one 4-channel block of inputs per operand = 48 more).  A 9th warp would cap every thread at 168.
+constexpr int kPairs = 3;
+constexpr int kConsumerWarps = 2 * kPairs;
+constexpr int kConsumers = kConsumerWarps * 32;
 constexpr int kThreads = kConsumers + 32;       // + producer warp
-constexpr int kTilePx = kConsumers * 4;         // 896 pixels per tile
-constexpr int kStages = 3;
-constexpr int kStageFloats = kC * kTilePx;      // 56 KB per stage
+constexpr int kPassPx = kPairs * 128;           // pixels one pass of the three pairs covers (4 per thread)
+constexpr int kPasses = 2;
+constexpr int kTilePx = kPassPx * kPasses;      // 768 pixels per tile
+constexpr int kStages = 4;
+constexpr int kStageFloats = kC * kTilePx;      // 48 KB per stage
+constexpr int kHalf = kTri / 2;                 // 68 entries per warp of a pair
 
 constexpr size_t kSmemBytes =
-    size_t(kStages) * kStageFloats * sizeof(float) + size_t(kConsumerWarps) * kTri * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    size_t(kStages) * kStageFloats * sizeof(float) + size_t(kConsumerWarps) * kHalf * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+
+// generic / channels-last per-thread kernels: one thread per pixel (quad), all 136 sums per thread
+constexpr int kGenThreads = 224;
+constexpr int kGenWarps = kGenThreads / 32;
 
 template <int HALF>
 __device__ __forceinline__ void halve(float (&a)[kTri], int lane, int mask) {
@@ -73,23 +86,45 @@ __device__ __forceinline__ void flush_gram_t(float (&acc)[kTri], float* red, int
     named_bar_sync(1, kWarps * 32);
 }
 
-__device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int warp, int lane, int tid, float* out) {
-    flush_gram_t<kConsumerWarps>(acc, red, warp, lane, tid, out);
-}
+// ---- the pair kernel's accumulators ------------------------------------------------------------------------------
+// index of entry (a, b) inside a 4x4 channel block: 10 entries (a <= b) for a diagonal block, 16 otherwise
+__host__ __device__ constexpr int blk_idx(bool tri, int a, int b) { return tri ? a * 4 - (a * (a - 1)) / 2 + (b - a) : a * 4 + b; }
 
-__device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4 (&x)[kC]) {
-#pragma unroll
-    for (int i = 0; i < kC; ++i) {
-#pragma unroll
-        for (int j = i; j < kC; ++j) {
-            float a = acc[tri_idx(i, j)];
-            a = fmaf(x[i].x, x[j].x, a);
-            a = fmaf(x[i].y, x[j].y, a);
-            a = fmaf(x[i].z, x[j].z, a);
-            a = fmaf(x[i].w, x[j].w, a);
-            acc[tri_idx(i, j)] = a;
+// packed upper-triangle index of accumulator e of warp type ty (0: AA AB BB AC AD, 1: CC CD DD BC BD)
+struct PairEntries { unsigned char v[2][kHalf]; };
+constexpr PairEntries make_pair_entries() {
+    PairEntries t{};
+    const int seq[2][5][2] = {{{0, 0}, {0, 1}, {1, 1}, {0, 2}, {0, 3}}, {{2, 2}, {2, 3}, {3, 3}, {1, 2}, {1, 3}}};
+    for (int ty = 0; ty < 2; ++ty) {
+        int e0 = 0;
+        for (int k = 0; k < 5; ++k) {
+            const int I = seq[ty][k][0], J = seq[ty][k][1];
+            const bool tri = I == J;
+            for (int a = 0; a < 4; ++a)
+                for (int b = tri ? a : 0; b < 4; ++b) t.v[ty][e0 + blk_idx(tri, a, b)] = (unsigned char)tri_idx(4 * I + a, 4 * J + b);
+            e0 += tri ? 10 : 16;
         }
     }
+    return t;
+}
+__constant__ PairEntries kPairEntries = make_pair_entries();
+
+__device__ __forceinline__ void load_block(float4 (&x)[4], const float* src, int c0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) x[c] = *reinterpret_cast<const float4*>(src + (c0 + c) * kTilePx);
+}
+
+// acc[E0 + (a, b)] += xi[a] * xj[b] over the thread's four pixels: two packed FMAs (px0, px1), (px2, px3)
+template <bool TRI, int E0>
+__device__ __forceinline__ void block_fma(float2 (&acc)[kHalf], const float4 (&xi)[4], const float4 (&xj)[4]) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = TRI ? a : 0; b < 4; ++b) {
+            const int e = E0 + blk_idx(TRI, a, b);
+            acc[e] = __ffma2_rn(make_float2(xi[a].x, xi[a].y), make_float2(xj[b].x, xj[b].y), acc[e]);
+            acc[e] = __ffma2_rn(make_float2(xi[a].z, xi[a].w), make_float2(xj[b].z, xj[b].w), acc[e]);
+        }
 }
 
 // ReLU of the DeepWT tail (algorithms.py:1105,1112: `F.relu(z_instance)` right after the embedding that feeds the loss).
@@ -97,10 +132,78 @@ __device__ __forceinline__ void gram_accumulate(float (&acc)[kTri], const float4
 __device__ __forceinline__ float4 relu4(const float4& v) {
     return make_float4(v.x < 0.f ? 0.f : v.x, v.y < 0.f ? 0.f : v.y, v.z < 0.f ? 0.f : v.z, v.w < 0.f ? 0.f : v.w);
 }
+__device__ __forceinline__ void store_relu_block(float* dst, const float4 (&x)[4], int c0, long long P) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) *reinterpret_cast<float4*>(dst + (c0 + c) * P) = relu4(x[c]);
+}
+
+// One pass of one warp over its four pixels per thread.  src: the thread's first pixel in channel row 0 of the stage;
+// relu_dst: the same pixel in channel 0 of relu_out.  kRelu: the even warp also writes relu of channels 0..7, the odd
+// warp of channels 8..15 (each writes what it has loaded anyway; 512 B coalesced per warp and channel).
+template <int TYPE, bool kRelu>
+__device__ __forceinline__ void pair_accumulate(float2 (&acc)[kHalf], const float* src, float* relu_dst, long long P) {
+    float4 p[4], q[4], r[4];
+    if constexpr (TYPE == 0) {
+        load_block(p, src, 0);                   // A
+        load_block(q, src, 4);                   // B
+        if (kRelu) { store_relu_block(relu_dst, p, 0, P); store_relu_block(relu_dst, q, 4, P); }
+        block_fma<true, 0>(acc, p, p);           // AA
+        block_fma<false, 10>(acc, p, q);         // AB
+        block_fma<true, 26>(acc, q, q);          // BB
+        load_block(r, src, 8);                   // C
+        block_fma<false, 36>(acc, p, r);         // AC
+        load_block(q, src, 12);                  // D
+        block_fma<false, 52>(acc, p, q);         // AD
+    } else {
+        load_block(p, src, 8);                   // C
+        load_block(q, src, 12);                  // D
+        if (kRelu) { store_relu_block(relu_dst, p, 8, P); store_relu_block(relu_dst, q, 12, P); }
+        block_fma<true, 0>(acc, p, p);           // CC
+        block_fma<false, 10>(acc, p, q);         // CD
+        block_fma<true, 26>(acc, q, q);          // DD
+        load_block(r, src, 4);                   // B
+        block_fma<false, 36>(acc, r, p);         // BC
+        block_fma<false, 52>(acc, r, q);         // BD
+    }
+}
+
+// The warp's 68 sums over its 32 lanes -> red_w[68]: even + odd pixel, halving butterfly 68 -> 34 -> 17 (51 shuffles),
+// then the 17 survivors over the remaining 8 lanes (51 shuffles).  Fixed order.
+__device__ __forceinline__ void pair_warp_fold(const float2 (&acc)[kHalf], float* red_w, int lane) {
+    float s[kHalf];
+#pragma unroll
+    for (int e = 0; e < kHalf; ++e) s[e] = acc[e].x + acc[e].y;
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int k = 0; k < 34; ++k) {
+            const float keep = up ? s[k + 34] : s[k], send = up ? s[k] : s[k + 34];
+            s[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) {
+            const float keep = up ? s[k + 17] : s[k], send = up ? s[k] : s[k + 17];
+            s[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 17; ++k) {
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 4);
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 2);
+        s[k] += __shfl_xor_sync(0xffffffffu, s[k], 1);
+    }
+    if ((lane & 7) == 0) {
+        const int b0 = ((lane >> 4) & 1) * 34 + ((lane >> 3) & 1) * 17;
+#pragma unroll
+        for (int k = 0; k < 17; ++k) red_w[b0 + k] = s[k];
+    }
+}
 
 // kRelu: the same pass also writes relu(z) (SURVEY 8(f).1 -- the activation that follows the embedding no longer
-// re-reads z); the consumers store the 4 pixels x 16 channels they hold anyway, one coalesced 512 B row piece per
-// warp and channel.  Default-policy stores: the next convolution reads relu(z) right away.
+// re-reads z).  Default-policy stores: the next convolution reads relu(z) right away.
 template <bool kRelu>
 __global__ void __launch_bounds__(kThreads, 1)
 gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial,
@@ -109,7 +212,7 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* stage_buf = reinterpret_cast<float*>(smem_raw);
     float* red = stage_buf + size_t(kStages) * kStageFloats;
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + kConsumerWarps * kTri);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + kConsumerWarps * kHalf);
     uint64_t* empty = full + kStages;
     __shared__ IndexTables tab;
     __shared__ float wred[16];
@@ -167,9 +270,13 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
 
     // ---------------- consumers ----------------
     TailClock clk;
-    float acc[kTri];
+    const int type = warp & 1;                                  // which half of the triangle this warp keeps
+    const int px_in_pass = ((warp >> 1) * 32 + lane) * 4;       // both warps of a pair: the same pixels
+    // the packed upper-triangle entry thread tid < 136 sums across the pairs at every flush
+    const int out_entry = tid < kTri ? kPairEntries.v[tid >= kHalf ? 1 : 0][tid >= kHalf ? tid - kHalf : tid] : 0;
+    float2 acc[kHalf];
 #pragma unroll
-    for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+    for (int e = 0; e < kHalf; ++e) acc[e] = make_float2(0.f, 0.f);
 
     int stage = 0;
     uint32_t phase = 0;
@@ -181,17 +288,14 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
             const long long px0 = (t - b * tiles_per_sample) * kTilePx;
             const long long rem = P - px0;
             mbar_wait(&full[stage], phase);
-            if (4LL * tid < rem) {
-                const float* src = stage_buf + size_t(stage) * kStageFloats + 4 * tid;
-                float4 x[kC];
+            const float* src = stage_buf + size_t(stage) * kStageFloats + px_in_pass;
+            float* rdst = kRelu ? relu_out + (b * kC) * P + px0 + px_in_pass : nullptr;
 #pragma unroll
-                for (int c = 0; c < kC; ++c) x[c] = *reinterpret_cast<const float4*>(src + c * kTilePx);
-                if (kRelu) {
-                    float* dst = relu_out + (b * kC) * P + px0 + 4 * tid;
-#pragma unroll
-                    for (int c = 0; c < kC; ++c) *reinterpret_cast<float4*>(dst + c * P) = relu4(x[c]);
+            for (int pass = 0; pass < kPasses; ++pass) {
+                if (pass * kPassPx + px_in_pass < rem) {
+                    if (type == 0) pair_accumulate<0, kRelu>(acc, src + pass * kPassPx, rdst + pass * kPassPx, P);
+                    else pair_accumulate<1, kRelu>(acc, src + pass * kPassPx, rdst + pass * kPassPx, P);
                 }
-                gram_accumulate(acc, x);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
@@ -200,7 +304,17 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
         const long long first_grp = part_owner(b * tiles_per_sample, T, Gg);
         const long long slot = (grp - first_grp) * walk.g + walk.r;
         clk.mark(0);
-        flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+        // flush: per-warp fold, then thread tid < 136 adds the three pairs' values of its entry in pair order
+        pair_warp_fold(acc, red + warp * kHalf, lane);
+        named_bar_sync(1, kConsumers);
+        if (tid < kTri) {
+            const int ty = tid >= kHalf ? 1 : 0, e = tid - ty * kHalf;
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < kPairs; ++g) s += red[(2 * g + ty) * kHalf + e];
+            partial[(b * nslots + slot) * kTri + out_entry] = s;
+        }
+        named_bar_sync(1, kConsumers);
         clk.mark(1);
         if (fused_tail) {
             // every CTA whose range touches sample b stores exactly one partial for it
@@ -211,7 +325,7 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
             slot_count[b] = int(grp - first_grp + 1);
         }
 #pragma unroll
-        for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+        for (int e = 0; e < kHalf; ++e) acc[e] = make_float2(0.f, 0.f);
     }
 }
 
@@ -219,10 +333,10 @@ gram_tma_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float
 // aligned): same arithmetic, plain coalesced scalar loads, one pixel per thread per step.
 // grid = (nslots, B); block = 256.
 template <bool kRelu>
-__global__ void __launch_bounds__(kConsumers)
+__global__ void __launch_bounds__(kGenThreads)
 gram_generic_kernel(const float* __restrict__ z, float* __restrict__ relu_out, float* __restrict__ partial,
                     int* __restrict__ slot_count, long long P, int nslots) {
-    __shared__ float red[kConsumerWarps * kTri];
+    __shared__ float red[kGenWarps * kTri];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long b = blockIdx.y;
     const int slot = blockIdx.x;
@@ -234,7 +348,7 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ relu_out, f
     float acc[kTri];
 #pragma unroll
     for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
-    for (long long p = p0 + tid; p < p1; p += kConsumers) {
+    for (long long p = p0 + tid; p < p1; p += kGenThreads) {
         float x[kC];
 #pragma unroll
         for (int c = 0; c < kC; ++c) x[c] = __ldg(zb + c * P + p);
@@ -247,7 +361,7 @@ gram_generic_kernel(const float* __restrict__ z, float* __restrict__ relu_out, f
 #pragma unroll
             for (int j = i; j < kC; ++j) acc[tri_idx(i, j)] = fmaf(x[i], x[j], acc[tri_idx(i, j)]);
     }
-    flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+    flush_gram_t<kGenWarps>(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
     if (slot == 0 && tid == 0) slot_count[b] = nslots;
 }
 
@@ -342,7 +456,7 @@ GramPlan plan_gram(const float* z, int B, long long P, int sm_count, const float
         g.nslots = nslots;
     } else {
         long long want = (2LL * sm_count + B - 1) / B;           // ~2 CTAs per SM in total
-        const long long max_useful = (P + 4 * kConsumers - 1) / (4 * kConsumers);
+        const long long max_useful = (P + 4 * kGenThreads - 1) / (4 * kGenThreads);
         if (want > max_useful) want = max_useful;
         if (want < 1) want = 1;
         g.nslots = int(want);
@@ -387,11 +501,11 @@ cudaError_t launch_gram_cl(const float* z, float* relu_out, float* partial, int*
 }
 
 size_t gram_partial_floats(int B, long long P, int sm_count) {
-    // upper bound over all paths.  Persistent pipelines (contiguous ranges of `tile`-pixel tiles, NCHW: 896, channels-last
+    // upper bound over all paths.  Persistent pipelines (contiguous ranges of `tile`-pixel tiles, NCHW: 768, channels-last
     // TMA: 448): a sample spans at most ceil(tiles per sample / smallest range) + 1 CTAs.  Generic kernel: <= 2 * sm_count
     // slots in total.  Per-thread channels-last kernel: items of >= 8192 pixels, <= 256 per sample.
     long long slots = 1;
-    for (long long tile : {896LL, 448LL}) {
+    for (long long tile : {(long long)kTilePx, 448LL}) {
         const long long tps = (P + tile - 1) / tile;
         const long long T = tps * B;
         const long long G = T < sm_count ? T : sm_count;
@@ -430,7 +544,7 @@ cudaError_t launch_gram_t(const float* z, float* relu_out, float* partial, int* 
         return cudaLaunchKernelEx(&cfg, gram_tma_kernel<kRelu>, z, relu_out, partial, slot_count, (long long)P,
                                   g.tiles_per_sample, g.T, g.nslots, g_l2_evict_first, tail ? 1 : 0, tp);
     } else {
-        gram_generic_kernel<kRelu><<<dim3(unsigned(g.nslots), unsigned(B)), kConsumers, 0, stream>>>(z, relu_out, partial,
+        gram_generic_kernel<kRelu><<<dim3(unsigned(g.nslots), unsigned(B)), kGenThreads, 0, stream>>>(z, relu_out, partial,
                                                                                                    slot_count, P, g.nslots);
     }
     return cudaGetLastError();
