@@ -105,7 +105,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"])
     ap.add_argument("--size", type=int, default=WORKLOAD["H"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--train-steps", type=int, default=6, help="timed iterations of the full WT-PSE train step (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed iterations of the full WT-PSE train step (0 = skip)")
+    ap.add_argument("--train-grad-segments", type=int, default=3,
+                    help="pieces each network's gradient buffer is all-reduced in, started from autograd hooks during the backward pass (1 = one collective after it)")
+    ap.add_argument("--train-segments-compare", type=int, default=1, help="N > 1: also time the train step with one un-overlapped all-reduce per backward")
     ap.add_argument("--train-size", type=int, default=512)
     ap.add_argument("--train-graph", type=int, default=1, help="replay the train iteration as a CUDA graph")
     ap.add_argument("--train-batch", type=int, default=16, help="nominal per-GPU batch (the reference uses 3 * (batch // 3))")
@@ -830,6 +833,22 @@ def time_train_step(args, dev, rank, world, barrier):
         torch.cuda.empty_cache()
         ref = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=True, steps=max(2, args.train_steps // 2))
         res["with_teacher_backward"] = {k: ref[k] for k in ("value", "unit", "ms_per_step", "steps", "launch_mode")}
+    if world > 1 and args.train_segments_compare and args.train_grad_segments > 1:
+        gc.collect()
+        torch.cuda.empty_cache()
+        alt = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=False, steps=max(2, args.train_steps // 2),
+                                  fuse_relu=bool(args.train_fuse_relu), grad_segments=1)
+        res["one_allreduce_after_backward"] = {k: alt[k] for k in ("value", "unit", "ms_per_step", "steps", "launch_mode", "grad_allreduce")}
+        gc.collect()
+        torch.cuda.empty_cache()
+        # scaling diagnostic: the same N processes WITHOUT any gradient exchange.  max - min over ranks is how much the
+        # GPUs / processes differ on their own (clocks, cuDNN's per-process algorithm choice); what the all-reduce variants
+        # lose beyond that is the collectives' cost.  Not a valid training configuration, never the reported value.
+        alt = _time_train_variant(args, dev, rank, world, barrier, teacher_backward=False, steps=max(2, args.train_steps // 2),
+                                  fuse_relu=bool(args.train_fuse_relu), grad_allreduce=False)
+        res["replicas_without_allreduce"] = {"ms_per_step_slowest_rank": alt["ms_per_step"],
+                                             "ms_per_step_fastest_rank": alt["ms_per_step_fastest_rank"], "steps": alt["steps"],
+                                             "what": "diagnostic: N independent replicas, no gradient exchange"}
     if args.train_fuse_compare:
         gc.collect()
         torch.cuda.empty_cache()
@@ -911,7 +930,8 @@ def time_reference_train(args, dev, rank):
     return res
 
 
-def _time_train_variant(args, dev, rank, world, barrier, teacher_backward, steps, fuse_relu=False):
+def _time_train_variant(args, dev, rank, world, barrier, teacher_backward, steps, fuse_relu=False, grad_segments=None,
+                        grad_allreduce=True):
     import torch
     import torch.distributed as dist
 
@@ -921,8 +941,9 @@ def _time_train_variant(args, dev, rank, world, barrier, teacher_backward, steps
     torch.backends.cudnn.benchmark = bool(args.train_cudnn_benchmark)
     n_per_domain, used = wb.dp.per_rank_batch(args.train_batch * world, world, 3)
     S = args.train_size
+    grad_segments = args.train_grad_segments if grad_segments is None else grad_segments
     ts = wb.TrainStep(n_per_domain=n_per_domain, n_domains=3, device=dev, seed=0, teacher_backward=teacher_backward,
-                      fuse_relu=fuse_relu)
+                      fuse_relu=fuse_relu, grad_segments=grad_segments, grad_allreduce=grad_allreduce)
     lib = wb._lib.load()
 
     mode = "eager"
@@ -955,13 +976,18 @@ def _time_train_variant(args, dev, rank, world, barrier, teacher_backward, steps
     barrier()
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    tmin = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     ms = float(t.item()) / steps
     return {"metric": "train images/s", "value": world * used / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+            "ms_per_step_fastest_rank": float(tmin.item()) / steps,
             "steps": steps, "launch_mode": mode, "image_size": S, "per_gpu_batch_nominal": args.train_batch, "per_gpu_batch_used": used,
             "global_batch_used": world * used, "our_kernels_per_iteration": kernels_per_iteration,
-            "backbone": "PyTorch/cuDNN (benchmark=%d), channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam" % int(args.train_cudnn_benchmark), "grad_allreduce": "NCCL, 1 bucket per backward" if world > 1 else None,
+            "backbone": "PyTorch/cuDNN (benchmark=%d), channels-last weights, fp32 storage (torch-default TF32 convs), fused Adam" % int(args.train_cudnn_benchmark), "grad_allreduce": ("NCCL all-reduce(AVG) of each network's flat gradient buffer in %d segment(s)%s" % (
+                max(len(b.segments) for b in ts.buckets), ", started from autograd hooks during the backward pass (async, own stream)"
+                if grad_segments > 1 else " after the backward pass")) if world > 1 else None,
             "losses": {k: float(v) for k, v in out.items()}}
 
 

@@ -28,7 +28,7 @@ class TrainStep:
     def __init__(self, n_per_domain, n_domains=3, device="cuda", hparams=None, lr=5e-4, seed=0, process_group=None,
                  channels_last=True, fused_adam=True, teacher_backward=False, fuse_relu=True,
                  fold_conv_bias=True, cuda_upsample=True, fast_bias=True, cuda_batchnorm=True,
-                 cuda_pool=True):
+                 cuda_pool=True, grad_segments=3, grad_allreduce=True):
         self.hp = dict(DEFAULT_HPARAMS if hparams is None else hparams)
         self.device = torch.device(device)
         torch.manual_seed(seed)                                   # identical initial weights on every rank
@@ -61,16 +61,22 @@ class TrainStep:
                 # Gram + ReLU in one pass over each embedding (the *_cl kernels read the channels-last
                 # embeddings in place, so there is no layout conversion around the loss either way)
                 seg.enable_relu_fusion(m, True)
-        self.buckets = [FlatGradBucket(m, process_group) for m in self.nets]
+        # each network's gradients are reduced in `grad_segments` pieces, started from autograd hooks while the rest of the
+        # backward pass is still running (dp.FlatGradBucket); 1 = one collective after the backward pass
+        self.buckets = [FlatGradBucket(m, process_group, segments=grad_segments) for m in self.nets]
         fused = bool(fused_adam) and self.device.type == "cuda"       # one multi-tensor kernel per optimizer step
         self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused, capturable=fused)
                        for m in self.nets]
         self._graph = None
         self.iteration = 0
+        self.grad_allreduce = bool(grad_allreduce)     # False: independent replicas (bench.py's scaling diagnostic)
 
     def _finish(self, idx, loss):
+        if self.grad_allreduce:
+            self.buckets[idx].arm()
         loss.backward()
-        self.buckets[idx].allreduce_mean()
+        if self.grad_allreduce:
+            self.buckets[idx].finish()
         self.optims[idx].step()
 
     def step(self, image, target_od, target_oc):
