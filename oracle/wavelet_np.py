@@ -22,6 +22,30 @@ Conventions
 * Shape-regularization loss on a batch of maps x[N][H][W] (N = batch * channels, e.g. the softmax OC/OD
   probabilities):   L = (1/N) sum_n sum_{j=1..J} w_j * mean(|detail coefficients of level j of map n|)
   i.e. an L1 sparsity penalty on the detail sub-bands (ragged boundaries cost more than smooth ones).
+
+Relation to a published implementation (PyWavelets; NOT installed in this image, so stated, not executed)
+---------------------------------------------------------------------------------------------------
+``h`` above is PyWavelets' ``Wavelet(name).rec_lo`` and ``g`` its ``rec_hi`` (db2: rec_lo = [0.48296, 0.83652, 0.22414,
+-0.12941], rec_hi = [-0.12941, -0.22414, 0.83652, -0.48296]); ``dec_lo`` / ``dec_hi`` are those reversed.
+``pywt.dwt(x, name, mode='periodization')`` evaluates  cA[n] = sum_j dec_lo[j] x[(2n + F/2 - j) mod N]  (F = filter
+length), i.e.  cA[n] = sum_k h[k] x[(2n + k - (F/2 - 1)) mod N]:  the SAME filters and decimation, input phase shifted
+by F/2 - 1 samples.  Hence, per axis,
+
+      haar:  dwt_here(x) == pywt.dwt(x, 'haar', mode='periodization')              (F/2 - 1 = 0)
+      db2 :  dwt_here(x) == pywt.dwt(np.roll(x, -1), 'db2', mode='periodization')  (F/2 - 1 = 1)
+
+The 2-D transform is the separable one: every row of the block is filtered along W, then every column along H (pywt.dwt
+along axis -1, then along axis -2, with the roll above on each axis for db2).
+
+Known-answer vectors that can be derived by hand from the formulas above (tests/test_wavelet_spec_cpu.py checks this
+file against them, tests/test_gpu_wavelet.py the CUDA kernels), N = 8, 1-D unless noted:
+
+  constant x = c          a[n] = c * sum(h) = c * sqrt2,  d[n] = c * sum(g) = 0;  2-D, J levels: LL_J = 2^J * c, details 0
+  impulse  x = delta_m    a[n] = h[(m - 2n) mod N] if (m - 2n) mod N < F else 0,  d[n] likewise with g
+  ramp     x[m] = m       haar:  a[n] = (4n + 1) / sqrt2,  d[n] = -1 / sqrt2
+                          db2 :  two vanishing moments -> d[n] = 0 and a[n] = 2 sqrt2 n + (3 - sqrt3) / sqrt2 for every n
+                                 whose taps do not wrap (n <= N/2 - 2); the last one (taps at N-2, N-1, 0, 1) is
+                                 a = h0 (N-2) + h1 (N-1) + h3,   d = g0 (N-2) + g1 (N-1) + g3
 """
 import numpy as np
 

@@ -46,6 +46,41 @@ def test_dwt_matches_spec_and_identities(wavelet, shape, J):
     assert rel_err(xg.grad.cpu().numpy(), wn.idwt2d(y.cpu().numpy(), wavelet, J)) < TOL
 
 
+def test_dwt_hand_derived_known_answers():
+    """Constant, unit impulse and ramp through the CUDA transform, against closed forms derived by hand in
+    oracle/wavelet_np.py's header -- no oracle code in the comparison."""
+    import wtpse_b200 as wb
+
+    s2, s3 = np.sqrt(2.0), np.sqrt(3.0)
+    h = {"haar": np.array([1, 1]) / s2, "db2": np.array([1 + s3, 3 + s3, 3 - s3, 1 - s3]) / (4 * s2)}
+    g = {"haar": np.array([1, -1]) / s2, "db2": np.array([1 - s3, -(3 - s3), 3 + s3, -(1 + s3)]) / (4 * s2)}
+    N = 16
+    for wv in ("haar", "db2"):
+        F = len(h[wv])
+        # rows = the N unit impulses, repeated down the H axis (constant columns: column pass gives sqrt2 * a, 0)
+        x = torch.eye(N).repeat_interleave(N, 0).reshape(N, 1, N, N).to(_dev())        # map m: every row = delta_m
+        c = wb.dwt2d(x, wv, 1).cpu().numpy()[:, 0]
+        for m in range(N):
+            for n in range(N // 2):
+                k = (m - 2 * n) % N
+                assert abs(c[m, 0, n] / s2 - (h[wv][k] if k < F else 0.0)) < 1e-6            # LL row 0 = sqrt2 * a
+                assert abs(c[m, 0, N // 2 + n] / s2 - (g[wv][k] if k < F else 0.0)) < 1e-6   # LH row 0 = sqrt2 * d
+            assert np.abs(c[m, N // 2:, :]).max() < 1e-6                                     # HL, HH: zero
+        # constant map, 3 levels: LL_3 = 8 c, every detail 0
+        c = wb.dwt2d(torch.full((1, 1, N, N), 0.5, device=_dev()), wv, 3).cpu().numpy()[0, 0]
+        assert np.abs(c[:2, :2] - 4.0).max() < 1e-5
+        c[:2, :2] = 0
+        assert np.abs(c).max() < 1e-6
+    ramp = torch.arange(N, dtype=torch.float32).repeat(N, 1).reshape(1, 1, N, N).to(_dev())
+    c = wb.dwt2d(ramp, "haar", 1).cpu().numpy()[0, 0, 0] / s2
+    assert np.allclose(c[:N // 2], (4 * np.arange(N // 2) + 1) / s2, atol=1e-5) and np.allclose(c[N // 2:], -1 / s2, atol=1e-6)
+    c = wb.dwt2d(ramp, "db2", 1).cpu().numpy()[0, 0, 0] / s2
+    n = np.arange(N // 2 - 1)
+    assert np.allclose(c[:N // 2 - 1], 2 * s2 * n + (3 - s3) / s2, atol=1e-5) and np.abs(c[N // 2:N - 1]).max() < 2e-6
+    assert abs(c[N // 2 - 1] - (h["db2"][0] * (N - 2) + h["db2"][1] * (N - 1) + h["db2"][3])) < 1e-5
+    assert abs(c[N - 1] - (g["db2"][0] * (N - 2) + g["db2"][1] * (N - 1) + g["db2"][3])) < 1e-5
+
+
 @pytest.mark.parametrize("wavelet,J,weights", [("haar", 3, None), ("db2", 4, None), ("db2", 2, (0.5, 2.0)), ("haar", 1, (3.0,))])
 def test_wavelet_shape_loss_forward_backward(wavelet, J, weights):
     import wtpse_b200 as wb
