@@ -491,20 +491,54 @@ def time_track_r_configs(dev, peak, steps=20):
         for i in range(nbuf + 4):                                # every buffer's gradient block comes from the allocator cache
             step(i)
         torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(steps):
-            ins, dom = step(i)
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / steps
+
+        def timed(fn):
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                r = fn(i)
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / steps, r
+
+        ms, (ins, dom) = timed(step)
         pix = B * S * S
-        frac = 192.0 * pix / (ms * 1e-3) / 1e9 / peak
-        out[name] = {"ms_per_step": ms, "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": steps, "n_per_domain": n,
-                     "step_frac": frac if S >= 512 else None,
-                     "note": None if S >= 512 else "launch-bound (100.7 MB per step = 15 us at the HBM peak): no roofline claim",
-                     "l2": "%d alternating inputs of %.0f MB" % (nbuf, B * 16 * S * S * 4 / 1e6),
-                     "losses": [float(ins.detach()), float(dom.detach())]}
+        entry = {"ms_per_step": ms, "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": steps, "n_per_domain": n,
+                 "launch_mode": "eager (two C-ABI calls per step from Python)",
+                 "step_frac": 192.0 * pix / (ms * 1e-3) / 1e9 / peak if S >= 512 else None,
+                 "note": None if S >= 512 else "100.7 MB per step = 15 us at the HBM peak: bound by launch and forward-tail latency, no roofline claim",
+                 "l2": "%d alternating inputs of %.0f MB" % (nbuf, B * 16 * S * S * 4 / 1e6),
+                 "losses": [float(ins.detach()), float(dom.detach())]}
+        if S < 512:
+            # a step this short is bound by the host's launch path: replay it as a CUDA graph (one graph per input buffer;
+            # the C ABI neither allocates nor synchronises, so forward + backward capture as they are)
+            try:
+                graphs, outs = [], []
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for i in range(nbuf):
+                        step(i)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                for i in range(nbuf):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        outs.append(step(i))
+                    graphs.append(g)
+
+                def replay(i):
+                    graphs[i % nbuf].replay()
+                    return outs[i % nbuf]
+                for i in range(nbuf):
+                    replay(i)
+                torch.cuda.synchronize()
+                ms_g, (ins_g, dom_g) = timed(replay)
+                entry.update({"eager_ms_per_step": ms, "ms_per_step": ms_g, "value": pix / (ms_g * 1e-3) / 1e6,
+                              "launch_mode": "cuda-graph replay of forward + backward (eager: eager_ms_per_step)"})
+                del graphs, outs
+            except Exception as exc:
+                entry["graph_capture_failed"] = str(exc).splitlines()[0][:160]
+        out[name] = entry
         del zs
         torch.cuda.empty_cache()
     return out

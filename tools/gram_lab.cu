@@ -18,6 +18,7 @@
 #include <cstring>
 #include <cmath>
 #include <vector>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -352,6 +353,138 @@ __global__ void __launch_bounds__(C::kThreads, 1) kernel(const float* __restrict
 }  // namespace pairk
 
 // ------------------------------------------------------------------------------------------------------------------
+// channels-last designs: z is [B][P][16]; a stage is 448 contiguous pixels (28 KB); warp w owns pixels 64w..64w+63 of a
+// stage, lane l the pixels l and l + 32; packed accumulation over channel pairs (72 FFMA2 per pixel)
+//   cl_tm   the stage arrives as 7 tensor-map boxes of 16 x 64 (cp.async.bulk.tensor.3d, 64-byte swizzle): the shipped path
+//   cl_1d   the stage arrives as ONE 1-D bulk copy of 28 KB, no swizzle: the per-pixel LDS.128 are 4-way bank-conflicted
+// ------------------------------------------------------------------------------------------------------------------
+namespace cl {
+constexpr int kConsumers = 224, kWarps = 7, kThreads = 256, kStagePx = 448, kStages = 6, kBoxPx = 64;
+constexpr int kPartBytes = kStagePx * kC * 4;
+constexpr size_t kSmem = 1024 + size_t(kStages) * kPartBytes + kWarps * kTri * 4 + 2 * kStages * 8;
+constexpr int kPairAcc = 72;
+__host__ __device__ constexpr int blk36(int I, int J) { return I * 8 - (I * (I - 1)) / 2 + (J - I); }
+
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* tm, int px, int b, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;" ::
+                 "r"(smem_u32(dst)), "l"(tm), "r"(0), "r"(px), "r"(b), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint32_t swz(int p, int q) { return uint32_t(p) * 64u + (uint32_t(q ^ ((p >> 1) & 3)) << 4); }
+
+__device__ __forceinline__ void accumulate(float2 (&acc2)[kPairAcc], const float4 (&r)[4]) {
+    const float2 P[8] = {make_float2(r[0].x, r[0].y), make_float2(r[0].z, r[0].w), make_float2(r[1].x, r[1].y), make_float2(r[1].z, r[1].w),
+                         make_float2(r[2].x, r[2].y), make_float2(r[2].z, r[2].w), make_float2(r[3].x, r[3].y), make_float2(r[3].z, r[3].w)};
+    float2 S[8];
+#pragma unroll
+    for (int J = 0; J < 8; ++J) S[J] = make_float2(P[J].y, P[J].x);
+#pragma unroll
+    for (int I = 0; I < 8; ++I)
+#pragma unroll
+        for (int J = I; J < 8; ++J) {
+            acc2[2 * blk36(I, J)] = __ffma2_rn(P[I], P[J], acc2[2 * blk36(I, J)]);
+            acc2[2 * blk36(I, J) + 1] = __ffma2_rn(P[I], S[J], acc2[2 * blk36(I, J) + 1]);
+        }
+}
+__device__ __forceinline__ void unpack(const float2 (&acc2)[kPairAcc], float (&acc)[kTri]) {
+#pragma unroll
+    for (int I = 0; I < 8; ++I)
+#pragma unroll
+        for (int J = I; J < 8; ++J) {
+            const float2 D = acc2[2 * blk36(I, J)], A = acc2[2 * blk36(I, J) + 1];
+            acc[tri_idx(2 * I, 2 * J)] = D.x; acc[tri_idx(2 * I + 1, 2 * J + 1)] = D.y; acc[tri_idx(2 * I, 2 * J + 1)] = A.x;
+            if (I < J) acc[tri_idx(2 * I + 1, 2 * J)] = A.y;
+        }
+}
+
+template <int MODE, bool kTensorMap>
+__global__ void __launch_bounds__(kThreads, 1) kernel(const __grid_constant__ CUtensorMap tm, const float* __restrict__ z, float* __restrict__ partial,
+                                                      long long P, long long sps, long long T, int nslots) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* stage_buf = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    float* red = reinterpret_cast<float*>(stage_buf + size_t(kStages) * kPartBytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + kWarps * kTri);
+    uint64_t* empty = full + kStages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long G = gridDim.x, k = blockIdx.x;
+    const long long t0 = part_begin(k, T, G), t1 = part_begin(k + 1, T, G);
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kWarps); }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (warp == kWarps) {
+        if (lane == 0 && MODE != ALU) {
+            const uint64_t policy = make_evict_first_policy();
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = t0; t < t1; ++t) {
+                const long long b = t / sps;
+                mbar_wait(&empty[stage], phase ^ 1);
+                const long long px0 = (t - b * sps) * kStagePx;
+                unsigned char* dst = stage_buf + size_t(stage) * kPartBytes;
+                if (kTensorMap) {
+                    mbar_arrive_expect_tx(&full[stage], kPartBytes);
+#pragma unroll
+                    for (int q = 0; q < kWarps; ++q) tma_load_box(dst + q * kBoxPx * kC * 4, &tm, int(px0) + q * kBoxPx, int(b), &full[stage], policy);
+                } else {
+                    const long long rem = P - px0;
+                    const uint32_t bytes = uint32_t(rem < kStagePx ? rem : kStagePx) * kC * 4u;
+                    mbar_arrive_expect_tx(&full[stage], bytes);
+                    tma_load_1d_hint(dst, z + (b * P + px0) * kC, bytes, &full[stage], policy);
+                }
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+        }
+        return;
+    }
+    float2 acc2[kPairAcc];
+#pragma unroll
+    for (int e = 0; e < kPairAcc; ++e) acc2[e] = make_float2(0.f, 0.f);
+    int stage = 0; uint32_t phase = 0;
+    long long b_cur = t0 / sps;
+    auto flush = [&](long long b) {
+        float acc[kTri];
+        unpack(acc2, acc);
+        const long long first = part_owner(b * sps, T, G);
+        base::flush(acc, red, warp, lane, tid, partial + (b * nslots + (k - first)) * kTri);
+#pragma unroll
+        for (int e = 0; e < kPairAcc; ++e) acc2[e] = make_float2(0.f, 0.f);
+    };
+    for (long long t = t0; t < t1; ++t) {
+        const long long b = t / sps;
+        if (b != b_cur) { flush(b_cur); b_cur = b; }
+        const long long rem = P - (t - b * sps) * kStagePx;
+        if (MODE != ALU) mbar_wait(&full[stage], phase);
+        if (MODE != MEM) {
+            const unsigned char* sb = stage_buf + size_t(stage) * kPartBytes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int p = warp * kBoxPx + j * 32 + lane;
+                if (kTensorMap || p < rem) {
+                    float4 r[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) r[q] = *reinterpret_cast<const float4*>(sb + (kTensorMap ? swz(p, q) : uint32_t(p) * 64u + q * 16u));
+                    accumulate(acc2, r);
+                }
+            }
+        }
+        if (MODE != ALU) { __syncwarp(); if (lane == 0) mbar_arrive(&empty[stage]); }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    flush(b_cur);
+}
+}  // namespace cl
+
+__global__ void ref_gram_cl(const float* z, double* out, long long P) {   // grid (136, B), block 256; z [B][P][16]
+    const int e = blockIdx.x; const long long b = blockIdx.y;
+    int i = 0, rem = e; while (rem >= kC - i) { rem -= kC - i; ++i; } const int j = i + rem;
+    const float* zb = z + b * P * kC;
+    double s = 0; for (long long p = threadIdx.x; p < P; p += blockDim.x) s += double(zb[p * kC + i]) * double(zb[p * kC + j]);
+    __shared__ double sh[256]; sh[threadIdx.x] = s; __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) out[b * kTri + e] = sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 __global__ void ref_gram(const float* z, double* out, long long P) {   // grid (136, B), block 256
     const int e = blockIdx.x; const long long b = blockIdx.y;
     int i = 0, rem = e; while (rem >= kC - i) { rem -= kC - i; ++i; } const int j = i + rem;
@@ -417,6 +550,29 @@ static void launch_pair(const float* z, float* partial, long long P, long long t
     pairk::kernel<C, MODE><<<unsigned(G), C::kThreads, C::kSmem>>>(z, partial, P, tps, T, nslots);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CUtensorMap g_tm[2];
+static const float* g_tm_base[2];
+static void make_maps(Ctx& c) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(p);
+    for (int i = 0; i < 2; ++i) {
+        const cuuint64_t dims[3] = {16, cuuint64_t(c.P), cuuint64_t(c.B)};
+        const cuuint64_t strides[2] = {64, cuuint64_t(c.P) * 64};
+        const cuuint32_t box[3] = {16, 64, 1}, estr[3] = {1, 1, 1};
+        if (fn(&g_tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.z[i], dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) { printf("tensor map failed\n"); exit(1); }
+        g_tm_base[i] = c.z[i];
+    }
+}
+template <int MODE, bool TM>
+static void launch_cl(const float* z, float* partial, long long P, long long sps, long long T, int nslots, long long G) {
+    CK(cudaFuncSetAttribute(cl::kernel<MODE, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cl::kSmem)));
+    cl::kernel<MODE, TM><<<unsigned(G), cl::kThreads, cl::kSmem>>>(g_tm[z == g_tm_base[0] ? 0 : 1], z, partial, P, sps, T, nslots);
+}
+
 int main(int argc, char** argv) {
     Ctx c{};
     c.B = argc > 1 ? atoi(argv[1]) : 32;
@@ -454,5 +610,15 @@ int main(int argc, char** argv) {
     { using C = pairk::Cfg<3, 3, 3, 4>; run("p4_3x3s3", c, C::kTilePx, true, launch_pair<C, FULL>); }   // 1152-px tiles (72 KB), 3 stages
     { using C = pairk::Cfg<3, 1, 8, 4>; run("p4_3x1s8", c, C::kTilePx, true, launch_pair<C, FULL>); }   // 384-px tiles (24 KB), 8 stages
     { using C = pairk::Cfg<3, 2, 4, 2>; run("p2_3x2s4", c, C::kTilePx, true, launch_pair<C, FULL>); }   // 6 + 1 warps, 2 px/thread, 384-px tiles
+    // channels-last: the same buffers read as [B][P][16]
+    make_maps(c);
+    ref_gram_cl<<<dim3(kTri, c.B), 256>>>(c.z[0], c.ref, c.P);
+    CK(cudaDeviceSynchronize());
+    run("cl_tm (shipped)", c, cl::kStagePx, true, launch_cl<FULL, true>);
+    run("cl_tm_mem", c, cl::kStagePx, false, launch_cl<MEM, true>);
+    run("cl_tm_alu", c, cl::kStagePx, false, launch_cl<ALU, true>);
+    run("cl_1d", c, cl::kStagePx, true, launch_cl<FULL, false>);
+    run("cl_1d_mem", c, cl::kStagePx, false, launch_cl<MEM, false>);
+    run("cl_1d_alu", c, cl::kStagePx, false, launch_cl<ALU, false>);
     return 0;
 }

@@ -181,29 +181,53 @@ __device__ __forceinline__ EpiMem resolve_mem(void* smem, void* global, int B, i
     return m;
 }
 
-// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M, one LANE per pair (no shuffle chain);
-// emit(a, c, D) is expected to fill both (a, c) and (c, a).  Consecutive lanes share a and walk c, so the
-// v_a loads broadcast and the v_c loads hit distinct banks (row stride 124 floats).  nthreads cooperate.
-// (a, c) of flat index pidx into the strict upper triangle of an M x M matrix (row a starts at a*(2M-a-1)/2)
-__device__ __forceinline__ void upper_pair(int pidx, int M, int& a, int& c) {
-    const float t = float(2 * M - 1);
-    a = int((t - sqrtf(t * t - 8.0f * float(pidx))) * 0.5f);
-    while (a > 0 && a * (2 * M - a - 1) / 2 > pidx) --a;
-    while ((a + 1) * (2 * M - a - 2) / 2 <= pidx) ++a;
-    c = a + 1 + (pidx - a * (2 * M - a - 1) / 2);
+// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M; emit(a, c, D) is expected to fill both (a, c)
+// and (c, a).  nthreads cooperate.
+//
+// Register-blocked: one thread owns FOUR rows a0 .. a0+3 (a0 a multiple of 4) against ONE column c, so a step of four
+// components costs five LDS.128 (four broadcast rows + one column) for four pairs instead of eight, and carries 16
+// independent FMA chains -- the one-pair-per-lane version ran at 0.35 instructions per cycle and scheduler with the 6-7
+// warps a tail has (3.3 us for 435 pairs; this one: tools/tail_phases.py).  Consecutive lanes walk c: the row loads
+// broadcast, the column loads hit distinct banks (row stride 124 floats).  Per pair the operations and their order are
+// exactly mmd_distance's, so D -- and everything derived from it -- keeps its bits.
+__device__ __forceinline__ int pair_tasks(int M) {            // sum over row blocks i of the columns c > 4i
+    int n = 0;
+    for (int a0 = 0; a0 + 1 < M; a0 += 4) n += M - 1 - a0;
+    return n;
 }
 
-// D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M, one LANE per pair (no shuffle chain);
-// emit(a, c, D) is expected to fill both (a, c) and (c, a).  Consecutive lanes share a and walk c, so the
-// v_a loads broadcast and the v_c loads hit distinct banks (row stride 124 floats).  nthreads cooperate.
-// (Two pairs per lane and step, interleaved for twice the independent chains, measured no faster: 2.7 vs 2.6 us.)
 template <typename F>
 __device__ __forceinline__ void pairwise_upper_n(const float* __restrict__ v, int M, int tid, int nthreads, F&& emit) {
-    const int npairs = M * (M - 1) / 2;
-    for (int pidx = tid; pidx < npairs; pidx += nthreads) {
-        int a, c;
-        upper_pair(pidx, M, a, c);
-        emit(a, c, mmd_distance(v + size_t(a) * kVStride, v + size_t(c) * kVStride));
+    const int ntasks = pair_tasks(M);
+    for (int t = tid; t < ntasks; t += nthreads) {
+        int a0 = 0, r = t;
+        while (r >= M - 1 - a0) { r -= M - 1 - a0; a0 += 4; }
+        const int c = a0 + 1 + r;
+        const float4* xc = reinterpret_cast<const float4*>(v + size_t(c) * kVStride);
+        const float4* xa[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xa[u] = reinterpret_cast<const float4*>(v + size_t(a0 + u < M ? a0 + u : M - 1) * kVStride);
+        float p[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) p[u][w] = 0.f;
+#pragma unroll 3
+        for (int e = 0; e < kOff / 4; ++e) {
+            const float4 y = xc[e];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float4 x = xa[u][e];
+                float d;
+                d = x.x - y.x; p[u][0] = fmaf(d, d, p[u][0]);
+                d = x.y - y.y; p[u][1] = fmaf(d, d, p[u][1]);
+                d = x.z - y.z; p[u][2] = fmaf(d, d, p[u][2]);
+                d = x.w - y.w; p[u][3] = fmaf(d, d, p[u][3]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (a0 + u < c) emit(a0 + u, c, clamp_tiny((p[u][0] + p[u][1]) + (p[u][2] + p[u][3])));
     }
 }
 
@@ -213,9 +237,11 @@ __device__ __forceinline__ void pairwise_upper_n(const float* __restrict__ v, in
 __device__ inline void domain_block_sums(const float* __restrict__ U, const DomainInfo& dom, double* __restrict__ blk,
                                          int first_warp, int nwarps, int warp, int lane) {
     const int K = dom.K;
-    for (int pr = warp - first_warp; pr < K * K; pr += nwarps) {
-        const int k = pr / K, l = pr - k * K;
-        if (l < k) continue;
+    // the K (K + 1) / 2 blocks with k <= l, dealt evenly to the warps (row-major over the upper triangle)
+    for (int pr = warp - first_warp; pr < K * (K + 1) / 2; pr += nwarps) {
+        int k = 0, l = pr;
+        while (l >= K - k) { l -= K - k; ++k; }
+        l += k;
         const int a0 = chunk_lo(k, dom.n, dom.B), a1 = chunk_lo(k + 1, dom.n, dom.B);
         const int c0 = chunk_lo(l, dom.n, dom.B), c1 = chunk_lo(l + 1, dom.n, dom.B);
         float s = 0.f;

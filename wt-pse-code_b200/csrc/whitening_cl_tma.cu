@@ -69,6 +69,11 @@ __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
 // phase) then touch all 32 banks exactly once.
 __device__ __forceinline__ uint32_t swz(int p, int q) { return uint32_t(p) * 64u + (uint32_t(q ^ ((p >> 1) & 3)) << 4); }
 
+// First 1024-byte boundary at or after p (the swizzled boxes need it).  Plain pointer arithmetic on the shared-memory
+// pointer: rounding through an integer makes the compiler lose the address space and every access to the stage buffers,
+// the matrices and the tail's working set becomes a generic LD / ST (the address-divergence unit).
+__device__ __forceinline__ unsigned char* align1024(unsigned char* p) { return p + ((1024u - (smem_u32(p) & 1023u)) & 1023u); }
+
 __device__ __forceinline__ float4 lds4(const unsigned char* base, uint32_t off) { return *reinterpret_cast<const float4*>(base + off); }
 __device__ __forceinline__ void sts4(unsigned char* base, uint32_t off, const float4& v) { *reinterpret_cast<float4*>(base + off) = v; }
 
@@ -112,6 +117,47 @@ __device__ __forceinline__ void flush_gram(float (&acc)[kTri], float* red, int w
     named_bar_sync(1, kConsumers);
 }
 
+// ---- packed accumulation (fma.rn.f32x2, SASS FFMA2) ----------------------------------------------------------------------
+// A pixel's 16 channels arrive as four float4: eight natural register pairs P_I = (x_2I, x_2I+1).  For a 2x2 block of
+// Gram entries (channel pairs I <= J) two packed FMAs cover all four products:
+//     D[I][J] += P_I * P_J        = (x_2I x_2J   , x_2I+1 x_2J+1)      "diagonal" of the block
+//     A[I][J] += P_I * swap(P_J)  = (x_2I x_2J+1 , x_2I+1 x_2J  )      "anti-diagonal"
+// so a pixel costs 72 FFMA2 + 16 moves (the eight swapped pairs) instead of 136 FFMA -- the kernel was bound by
+// instruction issue, not by HBM.  On the diagonal blocks (I == J) A's two lanes hold the same product; eight of the
+// 144 lanes are redundant.  Every lane is an IEEE fma of the same operands in the same pixel order as the scalar
+// loop it replaces: the sums are bit-identical to it.
+constexpr int kPairAcc = 72;                         // 36 blocks (I <= J) x {D, A}
+__host__ __device__ constexpr int blk36(int I, int J) { return I * 8 - (I * (I - 1)) / 2 + (J - I); }
+
+__device__ __forceinline__ void gram_accumulate_pairs(float2 (&acc2)[kPairAcc], const float4 (&r)[4]) {
+    const float2 P[8] = {make_float2(r[0].x, r[0].y), make_float2(r[0].z, r[0].w), make_float2(r[1].x, r[1].y), make_float2(r[1].z, r[1].w),
+                         make_float2(r[2].x, r[2].y), make_float2(r[2].z, r[2].w), make_float2(r[3].x, r[3].y), make_float2(r[3].z, r[3].w)};
+    float2 S[8];
+#pragma unroll
+    for (int J = 0; J < 8; ++J) S[J] = make_float2(P[J].y, P[J].x);
+#pragma unroll
+    for (int I = 0; I < 8; ++I)
+#pragma unroll
+        for (int J = I; J < 8; ++J) {
+            acc2[2 * blk36(I, J)] = __ffma2_rn(P[I], P[J], acc2[2 * blk36(I, J)]);
+            acc2[2 * blk36(I, J) + 1] = __ffma2_rn(P[I], S[J], acc2[2 * blk36(I, J) + 1]);
+        }
+}
+
+// packed accumulators -> the 136 upper-triangle sums in packed (tri_idx) order
+__device__ __forceinline__ void unpack_pairs(const float2 (&acc2)[kPairAcc], float (&acc)[kTri]) {
+#pragma unroll
+    for (int I = 0; I < 8; ++I)
+#pragma unroll
+        for (int J = I; J < 8; ++J) {
+            const float2 D = acc2[2 * blk36(I, J)], A = acc2[2 * blk36(I, J) + 1];
+            acc[tri_idx(2 * I, 2 * J)] = D.x;
+            acc[tri_idx(2 * I + 1, 2 * J + 1)] = D.y;
+            acc[tri_idx(2 * I, 2 * J + 1)] = A.x;
+            if (I < J) acc[tri_idx(2 * I + 1, 2 * J)] = A.y;
+        }
+}
+
 // ------------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------------
@@ -124,7 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 gram_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_relu, float* __restrict__ partial,
                    int* __restrict__ slot_count, long long stages_per_sample, long long T, int nslots, int fused_tail, TailParams tp) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* stage_buf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* stage_buf = align1024(smem_dyn);
     float* red = reinterpret_cast<float*>(stage_buf + size_t(kGramStages) * kPartBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(red + kConsumerWarps * kTri);
     uint64_t* empty = full + kGramStages;
@@ -175,9 +221,9 @@ gram_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_consta
     }
 
     TailClock clk;
-    float acc[kTri];
+    float2 acc2[kPairAcc];
 #pragma unroll
-    for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+    for (int e = 0; e < kPairAcc; ++e) acc2[e] = make_float2(0.f, 0.f);
     int stage = 0, prev_stage = -1;
     uint32_t phase = 0;
     for (long long b = walk.b_first; b <= walk.b_last; ++b) {
@@ -196,12 +242,7 @@ gram_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 4; ++q) sts4(sb, swz(p, q), relu4(r[q]));
                 }
-                const float x[kC] = {r[0].x, r[0].y, r[0].z, r[0].w, r[1].x, r[1].y, r[1].z, r[1].w,
-                                     r[2].x, r[2].y, r[2].z, r[2].w, r[3].x, r[3].y, r[3].z, r[3].w};
-#pragma unroll
-                for (int i = 0; i < kC; ++i)
-#pragma unroll
-                    for (int jj = i; jj < kC; ++jj) acc[tri_idx(i, jj)] = fmaf(x[i], x[jj], acc[tri_idx(i, jj)]);
+                gram_accumulate_pairs(acc2, r);
             }
             if (kRelu) {
                 // the warp's 64 pixels of relu(z) leave from the stage itself; the stage goes back to the producer one
@@ -225,7 +266,11 @@ gram_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_consta
         const long long first_cta = part_owner(b * stages_per_sample, T, G);
         const long long slot = k - first_cta;
         clk.mark(0);
-        flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+        {
+            float acc[kTri];
+            unpack_pairs(acc2, acc);
+            flush_gram(acc, red, warp, lane, tid, partial + (b * nslots + slot) * kTri);
+        }
         clk.mark(1);
         if (fused_tail) {
             if (kRelu && lane == 0) tma_store_wait_read<0>();      // the tail's whole-batch phase reuses the stage buffers
@@ -235,7 +280,7 @@ gram_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_consta
             slot_count[b] = int(k - first_cta + 1);
         }
 #pragma unroll
-        for (int e = 0; e < kTri; ++e) acc[e] = 0.f;
+        for (int e = 0; e < kPairAcc; ++e) acc2[e] = make_float2(0.f, 0.f);
     }
     if (kRelu && lane == 0) tma_store_wait<0>();                   // all of this warp's stores have left before the CTA exits
 }
@@ -276,7 +321,7 @@ apply_cl_tma_kernel(const __grid_constant__ CUtensorMap tm_z, const __grid_const
     using Cfg = ApplyCfg<kReluGrad>;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* stage_buf = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* stage_buf = align1024(smem_dyn);
     unsigned char* out_buf = stage_buf + size_t(kStages) * Cfg::kStageBytes;       // [warp][box]: results on their way out
     float* msh2 = reinterpret_cast<float*>(out_buf + Cfg::kPartBytes);
     uint64_t* full = reinterpret_cast<uint64_t*>(msh2 + 512);

@@ -142,25 +142,29 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
     float* coef = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + epi_mem_bytes(B, M, tp.K));
     float* wdom = coef + round4(size_t(M) * M);        // [K][K]: the domain-pair weight of mmd_coefficient, computed once
 
-    // A. stage the vectors and the row statistics the sample reducers left in global memory
+    // A. stage the vectors and the row statistics the sample reducers left in global memory.  Every load of the first
+    //    pass (8 vector pieces + one statistic per thread) is issued before anything is stored: one L2 round trip for
+    //    M <= 48, B <= NT / 2.
     {
         const float4* src4 = reinterpret_cast<const float4*>(tp.vd);
         float4* dst4 = reinterpret_cast<float4*>(mem.v);
         const int n4 = M * (kVStride / 4);
-        for (int base = 0; base < n4; base += 4 * NT) {
-            float4 v[4];
+        const float st0 = tid < 2 * B ? __ldcg(tp.rowstat + tid) : 0.f;
+        for (int base = 0; base < n4; base += 8 * NT) {
+            float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int idx = base + u * NT + tid;
                 v[u] = idx < n4 ? __ldcg(src4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < 8; ++u) {
                 const int idx = base + u * NT + tid;
                 if (idx < n4) dst4[idx] = v[u];
             }
         }
-        for (int idx = tid; idx < 2 * B; idx += NT) mem.stat[idx] = __ldcg(tp.rowstat + idx);
+        if (tid < 2 * B) mem.stat[tid] = st0;
+        for (int idx = NT + tid; idx < 2 * B; idx += NT) mem.stat[idx] = __ldcg(tp.rowstat + idx);
         // mmd_coefficient(dom, a, c, E) = E * w(domain of a, domain of c) / npairs: tabulate w * (1 / 1) per domain pair
         // with the very expressions mmd_coefficient uses, so the product below has its bits
         for (int idx = tid; idx < tp.K * tp.K; idx += NT) {
@@ -200,7 +204,8 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
     named_bar_sync(bar, NT);
     if (stamp) tp.stamps[8] = clock64();
 
-    // C. instance terms (warp 0), per-domain-pair block sums (the other warps)
+    // C. per-domain-pair block sums (all warps, one block each for K = 3), instance terms (warp 0)
+    if (M > 0) domain_block_sums(mem.U, dom, mem.blk, 0, kWarps, warp, lane);
     if (warp == 0) {
         float so = 0.f, sd = 0.f;
         for (int b = lane; b < B; b += 32) {
@@ -214,8 +219,6 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
             tp.losses[1] = sd;
             tp.losses[3] = so + sd;
         }
-    } else if (M > 0) {
-        domain_block_sums(mem.U, dom, mem.blk, 1, kWarps - 1, warp, lane);
     }
     // D'. d L_dom / d v_b[o] for every MMD sample (needs only v and coef: overlaps C's tail)
     for (int idx = tid; idx < M * (kOff / 4); idx += NT) {
