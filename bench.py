@@ -1052,6 +1052,9 @@ def run_wavelet(args):
     wb._lib.debug_set("wavelet_cluster_max", int(args.wavelet_cluster_max))
     wb._lib.debug_set("wavelet_tiles", int(args.wavelet_tiles))
     wb._lib.debug_set("wavelet_peel_max", int(args.wavelet_peel_max))
+    for item in args.debug:
+        name, _, val = item.partition("=")
+        wb._lib.debug_set(name, int(val))
     cs = wvm.resident_cluster_size(H, W, wv, J)
     xs = [torch.softmax(3 * torch.randn(B, C, H, W, device=dev), 1).requires_grad_(True) for _ in range(4)]
     one = torch.ones((), device=dev)

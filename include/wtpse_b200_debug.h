@@ -33,6 +33,8 @@ int         wtpse_profile_read(int id, long long* timed_launches, double* total_
  *   "wavelet_resident"     0 makes wtpse_wavelet_resident_cluster report 0 for every shape (per-level kernels)
  *   "wavelet_split"        fused-plan choice: -1 automatic, 0 whole map resident whenever it fits, 1 level 1 streamed
  *   "wavelet_tiles"        level 1 of the streamed plan as TMA pipelines (1, default) or per-thread loads (0)
+ *   "wavelet_db2"          db2 streamed levels: factored one-/two-level passes of wavelet_db2.cu (1, default) or the round-1 level kernels (0)
+ *   "wavelet_db2_two"      0: the factored passes take one level each (LL1 goes through memory)
  *   "wavelet_peel_max"     most levels streamed before the resident stage (default 8)
  *   "wavelet_cluster_max"  largest cluster size of the resident stage (1..8, default 8)
  * Return WTPSE_OK, or WTPSE_ERR_INVALID for an unknown name. */

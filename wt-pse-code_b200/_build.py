@@ -14,7 +14,7 @@ OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libwtpse_b200.so")
 SOURCES = ["api.cu", "whitening_gram.cu", "whitening_epilogue.cu", "whitening_apply.cu", "whitening_apply_relu.cu", "whitening_apply_cl.cu",
            "whitening_cl_tma.cu", "mse.cu", "profile.cu", "elementwise.cu", "backbone_elementwise.cu", "batchnorm.cu",
-           "wavelet.cu", "wavelet_resident.cu", "wavelet_stream.cu", "wavelet_tiles.cu"]
+           "wavelet.cu", "wavelet_resident.cu", "wavelet_stream.cu", "wavelet_tiles.cu", "wavelet_db2.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -246,6 +246,11 @@ const Knob* knobs(int* count) {
         {"cl_tma_launches", &g_cl_tma_launches, 0, 0},            // counter (setting it resets it to 0)                              // channels-last kernels: tensor-map TMA pipelines (1) or per-thread loads (0)
         {"wavelet_resident", &g_wavelet_resident, 0, 1},
         {"wavelet_tiles", &g_wavelet_tiles, 0, 1},
+        {"wavelet_db2", &g_wavelet_db2, 0, 1},
+        {"wavelet_db2_two", &g_wavelet_db2_two, 0, 1},
+        {"wavelet_db2_rf", &g_wavelet_db2_rf, 0, 64},
+        {"wavelet_db2_ri", &g_wavelet_db2_ri, 0, 128},
+        {"wavelet_db2_nw2", &g_wavelet_db2_nw2, 0, 12},
         {"wavelet_peel_max", &g_wavelet_peel_max, 1, 16},
         {"wavelet_split", &g_wavelet_split, -1, 1},
         {"wavelet_cluster_max", &g_wavelet_cluster_max, 1, 8},

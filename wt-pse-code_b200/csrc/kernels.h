@@ -158,6 +158,17 @@ cudaError_t launch_dwt1_tiles(const float* x, float* ll, unsigned char* sg, int 
 cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float* out, int nmaps, int H, int W, int taps, int R,
                                int S, float sc, const float* upstream, bool has_ll, const double* partial, int n_partials,
                                float* loss, int sm_count, cudaStream_t stream);
+// db2 levels in factored form, one or two levels per pass (wavelet_db2.cu)
+extern int g_wavelet_db2;
+extern int g_wavelet_db2_two;
+extern int g_wavelet_db2_rf, g_wavelet_db2_ri, g_wavelet_db2_nw2;
+bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv);
+cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,
+                                float sc1, float sc2, bool grad, bool pdl_wait, double* partial, int sm_count, cudaStream_t stream,
+                                int* n_partials);
+cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const unsigned char* sg2, float* out, int nmaps, int H, int W,
+                                 bool two, bool has_ll, float sc1, float sc2, const float* upstream, const double* partial, int n_partials,
+                                 float* loss, int sm_count, cudaStream_t stream);
 cudaError_t launch_scale_unless_one(float* data, long long n, const float* scale, int sm_count, cudaStream_t stream);
 
 }  // namespace wtpse

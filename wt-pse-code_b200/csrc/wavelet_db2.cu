@@ -1,0 +1,739 @@
+// Track W, db2: the streamed levels of the fused plan as persistent TMA pipelines that take ONE or TWO levels per pass,
+// with the 4-tap filter bank in factored form.  PARITY UNPINNED (oracle/wavelet_np.py is this repository's own spec).
+//
+// Factored db2.  With a_j = x[2j], b_j = x[2j+1] and h = [h0 h1 h2 h3] the orthonormal db2 filter, the ratios
+// h0/h1 = -h3/h2 = 1/sqrt3 and h1/h0 = -h2/h3 = sqrt3 give
+//     p_j = b_j + a_j / sqrt3,   q_j = b_j - sqrt3 a_j,
+//     lo_j = h1 (p_j + (h3/h1) q_{j+1}),        hi_j = -h2 (p_j + (h0/h2) q_{j+1})
+// i.e. 4 fused multiply-adds per (lo, hi) pair instead of 8, and the scales h1, -h2 never have to be applied: the L1
+// loss takes |.| and sign(.) of the detail bands (the scales are positive constants folded into the level weight, the
+// two sign flips into the synthesis constants), and only the low-low band that leaves the pass is multiplied by h1^2.
+// The adjoint runs the same two stages backwards: pbar_j = h1 lo_j - h2 hi_j, qbar_{j+1} = h3 lo_j - h0 hi_j,
+// a_j = (pbar_j - 3 qbar_j) / sqrt3, b_j = pbar_j + qbar_j (5 operations per pair instead of 10).
+//
+//   db2_analysis_kernel   strip of input rows (TMA ring) -> level 1 [-> low-low rows in shared memory -> level 2]
+//                         -> low-low band of the last level (global), one sign byte per site and level, |d| partial sums.
+//                         A thread owns two adjacent sites and walks down the rows of its segment.
+//   db2_synthesis_kernel  piece of coefficient rows: [gradient of LL2 + signs of level 2 -> gradient of LL1 in shared
+//                         memory ->] + signs of level 1 -> 2 output rows per coefficient row, 128-bit coalesced stores.
+//                         A WARP owns whole coefficient rows (lane l: sites 64k + 2l, 64k + 2l + 1), so the one value a
+//                         site needs from its left neighbour comes through a shuffle and the periodic wrap is lane 31 ->
+//                         lane 0; the row above is carried in registers.
+// Two levels per pass keep LL1 (a quarter of the map, written and read twice by the one-level plan) out of memory: the
+// pass moves 4.6 B per element instead of 5.25 + 1.3, and the resident stage that follows works on 1/16 of the map.
+#include <math.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace wtpse {
+
+namespace {
+
+constexpr double kS3d = 1.7320508075688772935;
+constexpr double kS2d = 1.4142135623730950488;
+constexpr double kH0d = (1.0 + kS3d) / (4.0 * kS2d), kH1d = (3.0 + kS3d) / (4.0 * kS2d);
+constexpr double kH2d = (3.0 - kS3d) / (4.0 * kS2d), kH3d = (1.0 - kS3d) / (4.0 * kS2d);
+constexpr float kI3 = float(1.0 / kS3d);            // 1 / sqrt3
+constexpr float kR3 = float(kS3d);                  // sqrt3
+constexpr float kKl = float(kH3d / kH1d);           // h3 / h1  (< 0)
+constexpr float kKh = float(kH0d / kH2d);           // h0 / h2
+constexpr float k3Kl = float(3.0 * kH3d / kH1d);
+constexpr float k3Kh = float(3.0 * kH0d / kH2d);
+constexpr float kThird = float(1.0 / 3.0);
+constexpr float kH11 = float(kH1d * kH1d);          // scale of LL
+constexpr float kH12 = float(kH1d * kH2d);          // |scale| of LH, HL
+constexpr float kH22 = float(kH2d * kH2d);          // scale of HH
+
+constexpr int kDb2MaxThreads = 544;                 // 16 consumer warps + the producer warp
+constexpr int kDb2Smem = 226 * 1024;
+constexpr uint32_t kDb2Chunk = 32 * 1024;
+
+__device__ __forceinline__ void bulk_rows(unsigned char* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy, bool hint) {
+    const char* s = static_cast<const char*>(src);
+    for (uint32_t o = 0; o < bytes; o += kDb2Chunk) {
+        const uint32_t n = min(kDb2Chunk, bytes - o);
+        if (hint) tma_load_1d_hint(dst + o, s + o, n, bar, policy);
+        else tma_load_1d(dst + o, s + o, n, bar);
+    }
+}
+
+// rows [a, a + n) of a periodic plane of `hrows` rows (a may be negative, a + n <= hrows + (a < 0 ? 0 : ...)): at most two
+// contiguous pieces.  Returns the bytes queued.
+__device__ __forceinline__ uint32_t bulk_rows_wrapped(unsigned char* dst, const unsigned char* plane, uint32_t row_bytes, int a, int n,
+                                                      int hrows, uint64_t* bar, uint64_t policy, bool hint) {
+    int done = 0;
+    while (done < n) {
+        int r = a + done;
+        r %= hrows;
+        if (r < 0) r += hrows;
+        const int len = min(n - done, hrows - r);
+        bulk_rows(dst + size_t(done) * row_bytes, plane + size_t(r) * row_bytes, uint32_t(len) * row_bytes, bar, policy, hint);
+        done += len;
+    }
+    return uint32_t(n) * row_bytes;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// analysis
+// ------------------------------------------------------------------------------------------------------------------
+
+// sign code of a detail value as HALF the 2-bit code: 0 (negative), 0.5 (zero), 1 (positive) -- one saturating FMA.
+// (|v| < 2^-126 counts as zero; NaN gives 0.)
+__device__ __forceinline__ float half_code(float v) { return __saturatef(fmaf(v, 4.2535295865117308e37f, 0.5f)); }
+
+// along W: unscaled low / high pass of one row for the two sites at input columns c0 .. c0+3 (c4 = c0 + 4, wrapped)
+__device__ __forceinline__ void db2_row(const float* row, int c0, int c4, float& l0, float& g0, float& l1, float& g1) {
+    const float4 v = *reinterpret_cast<const float4*>(row + c0);
+    const float2 u = *reinterpret_cast<const float2*>(row + c4);
+    const float p0 = fmaf(v.x, kI3, v.y), p1 = fmaf(v.z, kI3, v.w);
+    const float q1 = fmaf(v.z, -kR3, v.w), q2 = fmaf(u.x, -kR3, u.y);
+    l0 = fmaf(q1, kKl, p0); g0 = fmaf(q1, kKh, p0);
+    l1 = fmaf(q2, kKl, p1); g1 = fmaf(q2, kKh, p1);
+}
+
+struct Db2FwdArgs {
+    const float* x;         // [nmaps][H][W]
+    float* ll;              // low-low band of the LAST level of the pass: [nmaps][H/2][W/2] or [nmaps][H/4][W/4]
+    unsigned char* sg1;     // [nmaps][H/2][W/2]
+    unsigned char* sg2;     // [nmaps][H/4][W/4] (two levels)
+    int H, W, nmaps, R, stages, pdl_wait, nw2, seg1, seg2;   // R: rows of the last level per strip; nw2: warps of the level-2 group; segN: rows per thread task
+    float sc1, sc2;         // w_j / (3 * sites of level j * nmaps)
+    double* partial;        // one per CTA
+};
+
+// One level on a strip in shared memory.  in: rows_out * 2 + 2 rows of width w (row stride w) at byte offset in_off.
+// Output row i < n_own: sign byte + |d| (rows beyond are halo rows of the next level: low-low only).
+//   kLLSmem: low-low rows (times h1^2) -> shared memory at ll_off, row stride w / 2; else -> ll_g (row stride w / 2).
+template <bool kLLSmem, bool kGrad>
+__device__ __forceinline__ void db2_fwd_level(int in_off, int w, int rows_out, int n_own, int seg, int ll_off, float* __restrict__ ll_g,
+                                              unsigned char* __restrict__ sg_g, float sc, float& ab, int tid, int nthreads) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const float* in = reinterpret_cast<const float*>(smem + in_off);
+    float* ll_s = reinterpret_cast<float*>(smem + (kLLSmem ? ll_off : 0));
+    const bool store_ll = ll_g != nullptr;                  // the deepest level's low-low band is not needed by anybody
+    const int w2 = w >> 1, pairs = w >> 2;
+    const int nseg = (rows_out + seg - 1) / seg;
+    const int ntasks = nseg * pairs;
+    for (int task = tid; task < ntasks; task += nthreads) {
+        const int jj = task % pairs, si = task / pairs;
+        const int i0 = si * seg, i1 = min(i0 + seg, rows_out), c0 = 4 * jj;
+        int c4 = c0 + 4;
+        if (c4 >= w) c4 -= w;
+        // running pointers (byte arithmetic once per task, not per row)
+        const float* r0 = in + (2 * i0) * w + c0;                   // columns c0 .. c0 + 3 of the current even row
+        const float* r4 = in + (2 * i0) * w + c4;                   // columns c0 + 4, c0 + 5 (wrapped)
+        float P[4];
+        {
+            float a[4], b[4];
+            db2_row(r0, 0, int(r4 - r0), a[0], a[1], a[2], a[3]);
+            db2_row(r0 + w, 0, int(r4 - r0), b[0], b[1], b[2], b[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) P[u] = fmaf(a[u], kI3, b[u]);
+        }
+        const int d4 = int(r4 - r0);
+        float* llp_s = ll_s + i0 * w2 + 2 * jj;
+        float* llp_g = ll_g + (long long)i0 * w2 + 2 * jj;
+        unsigned char* sgp = sg_g + (long long)i0 * w2 + 2 * jj;
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = i0; i < i1; ++i) {
+            r0 += 2 * w;
+            float a[4], b[4], lo[4], hi[4];
+            db2_row(r0, 0, d4, a[0], a[1], a[2], a[3]);
+            db2_row(r0 + w, 0, d4, b[0], b[1], b[2], b[3]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float Pn = fmaf(a[u], kI3, b[u]), Qn = fmaf(a[u], -kR3, b[u]);
+                lo[u] = fmaf(Qn, kKl, P[u]);
+                hi[u] = fmaf(Qn, kKh, P[u]);
+                P[u] = Pn;
+            }
+            // arrays: 0 = low along W of site 0, 1 = high along W of site 0, 2 / 3 = the same for site 1
+            // unscaled bands: LL = lo[0], HL = hi[0] (high along H), LH = lo[1], HH = hi[1]
+            const float2 LL = make_float2(lo[0] * kH11, lo[2] * kH11);
+            if (kLLSmem) *reinterpret_cast<float2*>(llp_s) = LL;
+            else if (store_ll) *reinterpret_cast<float2*>(llp_g) = LL;
+            if (i < n_own) {
+                s1 += (fabsf(lo[1]) + fabsf(hi[0])) + (fabsf(lo[3]) + fabsf(hi[2]));
+                s2 += fabsf(hi[1]) + fabsf(hi[3]);
+                if (kGrad) {
+                    // 2-bit codes (0 negative, 1 zero, 2 positive) of LH | HL << 2 | HH << 4 per site, site 1 in the high byte,
+                    // accumulated in the integer part of a float (1.5 * 2^23 + n has bit pattern 0x4B400000 + n)
+                    float acc = 12582912.0f;
+                    acc = fmaf(half_code(lo[1]), 2.0f, acc);
+                    acc = fmaf(half_code(hi[0]), 8.0f, acc);
+                    acc = fmaf(half_code(hi[1]), 32.0f, acc);
+                    acc = fmaf(half_code(lo[3]), 512.0f, acc);
+                    acc = fmaf(half_code(hi[2]), 2048.0f, acc);
+                    acc = fmaf(half_code(hi[3]), 8192.0f, acc);
+                    *reinterpret_cast<unsigned short*>(sgp) = static_cast<unsigned short>(__float_as_uint(acc));
+                }
+            }
+            llp_s += w2;
+            llp_g += w2;
+            sgp += w2;
+        }
+        ab += sc * fmaf(kH12, s1, kH22 * s2);
+    }
+}
+
+template <bool kTwo, bool kGrad>
+__global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_analysis_kernel(Db2FwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int H = a.H, W = a.W, R = a.R, S = a.stages;
+    // warps: [0, NW1) level 1, [NW1, NW1 + NW2) level 2 (two-level pass only), then the producer warp.  The two consumer
+    // groups work on DIFFERENT strips at any time (level 2 of strip n overlaps level 1 of strip n + 1), handing the LL1 rows
+    // over through two shared-memory buffers guarded by mbarriers.
+    const int NW2 = kTwo ? a.nw2 : 0;
+    const int NW1 = int(blockDim.x) / 32 - 1 - NW2;
+    const int hl = kTwo ? H >> 2 : H >> 1;                  // rows of the last level
+    const int rows_in = kTwo ? 4 * R + 6 : 2 * R + 2;
+    const int n1 = kTwo ? 2 * R + 2 : R;                    // level-1 rows a strip computes
+    const uint32_t stage_bytes = uint32_t(rows_in) * W * 4u;
+    const int ll1_bytes = kTwo ? n1 * (W >> 1) * 4 : 0;     // one of the two LL1 buffers
+    const int ll1_off = int(S * stage_bytes);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + ll1_off + 2 * ll1_bytes);
+    uint64_t* empty = full + S;
+    uint64_t* ll_full = empty + S;                          // [2]
+    uint64_t* ll_empty = ll_full + 2;                       // [2]
+    const int spm = hl / R;                                 // strips per map
+    const long long T = (long long)a.nmaps * spm;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&ll_full[b], NW1);
+            mbar_init(&ll_empty[b], NW2 > 0 ? NW2 : 1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");     // input written by the pass in front of this one
+
+    double acc = 0.0;
+    const int h2 = H >> 1, w2 = W >> 1, w4 = W >> 2;
+    if (warp == NW1 + NW2) {
+        if (lane == 0) {
+            const uint64_t policy = make_evict_first_policy();
+            int n = 0;
+            for (long long t = blockIdx.x; t < T; t += gridDim.x, ++n) {
+                const int s = n % S;
+                if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
+                const long long m = t / spm;
+                const int r0 = (kTwo ? 4 : 2) * R * int(t % spm);
+                const unsigned char* plane = reinterpret_cast<const unsigned char*>(a.x + m * (long long)H * W);
+                mbar_arrive_expect_tx(&full[s], stage_bytes);
+                bulk_rows_wrapped(smem + size_t(s) * stage_bytes, plane, uint32_t(W) * 4u, r0, rows_in, H, &full[s], policy, true);
+            }
+        }
+    } else if (warp < NW1) {
+        const int tid = threadIdx.x, NC1 = NW1 * 32;
+        float ab = 0.f;
+        int n = 0;
+        for (long long t = blockIdx.x; t < T; t += gridDim.x, ++n) {
+            const int s = n % S;
+            const long long m = t / spm;
+            const int st = int(t % spm);
+            mbar_wait(&full[s], (n / S) & 1);
+            if (!kTwo) {
+                const long long row0 = m * h2 + (long long)R * st;
+                db2_fwd_level<false, kGrad>(int(s * stage_bytes), W, R, R, a.seg1, 0, a.ll ? a.ll + row0 * w2 : nullptr, a.sg1 + row0 * w2, a.sc1, ab, tid, NC1);
+            } else {
+                const int b = n & 1, k = n >> 1;
+                if (k > 0) mbar_wait(&ll_empty[b], (k & 1) ^ 1);                // level 2 is done with this buffer's previous strip
+                const long long row1 = m * h2 + (long long)2 * R * st;          // first level-1 row of the strip
+                db2_fwd_level<true, kGrad>(int(s * stage_bytes), W, n1, 2 * R, a.seg1, ll1_off + b * ll1_bytes, nullptr, a.sg1 + row1 * w2, a.sc1, ab, tid,
+                                           NC1);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ll_full[b]);                        // release: the LL1 rows this warp wrote
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);                              // the input rows are free
+            acc += double(ab);
+            ab = 0.f;
+        }
+    } else {
+        // level 2 of the two-level pass
+        const int tid = threadIdx.x - NW1 * 32, NC2 = NW2 * 32;
+        float ab = 0.f;
+        int n = 0;
+        for (long long t = blockIdx.x; t < T; t += gridDim.x, ++n) {
+            const long long m = t / spm;
+            const int st = int(t % spm);
+            const int b = n & 1, k = n >> 1;
+            mbar_wait(&ll_full[b], k & 1);
+            const long long row2 = m * (H >> 2) + (long long)R * st;
+            db2_fwd_level<false, kGrad>(ll1_off + b * ll1_bytes, w2, R, R, a.seg2, 0, a.ll ? a.ll + row2 * w4 : nullptr, a.sg2 + row2 * w4, a.sc2, ab, tid, NC2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ll_empty[b]);
+            acc += double(ab);
+            ab = 0.f;
+        }
+    }
+
+    __shared__ double red[kDb2MaxThreads / 32];
+    const double sum = warp_sum(acc);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int q = 0; q < int(blockDim.x) / 32; ++q) tot += red[q];
+        a.partial[blockIdx.x] = tot;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// synthesis
+// ------------------------------------------------------------------------------------------------------------------
+
+// 2-bit code -> -1 / 0 / +1 (0x4B400000 is 1.5 * 2^23)
+__device__ __forceinline__ float sgn2(unsigned b, int shift) {
+    return __uint_as_float(0x4B400000u | ((b >> shift) & 3u)) - 12582913.0f;
+}
+
+struct SynConst {
+    float cLL, cLLq, c1, c2, c2q;      // h1^2 g, 3 (h3/h1) h1^2 g, h1 h2 sc g, h2^2 sc g, 3 (h0/h2) h2^2 sc g   (g = upstream gradient)
+};
+
+__device__ __forceinline__ SynConst make_syn_const(float sc, float gs) {
+    SynConst c;
+    c.cLL = kH11 * gs;
+    c.cLLq = k3Kl * c.cLL;
+    c.c1 = kH12 * sc * gs;
+    c.c2 = kH22 * sc * gs;
+    c.c2q = k3Kh * c.c2;
+    return c;
+}
+
+// Synthesis along H of ONE site: its LL gradient g and sign byte bs, the carried 3 * qbar of the coefficient row above.
+// Outputs (when kOut): the column-synthesised values of the even (A) and odd (B) output row for the "low along W" array
+// (already times h1) and the "high along W" array (already times -h2); always: the carries of this row.
+template <bool kHasLL, bool kOut>
+__device__ __forceinline__ void syn_vert_site(float g, unsigned bs, const SynConst& c, float q3lo_in, float q3hi_in, float& q3lo_out,
+                                              float& q3hi_out, float& Alo, float& Blo, float& Ahi, float& Bhi) {
+    const float sLH = sgn2(bs, 0), sHL = sgn2(bs, 2), sHH = sgn2(bs, 4);
+    const float e = c.c1 * sHL;
+    const float pb = kHasLL ? fmaf(c.cLL, g, e) : e;
+    const float qn = kHasLL ? fmaf(k3Kh, e, c.cLLq * g) : k3Kh * e;
+    const float lam = c.c1 * sLH;
+    const float pbh = fmaf(c.c2, sHH, lam);
+    const float qnh = fmaf(c.c2q, sHH, k3Kl * lam);
+    if (kOut) {
+        Alo = kI3 * (pb - q3lo_in);
+        Blo = fmaf(q3lo_in, kThird, pb);
+        Ahi = kI3 * (pbh - q3hi_in);
+        Bhi = fmaf(q3hi_in, kThird, pbh);
+    }
+    q3lo_out = qn;
+    q3hi_out = qnh;
+}
+
+// One level, executed by one warp on the coefficient rows [ra, rb) of a shared-memory buffer whose row ra - 1 is the row
+// above (ra >= 1).  g rows: fp32, row stride wj = 64 K; sign rows: bytes, row stride wj.  Output row 2 (r - 1) + pr:
+//   kToSmem: shared memory at out_off + (2 (r - 1) + pr) * 2 wj floats;   else out_g + (2 (r - 1) + pr) * out_ld.
+template <int K, bool kHasLL, bool kToSmem>
+__device__ __forceinline__ void db2_inv_rows(int g_off, int sg_off, int ra, int rb, const SynConst& c, int out_off, float* __restrict__ out_g,
+                                             long long out_ld, int lane) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int wj = 64 * K;
+    const float* gbase = reinterpret_cast<const float*>(smem + (kHasLL ? g_off : 0));
+    const unsigned char* sbase = smem + sg_off;
+    float* outs = reinterpret_cast<float*>(smem + (kToSmem ? out_off : 0));
+    float q3lo[K][2], q3hi[K][2];
+    {   // the row above: carries only
+        const float* grow = gbase + (ra - 1) * wj + 2 * lane;
+        const unsigned char* srow = sbase + (ra - 1) * wj + 2 * lane;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float2 g2 = make_float2(0.f, 0.f);
+            if (kHasLL) g2 = *reinterpret_cast<const float2*>(grow + 64 * k);
+            const unsigned b = *reinterpret_cast<const unsigned short*>(srow + 64 * k);
+            float d0, d1, d2, d3;
+            syn_vert_site<kHasLL, false>(g2.x, b, c, 0.f, 0.f, q3lo[k][0], q3hi[k][0], d0, d1, d2, d3);
+            syn_vert_site<kHasLL, false>(g2.y, b >> 8, c, 0.f, 0.f, q3lo[k][1], q3hi[k][1], d0, d1, d2, d3);
+        }
+    }
+    for (int r = ra; r < rb; ++r) {
+        const float* grow = gbase + r * wj + 2 * lane;
+        const unsigned char* srow = sbase + r * wj + 2 * lane;
+        // the value lane 0 needs for its first site of chunk 0: 3 * qbar (along W) of the row's LAST site (lane 31, chunk K - 1,
+        // site 1), for both output rows -- computed by every lane for its own last site (pure, the carries are not touched)
+        float left[2];
+        {
+            float g = 0.f;
+            if (kHasLL) g = grow[64 * (K - 1) + 1];
+            const unsigned bs = srow[64 * (K - 1) + 1];
+            float qa, qb, Alo, Blo, Ahi, Bhi;
+            syn_vert_site<kHasLL, true>(g, bs, c, q3lo[K - 1][1], q3hi[K - 1][1], qa, qb, Alo, Blo, Ahi, Bhi);
+            const float w0 = fmaf(k3Kh, Ahi, k3Kl * Alo), w1 = fmaf(k3Kh, Bhi, k3Kl * Blo);
+            left[0] = __shfl_sync(0xffffffffu, w0, 31);
+            left[1] = __shfl_sync(0xffffffffu, w1, 31);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float2 g2 = make_float2(0.f, 0.f);
+            if (kHasLL) g2 = *reinterpret_cast<const float2*>(grow + 64 * k);
+            const unsigned b = *reinterpret_cast<const unsigned short*>(srow + 64 * k);
+            float Xlo[2][2], Xhi[2][2];                       // [output row parity][site]
+            syn_vert_site<kHasLL, true>(g2.x, b, c, q3lo[k][0], q3hi[k][0], q3lo[k][0], q3hi[k][0], Xlo[0][0], Xlo[1][0], Xhi[0][0], Xhi[1][0]);
+            syn_vert_site<kHasLL, true>(g2.y, b >> 8, c, q3lo[k][1], q3hi[k][1], q3lo[k][1], q3hi[k][1], Xlo[0][1], Xlo[1][1], Xhi[0][1], Xhi[1][1]);
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                const float pb0 = Xlo[pr][0] + Xhi[pr][0], pb1 = Xlo[pr][1] + Xhi[pr][1];
+                const float qn0 = fmaf(k3Kh, Xhi[pr][0], k3Kl * Xlo[pr][0]);      // for site 1
+                const float qn1 = fmaf(k3Kh, Xhi[pr][1], k3Kl * Xlo[pr][1]);      // for the next lane's site 0
+                const float recv = __shfl_sync(0xffffffffu, qn1, (lane + 31) & 31);
+                const float ql = lane == 0 ? left[pr] : recv;
+                left[pr] = recv;                              // lane 0: lane 31's value of THIS chunk = its neighbour in the next
+                float4 o;
+                o.x = kI3 * (pb0 - ql);
+                o.y = fmaf(ql, kThird, pb0);
+                o.z = kI3 * (pb1 - qn0);
+                o.w = fmaf(qn0, kThird, pb1);
+                if (kToSmem) *reinterpret_cast<float4*>(outs + (2 * (r - 1) + pr) * (2 * wj) + 128 * k + 4 * lane) = o;
+                else *reinterpret_cast<float4*>(out_g + (long long)(2 * (r - 1) + pr) * out_ld + 128 * k + 4 * lane) = o;
+            }
+        }
+    }
+}
+
+struct Db2InvArgs {
+    const float* g;             // gradient of the low-low band that enters the pass (ignored when !kHasLL)
+    const unsigned char* sg1;   // [nmaps][H/2][W/2]
+    const unsigned char* sg2;   // [nmaps][H/4][W/4] (two levels)
+    float* out;                 // [nmaps][H][W]
+    int H, W, nmaps, R, stages, nw2; // R: most level-1 coefficient rows per piece; nw2: warps of the level-2 group
+    float sc1, sc2;
+    const float* upstream;      // device scalar multiplied into out (nullptr: 1)
+    const double* partial;      // loss partials of the preceding kernels, summed in fixed order by CTA 0 ...
+    int n_partials;
+    float* loss;                // ... into loss (nullptr: somebody else does it)
+};
+
+// contiguous, balanced ranges of the nmaps * h2 coefficient rows, cut into pieces of at most R rows that stay inside a map
+struct Db2Pieces {
+    long long r, e;
+    int h2, R;
+    __device__ Db2Pieces(long long total, int h2_, int R_) : h2(h2_), R(R_) {
+        r = total * blockIdx.x / gridDim.x;
+        e = total * (blockIdx.x + 1) / gridDim.x;
+    }
+    __device__ bool next(long long& m, int& i_first, int& len) {
+        if (r >= e) return false;
+        m = r / h2;
+        i_first = int(r - m * h2);
+        len = int(min((long long)min(R, h2 - i_first), e - r));
+        r += len;
+        return true;
+    }
+};
+
+__device__ __forceinline__ int floor_half(int v) { return v >= 0 ? v >> 1 : -((1 - v) >> 1); }
+
+// Shared-memory carve of one stage (bytes).  One level: [g (R + 1) rows][sg1 (R + 1) rows].
+// Two levels: [g2 (R / 2 + 3) rows][sg2 (R / 2 + 3) rows][sg1 (R + 1) rows].
+struct Db2InvLayout {
+    int g, s2, s1, stage, g1buf, g1bytes;
+};
+__host__ __device__ inline Db2InvLayout db2_inv_layout(int W, int R, bool two, bool has_ll, int S) {
+    Db2InvLayout o;
+    const int w2 = W >> 1, w4 = W >> 2;
+    int off = 0;
+    o.g = off;
+    if (two) {
+        const int n2 = R / 2 + 3;
+        if (has_ll) off += n2 * w4 * 4;
+        o.s2 = off;
+        off += (n2 * w4 + 15) & ~15;
+    } else {
+        if (has_ll) off += (R + 1) * w2 * 4;
+        o.s2 = off;
+    }
+    o.s1 = off;
+    off += ((R + 1) * w2 + 15) & ~15;
+    o.stage = (off + 127) & ~127;
+    o.g1buf = S * o.stage;
+    o.g1bytes = two ? (R + 6) * w2 * 4 : 0;         // 2 (n2 - 1) <= R + 4 rows of dL/dLL1, one of two buffers
+    return o;
+}
+
+template <int K1, bool kTwo, bool kHasLL>
+__global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_synthesis_kernel(Db2InvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // warps: [0, NW1) level 1 -> global, [NW1, NW) level 2 -> dL/dLL1 in shared memory (two-level pass only), warp NW = producer.
+    // Level 2 of piece n + 1 overlaps level 1 of piece n: two dL/dLL1 buffers, handed over through mbarriers.
+    constexpr int NW = kDb2MaxThreads / 32 - 1;
+    constexpr int K2 = kTwo ? K1 / 2 : 1;
+    const int NW2 = kTwo ? a.nw2 : 0, NW1 = NW - NW2;
+    const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, h4 = H >> 2, w4 = W >> 2, R = a.R, S = a.stages;
+    const Db2InvLayout lay = db2_inv_layout(W, R, kTwo, kHasLL, S);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + lay.g1buf + 2 * lay.g1bytes);
+    uint64_t* empty = full + S;
+    uint64_t* g1_full = empty + S;          // [2]
+    uint64_t* g1_empty = g1_full + 2;       // [2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&g1_full[b], NW2 > 0 ? NW2 : 1);
+            mbar_init(&g1_empty[b], NW1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    Db2Pieces pieces((long long)a.nmaps * h2, h2, R);
+    long long m;
+    int i_first, len;
+    if (warp == NW) {
+        if (lane == 0) {
+            for (int n = 0; pieces.next(m, i_first, len); ++n) {
+                const int s = n % S;
+                if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
+                unsigned char* dst = smem + size_t(s) * lay.stage;
+                uint32_t bytes = uint32_t(len + 1) * w2;
+                if (kTwo) {
+                    const int lo2 = floor_half(i_first - 1) - 1, n2 = floor_half(i_first + len - 1) - lo2 + 1;
+                    bytes += uint32_t(n2) * w4 * (kHasLL ? 5u : 1u);
+                    mbar_arrive_expect_tx(&full[s], bytes);
+                    if (kHasLL)
+                        bulk_rows_wrapped(dst + lay.g, reinterpret_cast<const unsigned char*>(a.g + m * (long long)h4 * w4), uint32_t(w4) * 4u, lo2, n2,
+                                          h4, &full[s], 0, false);
+                    bulk_rows_wrapped(dst + lay.s2, a.sg2 + m * (long long)h4 * w4, uint32_t(w4), lo2, n2, h4, &full[s], 0, false);
+                } else {
+                    if (kHasLL) bytes += uint32_t(len + 1) * w2 * 4u;
+                    mbar_arrive_expect_tx(&full[s], bytes);
+                    if (kHasLL)
+                        bulk_rows_wrapped(dst + lay.g, reinterpret_cast<const unsigned char*>(a.g + m * (long long)h2 * w2), uint32_t(w2) * 4u,
+                                          i_first - 1, len + 1, h2, &full[s], 0, false);
+                }
+                bulk_rows_wrapped(dst + lay.s1, a.sg1 + m * (long long)h2 * w2, uint32_t(w2), i_first - 1, len + 1, h2, &full[s], 0, false);
+            }
+        }
+        __syncwarp();
+        if (a.loss && blockIdx.x == 0) {                    // fixed-order sum of the loss partials, once this CTA's loads are queued
+            double s = 0.0;
+            for (int i = lane; i < a.n_partials; i += 32) s += a.partial[i];
+            s = warp_sum(s);
+            if (lane == 0) a.loss[0] = float(s);
+        }
+    } else if (warp < NW1) {
+        const float gs = a.upstream ? __ldg(a.upstream) : 1.0f;
+        const SynConst c1 = make_syn_const(a.sc1, gs);
+        for (int n = 0; pieces.next(m, i_first, len); ++n) {
+            const int s = n % S;
+            const int st = s * lay.stage;
+            mbar_wait(&full[s], (n / S) & 1);
+            float* obase = a.out + m * (long long)H * W + (long long)(2 * i_first) * W;       // output row of coefficient row i_first
+            const int seg1 = (len + NW1 - 1) / NW1;
+            const int ra1 = 1 + warp * seg1, rb1 = min(ra1 + seg1, len + 1);
+            if (!kTwo) {
+                if (ra1 < rb1) db2_inv_rows<K1, kHasLL, false>(st + lay.g, st + lay.s1, ra1, rb1, c1, 0, obase, W, lane);
+            } else {
+                const int b = n & 1, k = n >> 1;
+                mbar_wait(&g1_full[b], k & 1);
+                // buffer row 0 of dL/dLL1 is row 2 (lo2 + 1); the row above the piece, i_first - 1, sits at offset
+                // i_first - 1 - 2 (lo2 + 1) in {0, 1}
+                const int lo2 = floor_half(i_first - 1) - 1;
+                const int shift = i_first - 1 - 2 * (lo2 + 1);
+                if (ra1 < rb1)
+                    db2_inv_rows<K1, true, false>(lay.g1buf + b * lay.g1bytes + shift * w2 * 4, st + lay.s1, ra1, rb1, c1, 0, obase, W, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&g1_empty[b]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    } else {
+        // level 2: coefficient rows lo2 + 1 .. hi2 -> dL/dLL1 rows 2 (lo2 + 1) .. 2 hi2 + 1 in this piece's buffer
+        const SynConst c2 = make_syn_const(a.sc2, 1.0f);
+        const int w = warp - NW1;
+        for (int n = 0; pieces.next(m, i_first, len); ++n) {
+            const int s = n % S;
+            const int st = s * lay.stage;
+            const int b = n & 1, k = n >> 1;
+            mbar_wait(&full[s], (n / S) & 1);
+            if (k > 0) mbar_wait(&g1_empty[b], (k & 1) ^ 1);
+            const int lo2 = floor_half(i_first - 1) - 1, rows2 = floor_half(i_first + len - 1) - lo2;
+            const int seg2 = (rows2 + NW2 - 1) / NW2;
+            const int ra2 = 1 + w * seg2, rb2 = min(ra2 + seg2, rows2 + 1);
+            if (ra2 < rb2) db2_inv_rows<K2, kHasLL, true>(st + lay.g, st + lay.s2, ra2, rb2, c2, lay.g1buf + b * lay.g1bytes, nullptr, 0, lane);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&g1_full[b]);
+                mbar_arrive(&empty[s]);
+            }
+        }
+    }
+}
+
+template <typename Kernel, typename Args>
+cudaError_t launch_db2(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t stream, const Args& args, bool pdl) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> opted_in;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), dev);
+        auto it = opted_in.find(key);
+        if (it == opted_in.end() || it->second < smem) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            opted_in[key] = smem;
+        }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
+int divisor_le(int n, int cap) {
+    for (int d = std::min(n, cap); d > 1; --d)
+        if (n % d == 0) return d;
+    return 1;
+}
+
+size_t db2_fwd_smem(int W, int R, int S, bool two) {
+    const size_t rows_in = two ? 4 * R + 6 : 2 * R + 2;
+    const size_t ll1 = two ? size_t(2 * R + 2) * (W / 2) * 4 : 0;
+    return S * rows_in * W * 4 + 2 * ll1 + size_t(2 * S + 4) * sizeof(uint64_t);
+}
+
+}  // namespace
+
+int g_wavelet_db2 = 1;          // diagnostics: 0 = the round-1 level kernels (wavelet_tiles.cu) for db2 as well
+int g_wavelet_db2_two = 1;      // diagnostics: 0 = one level per pass only
+
+int g_wavelet_db2_rf = 0, g_wavelet_db2_ri = 0, g_wavelet_db2_nw2 = 0;     // diagnostics: overrides of the geometry below (0 = automatic)
+
+namespace {
+// rows per thread task that minimise rounds * (rows + ~1.5 rows of task prologue) for `rows` rows x `pairs` column groups on `threads` threads
+int best_seg(int rows, int pairs, int threads) {
+    int best = rows;
+    double best_cost = 1e30;
+    for (int seg = 1; seg <= rows; ++seg) {
+        const int tasks = ((rows + seg - 1) / seg) * pairs;
+        const int rounds = (tasks + threads - 1) / threads;
+        const double cost = rounds * (seg + 1.5);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = seg; }
+    }
+    return best;
+}
+}  // namespace
+
+// Geometry of a pass over H x W planes; false: shape not taken (the caller falls back to wavelet_tiles.cu / wavelet_stream.cu).
+//   R_fwd: rows of the pass's last level per analysis strip, S_fwd ring depth, NC_fwd consumer threads (both groups)
+//   R_inv: level-1 coefficient rows per synthesis piece, S_inv ring depth
+bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv) {
+    if (!g_wavelet_db2 || (two && !g_wavelet_db2_two)) return false;
+    if (W != 128 && W != 256 && W != 512 && W != 1024) return false;    // warp-per-row synthesis: W / 128 chunks of 64 sites, unrolled
+    if (two && W < 256) return false;
+    if (H % (two ? 4 : 2) || H < (two ? 16 : 4)) return false;
+    const int hl = two ? H / 4 : H / 2;
+    int R = divisor_le(hl, g_wavelet_db2_rf > 0 ? g_wavelet_db2_rf : (two ? 8 : 16));
+    while (R > 1 && db2_fwd_smem(W, R, 2, two) > size_t(kDb2Smem)) R = divisor_le(hl, R - 1);
+    if (db2_fwd_smem(W, R, 2, two) > size_t(kDb2Smem)) return false;
+    int S = 2;
+    while (S < 4 && db2_fwd_smem(W, R, S + 1, two) <= size_t(kDb2Smem)) ++S;
+    *R_fwd = R; *S_fwd = S; *NC_fwd = kDb2MaxThreads - 32;
+    int Ri = g_wavelet_db2_ri > 0 ? g_wavelet_db2_ri : (two ? 48 : 64);
+    Ri = std::min(Ri, H / 2);
+    auto inv_smem = [&](int r, int s) {
+        const Db2InvLayout lay = db2_inv_layout(W, r, two, has_ll, s);
+        return size_t(lay.g1buf) + 2 * size_t(lay.g1bytes) + size_t(2 * s + 4) * sizeof(uint64_t);
+    };
+    while (Ri > 4 && inv_smem(Ri, 3) > size_t(kDb2Smem)) Ri -= 4;
+    int Si = 4;
+    while (Si > 2 && inv_smem(Ri, Si) > size_t(kDb2Smem)) --Si;
+    if (inv_smem(Ri, Si) > size_t(kDb2Smem)) return false;
+    *R_inv = Ri; *S_inv = Si;
+    return true;
+}
+
+cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,
+                                float sc1, float sc2, bool grad, bool pdl_wait, double* partial, int sm_count, cudaStream_t stream,
+                                int* n_partials) {
+    int Rf, Sf, NCf, Ri, Si;
+    if (!wavelet_db2_pass(H, W, two, true, &Rf, &Sf, &NCf, &Ri, &Si)) return cudaErrorInvalidValue;
+    Db2FwdArgs a;
+    a.x = x; a.ll = ll; a.sg1 = sg1; a.sg2 = sg2; a.H = H; a.W = W; a.nmaps = nmaps; a.R = Rf; a.stages = Sf; a.pdl_wait = pdl_wait ? 1 : 0;
+    a.sc1 = sc1; a.sc2 = sc2; a.partial = partial;
+    const int nw = NCf / 32;
+    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, nw - 1) : 4) : 0;
+    a.seg1 = best_seg(two ? 2 * Rf + 2 : Rf, W / 4, (nw - a.nw2) * 32);
+    a.seg2 = two ? best_seg(Rf, W / 8, a.nw2 * 32) : 1;
+    const long long T = (long long)nmaps * ((two ? H / 4 : H / 2) / Rf);
+    const int grid = int(std::min<long long>(sm_count, T));
+    const size_t smem = db2_fwd_smem(W, Rf, Sf, two);
+    *n_partials = grid;
+    const int threads = NCf + 32;
+    if (two) return grad ? launch_db2(db2_analysis_kernel<true, true>, grid, threads, smem, stream, a, pdl_wait)
+                         : launch_db2(db2_analysis_kernel<true, false>, grid, threads, smem, stream, a, pdl_wait);
+    return grad ? launch_db2(db2_analysis_kernel<false, true>, grid, threads, smem, stream, a, pdl_wait)
+                : launch_db2(db2_analysis_kernel<false, false>, grid, threads, smem, stream, a, pdl_wait);
+}
+
+namespace {
+template <int K1>
+cudaError_t launch_db2_synthesis_k(const Db2InvArgs& a, bool two, bool has_ll, int grid, size_t smem, cudaStream_t stream) {
+    if (two) {
+        if constexpr (K1 >= 2) {
+            return has_ll ? launch_db2(db2_synthesis_kernel<K1, true, true>, grid, kDb2MaxThreads, smem, stream, a, true)
+                          : launch_db2(db2_synthesis_kernel<K1, true, false>, grid, kDb2MaxThreads, smem, stream, a, true);
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    return has_ll ? launch_db2(db2_synthesis_kernel<K1, false, true>, grid, kDb2MaxThreads, smem, stream, a, true)
+                  : launch_db2(db2_synthesis_kernel<K1, false, false>, grid, kDb2MaxThreads, smem, stream, a, true);
+}
+}  // namespace
+
+// g: gradient of the low-low band entering the pass (level 2's when `two`), nullptr / has_ll == false: zero
+cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const unsigned char* sg2, float* out, int nmaps, int H, int W,
+                                 bool two, bool has_ll, float sc1, float sc2, const float* upstream, const double* partial, int n_partials,
+                                 float* loss, int sm_count, cudaStream_t stream) {
+    int Rf, Sf, NCf, Ri, Si;
+    if (!wavelet_db2_pass(H, W, two, has_ll, &Rf, &Sf, &NCf, &Ri, &Si)) return cudaErrorInvalidValue;
+    Db2InvArgs a;
+    a.g = g; a.sg1 = sg1; a.sg2 = sg2; a.out = out; a.H = H; a.W = W; a.nmaps = nmaps; a.R = Ri; a.stages = Si; a.sc1 = sc1; a.sc2 = sc2;
+    a.upstream = upstream; a.partial = partial; a.n_partials = n_partials; a.loss = loss;
+    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, kDb2MaxThreads / 32 - 2) : 4) : 0;
+    const long long rows = (long long)nmaps * (H / 2);
+    const int grid = int(std::min<long long>(sm_count, std::max<long long>(1, rows / 4)));
+    const Db2InvLayout lay = db2_inv_layout(W, Ri, two, has_ll, Si);
+    const size_t smem = size_t(lay.g1buf) + 2 * size_t(lay.g1bytes) + size_t(2 * Si + 4) * sizeof(uint64_t);
+    switch (W / 128) {
+        case 1: return launch_db2_synthesis_k<1>(a, two, has_ll, grid, smem, stream);
+        case 2: return launch_db2_synthesis_k<2>(a, two, has_ll, grid, smem, stream);
+        case 4: return launch_db2_synthesis_k<4>(a, two, has_ll, grid, smem, stream);
+        case 8: return launch_db2_synthesis_k<8>(a, two, has_ll, grid, smem, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace wtpse

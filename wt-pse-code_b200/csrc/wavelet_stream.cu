@@ -211,6 +211,41 @@ static bool level_tiled(int H, int W, int taps, bool has_ll) {
     return Rf > 0 && Ri > 0;
 }
 
+// db2, factored kernels (wavelet_db2.cu): the streamed levels as passes of two (or one) levels.  Fills pass[] with the
+// number of levels of each pass and returns the number of passes (0: the factored kernels do not take this shape);
+// *k = levels streamed, *cs = cluster size of the resident stage that follows (1 when k == J).
+static int db2_pass_plan(int H, int W, int J, int nmaps, int pass[16], int* k_out, int* cs) {
+    int k = 0, np = 0;
+    *cs = 0;
+    while (k < J && k < g_wavelet_peel_max) {
+        const int Hc = H >> k, Wc = W >> k, rem = J - k;
+        if (k > 0) {
+            const int c = wavelet_resident_cluster(Hc, Wc, 4, rem, nmaps);
+            if (c > 0 && c <= 2) { *cs = c; break; }
+        }
+        int Rf, Sf, NCf, Ri, Si;
+        if (rem >= 2 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &Rf, &Sf, &NCf, &Ri, &Si)) {
+            pass[np++] = 2;
+            k += 2;
+        } else if (wavelet_db2_pass(Hc, Wc, false, rem > 1, &Rf, &Sf, &NCf, &Ri, &Si)) {
+            pass[np++] = 1;
+            k += 1;
+        } else {
+            break;
+        }
+    }
+    if (k == 0) return 0;
+    if (k < J) {
+        const int c = wavelet_resident_cluster(H >> k, W >> k, 4, J - k, nmaps);
+        if (c == 0) return 0;
+        *cs = c;
+    } else {
+        *cs = 1;
+    }
+    *k_out = k;
+    return np;
+}
+
 // Streamed plan: the first k levels run global-to-global (TMA tile pipelines; level 1 may fall back to the per-thread
 // kernels), the remaining J-k levels in the cluster-resident kernel on the k-th low-low band.  k grows while that band
 // would still need a cluster of more than 2 CTAs (a 1024 x 1024 map peels two levels: 63 us of resident stage on
@@ -218,6 +253,11 @@ static bool level_tiled(int H, int W, int taps, bool has_ll) {
 // Returns k, 0 if the plan does not exist; *cs = cluster size of the resident stage (1 when k == J).
 int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs) {
     *cs = 0;
+    if (taps == 4) {
+        int pass[16], k = 0;
+        if (db2_pass_plan(H, W, J, nmaps, pass, &k, cs) > 0) return k;
+        *cs = 0;
+    }
     if (!level_streamable(H, W, taps)) return 0;
     int best_k = 0, best_cs = 0;
     for (int k = 1; k <= J && k <= g_wavelet_peel_max; ++k) {
@@ -277,6 +317,42 @@ cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, i
     auto scale_of = [&](int i) { return weights_host[i - 1] / (3.0f * float(H >> i) * float(W >> i) * float(nmaps)); };
     cudaError_t e = cudaSuccess;
     int np = 0;
+    if (taps == 4) {
+        // factored db2 passes (wavelet_db2.cu): 2 (or 1) levels per pass down, resident stage, the same passes up
+        int pass[16], kk = 0, cs2 = 0;
+        const int npass = db2_pass_plan(H, W, J, nmaps, pass, &kk, &cs2);
+        if (npass > 0 && kk == k) {
+            int lvl = 0;                                            // levels done
+            for (int q = 0; q < npass; ++q) {
+                const bool two = pass[q] == 2;
+                const int Hi = H >> lvl, Wi = W >> lvl, last = lvl + pass[q];
+                int n = 0;
+                e = launch_db2_analysis(lvl == 0 ? x : ll[lvl], last < J ? ll[last] : nullptr, sg[lvl + 1], two ? sg[lvl + 2] : nullptr, nmaps, Hi, Wi, two,
+                                        scale_of(lvl + 1), two ? scale_of(lvl + 2) : 0.f, grad != nullptr, q > 0, partial + np, sm_count, stream, &n);
+                if (e != cudaSuccess) return e;
+                np += n;
+                lvl = last;
+            }
+            if (k < J) {
+                int nb = 0;
+                e = launch_wavelet_resident(ll[k], nmaps, H >> k, W >> k, taps, J - k, weights_host + k, nullptr, nullptr, grad ? ll[k] : nullptr,
+                                            partial + np, stream, &nb);
+                if (e != cudaSuccess) return e;
+                np += nb;
+            }
+            if (!grad) return launch_wavelet_loss_final(partial, np, loss, stream);
+            for (int q = npass - 1; q >= 0; --q) {
+                const bool two = pass[q] == 2;
+                lvl -= pass[q];
+                const int Hi = H >> lvl, Wi = W >> lvl, last = lvl + pass[q];
+                e = launch_db2_synthesis(ll[last], sg[lvl + 1], two ? sg[lvl + 2] : nullptr, lvl == 0 ? grad : ll[lvl], nmaps, Hi, Wi, two,
+                                         last < J, scale_of(lvl + 1), two ? scale_of(lvl + 2) : 0.f, lvl == 0 ? upstream : nullptr, partial, np,
+                                         lvl == 0 ? loss : nullptr, sm_count, stream);
+                if (e != cudaSuccess) return e;
+            }
+            return cudaSuccess;
+        }
+    }
     // ---- analysis, levels 1..k ----
     for (int i = 1; i <= k; ++i) {
         const int Hi = H >> (i - 1), Wi = W >> (i - 1);             // input of this level
