@@ -20,6 +20,18 @@ def _maps(shape, seed=0):
     return torch.randn(*shape, generator=g)
 
 
+def _safe_maps(shape, J, seed, wavelet="db2"):
+    """Maps whose detail coefficients are bounded away from zero (the inverse transform of coefficients with |c| in
+    [0.1, 1]): the sign pattern -- the only discontinuity of the L1 loss -- cannot depend on rounding, so two correct
+    implementations with different operation orders (the filter bank and its factored form, csrc/wavelet_db2.cu) agree to
+    fp32 rounding.  With plain random maps one coefficient in ~10^6 lies within a few ulps of zero and flips."""
+    import wtpse_b200 as wb
+
+    g = torch.Generator().manual_seed(seed)
+    c = (0.1 + 0.9 * torch.rand(*shape, generator=g)) * (2.0 * torch.randint(0, 2, shape, generator=g) - 1.0)
+    return wb.idwt2d(c.to(_dev()), wavelet, J).contiguous()
+
+
 @pytest.mark.parametrize("wavelet", ["haar", "db2"])
 @pytest.mark.parametrize("shape,J", [((3, 2, 32, 32), 3), ((2, 2, 64, 48), 4), ((1, 1, 16, 80), 2), ((4, 2, 8, 8), 1),
                                      ((2, 2, 128, 64), 4), ((1, 2, 64, 192), 3), ((3, 1, 64, 64), 1), ((1, 1, 256, 128), 2)])
@@ -117,7 +129,7 @@ def test_fused_plans_match_per_level_path(wavelet, shape, J):
     from wtpse_b200 import wavelet as wv
 
     lib = wb._lib.load()
-    x = torch.rand(*shape, generator=torch.Generator().manual_seed(J + shape[0])).to(_dev())
+    x = _safe_maps(shape, J, J + shape[0], wavelet)
     weights = tuple(0.5 + 0.25 * j for j in range(J))
 
     def run():
@@ -160,7 +172,7 @@ def test_fused_plan_covers_maps_too_large_for_a_cluster():
     from wtpse_b200 import wavelet as wv
 
     lib = wb._lib.load()
-    x = torch.rand(2, 2, 1024, 1024, device=_dev())
+    x = _safe_maps((2, 2, 1024, 1024), 5, 11)
     res = []
     try:
         for resident, peel, cs in ((1, 8, 2), (1, 1, 8), (0, 8, 0)):
@@ -188,7 +200,7 @@ def test_streamed_plan_with_every_level_streamed(wavelet):
 
     lib = wb._lib.load()
     assert wv.resident_cluster_size(64, 96, wavelet, 5) == 0        # 96 % 2^(J+1) != 0 and 48, 24 .. are not tileable
-    x = torch.rand(1, 2, 1024, 1024, generator=torch.Generator().manual_seed(5)).to(_dev())
+    x = _safe_maps((1, 2, 1024, 1024), 2, 5, wavelet)
     res = []
     try:
         wb._lib.debug_set("wavelet_split", 1)            # Haar would otherwise take the single band kernel here
@@ -233,7 +245,7 @@ def test_fused_plans_random_shapes_and_determinism():
         if nmaps * H * W > 12 * 1024 * 1024:
             continue
         cases += 1
-        x = torch.rand(nmaps, 1, H, W, generator=torch.Generator().manual_seed(cases)).to(_dev())
+        x = _safe_maps((nmaps, 1, H, W), J, cases, wavelet)
         weights = tuple(rng.choice([0.25, 1.0, 3.0]) for _ in range(J))
 
         def run():
@@ -281,6 +293,68 @@ def test_wavelet_contract_errors():
         wb.dwt2d(x, "sym8", 1)
     with pytest.raises(RuntimeError):
         wb.dwt2d(x.cpu(), "haar", 1)
+
+
+@pytest.mark.parametrize("shape,J", [((3, 1, 64, 128), 1), ((2, 1, 64, 128), 3), ((5, 1, 32, 256), 2), ((3, 2, 256, 256), 4),
+                                     ((1, 2, 512, 512), 4), ((2, 2, 512, 512), 2), ((7, 1, 128, 512), 3), ((1, 1, 1024, 1024), 1),
+                                     ((1, 2, 1024, 1024), 2), ((2, 1, 1024, 1024), 5), ((37, 1, 96, 256), 2), ((2, 1, 16, 256), 2),
+                                     ((70, 1, 64, 256), 3)])
+def test_db2_factored_passes(shape, J):
+    """csrc/wavelet_db2.cu (factored db2, one or two levels per pass, level groups on separate warps) forced into the plan
+    (wavelet_split = 1) against the per-level kernels: loss, gradient with a non-unit upstream gradient, run-to-run bits;
+    one level per pass, two levels per pass and the round-1 level kernels must all agree.  The small cases also against the
+    float64 specification."""
+    import wtpse_b200 as wb
+    from oracle import wavelet_np as wn
+
+    x = _safe_maps(shape, J, seed=J + shape[0])
+    weights = tuple(0.5 + 0.25 * j for j in range(J))
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        loss = wb.wavelet_shape_loss(xg, "db2", J, weights)
+        (0.7 * loss).backward()
+        return float(loss.detach()), xg.grad.clone()
+
+    try:
+        wb._lib.debug_set("wavelet_resident", 0)
+        lp, gp = run()
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_split", 1)
+        for db2, two in ((0, 0), (1, 0), (1, 1)):
+            wb._lib.debug_set("wavelet_db2", db2)
+            wb._lib.debug_set("wavelet_db2_two", two)
+            l, g = run()
+            l2, g2 = run()
+            assert l2 == l and torch.equal(g, g2), (db2, two)
+            assert abs(l - lp) <= 2e-6 * abs(lp), (db2, two)
+            assert rel_err(g.cpu().numpy(), gp.cpu().numpy()) < 2e-6, (db2, two)
+        if x.numel() <= 1 << 18:
+            ref_loss, ref_grad = wn.shape_loss(x.cpu().numpy(), "db2", J, weights)
+            assert abs(l - ref_loss) <= TOL * abs(ref_loss)
+            assert rel_err(g.cpu().numpy(), 0.7 * ref_grad) < TOL
+    finally:
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_split", -1)
+        wb._lib.debug_set("wavelet_db2", 1)
+        wb._lib.debug_set("wavelet_db2_two", 1)
+
+
+def test_db2_factored_zero_and_flat_maps():
+    """sign(0) = 0: an all-zero map has zero loss and an exactly zero gradient; a constant map has (numerically) zero
+    detail coefficients, so its loss is at rounding level."""
+    import wtpse_b200 as wb
+
+    try:
+        wb._lib.debug_set("wavelet_split", 1)
+        x = torch.zeros(2, 1, 64, 256, device=_dev(), requires_grad=True)
+        loss = wb.wavelet_shape_loss(x, "db2", 2)
+        loss.backward()
+        assert float(loss) == 0.0 and float(x.grad.abs().max()) == 0.0
+        y = torch.full((2, 1, 64, 256), 0.75, device=_dev())
+        assert float(wb.wavelet_shape_loss(y, "db2", 2)) < 1e-6
+    finally:
+        wb._lib.debug_set("wavelet_split", -1)
 
 
 def test_wavelet_full_size_properties():

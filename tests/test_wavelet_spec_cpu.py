@@ -84,3 +84,68 @@ def test_spec_loss_gradient_matches_finite_differences():
         xm = x.copy(); xm[idx] -= eps
         fd = (wn.shape_loss(xp, "db2", 2, (1.0, 0.5))[0] - wn.shape_loss(xm, "db2", 2, (1.0, 0.5))[0]) / (2 * eps)
         assert abs(fd - grad[idx]) < 1e-7
+
+
+def test_factored_db2_equals_the_filter_bank():
+    """The factored form the db2 level kernels compute (csrc/wavelet_db2.cu), restated in numpy, against the specification:
+    p = b + a / sqrt3, q = b - sqrt3 a, lo = h1 (p + (h3 / h1) q_next), hi = -h2 (p + (h0 / h2) q_next) for the analysis and
+    pbar = h1 lo - h2 hi, 3 qbar_next = 3 h3 lo - 3 h0 hi, a = (pbar - 3 qbar) / sqrt3, b = pbar + qbar for its adjoint; in 2-D the
+    scales h1^2 (LL), h1 h2 (LH, HL; both with a sign flip) and h2^2 (HH) are folded into the level weight and the synthesis
+    constants, so the kernels only ever hold the unscaled bands and their signs."""
+    s3 = np.sqrt(3.0)
+    h0, h1, h2, h3 = wn.FILTERS["db2"]
+    i3, kl, kh = 1 / s3, h3 / h1, h0 / h2
+
+    def row_stage(x):                                        # along W
+        a, b = x[..., 0::2], x[..., 1::2]
+        p, q = a * i3 + b, b - s3 * a
+        qn = np.roll(q, -1, -1)
+        return p + kl * qn, p + kh * qn
+
+    def col_stage(u):                                        # along H
+        a, b = u[..., 0::2, :], u[..., 1::2, :]
+        p, q = a * i3 + b, b - s3 * a
+        qn = np.roll(q, -1, -2)
+        return p + kl * qn, p + kh * qn
+
+    def analysis(x, sc):
+        lt, ht = row_stage(x)
+        LLt, HLt = col_stage(lt)
+        LHt, HHt = col_stage(ht)
+        loss = sc * (h1 * h2 * (np.abs(LHt) + np.abs(HLt)).sum() + h2 * h2 * np.abs(HHt).sum())
+        return h1 * h1 * LLt, (np.sign(LHt), np.sign(HLt), np.sign(HHt)), loss
+
+    def synthesis(g, sg, sc):
+        sLH, sHL, sHH = sg
+        cLL, c1, c2 = h1 * h1, h1 * h2 * sc, h2 * h2 * sc
+        e = c1 * sHL
+        pb, qn = cLL * g + e, 3 * kh * e + 3 * kl * cLL * g
+        lam = c1 * sLH
+        pbh, qnh = c2 * sHH + lam, 3 * kh * c2 * sHH + 3 * kl * lam
+        q3lo, q3hi = np.roll(qn, 1, -2), np.roll(qnh, 1, -2)
+        rows = ((i3 * (pb - q3lo), i3 * (pbh - q3hi)), (pb + q3lo / 3, pbh + q3hi / 3))
+        out = np.empty(g.shape[:-2] + (2 * g.shape[-2], 2 * g.shape[-1]))
+        for pr, (xlo, xhi) in enumerate(rows):
+            p, ql = xlo + xhi, np.roll(3 * kh * xhi + 3 * kl * xlo, 1, -1)
+            out[..., pr::2, 0::2] = i3 * (p - ql)
+            out[..., pr::2, 1::2] = p + ql / 3
+        return out
+
+    rng = np.random.RandomState(3)
+    N, H, W = 3, 16, 32
+    x = rng.randn(N, H, W)
+    for J in (1, 2, 3):
+        wts = np.array([1.0, 0.7, 0.4])[:J]
+        ref_loss, ref_grad = wn.shape_loss(x, "db2", J, wts)
+        cur, signs, scales, loss = x, [], [], 0.0
+        for j in range(1, J + 1):
+            scales.append(wts[j - 1] / (3 * (H >> j) * (W >> j) * N))
+            cur, sg, l = analysis(cur, scales[-1])
+            signs.append(sg)
+            loss += l
+        assert np.allclose(cur, wn.dwt2d(x, "db2", J)[..., :H >> J, :W >> J], atol=1e-12)
+        assert abs(loss - ref_loss) < 1e-12
+        g = np.zeros_like(cur)
+        for j in range(J, 0, -1):
+            g = synthesis(g, signs[j - 1], scales[j - 1])
+        assert np.abs(g - ref_grad).max() < 1e-13
