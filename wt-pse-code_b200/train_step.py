@@ -67,6 +67,11 @@ class TrainStep:
         fused = bool(fused_adam) and self.device.type == "cuda"       # one multi-tensor kernel per optimizer step
         self.optims = [torch.optim.Adam(m.parameters(), lr=lr, betas=(0.9, 0.99), fused=fused, capturable=fused)
                        for m in self.nets]
+        # identical weights, DIFFERENT noise: the posterior's re-parameterisation noise (torch.randn in the shape networks) must
+        # not be the same on every data-parallel rank, so the generator is re-seeded by rank once the weights exist
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            rank = torch.distributed.get_rank(process_group)
+            torch.manual_seed(seed + 7919 * (rank + 1))
         self._graph = None
         self.iteration = 0
         self.grad_allreduce = bool(grad_allreduce)     # False: independent replicas (bench.py's scaling diagnostic)
