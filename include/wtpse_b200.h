@@ -231,6 +231,8 @@ size_t wtpse_od_roi_workspace_bytes(void);
  *   image_roi = image * od_pred - 1
  *   sums[0] = sum(od_pred), sums[1] = sum(od_pred * target_oc), sums[2] = sums[0]/sums[1] (1 if inf/nan)
  * target_oc and sums may be NULL.  Bit-exact against the same statements executed by ATen on the GPU.
+ * Precondition: target_oc holds {0, 1} labels (custom_transforms.py:466-499); sums[1] counts the non-zero products, which is
+ * exact and order-independent for binary targets and NOT the float sum for soft ones.
  */
 int wtpse_od_roi(const float* logits, const float* target_oc, float* image, float* od_pred, float* image_roi,
                  int B, int C, int64_t HW, float threshold, float* sums,

@@ -41,6 +41,12 @@ int         wtpse_profile_read(int id, long long* timed_launches, double* total_
 int wtpse_debug_set(const char* name, int value);
 int wtpse_debug_get(const char* name, int* value);
 
+/* ---- stress helper for the programmatic-dependent-launch paths ---------------------------------
+ * Enqueues a kernel that signals griddepcontrol.launch_dependents at once, spins for spin_cycles clocks and only then copies
+ * src -> dst (n floats).  A library kernel launched right behind it that read dst before its own griddepcontrol.wait would see
+ * dst's old bytes (tests/test_gpu_fusion.py fills them with NaN). */
+int wtpse_debug_pdl_slow_copy(float* dst, const float* src, long long n, long long spin_cycles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

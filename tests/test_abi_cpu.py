@@ -26,7 +26,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     debug = _declared_symbols("wtpse_b200_debug.h")
     assert len(declared) >= 12
     # the product header carries no diagnostics: switches and launch accounting live in wtpse_b200_debug.h
-    assert not [n for n in declared if "debug" in n or "profile" in n] and len(debug) == 8
+    assert not [n for n in declared if "debug" in n or "profile" in n] and len(debug) == 9
     for name in declared + debug:
         assert hasattr(lib, name), "header declares %s but the library does not export it" % name
     # and the ctypes binding covers exactly the two headers
@@ -97,14 +97,21 @@ def test_product_never_imports_oracle():
 
 def test_wavelet_planner_host_logic():
     """Track W planner (pure host code in the library, no GPU needed): which shapes get a fused plan and with what cluster
-    size for the resident stage.  512^2 db2 J=4 streams one level (256^2 band, cluster of 2), 1024^2 two levels, Haar never
-    needs a cluster, shapes whose widths are neither divisible by 2^(J+1) nor tileable have no fused plan."""
+    size for the resident stage.  512^2 db2 J=4 streams two levels in one factored pass (128^2 band, one CTA; with the round-1
+    level kernels: one level, 256^2 band, cluster of 2), 1024^2 two levels, Haar never needs a cluster, shapes whose widths are
+    neither divisible by 2^(J+1) nor tileable have no fused plan."""
     import wtpse_b200 as wb
 
     lib = wb._lib.load()
     plan = lib.wtpse_wavelet_resident_cluster
     try:
+        assert plan(512, 512, 1, 4) == 1
+        wb._lib.debug_set("wavelet_db2", 0)
         assert plan(512, 512, 1, 4) == 2
+        wb._lib.debug_set("wavelet_db2", 1)
+        wb._lib.debug_set("wavelet_db2_two", 0)
+        assert plan(512, 512, 1, 4) == 2                # one level per factored pass
+        wb._lib.debug_set("wavelet_db2_two", 1)
         assert plan(1024, 1024, 1, 5) == 2
         assert plan(2048, 2048, 1, 4) == 2
         assert plan(1024, 1024, 1, 2) == 1              # both levels streamed, nothing resident
@@ -120,6 +127,8 @@ def test_wavelet_planner_host_logic():
     finally:
         wb._lib.debug_set("wavelet_resident", 1)
         wb._lib.debug_set("wavelet_peel_max", 8)
+        wb._lib.debug_set("wavelet_db2", 1)
+        wb._lib.debug_set("wavelet_db2_two", 1)
     # workspace covers the low-low bands and sign planes of every streamed level
     n = 64 * 512 * 512
     assert lib.wtpse_wavelet_workspace_bytes(64, 512, 512, 4) >= 4 * (n // 4 + n // 16) + n // 4 + n // 16

@@ -215,3 +215,51 @@ def test_train_step_fused_tail_channels_last_matches_unfused():
     oa, ob = a.step(image.clone(), od, oc), b.step(image.clone(), od, oc)
     for k in ("ins_wt", "dom_wt"):          # sub-step 1's whitening losses see only the initial weights (no RNG)
         assert abs(float(oa[k]) - float(ob[k])) <= 2e-5 * max(abs(float(ob[k])), 1e-3), (k, float(oa[k]), float(ob[k]))
+
+
+@pytest.mark.parametrize("layout", ["nchw", "cl"])
+def test_fused_backward_waits_for_a_programmatic_producer_of_grad_relu(layout):
+    """Round-1 advisor finding: the fused backward runs as a programmatic dependent, and the upstream ReLU gradient is the output of
+    the kernel right in front of it, so the TMA loads of grad_relu must not be issued before griddepcontrol.wait (the z loads may).
+    Stress: a producer that signals launch_dependents at once, spins ~1 ms and only then writes grad_relu over a NaN-filled buffer
+    (wtpse_debug_pdl_slow_copy), the backward launched straight behind it through the C ABI -- twenty times, bitwise against the
+    result with grad_relu in place."""
+    import wtpse_b200 as wb
+    from wtpse_b200.functional import _forward_outputs, _ptr, _stream_ptr, _workspace
+
+    dev = torch.device("cuda:0")
+    lib = wb._lib.load()
+    B, H, W, n, K = 12, 96, 96, 4, 3
+    P = H * W
+    z = _z(B, H, W, 21, dev)
+    g = torch.randn(B, 16, H, W, generator=torch.Generator().manual_seed(5)).to(dev)
+    if layout == "cl":                       # [B][P][16] memory
+        z = z.permute(0, 2, 3, 1).contiguous()
+        g = g.permute(0, 2, 3, 1).contiguous()
+    relu = torch.empty_like(z)
+    dz_ref, dz = torch.empty_like(z), torch.empty_like(z)
+    ws, ws_bytes = _workspace(lib, B, P, dev)
+    losses, (gram, rowstat, domgrad) = _forward_outputs(B, dev)
+    one = torch.ones((), device=dev)
+    st = _stream_ptr(dev)
+    fwd = lib.wtpse_whitening_forward_cl if layout == "cl" else lib.wtpse_whitening_relu_forward
+    bwd = lib.wtpse_whitening_backward_cl if layout == "cl" else lib.wtpse_whitening_relu_backward
+    wb._lib.check(fwd(_ptr(z), _ptr(relu), B, 16, P, n, K, 0.0, 1e-5, _ptr(losses), _ptr(gram), _ptr(rowstat), _ptr(domgrad), _ptr(ws),
+                      ws_bytes, st))
+
+    def backward(grad_relu, out):
+        wb._lib.check(bwd(_ptr(z), _ptr(grad_relu), _ptr(gram), _ptr(rowstat), _ptr(domgrad), _ptr(one), _ptr(one), _ptr(one), B, 16, P, n, K,
+                          _ptr(out), st))
+
+    backward(g, dz_ref)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dz_ref).all()
+    late = torch.empty_like(g)
+    for _ in range(20):
+        late.fill_(float("nan"))
+        dz.zero_()
+        torch.cuda.synchronize()
+        wb._lib.check(lib.wtpse_debug_pdl_slow_copy(_ptr(late), _ptr(g), g.numel(), 2_000_000, st))
+        backward(late, dz)
+        torch.cuda.synchronize()
+        assert torch.equal(dz, dz_ref)

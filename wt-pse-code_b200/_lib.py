@@ -99,6 +99,7 @@ EXPORTS = {
     # include/wtpse_b200_debug.h (diagnostics: not part of the product ABI)
     "wtpse_debug_set": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "wtpse_debug_get": (_c.c_int, [_c.c_char_p, _c.POINTER(_c.c_int)]),
+    "wtpse_debug_pdl_slow_copy": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_void_p]),
     "wtpse_host_plan_create": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_void_p)]),
     "wtpse_host_plan_destroy": (None, [_c.c_void_p]),
     "wtpse_host_plan_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float,

@@ -110,3 +110,27 @@ int wtpse_profile_read(int id, long long* timed_launches, double* total_ms) {
 }
 
 }  // extern "C"
+
+// ---- stress helper for the programmatic-dependent-launch paths (tests/test_gpu_fusion.py) ---------------------------------------
+// A producer that behaves the worst legal way for its dependents: it signals griddepcontrol.launch_dependents at once, then spins
+// for `spin_cycles` clocks, and only then copies src -> dst.  A dependent kernel that reads dst before its own
+// griddepcontrol.wait sees the bytes dst held before (the test fills it with NaN), one that waits sees src.
+namespace wtpse {
+namespace {
+__global__ void __launch_bounds__(256) pdl_slow_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n,
+                                                            long long spin_cycles) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const long long t0 = clock64();
+    while (clock64() - t0 < spin_cycles) {
+    }
+    for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) dst[i] = src[i];
+}
+}  // namespace
+}  // namespace wtpse
+
+extern "C" int wtpse_debug_pdl_slow_copy(float* dst, const float* src, long long n, long long spin_cycles, void* stream) {
+    if (!dst || !src || n <= 0) return WTPSE_ERR_INVALID;
+    // few CTAs: the dependent grid must find free SMs to become resident while this one is still spinning
+    wtpse::pdl_slow_copy_kernel<<<16, 256, 0, static_cast<cudaStream_t>(stream)>>>(dst, src, (long long)n, (long long)spin_cycles);
+    return cudaGetLastError() == cudaSuccess ? WTPSE_OK : WTPSE_ERR_CUDA;
+}

@@ -49,7 +49,10 @@ def prepare_batch(raw_od, img_hwc=None, raw_oc=None):
 
 def od_roi(logits, image, target_oc=None, threshold=0.75):
     """Returns (od_pred, image_roi, sums) with sums = [sum(od_pred), sum(od_pred*target_oc), pos_weight] (device,
-    no host sync).  `image` is incremented by 1 IN PLACE exactly as Trainer.py:850 does."""
+    no host sync).  `image` is incremented by 1 IN PLACE exactly as Trainer.py:850 does (its autograd version counter is
+    bumped, so a graph that saved `image` earlier fails loudly instead of back-propagating through changed data).
+    Precondition: `target_oc` holds {0, 1} labels (what custom_transforms.py:466-499 produces): sum(od_pred * target_oc) is
+    counted as the number of non-zero products -- exact and order-independent for binary targets, wrong for soft ones."""
     _require_cuda_f32(logits, "logits")
     _require_cuda_f32(image, "image")
     if not image.is_contiguous():
@@ -72,6 +75,7 @@ def od_roi(logits, image, target_oc=None, threshold=0.75):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _lib.check(lib.wtpse_od_roi(_ptr(logits), _ptr(target_oc), _ptr(image), _ptr(od_pred), _ptr(roi), B, C, HW,
                                     float(threshold), _ptr(sums), _ptr(ws), ws_bytes, _stream_ptr(dev)))
+    torch.autograd.graph.increment_version(image)
     return od_pred, roi, sums
 
 
