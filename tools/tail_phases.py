@@ -15,7 +15,7 @@ dev = torch.device("cuda:0")
 z = (0.3 * torch.randn(B, 16, H, H, device=dev) + 0.2 * torch.randn(B, 16, 1, 1, device=dev))
 wb._lib.debug_set("tail_stamps", 1)
 names = ["flush begin", "flush end", "ticket(sample)", "reduce", "ticket(batch)", "(unused)", "final begin", "A stage v/stat",
-         "B pairwise", "C sums + domgrad", "D L_dom"]
+         "B pairwise", "C block sums", "D domgrad (warps 1..; warp 0: scalars)"]
 rows = []
 for it in range(6):
     wb.whitening_terms(z, n, 3)

@@ -115,6 +115,53 @@ __device__ __forceinline__ float4 mmd_grad_entry4(const float* __restrict__ v, c
     return make_float4(2.0f * (a0.x + a1.x), 2.0f * (a0.y + a1.y), 2.0f * (a0.z + a1.z), 2.0f * (a0.w + a1.w));
 }
 
+// The same entries for a BLOCK of kBlk consecutive samples b0 .. b0 + kBlk - 1 at one q: every v_c piece is loaded once and
+// used kBlk times.  One thread per (b, q) re-reads all of v for every b -- 0.5 MB through one SM's shared memory, which is what
+// bounded the forward tail's largest phase (2 us of its 4); here it is 36 instead of 80 bytes per four entries.  Per entry the
+// operations and their order are those of mmd_grad_entry (even samples into one accumulator, odd ones into the other):
+// identical bits.  Rows b >= M are skipped.
+template <int kBlk>
+__device__ __forceinline__ void mmd_grad_block4(const float* __restrict__ v, const float* __restrict__ coef, int M, int b0, int q,
+                                                float* __restrict__ out) {
+    float4 vb[kBlk], a0[kBlk], a1[kBlk];
+    const float* crow[kBlk];
+#pragma unroll
+    for (int u = 0; u < kBlk; ++u) {
+        const int b = b0 + u < M ? b0 + u : M - 1;
+        vb[u] = *reinterpret_cast<const float4*>(v + size_t(b) * kVStride + 4 * q);
+        a0[u] = a1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        crow[u] = coef + size_t(b) * M;
+    }
+    int c = 0;
+#pragma unroll 2
+    for (; c + 1 < M; c += 2) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v + size_t(c) * kVStride + 4 * q);
+        const float4 x1 = *reinterpret_cast<const float4*>(v + size_t(c + 1) * kVStride + 4 * q);
+#pragma unroll
+        for (int u = 0; u < kBlk; ++u) {
+            const float k0 = crow[u][c], k1 = crow[u][c + 1];
+            a0[u].x = fmaf(k0, vb[u].x - x0.x, a0[u].x); a0[u].y = fmaf(k0, vb[u].y - x0.y, a0[u].y);
+            a0[u].z = fmaf(k0, vb[u].z - x0.z, a0[u].z); a0[u].w = fmaf(k0, vb[u].w - x0.w, a0[u].w);
+            a1[u].x = fmaf(k1, vb[u].x - x1.x, a1[u].x); a1[u].y = fmaf(k1, vb[u].y - x1.y, a1[u].y);
+            a1[u].z = fmaf(k1, vb[u].z - x1.z, a1[u].z); a1[u].w = fmaf(k1, vb[u].w - x1.w, a1[u].w);
+        }
+    }
+    if (c < M) {
+        const float4 x0 = *reinterpret_cast<const float4*>(v + size_t(c) * kVStride + 4 * q);
+#pragma unroll
+        for (int u = 0; u < kBlk; ++u) {
+            const float k0 = crow[u][c];
+            a0[u].x = fmaf(k0, vb[u].x - x0.x, a0[u].x); a0[u].y = fmaf(k0, vb[u].y - x0.y, a0[u].y);
+            a0[u].z = fmaf(k0, vb[u].z - x0.z, a0[u].z); a0[u].w = fmaf(k0, vb[u].w - x0.w, a0[u].w);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kBlk; ++u)
+        if (b0 + u < M)
+            *reinterpret_cast<float4*>(out + size_t(b0 + u) * kOff + 4 * q) =
+                make_float4(2.0f * (a0[u].x + a1[u].x), 2.0f * (a0[u].y + a1[u].y), 2.0f * (a0[u].z + a1[u].z), 2.0f * (a0[u].w + a1[u].w));
+}
+
 // distance row: D(b, c) = max(sum_e (v_b[e] - v_c[e])^2, 1e-30); rows are kVStride floats, 16-byte aligned
 __device__ __forceinline__ float mmd_distance(const float* __restrict__ vb, const float* __restrict__ vc) {
     const float4* x = reinterpret_cast<const float4*>(vb);
@@ -184,15 +231,16 @@ __device__ __forceinline__ EpiMem resolve_mem(void* smem, void* global, int B, i
 // D(a, c) = max(sum_e (v_a[e] - v_c[e])^2, 1e-30) for all pairs a < c < M; emit(a, c, D) is expected to fill both (a, c)
 // and (c, a).  nthreads cooperate.
 //
-// Register-blocked: one thread owns FOUR rows a0 .. a0+3 (a0 a multiple of 4) against ONE column c, so a step of four
-// components costs five LDS.128 (four broadcast rows + one column) for four pairs instead of eight, and carries 16
+// Register-blocked: one thread owns kPairRows rows a0 .. (a0 a multiple of kPairRows) against ONE column c, so a step of four
+// components costs kPairRows + 1 LDS.128 (broadcast rows + one column) instead of two per pair, and carries 4 kPairRows
 // independent FMA chains -- the one-pair-per-lane version ran at 0.35 instructions per cycle and scheduler with the 6-7
 // warps a tail has (3.3 us for 435 pairs; this one: tools/tail_phases.py).  Consecutive lanes walk c: the row loads
 // broadcast, the column loads hit distinct banks (row stride 124 floats).  Per pair the operations and their order are
 // exactly mmd_distance's, so D -- and everything derived from it -- keeps its bits.
-__device__ __forceinline__ int pair_tasks(int M) {            // sum over row blocks i of the columns c > 4i
+constexpr int kPairRows = 3;                                   // rows per task: M = 30 gives 155 tasks -- one round for 192 or 224 threads
+__device__ __forceinline__ int pair_tasks(int M) {            // sum over row blocks of the columns c > a0
     int n = 0;
-    for (int a0 = 0; a0 + 1 < M; a0 += 4) n += M - 1 - a0;
+    for (int a0 = 0; a0 + 1 < M; a0 += kPairRows) n += M - 1 - a0;
     return n;
 }
 
@@ -201,22 +249,22 @@ __device__ __forceinline__ void pairwise_upper_n(const float* __restrict__ v, in
     const int ntasks = pair_tasks(M);
     for (int t = tid; t < ntasks; t += nthreads) {
         int a0 = 0, r = t;
-        while (r >= M - 1 - a0) { r -= M - 1 - a0; a0 += 4; }
+        while (r >= M - 1 - a0) { r -= M - 1 - a0; a0 += kPairRows; }
         const int c = a0 + 1 + r;
         const float4* xc = reinterpret_cast<const float4*>(v + size_t(c) * kVStride);
-        const float4* xa[4];
+        const float4* xa[kPairRows];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xa[u] = reinterpret_cast<const float4*>(v + size_t(a0 + u < M ? a0 + u : M - 1) * kVStride);
-        float p[4][4];
+        for (int u = 0; u < kPairRows; ++u) xa[u] = reinterpret_cast<const float4*>(v + size_t(a0 + u < M ? a0 + u : M - 1) * kVStride);
+        float p[kPairRows][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kPairRows; ++u)
 #pragma unroll
             for (int w = 0; w < 4; ++w) p[u][w] = 0.f;
 #pragma unroll 3
         for (int e = 0; e < kOff / 4; ++e) {
             const float4 y = xc[e];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kPairRows; ++u) {
                 const float4 x = xa[u][e];
                 float d;
                 d = x.x - y.x; p[u][0] = fmaf(d, d, p[u][0]);
@@ -226,7 +274,7 @@ __device__ __forceinline__ void pairwise_upper_n(const float* __restrict__ v, in
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < kPairRows; ++u)
             if (a0 + u < c) emit(a0 + u, c, clamp_tiny((p[u][0] + p[u][1]) + (p[u][2] + p[u][3])));
     }
 }

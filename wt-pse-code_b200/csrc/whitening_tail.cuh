@@ -45,10 +45,10 @@ struct TailClock {
     __device__ __forceinline__ void mark(int i) { t[i] = clock64(); }
 };
 
-// shared memory of the whole-batch phase: v [M][124] | U [M][M] | stat [B][2] | blk [K*K] f64 | coef [M][M] | wdom [K*K]
+// shared memory of the whole-batch phase: v [M][124] | U [M][M] | stat [B][2] | blk [K*K] f64 | coef [M][M] | wdom [K*K] | domk [M]
 __host__ __device__ inline size_t tail_smem_bytes(int B, int M, int K) {
     const size_t kk = size_t(K > 0 ? K : 1) * size_t(K > 0 ? K : 1);
-    return epi_mem_bytes(B, M, K) + (round4(size_t(M) * M) + round4(kk)) * sizeof(float);
+    return epi_mem_bytes(B, M, K) + (round4(size_t(M) * M) + round4(kk) + round4(size_t(M))) * sizeof(float);
 }
 
 // All NT threads of the calling group (named barrier `bar`) have stored what the ticket publishes.  Returns true, in
@@ -141,6 +141,7 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
     const EpiMem mem = resolve_mem<true>(smem, nullptr, B, M);
     float* coef = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(smem) + epi_mem_bytes(B, M, tp.K));
     float* wdom = coef + round4(size_t(M) * M);        // [K][K]: the domain-pair weight of mmd_coefficient, computed once
+    int* domk = reinterpret_cast<int*>(wdom + round4(size_t(tp.K > 0 ? tp.K : 1) * size_t(tp.K > 0 ? tp.K : 1)));   // [M]: domain of a sample (an integer division each, once)
 
     // A. stage the vectors and the row statistics the sample reducers left in global memory.  Every load of the first
     //    pass (8 vector pieces + one statistic per thread) is issued before anything is stored: one L2 round trip for
@@ -167,6 +168,7 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
         for (int idx = NT + tid; idx < 2 * B; idx += NT) mem.stat[idx] = __ldcg(tp.rowstat + idx);
         // mmd_coefficient(dom, a, c, E) = E * w(domain of a, domain of c) / npairs: tabulate w * (1 / 1) per domain pair
         // with the very expressions mmd_coefficient uses, so the product below has its bits
+        for (int a = tid; a < M; a += NT) domk[a] = dom.domain_of(a);
         for (int idx = tid; idx < tp.K * tp.K; idx += NT) {
             const int ka = idx / tp.K, kc = idx - ka * tp.K;
             float w;
@@ -187,12 +189,12 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
         float* U = mem.U;
         const float npairs = float(dom.K) * float(dom.K - 1) * 0.5f;
         const int K = tp.K;
-        pairwise_upper_n(mem.v, M, tid, NT, [U, coef, wdom, M, K, npairs, &dom](int a, int c, float D) {
+        pairwise_upper_n(mem.v, M, tid, NT, [U, coef, wdom, domk, M, K, npairs](int a, int c, float D) {
             const float u = expm1f(-D);
             U[a * M + c] = u;
             U[c * M + a] = u;
             // == mmd_coefficient(dom, a, c, expf(-D)), which is symmetric in (a, c)
-            const float cf = expf(-D) * wdom[dom.domain_of(a) * K + dom.domain_of(c)] / npairs;
+            const float cf = expf(-D) * wdom[domk[a] * K + domk[c]] / npairs;
             coef[a * M + c] = cf;
             coef[c * M + a] = cf;
         });
@@ -204,8 +206,17 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
     named_bar_sync(bar, NT);
     if (stamp) tp.stamps[8] = clock64();
 
-    // C. per-domain-pair block sums (all warps, one block each for K = 3), instance terms (warp 0)
+    // C. per-domain-pair block sums (all warps, one block each for K = 3)
     if (M > 0) domain_block_sums(mem.U, dom, mem.blk, 0, kWarps, warp, lane);
+    named_bar_sync(bar, NT);
+    if (stamp) tp.stamps[9] = clock64();
+    // D. Two independent strands:
+    //   warp 0        the scalars: instance terms and L_dom (float64 combine: a latency chain of one warp);
+    //   warps 1 ..    d L_dom / d v_b[o] for every MMD sample (`domgrad`), register-blocked over 5 samples per thread so that
+    //                 every piece of v is read from shared memory once per block instead of once per sample
+    //                 (M = 30: one round of tasks for the six or five warps there are).
+    // (Before: every warp in both, one after the other, one thread per (sample, piece): 4.1 + 1.1 us, the first bound by
+    // shared-memory bandwidth -- 0.5 MB through one SM.)
     if (warp == 0) {
         float so = 0.f, sd = 0.f;
         for (int b = lane; b < B; b += 32) {
@@ -214,28 +225,22 @@ __device__ __forceinline__ void tail_final(const TailParams& tp, float* smem, co
         }
         so = warp_sum(so) / float(B);
         sd = warp_sum(sd) / float(B);
+        const float pen = mmd_from_blocks(mem.blk, dom, lane);
         if (lane == 0) {
             tp.losses[0] = so;
             tp.losses[1] = sd;
             tp.losses[3] = so + sd;
-        }
-    }
-    // D'. d L_dom / d v_b[o] for every MMD sample (needs only v and coef: overlaps C's tail)
-    for (int idx = tid; idx < M * (kOff / 4); idx += NT) {
-        const int b = idx / (kOff / 4), q = idx - b * (kOff / 4);
-        *reinterpret_cast<float4*>(tp.domgrad + size_t(b) * kOff + 4 * q) = mmd_grad_entry4(mem.v, coef + size_t(b) * M, M, b, q);
-    }
-    named_bar_sync(bar, NT);
-    if (stamp) tp.stamps[9] = clock64();
-
-    // D. L_dom
-    if (warp == 0) {
-        const float pen = mmd_from_blocks(mem.blk, dom, lane);
-        if (lane == 0) {
             tp.losses[2] = pen;
             tp.ticket[B] = 0;
-            if (stamp) tp.stamps[10] = clock64();
         }
+    } else {
+        constexpr int kBlk = NT >= 224 ? 5 : 6;       // M = 30: 6 x 30 = 180 tasks on 192 threads, or 5 x 30 = 150 on 160
+        const int nblk = (M + kBlk - 1) / kBlk;
+        for (int t = tid - 32; t < nblk * (kOff / 4); t += NT - 32) {
+            const int blk = t / (kOff / 4), q = t - blk * (kOff / 4);
+            mmd_grad_block4<kBlk>(mem.v, coef, M, blk * kBlk, q, tp.domgrad);
+        }
+        if (tp.stamps != nullptr && tid == 32) tp.stamps[10] = clock64();
     }
 }
 
