@@ -103,7 +103,10 @@ def _check_grads(got, want, noise):
         if k.endswith(".bias") and k[:-4] + "weight" in want:
             # a bias gradient is the plain sum of the same output gradients whose products with the layer input make up
             # the weight gradient: its rounding error scales with the layer's gradient, not with its own (possibly zero) value
-            scale = max(scale, float(want[k[:-4] + "weight"].abs().max()))
+            # (the bias of a convolution in front of a BatchNorm has an exactly-zero true gradient: both implementations return
+            # the rounding noise of a sum over B*H*W output gradients, which grows with the image size -- 2.5e-9 at 15x3x512x512
+            # against 0.87 for the run's largest gradient; floor its scale at 3e-4 of that)
+            scale = max(scale, float(want[k[:-4] + "weight"].abs().max()), 3e-4 * gmax)
         err = float((got[k] - w).abs().max())
         floor = 4.0 * float((noise[k] - w).abs().max())
         rel = max(err - floor, 0.0) / scale

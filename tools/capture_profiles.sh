@@ -11,11 +11,11 @@ BENCH="python bench.py --steps 3 --warmup 3 --train-steps 0 --no-cpu-baseline --
 $BENCH > $out/${tag}_plain_bench.log 2>&1 || { echo "bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench_steps3.csv $BENCH > $out/${tag}_ncu_bench.log 2>&1
 python tools/loss_probe.py 2 > $out/${tag}_plain_probe.log 2>&1 || { echo "probe failed"; exit 1; }
-ncu --set full --clock-control none --import-source on -k regex:'gram|apply' --launch-skip 8 -c 8 -f -o $out/${tag}_full_loss \
+ncu --set full --clock-control none --import-source on -k regex:'gram|apply' --launch-skip 0 -c 16 -f -o $out/${tag}_full_loss \
     python tools/loss_probe.py 2 > $out/${tag}_ncu_probe.log 2>&1
 WAVE="python bench.py --track wavelet --steps 2 --warmup 2 --no-cpu-baseline"
 $WAVE > $out/${tag}_plain_wavelet.log 2>&1 || { echo "wavelet bench failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/${tag}_launches_wavelet.csv $WAVE > $out/${tag}_ncu_wavelet_list.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'wavelet|dwt' --launch-skip 6 -c 6 -f -o $out/${tag}_full_wavelet \
+ncu --set full --clock-control none --import-source on -k regex:'wavelet_res|db2_' --launch-skip 9 -c 3 -f -o $out/${tag}_full_wavelet \
     $WAVE > $out/${tag}_ncu_wavelet.log 2>&1
 echo capture done

@@ -28,6 +28,14 @@ def launches(rep):
              float(r[ix["gpu__time_duration.sum"]].replace(",", "")), units[ix["gpu__time_duration.sum"]]) for r in data]
 
 
+def short_name(name):
+    """'void wtpse::<unnamed>::db2_analysis_kernel<1, 1>(wtpse::<unnamed>::Db2FwdArgs)' -> 'db2_analysis_kernel<1, 1>'"""
+    import re
+    head = name.split("(")[0]
+    m = re.search(r"([A-Za-z_0-9]+(?:<[^>]*>)?)\s*$", head)
+    return m.group(1) if m else head
+
+
 def main():
     path = os.path.join(ROOT, "profiles", "traffic.json")
     t = json.load(open(path)) if os.path.exists(path) else {}
@@ -39,8 +47,7 @@ def main():
             t[key] = int(sum(v) / len(v))
     t["per_kernel"] = {}
     for name, b, _, _ in loss:
-        short = name.split("::")[-1].split("(")[0]
-        t["per_kernel"].setdefault(short, []).append(int(b))
+        t["per_kernel"].setdefault(short_name(name), []).append(int(b))
     t["per_kernel"] = {k: int(sum(v) / len(v)) for k, v in t["per_kernel"].items()}
     t["source"] = "ncu --set full --clock-control none of tools/loss_probe.py at 32x16x512x512 (%s): dram__bytes_read.sum + " \
                   "dram__bytes_write.sum per launch, mean over the captured launches" % os.path.basename(sys.argv[1])
@@ -48,7 +55,7 @@ def main():
         wav = launches(sys.argv[2])
         per = {}
         for name, b, _, _ in wav:
-            per.setdefault(name.split("::")[-1].split("(")[0], []).append(b)
+            per.setdefault(short_name(name), []).append(b)
         t["wavelet_fused_step_32x2x512x512_db2_J4"] = int(sum(sum(v) / len(v) for v in per.values()))
         t["wavelet_per_kernel"] = {k: int(sum(v) / len(v)) for k, v in per.items()}
         t["wavelet_source"] = "ncu --set full of `bench.py --track wavelet` (%s): one launch of each kernel of the fused plan at " \
