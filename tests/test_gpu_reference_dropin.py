@@ -108,7 +108,9 @@ def _check_grads(got, want, noise):
             # against 0.87 for the run's largest gradient; floor its scale at 3e-4 of that)
             scale = max(scale, float(want[k[:-4] + "weight"].abs().max()), 3e-4 * gmax)
         err = float((got[k] - w).abs().max())
-        floor = 4.0 * float((noise[k] - w).abs().max())
+        # `noise` is ONE sample of the reference's own run-to-run difference (two stock runs, same seed: ATen's bilinear backward
+        # accumulates with float atomics); the drop-in's difference goes through the same amplification, so allow a few of them
+        floor = 8.0 * float((noise[k] - w).abs().max())
         rel = max(err - floor, 0.0) / scale
         if rel > worst[0]:
             worst = (rel, k)
