@@ -371,3 +371,46 @@ def test_wavelet_full_size_properties():
     loss.backward()
     # the loss is 1-homogeneous in x: <grad, x> == loss (Euler), a size-independent gradient check
     assert abs(float((xg.grad.double() * x.double()).sum()) - float(loss)) <= 1e-4 * float(loss)
+
+
+@pytest.mark.parametrize("wavelet,shape,J", [("db2", (3, 1, 64, 128), 1), ("db2", (5, 1, 32, 256), 2), ("db2", (3, 1, 512, 512), 4),
+                                             ("db2", (1, 1, 1024, 1024), 2), ("db2", (7, 1, 96, 256), 3), ("haar", (3, 1, 512, 512), 3)])
+def test_fused_plans_stay_inside_their_buffers(wavelet, shape, J):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): input, gradient and workspace sit inside larger
+    buffers filled with a byte pattern; after the fused call through the C ABI every guard byte is untouched, the input is
+    unchanged and the result equals the ordinary call's -- for the streamed db2 passes (wavelet_split = 1) and the default plan."""
+    import wtpse_b200 as wb
+    from wtpse_b200.functional import _ptr, _stream_ptr
+    from wtpse_b200.wavelet import _weights
+
+    dev = _dev()
+    lib = wb._lib.load()
+    nmaps, H, W = shape[0] * shape[1], shape[2], shape[3]
+    wid = {"haar": 0, "db2": 1}[wavelet]
+    x = _safe_maps(shape, J, 3, wavelet)
+    n = x.numel()
+    G = 4096                                                     # guard floats / bytes on each side
+    try:
+        for split in (1, -1):
+            wb._lib.debug_set("wavelet_split", split)
+            if lib.wtpse_wavelet_resident_cluster(H, W, wid, J) == 0:
+                continue
+            xg = x.clone().requires_grad_(True)
+            ref_loss = wb.wavelet_shape_loss(xg, wavelet, J)
+            ref_loss.backward()
+            nbytes = lib.wtpse_wavelet_workspace_bytes(nmaps, H, W, J)
+            xin = torch.full((n + 2 * G,), 7.0, device=dev)
+            xin[G:G + n] = x.reshape(-1)
+            gbuf = torch.full((n + 2 * G,), -3.0, device=dev)
+            wbuf = torch.full((nbytes + 2 * G,), 0x5A, dtype=torch.uint8, device=dev)
+            loss = torch.zeros(2, device=dev)
+            wb._lib.check(lib.wtpse_wavelet_loss_resident(_ptr(xin[G:]), nmaps, H, W, wid, J, _weights(None, J), None, _ptr(loss),
+                                                          _ptr(gbuf[G:]), _ptr(wbuf[G:]), nbytes, _stream_ptr(dev)))
+            torch.cuda.synchronize()
+            assert bool((xin[:G] == 7.0).all()) and bool((xin[G + n:] == 7.0).all()) and torch.equal(xin[G:G + n], x.reshape(-1))
+            assert bool((gbuf[:G] == -3.0).all()) and bool((gbuf[G + n:] == -3.0).all())
+            assert bool((wbuf[:G] == 0x5A).all()) and bool((wbuf[G + nbytes:] == 0x5A).all())
+            assert float(loss[1]) == 0.0 and float(loss[0]) == float(ref_loss)
+            assert torch.equal(gbuf[G:G + n].view_as(x), xg.grad)
+    finally:
+        wb._lib.debug_set("wavelet_split", -1)
