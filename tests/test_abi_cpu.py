@@ -112,7 +112,8 @@ def test_wavelet_planner_host_logic():
         wb._lib.debug_set("wavelet_db2_two", 0)
         assert plan(512, 512, 1, 4) == 2                # one level per factored pass
         wb._lib.debug_set("wavelet_db2_two", 1)
-        assert plan(1024, 1024, 1, 5) == 2
+        assert plan(1024, 1024, 1, 5) == 1              # two two-level passes (1024 -> 256 -> 64), level 5 resident in one CTA
+        assert plan(1024, 1024, 1, 3) == 2              # one two-level pass, level 3 resident on the 256^2 bands (cluster of 2)
         assert plan(2048, 2048, 1, 4) == 2
         assert plan(1024, 1024, 1, 2) == 1              # both levels streamed, nothing resident
         assert plan(256, 256, 0, 3) == 1 and plan(1024, 1024, 0, 2) == 1 and plan(512, 512, 0, 4) == 1

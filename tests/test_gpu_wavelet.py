@@ -165,9 +165,9 @@ def test_fused_plans_match_per_level_path(wavelet, shape, J):
 
 
 def test_fused_plan_covers_maps_too_large_for_a_cluster():
-    """1024 x 1024 (BASELINE configs[4]): 4 MB per map does not fit a cluster.  The streamed plan peels levels until the
-    low-low band fits a cluster of <= 2 CTAs (two levels here: 256 x 256 bands); with one peeled level the 512 x 512
-    bands go resident in clusters of 8.  Both against the per-level kernels."""
+    """1024 x 1024 (BASELINE configs[4]): 4 MB per map does not fit a cluster.  The streamed plan peels levels two at a time
+    (1024 -> 256 -> 64, level 5 resident in one CTA per band); with one peeled level the 512 x 512 bands go resident in
+    clusters of 8.  Both against the per-level kernels."""
     import wtpse_b200 as wb
     from wtpse_b200 import wavelet as wv
 
@@ -175,7 +175,7 @@ def test_fused_plan_covers_maps_too_large_for_a_cluster():
     x = _safe_maps((2, 2, 1024, 1024), 5, 11)
     res = []
     try:
-        for resident, peel, cs in ((1, 8, 2), (1, 1, 8), (0, 8, 0)):
+        for resident, peel, cs in ((1, 8, 1), (1, 1, 8), (0, 8, 0)):
             wb._lib.debug_set("wavelet_resident", resident)
             wb._lib.debug_set("wavelet_peel_max", peel)
             assert wv.resident_cluster_size(1024, 1024, "db2", 5) == cs

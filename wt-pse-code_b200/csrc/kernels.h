@@ -161,6 +161,7 @@ cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float*
 // db2 levels in factored form, one or two levels per pass (wavelet_db2.cu)
 extern int g_wavelet_db2;
 extern int g_wavelet_db2_two;
+extern int g_wavelet_db2_deep;
 extern int g_wavelet_db2_rf, g_wavelet_db2_ri, g_wavelet_db2_nw2;
 bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv);
 cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,

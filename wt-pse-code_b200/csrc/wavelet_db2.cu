@@ -676,6 +676,7 @@ size_t db2_fwd_smem(int W, int R, int S, bool two) {
 
 int g_wavelet_db2 = 1;          // diagnostics: 0 = the round-1 level kernels (wavelet_tiles.cu) for db2 as well
 int g_wavelet_db2_two = 1;      // diagnostics: 0 = one level per pass only
+int g_wavelet_db2_deep = 0;     // 1: keep peeling levels with the factored passes as long as the band's width allows, resident stage only for the rest
 
 int g_wavelet_db2_rf = 0, g_wavelet_db2_ri = 0, g_wavelet_db2_nw2 = 0;     // diagnostics: overrides of the geometry below (0 = automatic)
 
