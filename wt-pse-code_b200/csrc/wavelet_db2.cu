@@ -454,6 +454,64 @@ __device__ __forceinline__ void db2_inv_rows(int g_off, int sg_off, int ra, int 
     }
 }
 
+// The same for rows of only 32 sites (level 2 of a pass over 128-wide planes): a warp takes TWO rows at a time, one per half-warp
+// (lane l: sites 2 (l & 15), 2 (l & 15) + 1 of the row of half l >> 4), each half with its own row segment, carried row above and
+// periodic wrap (lane 15 -> lane 0 of the same half).  Both halves run the same instruction stream; a half that has run out of
+// rows repeats its last row without storing.
+template <bool kHasLL, bool kToSmem>
+__device__ __forceinline__ void db2_inv_rows_half(int g_off, int sg_off, int ra, int rb, const SynConst& c, int out_off, float* __restrict__ out_g,
+                                                  long long out_ld, int lane) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int wj = 32;
+    const int l16 = lane & 15, half = lane >> 4;
+    const int mid = ra + (rb - ra + 1) / 2;
+    const int r_first = half ? mid : ra, r_end = half ? rb : mid;            // this half's rows [r_first, r_end)
+    const int iters = mid - ra;                                                // >= the other half's count
+    const float* gbase = reinterpret_cast<const float*>(smem + (kHasLL ? g_off : 0));
+    const unsigned char* sbase = smem + sg_off;
+    float* outs = reinterpret_cast<float*>(smem + (kToSmem ? out_off : 0));
+    float2 q3lo, q3hi;
+    {
+        const int r0 = (r_first < r_end ? r_first : ra) - 1;                  // an empty half still executes (on valid memory)
+        float2 g2 = make_float2(0.f, 0.f);
+        if (kHasLL) g2 = *reinterpret_cast<const float2*>(gbase + r0 * wj + 2 * l16);
+        const unsigned b = *reinterpret_cast<const unsigned short*>(sbase + r0 * wj + 2 * l16);
+        SynPair d;
+        syn_vert_pair<kHasLL, false>(g2, b, c, q3lo, q3hi, d);
+    }
+    for (int i = 0; i < iters; ++i) {
+        const bool valid = r_first + i < r_end;
+        const int r = valid ? r_first + i : (r_first < r_end ? r_end - 1 : ra);
+        const float* grow = gbase + r * wj + 2 * l16;
+        const unsigned char* srow = sbase + r * wj + 2 * l16;
+        float2 g2 = make_float2(0.f, 0.f);
+        if (kHasLL) g2 = *reinterpret_cast<const float2*>(grow);
+        const unsigned b = *reinterpret_cast<const unsigned short*>(srow);
+        // the row's last site (lane 15 of this half, site 1) supplies the first site's left neighbour: compute this lane's own
+        // site-1 neighbour terms first (they are needed anyway), pass lane 15's to lane 0
+        float2 cq_lo = q3lo, cq_hi = q3hi;
+        SynPair v;
+        syn_vert_pair<kHasLL, true>(g2, b, c, cq_lo, cq_hi, v);
+        if (valid) { q3lo = cq_lo; q3hi = cq_hi; }
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+            const float2 Xlo = pr ? v.Blo : v.Alo, Xhi = pr ? v.Bhi : v.Ahi;
+            const float2 pb = __fadd2_rn(Xlo, Xhi);
+            const float2 qn = __ffma2_rn(splat(kRho), Xhi, Xlo);               // qt: .x for site 1, .y for the next lane's site 0
+            const float ql = __shfl_sync(0xffffffffu, qn.y, (lane & 16) | ((l16 + 15) & 15));     // lane 0 of a half: from its lane 15 (wrap)
+            float4 o;
+            o.x = fmaf(ql, kCA, kI3 * pb.x);
+            o.y = fmaf(ql, kCB, pb.x);
+            o.z = fmaf(qn.x, kCA, kI3 * pb.y);
+            o.w = fmaf(qn.x, kCB, pb.y);
+            if (valid) {
+                if (kToSmem) *reinterpret_cast<float4*>(outs + (2 * (r - 1) + pr) * (2 * wj) + 4 * l16) = o;
+                else *reinterpret_cast<float4*>(out_g + (long long)(2 * (r - 1) + pr) * out_ld + 4 * l16) = o;
+            }
+        }
+    }
+}
+
 struct Db2InvArgs {
     const float* g;             // gradient of the low-low band that enters the pass (ignored when !kHasLL)
     const unsigned char* sg1;   // [nmaps][H/2][W/2]
@@ -522,7 +580,7 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_synthesis_kernel(Db2Inv
     // warps: [0, NW1) level 1 -> global, [NW1, NW) level 2 -> dL/dLL1 in shared memory (two-level pass only), warp NW = producer.
     // Level 2 of piece n + 1 overlaps level 1 of piece n: two dL/dLL1 buffers, handed over through mbarriers.
     constexpr int NW = kDb2MaxThreads / 32 - 1;
-    constexpr int K2 = kTwo ? K1 / 2 : 1;
+    constexpr int K2 = (kTwo && K1 >= 2) ? K1 / 2 : 1;       // K1 == 1 (128-wide planes): level 2 has 32 sites per row -> db2_inv_rows_half
     const int NW2 = kTwo ? a.nw2 : 0, NW1 = NW - NW2;
     const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, h4 = H >> 2, w4 = W >> 2, R = a.R, S = a.stages;
     const Db2InvLayout lay = db2_inv_layout(W, R, kTwo, kHasLL, S);
@@ -618,9 +676,13 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_synthesis_kernel(Db2Inv
             mbar_wait(&full[s], (n / S) & 1);
             if (k > 0) mbar_wait(&g1_empty[b], (k & 1) ^ 1);
             const int lo2 = floor_half(i_first - 1) - 1, rows2 = floor_half(i_first + len - 1) - lo2;
-            const int seg2 = (rows2 + NW2 - 1) / NW2;
+            const int nw2d = kTwo ? NW2 : 1;
+            const int seg2 = (rows2 + nw2d - 1) / nw2d;
             const int ra2 = 1 + w * seg2, rb2 = min(ra2 + seg2, rows2 + 1);
-            if (ra2 < rb2) db2_inv_rows<K2, kHasLL, true>(st + lay.g, st + lay.s2, ra2, rb2, c2, lay.g1buf + b * lay.g1bytes, nullptr, 0, lane);
+            if (ra2 < rb2) {
+                if constexpr (K1 >= 2) db2_inv_rows<K2, kHasLL, true>(st + lay.g, st + lay.s2, ra2, rb2, c2, lay.g1buf + b * lay.g1bytes, nullptr, 0, lane);
+                else db2_inv_rows_half<kHasLL, true>(st + lay.g, st + lay.s2, ra2, rb2, c2, lay.g1buf + b * lay.g1bytes, nullptr, 0, lane);
+            }
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(&g1_full[b]);
@@ -701,7 +763,6 @@ int best_seg(int rows, int pairs, int threads) {
 bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv) {
     if (!g_wavelet_db2 || (two && !g_wavelet_db2_two)) return false;
     if (W != 128 && W != 256 && W != 512 && W != 1024) return false;    // warp-per-row synthesis: W / 128 chunks of 64 sites, unrolled
-    if (two && W < 256) return false;
     if (H % (two ? 4 : 2) || H < (two ? 16 : 4)) return false;
     const int hl = two ? H / 4 : H / 2;
     int R = divisor_le(hl, g_wavelet_db2_rf > 0 ? g_wavelet_db2_rf : (two ? 8 : 16));
@@ -750,14 +811,9 @@ cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, u
 namespace {
 template <int K1>
 cudaError_t launch_db2_synthesis_k(const Db2InvArgs& a, bool two, bool has_ll, int grid, size_t smem, cudaStream_t stream) {
-    if (two) {
-        if constexpr (K1 >= 2) {
-            return has_ll ? launch_db2(db2_synthesis_kernel<K1, true, true>, grid, kDb2MaxThreads, smem, stream, a, true)
-                          : launch_db2(db2_synthesis_kernel<K1, true, false>, grid, kDb2MaxThreads, smem, stream, a, true);
-        } else {
-            return cudaErrorInvalidValue;
-        }
-    }
+    if (two)
+        return has_ll ? launch_db2(db2_synthesis_kernel<K1, true, true>, grid, kDb2MaxThreads, smem, stream, a, true)
+                      : launch_db2(db2_synthesis_kernel<K1, true, false>, grid, kDb2MaxThreads, smem, stream, a, true);
     return has_ll ? launch_db2(db2_synthesis_kernel<K1, false, true>, grid, kDb2MaxThreads, smem, stream, a, true)
                   : launch_db2(db2_synthesis_kernel<K1, false, false>, grid, kDb2MaxThreads, smem, stream, a, true);
 }

@@ -221,11 +221,12 @@ static int db2_pass_plan(int H, int W, int J, int nmaps, int pass[16], int* k_ou
         const int Hc = H >> k, Wc = W >> k, rem = J - k;
         if (k > 0 && !g_wavelet_db2_deep) {
             // the band fits a cluster of <= 2: go resident -- unless two more levels can be taken by a two-level pass, which beats the
-            // resident stage on bands of 256^2 and larger (1024^2 maps, J = 4: 265.5 -> 259.5 us; on 128^2 bands only one-level
-            // passes exist and the resident stage wins: 52.3 vs 56.1 us)
+            // resident stage on bands of 256^2 and larger (1024^2 maps, J = 4: 265.5 -> 259.5 us).  On 128^2 bands a pass pair
+            // costs what the resident stage costs (each extra kernel boundary is ~3-4 us of drain and fill: 512^2 J = 4 51.4 vs 52.2 us,
+            // J = 5 57.5 vs 54.2 us), so the band goes resident
             const int c = wavelet_resident_cluster(Hc, Wc, 4, rem, nmaps);
             int r0, r1, r2, r3, r4;
-            const bool two_more = rem >= 2 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &r0, &r1, &r2, &r3, &r4);
+            const bool two_more = rem >= 2 && Wc >= 256 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &r0, &r1, &r2, &r3, &r4);
             if (c > 0 && c <= 2 && !two_more) { *cs = c; break; }
         }
         int Rf, Sf, NCf, Ri, Si;
