@@ -35,6 +35,10 @@ int         wtpse_profile_read(int id, long long* timed_launches, double* total_
  *   "wavelet_tiles"        level 1 of the streamed plan as TMA pipelines (1, default) or per-thread loads (0)
  *   "wavelet_db2"          db2 streamed levels: factored one-/two-level passes of wavelet_db2.cu (1, default) or the round-1 level kernels (0)
  *   "wavelet_db2_two"      0: the factored passes take one level each (LL1 goes through memory)
+ *   "wavelet_db2_deep"     1: keep peeling levels with the pass kernels as long as the band's width allows (default 0: see the planner)
+ *   "wavelet_db2_rf" / "_ri" / "_nw2"   overrides of the pass geometry (strip rows, piece rows, warps of the level-2 group; 0 = automatic)
+ *   "wavelet_haar_passes"  Haar levels through the pass kernels (1, default) or the band kernel / round-1 level kernels only (0)
+ *   "wavelet_haar_min_log2px"  smallest map (log2 of its pixels, default 16) for which Haar takes the pass kernels
  *   "wavelet_peel_max"     most levels streamed before the resident stage (default 8)
  *   "wavelet_cluster_max"  largest cluster size of the resident stage (1..8, default 8)
  * Return WTPSE_OK, or WTPSE_ERR_INVALID for an unknown name. */

@@ -414,3 +414,45 @@ def test_fused_plans_stay_inside_their_buffers(wavelet, shape, J):
             assert torch.equal(gbuf[G:G + n].view_as(x), xg.grad)
     finally:
         wb._lib.debug_set("wavelet_split", -1)
+
+
+@pytest.mark.parametrize("shape,J", [((3, 1, 64, 128), 1), ((5, 1, 32, 256), 2), ((3, 2, 256, 256), 4), ((2, 1, 512, 512), 3),
+                                     ((7, 1, 128, 512), 2), ((1, 2, 1024, 1024), 5), ((37, 1, 96, 256), 3), ((2, 1, 16, 256), 2)])
+def test_haar_through_the_pass_kernels(shape, J):
+    """Haar levels through the one- / two-level pass kernels of csrc/wavelet_db2.cu (no overlap: no halo rows, no neighbour
+    exchange, a 2 x 2 Hadamard butterfly per site in the synthesis) against the per-level kernels and, for the small cases,
+    the float64 specification; the band kernel (wavelet_haar_passes = 0) must agree too."""
+    import wtpse_b200 as wb
+    from oracle import wavelet_np as wn
+
+    x = _safe_maps(shape, J, seed=2 * J + shape[0], wavelet="haar")
+    weights = tuple(1.0 - 0.15 * j for j in range(J))
+
+    def run():
+        xg = x.clone().requires_grad_(True)
+        loss = wb.wavelet_shape_loss(xg, "haar", J, weights)
+        (1.3 * loss).backward()
+        return float(loss.detach()), xg.grad.clone()
+
+    try:
+        wb._lib.debug_set("wavelet_resident", 0)
+        lp, gp = run()
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_haar_min_log2px", 0)          # every size that has a pass plan takes it
+        for passes, split in ((1, -1), (1, 1), (0, -1)):
+            wb._lib.debug_set("wavelet_haar_passes", passes)
+            wb._lib.debug_set("wavelet_split", split)
+            l, g = run()
+            l2, g2 = run()
+            assert l2 == l and torch.equal(g, g2), (passes, split)
+            assert abs(l - lp) <= 2e-6 * abs(lp), (passes, split)
+            assert rel_err(g.cpu().numpy(), gp.cpu().numpy()) < 2e-6, (passes, split)
+        if x.numel() <= 1 << 18:
+            ref_loss, ref_grad = wn.shape_loss(x.cpu().numpy(), "haar", J, weights)
+            assert abs(l - ref_loss) <= TOL * abs(ref_loss)
+            assert rel_err(g.cpu().numpy(), 1.3 * ref_grad) < TOL
+    finally:
+        wb._lib.debug_set("wavelet_resident", 1)
+        wb._lib.debug_set("wavelet_split", -1)
+        wb._lib.debug_set("wavelet_haar_passes", 1)
+        wb._lib.debug_set("wavelet_haar_min_log2px", 16)

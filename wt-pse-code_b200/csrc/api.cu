@@ -248,6 +248,8 @@ const Knob* knobs(int* count) {
         {"wavelet_tiles", &g_wavelet_tiles, 0, 1},
         {"wavelet_db2", &g_wavelet_db2, 0, 1},
         {"wavelet_db2_two", &g_wavelet_db2_two, 0, 1},
+        {"wavelet_haar_passes", &g_wavelet_haar_passes, 0, 1},
+        {"wavelet_haar_min_log2px", &g_wavelet_haar_min_log2px, 0, 40},
         {"wavelet_db2_deep", &g_wavelet_db2_deep, 0, 1},
         {"wavelet_db2_rf", &g_wavelet_db2_rf, 0, 64},
         {"wavelet_db2_ri", &g_wavelet_db2_ri, 0, 128},

@@ -144,6 +144,7 @@ cudaError_t launch_wavelet_resident(const float* x, int nmaps, int H, int W, int
 // streaming level 1 + resident levels 2..J (wavelet_stream.cu)
 extern int g_wavelet_split;
 extern int g_wavelet_peel_max;
+extern int g_wavelet_haar_min_log2px;
 int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps = 0);          // 0 none, 1 whole map resident, 2 streamed plan
 int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs);  // streamed levels k (0: no such plan)
 size_t wavelet_stream_partials(int nmaps, int H, int W);
@@ -163,13 +164,14 @@ extern int g_wavelet_db2;
 extern int g_wavelet_db2_two;
 extern int g_wavelet_db2_deep;
 extern int g_wavelet_db2_rf, g_wavelet_db2_ri, g_wavelet_db2_nw2;
-bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv);
+extern int g_wavelet_haar_passes;
+bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv, bool haar = false);
 cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,
                                 float sc1, float sc2, bool grad, bool pdl_wait, double* partial, int sm_count, cudaStream_t stream,
-                                int* n_partials);
+                                int* n_partials, bool haar = false);
 cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const unsigned char* sg2, float* out, int nmaps, int H, int W,
                                  bool two, bool has_ll, float sc1, float sc2, const float* upstream, const double* partial, int n_partials,
-                                 float* loss, int sm_count, cudaStream_t stream);
+                                 float* loss, int sm_count, cudaStream_t stream, bool haar = false);
 cudaError_t launch_scale_unless_one(float* data, long long n, const float* scale, int sm_count, cudaStream_t stream);
 
 }  // namespace wtpse

@@ -107,7 +107,7 @@ struct Db2FwdArgs {
 // One level on a strip in shared memory.  in: rows_out * 2 + 2 rows of width w (row stride w) at byte offset in_off.
 // Output row i < n_own: sign byte + |d| (rows beyond are halo rows of the next level: low-low only).
 //   kLLSmem: low-low rows (times h1^2) -> shared memory at ll_off, row stride w / 2; else -> ll_g (row stride w / 2).
-template <bool kLLSmem, bool kGrad>
+template <bool kLLSmem, bool kGrad, bool kHaar>
 __device__ __forceinline__ void db2_fwd_level(int in_off, int w, int rows_out, int n_own, int seg, int ll_off, float* __restrict__ ll_g,
                                               unsigned char* __restrict__ sg_g, float sc, float& ab, int tid, int nthreads) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -125,13 +125,17 @@ __device__ __forceinline__ void db2_fwd_level(int in_off, int w, int rows_out, i
         // running pointers (byte arithmetic once per task, not per row)
         const float* r0 = in + (2 * i0) * w + c0;                   // columns c0 .. c0 + 3 of the current even row
         const float* r4 = in + (2 * i0) * w + c4;                   // columns c0 + 4, c0 + 5 (wrapped)
-        float P[4];
-        {
+        // Haar (kHaar): the filters do not overlap -- output row i reads input rows 2 i, 2 i + 1 only, nothing is carried, and the
+        // unscaled bands are plain sums / differences (scale 1/2 each, folded like db2's)
+        float P[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!kHaar) {
             float a[4], b[4];
             db2_row(r0, 0, int(r4 - r0), a[0], a[1], a[2], a[3]);
             db2_row(r0 + w, 0, int(r4 - r0), b[0], b[1], b[2], b[3]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) P[u] = fmaf(a[u], kI3, b[u]);
+        } else {
+            r0 -= 2 * w;                                            // the loop advances before it reads
         }
         const int d4 = int(r4 - r0);
         float* llp_s = ll_s + i0 * w2 + 2 * jj;
@@ -141,18 +145,26 @@ __device__ __forceinline__ void db2_fwd_level(int in_off, int w, int rows_out, i
         for (int i = i0; i < i1; ++i) {
             r0 += 2 * w;
             float a[4], b[4], lo[4], hi[4];
-            db2_row(r0, 0, d4, a[0], a[1], a[2], a[3]);
-            db2_row(r0 + w, 0, d4, b[0], b[1], b[2], b[3]);
+            if (!kHaar) {
+                db2_row(r0, 0, d4, a[0], a[1], a[2], a[3]);
+                db2_row(r0 + w, 0, d4, b[0], b[1], b[2], b[3]);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float Pn = fmaf(a[u], kI3, b[u]), Qn = fmaf(a[u], -kR3, b[u]);
-                lo[u] = fmaf(Qn, kKl, P[u]);
-                hi[u] = fmaf(Qn, kKh, P[u]);
-                P[u] = Pn;
+                for (int u = 0; u < 4; ++u) {
+                    const float Pn = fmaf(a[u], kI3, b[u]), Qn = fmaf(a[u], -kR3, b[u]);
+                    lo[u] = fmaf(Qn, kKl, P[u]);
+                    hi[u] = fmaf(Qn, kKh, P[u]);
+                    P[u] = Pn;
+                }
+            } else {
+                const float4 va = *reinterpret_cast<const float4*>(r0), vb = *reinterpret_cast<const float4*>(r0 + w);
+                a[0] = va.x + va.y; a[1] = va.x - va.y; a[2] = va.z + va.w; a[3] = va.z - va.w;      // along W: low, high of sites 0, 1
+                b[0] = vb.x + vb.y; b[1] = vb.x - vb.y; b[2] = vb.z + vb.w; b[3] = vb.z - vb.w;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { lo[u] = a[u] + b[u]; hi[u] = a[u] - b[u]; }                // along H
             }
             // arrays: 0 = low along W of site 0, 1 = high along W of site 0, 2 / 3 = the same for site 1
             // unscaled bands: LL = lo[0], HL = hi[0] (high along H), LH = lo[1], HH = hi[1]
-            const float2 LL = make_float2(lo[0] * kH11, lo[2] * kH11);
+            const float2 LL = make_float2(lo[0] * (kHaar ? 0.5f : kH11), lo[2] * (kHaar ? 0.5f : kH11));
             if (kLLSmem) *reinterpret_cast<float2*>(llp_s) = LL;
             else if (store_ll) *reinterpret_cast<float2*>(llp_g) = LL;
             if (i < n_own) {
@@ -175,11 +187,11 @@ __device__ __forceinline__ void db2_fwd_level(int in_off, int w, int rows_out, i
             llp_g += w2;
             sgp += w2;
         }
-        ab += sc * fmaf(kH12, s1, kH22 * s2);
+        ab += kHaar ? sc * (0.5f * (s1 + s2)) : sc * fmaf(kH12, s1, kH22 * s2);
     }
 }
 
-template <bool kTwo, bool kGrad>
+template <bool kTwo, bool kGrad, bool kHaar>
 __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_analysis_kernel(Db2FwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -190,8 +202,9 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_analysis_kernel(Db2FwdA
     const int NW2 = kTwo ? a.nw2 : 0;
     const int NW1 = int(blockDim.x) / 32 - 1 - NW2;
     const int hl = kTwo ? H >> 2 : H >> 1;                  // rows of the last level
-    const int rows_in = kTwo ? 4 * R + 6 : 2 * R + 2;
-    const int n1 = kTwo ? 2 * R + 2 : R;                    // level-1 rows a strip computes
+    constexpr int HALO = kHaar ? 0 : 2;                     // overlap rows of one level (db2: 2, Haar: none)
+    const int rows_in = kTwo ? 4 * R + 3 * HALO : 2 * R + HALO;
+    const int n1 = kTwo ? 2 * R + HALO : R;                 // level-1 rows a strip computes
     const uint32_t stage_bytes = uint32_t(rows_in) * W * 4u;
     const int ll1_bytes = kTwo ? n1 * (W >> 1) * 4 : 0;     // one of the two LL1 buffers
     const int ll1_off = int(S * stage_bytes);
@@ -243,12 +256,12 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_analysis_kernel(Db2FwdA
             mbar_wait(&full[s], (n / S) & 1);
             if (!kTwo) {
                 const long long row0 = m * h2 + (long long)R * st;
-                db2_fwd_level<false, kGrad>(int(s * stage_bytes), W, R, R, a.seg1, 0, a.ll ? a.ll + row0 * w2 : nullptr, a.sg1 + row0 * w2, a.sc1, ab, tid, NC1);
+                db2_fwd_level<false, kGrad, kHaar>(int(s * stage_bytes), W, R, R, a.seg1, 0, a.ll ? a.ll + row0 * w2 : nullptr, a.sg1 + row0 * w2, a.sc1, ab, tid, NC1);
             } else {
                 const int b = n & 1, k = n >> 1;
                 if (k > 0) mbar_wait(&ll_empty[b], (k & 1) ^ 1);                // level 2 is done with this buffer's previous strip
                 const long long row1 = m * h2 + (long long)2 * R * st;          // first level-1 row of the strip
-                db2_fwd_level<true, kGrad>(int(s * stage_bytes), W, n1, 2 * R, a.seg1, ll1_off + b * ll1_bytes, nullptr, a.sg1 + row1 * w2, a.sc1, ab, tid,
+                db2_fwd_level<true, kGrad, kHaar>(int(s * stage_bytes), W, n1, 2 * R, a.seg1, ll1_off + b * ll1_bytes, nullptr, a.sg1 + row1 * w2, a.sc1, ab, tid,
                                            NC1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ll_full[b]);                        // release: the LL1 rows this warp wrote
@@ -269,7 +282,7 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_analysis_kernel(Db2FwdA
             const int b = n & 1, k = n >> 1;
             mbar_wait(&ll_full[b], k & 1);
             const long long row2 = m * (H >> 2) + (long long)R * st;
-            db2_fwd_level<false, kGrad>(ll1_off + b * ll1_bytes, w2, R, R, a.seg2, 0, a.ll ? a.ll + row2 * w4 : nullptr, a.sg2 + row2 * w4, a.sc2, ab, tid, NC2);
+            db2_fwd_level<false, kGrad, kHaar>(ll1_off + b * ll1_bytes, w2, R, R, a.seg2, 0, a.ll ? a.ll + row2 * w4 : nullptr, a.sg2 + row2 * w4, a.sc2, ab, tid, NC2);
             __syncwarp();
             if (lane == 0) mbar_arrive(&ll_empty[b]);
             acc += double(ab);
@@ -551,25 +564,26 @@ __device__ __forceinline__ int floor_half(int v) { return v >= 0 ? v >> 1 : -((1
 struct Db2InvLayout {
     int g, s2, s1, stage, g1buf, g1bytes;
 };
-__host__ __device__ inline Db2InvLayout db2_inv_layout(int W, int R, bool two, bool has_ll, int S) {
+__host__ __device__ inline Db2InvLayout db2_inv_layout(int W, int R, bool two, bool has_ll, int S, bool haar = false) {
     Db2InvLayout o;
     const int w2 = W >> 1, w4 = W >> 2;
+    const int above = haar ? 0 : 1;                 // coefficient rows above a piece (db2 overlap)
     int off = 0;
     o.g = off;
     if (two) {
-        const int n2 = R / 2 + 3;
+        const int n2 = R / 2 + 1 + 2 * above;
         if (has_ll) off += n2 * w4 * 4;
         o.s2 = off;
         off += (n2 * w4 + 15) & ~15;
     } else {
-        if (has_ll) off += (R + 1) * w2 * 4;
+        if (has_ll) off += (R + above) * w2 * 4;
         o.s2 = off;
     }
     o.s1 = off;
-    off += ((R + 1) * w2 + 15) & ~15;
+    off += ((R + above) * w2 + 15) & ~15;
     o.stage = (off + 127) & ~127;
     o.g1buf = S * o.stage;
-    o.g1bytes = two ? (R + 6) * w2 * 4 : 0;         // 2 (n2 - 1) <= R + 4 rows of dL/dLL1, one of two buffers
+    o.g1bytes = two ? (R + 2 + 4 * above) * w2 * 4 : 0;     // rows of dL/dLL1 one piece needs, one of two buffers
     return o;
 }
 
@@ -692,6 +706,157 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_synthesis_kernel(Db2Inv
     }
 }
 
+// ---- Haar synthesis: no overlap, so no carried row, no neighbour exchange -- a 2 x 2 output block is the Hadamard butterfly of
+// its site's four gradient coefficients:  x[2i + pr][2j + pc] = 1/2 (gLL + (-1)^pc gLH + (-1)^pr gHL + (-1)^(pr + pc) gHH).
+// Same warp-per-row layout, sign bytes and packed site pairs as the db2 rows above.
+template <int K, bool kHasLL, bool kToSmem>
+__device__ __forceinline__ void haar_inv_rows(int g_off, int sg_off, int ra, int rb, float cLL, float cD, const SynConst& c, int out_off,
+                                              float* __restrict__ out_g, long long out_ld, int lane) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int wj = 64 * K;
+    const float* grow = reinterpret_cast<const float*>(smem + (kHasLL ? g_off : 0)) + ra * wj + 2 * lane;
+    const unsigned char* srow = smem + sg_off + ra * wj + 2 * lane;
+    float* orow_s = reinterpret_cast<float*>(smem + (kToSmem ? out_off : 0)) + (2 * ra) * (2 * wj) + 4 * lane;
+    float* orow_g = out_g + (long long)(2 * ra) * out_ld + 4 * lane;
+    for (int r = ra; r < rb; ++r) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float2 t0 = make_float2(0.f, 0.f);
+            if (kHasLL) t0 = __fmul2_rn(splat(cLL), *reinterpret_cast<const float2*>(grow + 64 * k));
+            const unsigned b = *reinterpret_cast<const unsigned short*>(srow + 64 * k);
+            const float2 sLH = __fadd2_rn(make_float2(code_float<0>(b, c.m0), code_float<8>(b, c.m8)), make_float2(code_bias<0>(), code_bias<8>()));
+            const float2 sHL = __fadd2_rn(make_float2(code_float<2>(b, c.m2), code_float<10>(b, c.m10)), make_float2(code_bias<2>(), code_bias<10>()));
+            const float2 sHH = __fadd2_rn(make_float2(code_float<4>(b, c.m4), code_float<12>(b, c.m12)), make_float2(code_bias<4>(), code_bias<12>()));
+            const float2 eHL = __fmul2_rn(splat(cD), sHL);
+            const float2 p = __ffma2_rn(splat(cD), sHL, t0), m = __fadd2_rn(t0, make_float2(-eHL.x, -eHL.y));        // rows 2i, 2i + 1
+            const float2 eHH = __fmul2_rn(splat(cD), sHH);
+            const float2 q = __ffma2_rn(splat(cD), sLH, eHH), rr = __ffma2_rn(splat(cD), sLH, make_float2(-eHH.x, -eHH.y));
+            const float4 o0 = make_float4(p.x + q.x, p.x - q.x, p.y + q.y, p.y - q.y);
+            const float4 o1 = make_float4(m.x + rr.x, m.x - rr.x, m.y + rr.y, m.y - rr.y);
+            if (kToSmem) {
+                *reinterpret_cast<float4*>(orow_s + 128 * k) = o0;
+                *reinterpret_cast<float4*>(orow_s + 2 * wj + 128 * k) = o1;
+            } else {
+                *reinterpret_cast<float4*>(orow_g + 128 * k) = o0;
+                *reinterpret_cast<float4*>(orow_g + out_ld + 128 * k) = o1;
+            }
+        }
+        grow += wj;
+        srow += wj;
+        orow_s += 2 * (2 * wj);
+        orow_g += 2 * out_ld;
+    }
+}
+
+template <int K1, bool kTwo, bool kHasLL>
+__global__ void __launch_bounds__(kDb2MaxThreads, 1) haar_synthesis_kernel(Db2InvArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    constexpr int NW = kDb2MaxThreads / 32 - 1;
+    constexpr int K2 = kTwo ? K1 / 2 : 1;
+    const int NW2 = kTwo ? a.nw2 : 0, NW1 = NW - NW2;
+    const int H = a.H, W = a.W, h2 = H >> 1, w2 = W >> 1, h4 = H >> 2, w4 = W >> 2, R = a.R, S = a.stages;
+    const Db2InvLayout lay = db2_inv_layout(W, R, kTwo, kHasLL, S, true);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + lay.g1buf + 2 * lay.g1bytes);
+    uint64_t* empty = full + S;
+    uint64_t* g1_full = empty + S;
+    uint64_t* g1_empty = g1_full + 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&g1_full[b], NW2 > 0 ? NW2 : 1);
+            mbar_init(&g1_empty[b], NW1);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    Db2Pieces pieces((long long)a.nmaps * h2, h2, R);
+    long long m;
+    int i_first, len;
+    if (warp == NW) {
+        if (lane == 0) {
+            for (int n = 0; pieces.next(m, i_first, len); ++n) {
+                const int s = n % S;
+                if (n >= S) mbar_wait(&empty[s], ((n / S) & 1) ^ 1);
+                unsigned char* dst = smem + size_t(s) * lay.stage;
+                uint32_t bytes = uint32_t(len) * w2;
+                if (kTwo) {
+                    const int lo2 = i_first >> 1, n2 = ((i_first + len - 1) >> 1) - lo2 + 1;
+                    bytes += uint32_t(n2) * w4 * (kHasLL ? 5u : 1u);
+                    mbar_arrive_expect_tx(&full[s], bytes);
+                    if (kHasLL)
+                        bulk_rows(dst + lay.g, a.g + (m * (long long)h4 + lo2) * w4, uint32_t(n2) * w4 * 4u, &full[s], 0, false);
+                    bulk_rows(dst + lay.s2, a.sg2 + (m * (long long)h4 + lo2) * w4, uint32_t(n2) * w4, &full[s], 0, false);
+                } else {
+                    if (kHasLL) bytes += uint32_t(len) * w2 * 4u;
+                    mbar_arrive_expect_tx(&full[s], bytes);
+                    if (kHasLL) bulk_rows(dst + lay.g, a.g + (m * (long long)h2 + i_first) * w2, uint32_t(len) * w2 * 4u, &full[s], 0, false);
+                }
+                bulk_rows(dst + lay.s1, a.sg1 + (m * (long long)h2 + i_first) * w2, uint32_t(len) * w2, &full[s], 0, false);
+            }
+        }
+        __syncwarp();
+        if (a.loss && blockIdx.x == 0) {                    // fixed-order sum of the loss partials, once this CTA's loads are queued
+            double s = 0.0;
+            for (int i = lane; i < a.n_partials; i += 32) s += a.partial[i];
+            s = warp_sum(s);
+            if (lane == 0) a.loss[0] = float(s);
+        }
+    } else if (warp < NW1) {
+        const float gs = a.upstream ? __ldg(a.upstream) : 1.0f;
+        const SynConst c = make_syn_const(a.sc1, gs, a.magic);
+        const float cLL = 0.5f * gs, cD = 0.5f * a.sc1 * gs;
+        for (int n = 0; pieces.next(m, i_first, len); ++n) {
+            const int s = n % S;
+            const int st = s * lay.stage;
+            mbar_wait(&full[s], (n / S) & 1);
+            float* obase = a.out + m * (long long)H * W + (long long)(2 * i_first) * W;
+            const int seg1 = (len + NW1 - 1) / NW1;
+            const int ra1 = warp * seg1, rb1 = min(ra1 + seg1, len);
+            if (!kTwo) {
+                if (ra1 < rb1) haar_inv_rows<K1, kHasLL, false>(st + lay.g, st + lay.s1, ra1, rb1, cLL, cD, c, 0, obase, W, lane);
+            } else {
+                const int b = n & 1, k = n >> 1;
+                mbar_wait(&g1_full[b], k & 1);
+                const int shift = i_first - 2 * (i_first >> 1);                 // the piece's first row inside its dL/dLL1 buffer
+                if (ra1 < rb1)
+                    haar_inv_rows<K1, true, false>(lay.g1buf + b * lay.g1bytes + shift * w2 * 4, st + lay.s1, ra1, rb1, cLL, cD, c, 0, obase, W, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&g1_empty[b]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    } else if (kTwo) {
+        const SynConst c = make_syn_const(a.sc2, 1.0f, a.magic);
+        const float cLL = 0.5f, cD = 0.5f * a.sc2;
+        const int w = warp - NW1;
+        for (int n = 0; pieces.next(m, i_first, len); ++n) {
+            const int s = n % S;
+            const int st = s * lay.stage;
+            const int b = n & 1, k = n >> 1;
+            mbar_wait(&full[s], (n / S) & 1);
+            if (k > 0) mbar_wait(&g1_empty[b], (k & 1) ^ 1);
+            const int rows2 = ((i_first + len - 1) >> 1) - (i_first >> 1) + 1;
+            const int nw2d = kTwo ? NW2 : 1;
+            const int seg2 = (rows2 + nw2d - 1) / nw2d;
+            const int ra2 = w * seg2, rb2 = min(ra2 + seg2, rows2);
+            if (ra2 < rb2) haar_inv_rows<K2, kHasLL, true>(st + lay.g, st + lay.s2, ra2, rb2, cLL, cD, c, lay.g1buf + b * lay.g1bytes, nullptr, 0, lane);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&g1_full[b]);
+                mbar_arrive(&empty[s]);
+            }
+        }
+    }
+}
+
 template <typename Kernel, typename Args>
 cudaError_t launch_db2(Kernel kernel, int grid, int threads, size_t smem, cudaStream_t stream, const Args& args, bool pdl) {
     static std::mutex mu;
@@ -728,9 +893,10 @@ int divisor_le(int n, int cap) {
     return 1;
 }
 
-size_t db2_fwd_smem(int W, int R, int S, bool two) {
-    const size_t rows_in = two ? 4 * R + 6 : 2 * R + 2;
-    const size_t ll1 = two ? size_t(2 * R + 2) * (W / 2) * 4 : 0;
+size_t db2_fwd_smem(int W, int R, int S, bool two, bool haar = false) {
+    const int halo = haar ? 0 : 2;
+    const size_t rows_in = two ? 4 * R + 3 * halo : 2 * R + halo;
+    const size_t ll1 = two ? size_t(2 * R + halo) * (W / 2) * 4 : 0;
     return S * rows_in * W * 4 + 2 * ll1 + size_t(2 * S + 4) * sizeof(uint64_t);
 }
 
@@ -738,6 +904,7 @@ size_t db2_fwd_smem(int W, int R, int S, bool two) {
 
 int g_wavelet_db2 = 1;          // diagnostics: 0 = the round-1 level kernels (wavelet_tiles.cu) for db2 as well
 int g_wavelet_db2_two = 1;      // diagnostics: 0 = one level per pass only
+int g_wavelet_haar_passes = 1;   // Haar: streamed levels through the same passes (1) or the round-1 level kernels / band kernel only (0)
 int g_wavelet_db2_deep = 0;     // 1: keep peeling levels with the factored passes as long as the band's width allows, resident stage only for the rest
 
 int g_wavelet_db2_rf = 0, g_wavelet_db2_ri = 0, g_wavelet_db2_nw2 = 0;     // diagnostics: overrides of the geometry below (0 = automatic)
@@ -760,21 +927,23 @@ int best_seg(int rows, int pairs, int threads) {
 // Geometry of a pass over H x W planes; false: shape not taken (the caller falls back to wavelet_tiles.cu / wavelet_stream.cu).
 //   R_fwd: rows of the pass's last level per analysis strip, S_fwd ring depth, NC_fwd consumer threads (both groups)
 //   R_inv: level-1 coefficient rows per synthesis piece, S_inv ring depth
-bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv) {
+bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv, bool haar) {
     if (!g_wavelet_db2 || (two && !g_wavelet_db2_two)) return false;
+    if (haar && !g_wavelet_haar_passes) return false;
     if (W != 128 && W != 256 && W != 512 && W != 1024) return false;    // warp-per-row synthesis: W / 128 chunks of 64 sites, unrolled
+    if (haar && two && W < 256) return false;                           // (32-site rows exist for db2 only)
     if (H % (two ? 4 : 2) || H < (two ? 16 : 4)) return false;
     const int hl = two ? H / 4 : H / 2;
     int R = divisor_le(hl, g_wavelet_db2_rf > 0 ? g_wavelet_db2_rf : (two ? 8 : 16));
-    while (R > 1 && db2_fwd_smem(W, R, 2, two) > size_t(kDb2Smem)) R = divisor_le(hl, R - 1);
-    if (db2_fwd_smem(W, R, 2, two) > size_t(kDb2Smem)) return false;
+    while (R > 1 && db2_fwd_smem(W, R, 2, two, haar) > size_t(kDb2Smem)) R = divisor_le(hl, R - 1);
+    if (db2_fwd_smem(W, R, 2, two, haar) > size_t(kDb2Smem)) return false;
     int S = 2;
-    while (S < 4 && db2_fwd_smem(W, R, S + 1, two) <= size_t(kDb2Smem)) ++S;
+    while (S < 4 && db2_fwd_smem(W, R, S + 1, two, haar) <= size_t(kDb2Smem)) ++S;
     *R_fwd = R; *S_fwd = S; *NC_fwd = kDb2MaxThreads - 32;
     int Ri = g_wavelet_db2_ri > 0 ? g_wavelet_db2_ri : (two ? 48 : 64);
     Ri = std::min(Ri, H / 2);
     auto inv_smem = [&](int r, int s) {
-        const Db2InvLayout lay = db2_inv_layout(W, r, two, has_ll, s);
+        const Db2InvLayout lay = db2_inv_layout(W, r, two, has_ll, s, haar);
         return size_t(lay.g1buf) + 2 * size_t(lay.g1bytes) + size_t(2 * s + 4) * sizeof(uint64_t);
     };
     while (Ri > 4 && inv_smem(Ri, 3) > size_t(kDb2Smem)) Ri -= 4;
@@ -787,30 +956,44 @@ bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fw
 
 cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,
                                 float sc1, float sc2, bool grad, bool pdl_wait, double* partial, int sm_count, cudaStream_t stream,
-                                int* n_partials) {
+                                int* n_partials, bool haar) {
     int Rf, Sf, NCf, Ri, Si;
-    if (!wavelet_db2_pass(H, W, two, true, &Rf, &Sf, &NCf, &Ri, &Si)) return cudaErrorInvalidValue;
+    if (!wavelet_db2_pass(H, W, two, true, &Rf, &Sf, &NCf, &Ri, &Si, haar)) return cudaErrorInvalidValue;
     Db2FwdArgs a;
     a.x = x; a.ll = ll; a.sg1 = sg1; a.sg2 = sg2; a.H = H; a.W = W; a.nmaps = nmaps; a.R = Rf; a.stages = Sf; a.pdl_wait = pdl_wait ? 1 : 0;
     a.sc1 = sc1; a.sc2 = sc2; a.partial = partial;
-    const int nw = NCf / 32;
+    const int nw = NCf / 32, halo = haar ? 0 : 2;
     a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, nw - 1) : (W >= 1024 ? 6 : 4)) : 0;     // measured: 1024^2 J=2 236 -> 227 us with 6
-    a.seg1 = best_seg(two ? 2 * Rf + 2 : Rf, W / 4, (nw - a.nw2) * 32);
+    a.seg1 = best_seg(two ? 2 * Rf + halo : Rf, W / 4, (nw - a.nw2) * 32);
     a.seg2 = two ? best_seg(Rf, W / 8, a.nw2 * 32) : 1;
     const long long T = (long long)nmaps * ((two ? H / 4 : H / 2) / Rf);
     const int grid = int(std::min<long long>(sm_count, T));
-    const size_t smem = db2_fwd_smem(W, Rf, Sf, two);
+    const size_t smem = db2_fwd_smem(W, Rf, Sf, two, haar);
     *n_partials = grid;
     const int threads = NCf + 32;
-    if (two) return grad ? launch_db2(db2_analysis_kernel<true, true>, grid, threads, smem, stream, a, pdl_wait)
-                         : launch_db2(db2_analysis_kernel<true, false>, grid, threads, smem, stream, a, pdl_wait);
-    return grad ? launch_db2(db2_analysis_kernel<false, true>, grid, threads, smem, stream, a, pdl_wait)
-                : launch_db2(db2_analysis_kernel<false, false>, grid, threads, smem, stream, a, pdl_wait);
+#define WTPSE_DB2_FWD(TWO, GRAD)                                                                                              \
+    (haar ? launch_db2(db2_analysis_kernel<TWO, GRAD, true>, grid, threads, smem, stream, a, pdl_wait)                         \
+          : launch_db2(db2_analysis_kernel<TWO, GRAD, false>, grid, threads, smem, stream, a, pdl_wait))
+    if (two) return grad ? WTPSE_DB2_FWD(true, true) : WTPSE_DB2_FWD(true, false);
+    return grad ? WTPSE_DB2_FWD(false, true) : WTPSE_DB2_FWD(false, false);
+#undef WTPSE_DB2_FWD
 }
 
 namespace {
 template <int K1>
-cudaError_t launch_db2_synthesis_k(const Db2InvArgs& a, bool two, bool has_ll, int grid, size_t smem, cudaStream_t stream) {
+cudaError_t launch_db2_synthesis_k(const Db2InvArgs& a, bool two, bool has_ll, bool haar, int grid, size_t smem, cudaStream_t stream) {
+    if (haar) {
+        if (two) {
+            if constexpr (K1 >= 2) {
+                return has_ll ? launch_db2(haar_synthesis_kernel<K1, true, true>, grid, kDb2MaxThreads, smem, stream, a, true)
+                              : launch_db2(haar_synthesis_kernel<K1, true, false>, grid, kDb2MaxThreads, smem, stream, a, true);
+            } else {
+                return cudaErrorInvalidValue;
+            }
+        }
+        return has_ll ? launch_db2(haar_synthesis_kernel<K1, false, true>, grid, kDb2MaxThreads, smem, stream, a, true)
+                      : launch_db2(haar_synthesis_kernel<K1, false, false>, grid, kDb2MaxThreads, smem, stream, a, true);
+    }
     if (two)
         return has_ll ? launch_db2(db2_synthesis_kernel<K1, true, true>, grid, kDb2MaxThreads, smem, stream, a, true)
                       : launch_db2(db2_synthesis_kernel<K1, true, false>, grid, kDb2MaxThreads, smem, stream, a, true);
@@ -822,9 +1005,9 @@ cudaError_t launch_db2_synthesis_k(const Db2InvArgs& a, bool two, bool has_ll, i
 // g: gradient of the low-low band entering the pass (level 2's when `two`), nullptr / has_ll == false: zero
 cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const unsigned char* sg2, float* out, int nmaps, int H, int W,
                                  bool two, bool has_ll, float sc1, float sc2, const float* upstream, const double* partial, int n_partials,
-                                 float* loss, int sm_count, cudaStream_t stream) {
+                                 float* loss, int sm_count, cudaStream_t stream, bool haar) {
     int Rf, Sf, NCf, Ri, Si;
-    if (!wavelet_db2_pass(H, W, two, has_ll, &Rf, &Sf, &NCf, &Ri, &Si)) return cudaErrorInvalidValue;
+    if (!wavelet_db2_pass(H, W, two, has_ll, &Rf, &Sf, &NCf, &Ri, &Si, haar)) return cudaErrorInvalidValue;
     Db2InvArgs a;
     a.g = g; a.sg1 = sg1; a.sg2 = sg2; a.out = out; a.H = H; a.W = W; a.nmaps = nmaps; a.R = Ri; a.stages = Si; a.sc1 = sc1; a.sc2 = sc2;
     a.upstream = upstream; a.partial = partial; a.n_partials = n_partials; a.loss = loss;
@@ -833,13 +1016,13 @@ cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const
     a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, kDb2MaxThreads / 32 - 2) : (W >= 1024 ? 6 : 4)) : 0;
     const long long rows = (long long)nmaps * (H / 2);
     const int grid = int(std::min<long long>(sm_count, std::max<long long>(1, rows / 4)));
-    const Db2InvLayout lay = db2_inv_layout(W, Ri, two, has_ll, Si);
+    const Db2InvLayout lay = db2_inv_layout(W, Ri, two, has_ll, Si, haar);
     const size_t smem = size_t(lay.g1buf) + 2 * size_t(lay.g1bytes) + size_t(2 * Si + 4) * sizeof(uint64_t);
     switch (W / 128) {
-        case 1: return launch_db2_synthesis_k<1>(a, two, has_ll, grid, smem, stream);
-        case 2: return launch_db2_synthesis_k<2>(a, two, has_ll, grid, smem, stream);
-        case 4: return launch_db2_synthesis_k<4>(a, two, has_ll, grid, smem, stream);
-        case 8: return launch_db2_synthesis_k<8>(a, two, has_ll, grid, smem, stream);
+        case 1: return launch_db2_synthesis_k<1>(a, two, has_ll, haar, grid, smem, stream);
+        case 2: return launch_db2_synthesis_k<2>(a, two, has_ll, haar, grid, smem, stream);
+        case 4: return launch_db2_synthesis_k<4>(a, two, has_ll, haar, grid, smem, stream);
+        case 8: return launch_db2_synthesis_k<8>(a, two, has_ll, haar, grid, smem, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -200,6 +200,7 @@ int stream_seg(int h2) { return h2 >= 64 ? 16 : (h2 >= 16 ? 8 : h2); }
 }  // namespace
 
 int g_wavelet_split = -1;       // -1: automatic, 0: whole map resident (when it fits), 1: level 1 streamed (when possible)
+int g_wavelet_haar_min_log2px = 16;     // Haar: smallest map (log2 pixels) that takes the pass kernels instead of the band kernel
 int g_wavelet_peel_max = 8;     // diagnostics: most levels the streamed plan may peel off before the resident stage
 
 static bool level_streamable(int H, int W, int taps) {
@@ -211,29 +212,30 @@ static bool level_tiled(int H, int W, int taps, bool has_ll) {
     return Rf > 0 && Ri > 0;
 }
 
-// db2, factored kernels (wavelet_db2.cu): the streamed levels as passes of two (or one) levels.  Fills pass[] with the
-// number of levels of each pass and returns the number of passes (0: the factored kernels do not take this shape);
-// *k = levels streamed, *cs = cluster size of the resident stage that follows (1 when k == J).
-static int db2_pass_plan(int H, int W, int J, int nmaps, int pass[16], int* k_out, int* cs) {
+// Factored pass kernels (wavelet_db2.cu): the streamed levels as passes of two (or one) levels.  Fills pass[] with the
+// number of levels of each pass and returns the number of passes (0: the pass kernels do not take this shape);
+// *k = levels streamed, *cs = cluster size (Haar: bands per map) of the resident stage that follows (1 when k == J).
+static int db2_pass_plan(int H, int W, int taps, int J, int nmaps, int pass[16], int* k_out, int* cs) {
+    const bool haar = taps == 2;
     int k = 0, np = 0;
     *cs = 0;
     while (k < J && k < g_wavelet_peel_max) {
         const int Hc = H >> k, Wc = W >> k, rem = J - k;
+        int r0, r1, r2, r3, r4;
         if (k > 0 && !g_wavelet_db2_deep) {
             // the band fits a cluster of <= 2: go resident -- unless two more levels can be taken by a two-level pass, which beats the
             // resident stage on bands of 256^2 and larger (1024^2 maps, J = 4: 265.5 -> 259.5 us).  On 128^2 bands a pass pair
             // costs what the resident stage costs (each extra kernel boundary is ~3-4 us of drain and fill: 512^2 J = 4 51.4 vs 52.2 us,
-            // J = 5 57.5 vs 54.2 us), so the band goes resident
-            const int c = wavelet_resident_cluster(Hc, Wc, 4, rem, nmaps);
-            int r0, r1, r2, r3, r4;
-            const bool two_more = rem >= 2 && Wc >= 256 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &r0, &r1, &r2, &r3, &r4);
-            if (c > 0 && c <= 2 && !two_more) { *cs = c; break; }
+            // J = 5 57.5 vs 54.2 us), so the band goes resident.  Haar: the same rule with its band kernel (no clusters) as the
+            // resident stage.
+            const int c = wavelet_resident_cluster(Hc, Wc, taps, rem, nmaps);
+            const bool two_more = rem >= 2 && Wc >= 256 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &r0, &r1, &r2, &r3, &r4, haar);
+            if (c > 0 && (haar || c <= 2) && !two_more) { *cs = haar ? 1 : c; break; }
         }
-        int Rf, Sf, NCf, Ri, Si;
-        if (rem >= 2 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &Rf, &Sf, &NCf, &Ri, &Si)) {
+        if (rem >= 2 && k + 2 <= g_wavelet_peel_max && wavelet_db2_pass(Hc, Wc, true, rem > 2, &r0, &r1, &r2, &r3, &r4, haar)) {
             pass[np++] = 2;
             k += 2;
-        } else if (wavelet_db2_pass(Hc, Wc, false, rem > 1, &Rf, &Sf, &NCf, &Ri, &Si)) {
+        } else if (wavelet_db2_pass(Hc, Wc, false, rem > 1, &r0, &r1, &r2, &r3, &r4, haar)) {
             pass[np++] = 1;
             k += 1;
         } else {
@@ -242,9 +244,9 @@ static int db2_pass_plan(int H, int W, int J, int nmaps, int pass[16], int* k_ou
     }
     if (k == 0) return 0;
     if (k < J) {
-        const int c = wavelet_resident_cluster(H >> k, W >> k, 4, J - k, nmaps);
+        const int c = wavelet_resident_cluster(H >> k, W >> k, taps, J - k, nmaps);
         if (c == 0) return 0;
-        *cs = c;
+        *cs = haar ? 1 : c;
     } else {
         *cs = 1;
     }
@@ -259,9 +261,9 @@ static int db2_pass_plan(int H, int W, int J, int nmaps, int pass[16], int* k_ou
 // Returns k, 0 if the plan does not exist; *cs = cluster size of the resident stage (1 when k == J).
 int wavelet_stream_levels(int H, int W, int taps, int J, int nmaps, int* cs) {
     *cs = 0;
-    if (taps == 4) {
+    {
         int pass[16], k = 0;
-        if (db2_pass_plan(H, W, J, nmaps, pass, &k, cs) > 0) return k;
+        if (db2_pass_plan(H, W, taps, J, nmaps, pass, &k, cs) > 0) return k;
         *cs = 0;
     }
     if (!level_streamable(H, W, taps)) return 0;
@@ -291,6 +293,9 @@ int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps) {
     // plan, 32 x 2 maps: 1024^2, J = 1 / 3 / 5: 106 / 146 / 177 us vs 120 / 165 / 177; 512^2: 35 / 47 / 55 vs 37 / 46 / 48.
     if (whole && taps == 2) {
         const long long px = (long long)H * W;
+        // Haar through the two-level passes (wavelet_db2.cu) from J = 2 on large maps: the band kernel reaches 0.69 / 0.59 / 0.52 of the
+        // roofline at 1024^2 for J = 2 / 3 / 4 (its deep levels have little parallelism per band)
+        if (g_wavelet_haar_passes && g_wavelet_db2 && split && J >= 2 && px >= (1ll << g_wavelet_haar_min_log2px)) return 2;
         if (J <= 2 || px >= (1ll << 20) || px <= (1ll << 16) || !split) return 1;
     } else if (whole && whole <= 2) {
         return 1;
@@ -323,10 +328,11 @@ cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, i
     auto scale_of = [&](int i) { return weights_host[i - 1] / (3.0f * float(H >> i) * float(W >> i) * float(nmaps)); };
     cudaError_t e = cudaSuccess;
     int np = 0;
-    if (taps == 4) {
-        // factored db2 passes (wavelet_db2.cu): 2 (or 1) levels per pass down, resident stage, the same passes up
+    {
+        // pass kernels (wavelet_db2.cu; factored db2 or Haar): 2 (or 1) levels per pass down, resident stage, the same passes up
+        const bool haar = taps == 2;
         int pass[16], kk = 0, cs2 = 0;
-        const int npass = db2_pass_plan(H, W, J, nmaps, pass, &kk, &cs2);
+        const int npass = db2_pass_plan(H, W, taps, J, nmaps, pass, &kk, &cs2);
         if (npass > 0 && kk == k) {
             int lvl = 0;                                            // levels done
             for (int q = 0; q < npass; ++q) {
@@ -334,7 +340,7 @@ cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, i
                 const int Hi = H >> lvl, Wi = W >> lvl, last = lvl + pass[q];
                 int n = 0;
                 e = launch_db2_analysis(lvl == 0 ? x : ll[lvl], last < J ? ll[last] : nullptr, sg[lvl + 1], two ? sg[lvl + 2] : nullptr, nmaps, Hi, Wi, two,
-                                        scale_of(lvl + 1), two ? scale_of(lvl + 2) : 0.f, grad != nullptr, q > 0, partial + np, sm_count, stream, &n);
+                                        scale_of(lvl + 1), two ? scale_of(lvl + 2) : 0.f, grad != nullptr, q > 0, partial + np, sm_count, stream, &n, haar);
                 if (e != cudaSuccess) return e;
                 np += n;
                 lvl = last;
@@ -353,7 +359,7 @@ cudaError_t launch_wavelet_loss_split(const float* x, int nmaps, int H, int W, i
                 const int Hi = H >> lvl, Wi = W >> lvl, last = lvl + pass[q];
                 e = launch_db2_synthesis(ll[last], sg[lvl + 1], two ? sg[lvl + 2] : nullptr, lvl == 0 ? grad : ll[lvl], nmaps, Hi, Wi, two,
                                          last < J, scale_of(lvl + 1), two ? scale_of(lvl + 2) : 0.f, lvl == 0 ? upstream : nullptr, partial, np,
-                                         lvl == 0 ? loss : nullptr, sm_count, stream);
+                                         lvl == 0 ? loss : nullptr, sm_count, stream, haar);
                 if (e != cudaSuccess) return e;
             }
             return cudaSuccess;
