@@ -298,6 +298,11 @@ int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps) {
         if (g_wavelet_haar_passes && g_wavelet_db2 && split && J >= 2 && px >= (1ll << g_wavelet_haar_min_log2px)) return 2;
         if (J <= 2 || px >= (1ll << 20) || px <= (1ll << 16) || !split) return 1;
     } else if (whole && whole <= 2) {
+        // db2 maps that fit a cluster of <= 2 (256^2 and smaller): the pass kernels beat the whole-map-resident kernel by a third
+        // (128 x 2 maps of 256^2: J = 2 / 3 / 4 70.1 / 80.2 / 89.0 -> 45.4 / 56.0 / 60.2 us; 512 x 2 maps of 128^2, J = 2: 76.5 -> 65.9 us),
+        // and still by a few microseconds when a handful of maps leaves everything launch-bound (4 x 2 maps of 256^2, J = 3: 25.0 -> 21.4 us)
+        int pass[16], kk = 0, c2 = 0;
+        if (split && g_wavelet_db2 && db2_pass_plan(H, W, taps, J, nmaps, pass, &kk, &c2) > 0) return 2;
         return 1;
     }
     return split ? 2 : (whole ? 1 : 0);
