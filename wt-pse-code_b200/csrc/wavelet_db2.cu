@@ -457,7 +457,7 @@ __device__ __forceinline__ void db2_inv_rows(int g_off, int sg_off, int ra, int 
                 o.z = fmaf(qn.x, kCA, kI3 * pb.y);
                 o.w = fmaf(qn.x, kCB, pb.y);
                 if (kToSmem) *reinterpret_cast<float4*>(orow_s + pr * (2 * wj) + 128 * k) = o;
-                else *reinterpret_cast<float4*>(orow_g + pr * out_ld + 128 * k) = o;
+                else __stcs(reinterpret_cast<float4*>(orow_g + pr * out_ld + 128 * k), o);     // written once, read by somebody else later: streaming store
             }
         }
         grow += wj;
@@ -519,7 +519,7 @@ __device__ __forceinline__ void db2_inv_rows_half(int g_off, int sg_off, int ra,
             o.w = fmaf(qn.x, kCB, pb.y);
             if (valid) {
                 if (kToSmem) *reinterpret_cast<float4*>(outs + (2 * (r - 1) + pr) * (2 * wj) + 4 * l16) = o;
-                else *reinterpret_cast<float4*>(out_g + (long long)(2 * (r - 1) + pr) * out_ld + 4 * l16) = o;
+                else __stcs(reinterpret_cast<float4*>(out_g + (long long)(2 * (r - 1) + pr) * out_ld + 4 * l16), o);
             }
         }
     }
@@ -737,8 +737,8 @@ __device__ __forceinline__ void haar_inv_rows(int g_off, int sg_off, int ra, int
                 *reinterpret_cast<float4*>(orow_s + 128 * k) = o0;
                 *reinterpret_cast<float4*>(orow_s + 2 * wj + 128 * k) = o1;
             } else {
-                *reinterpret_cast<float4*>(orow_g + 128 * k) = o0;
-                *reinterpret_cast<float4*>(orow_g + out_ld + 128 * k) = o1;
+                __stcs(reinterpret_cast<float4*>(orow_g + 128 * k), o0);
+                __stcs(reinterpret_cast<float4*>(orow_g + out_ld + 128 * k), o1);
             }
         }
         grow += wj;
@@ -940,7 +940,8 @@ bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fw
     int S = 2;
     while (S < 4 && db2_fwd_smem(W, R, S + 1, two, haar) <= size_t(kDb2Smem)) ++S;
     *R_fwd = R; *S_fwd = S; *NC_fwd = kDb2MaxThreads - 32;
-    int Ri = g_wavelet_db2_ri > 0 ? g_wavelet_db2_ri : (two ? 48 : 64);
+    // measured at 64 x 2 x 1024^2, J = 2, db2: pieces of 24 (what fits) / 20 / 16 / 12 rows: 219.6 / 215.8 / 214.8 / 234.1 us
+    int Ri = g_wavelet_db2_ri > 0 ? g_wavelet_db2_ri : (two ? (W >= 1024 && !haar ? 16 : 48) : 64);
     Ri = std::min(Ri, H / 2);
     auto inv_smem = [&](int r, int s) {
         const Db2InvLayout lay = db2_inv_layout(W, r, two, has_ll, s, haar);
@@ -963,7 +964,7 @@ cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, u
     a.x = x; a.ll = ll; a.sg1 = sg1; a.sg2 = sg2; a.H = H; a.W = W; a.nmaps = nmaps; a.R = Rf; a.stages = Sf; a.pdl_wait = pdl_wait ? 1 : 0;
     a.sc1 = sc1; a.sc2 = sc2; a.partial = partial;
     const int nw = NCf / 32, halo = haar ? 0 : 2;
-    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, nw - 1) : (W >= 1024 ? 6 : 4)) : 0;     // measured: 1024^2 J=2 236 -> 227 us with 6
+    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, nw - 1) : (W >= 1024 && !haar ? 6 : 4)) : 0;     // measured: db2 1024^2 J=2 236 -> 227 us with 6; Haar: 203 -> 196 us with 4
     a.seg1 = best_seg(two ? 2 * Rf + halo : Rf, W / 4, (nw - a.nw2) * 32);
     a.seg2 = two ? best_seg(Rf, W / 8, a.nw2 * 32) : 1;
     const long long T = (long long)nmaps * ((two ? H / 4 : H / 2) / Rf);
@@ -1013,7 +1014,7 @@ cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const
     a.upstream = upstream; a.partial = partial; a.n_partials = n_partials; a.loss = loss;
     a.magic[0] = code_magic<0>(); a.magic[1] = code_magic<2>(); a.magic[2] = code_magic<4>();
     a.magic[3] = code_magic<8>(); a.magic[4] = code_magic<10>(); a.magic[5] = code_magic<12>();
-    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, kDb2MaxThreads / 32 - 2) : (W >= 1024 ? 6 : 4)) : 0;
+    a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, kDb2MaxThreads / 32 - 2) : (W >= 1024 && !haar ? 6 : 4)) : 0;
     const long long rows = (long long)nmaps * (H / 2);
     const int grid = int(std::min<long long>(sm_count, std::max<long long>(1, rows / 4)));
     const Db2InvLayout lay = db2_inv_layout(W, Ri, two, has_ll, Si, haar);
