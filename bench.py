@@ -54,29 +54,36 @@ def workload_dims(args):
     return B, H, H, n, WORKLOAD["n_domains"]
 
 
-def kernel_source_hash():
-    """sha256 over the CUDA sources the loaded library was built from (the GPU box has no .git): profiles/traffic.json
-    records the hash its ncu capture was taken at, so a stale `roofline.traffic` is flagged instead of silently reused."""
+# the CUDA sources each traffic entry of profiles/traffic.json depends on (kernels + the host code that picks and shapes them)
+TRAFFIC_SOURCES = {
+    "whitening": ("common.cuh", "mmd_device.cuh", "whitening_tail.cuh", "whitening_matrix.cuh", "whitening_gram.cu", "whitening_apply.cu"),
+    "wavelet": ("common.cuh", "wavelet_db2.cu", "wavelet_resident.cu", "wavelet_stream.cu", "wavelet_tiles.cu", "wavelet_level.cuh",
+                "wavelet_bank.cuh"),
+}
+
+
+def kernel_source_hash(group="whitening"):
+    """sha256 over the CUDA sources a traffic entry was captured with (the GPU box has no .git): profiles/traffic.json records the hash
+    per group, so a stale `roofline.traffic` is flagged instead of silently reused -- and a change to an unrelated kernel does not."""
     import hashlib
 
     csrc = os.path.join(ROOT, "wt-pse-code_b200", "csrc")
     h = hashlib.sha256()
-    for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".h")):
-            h.update(name.encode())
-            with open(os.path.join(csrc, name), "rb") as f:
-                h.update(f.read())
+    for name in TRAFFIC_SOURCES[group]:
+        h.update(name.encode())
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(f.read())
     return h.hexdigest()[:16]
 
 
-def traffic_entry(key):
+def traffic_entry(key, group="whitening"):
     """(bytes per launch or None, stale flag, capture hash) from profiles/traffic.json."""
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(tpath):
         return None, None, None
     t = json.load(open(tpath))
-    cap = t.get("kernel_source_hash")
-    return t.get(key), (cap != kernel_source_hash()), cap
+    cap = t.get("kernel_source_hash" if group == "whitening" else group + "_source_hash")
+    return t.get(key), (cap != kernel_source_hash(group)), cap
 
 
 def parse_args():
@@ -1129,10 +1136,9 @@ def run_wavelet(args):
     algo = 8.0 * elems                      # SURVEY 8(d) Track W: 4N read forward + 4N written backward
     # bytes the kernels actually move: resident = one read + one write; per-level = (read + write) * 4/3 per pass, two passes
     moved = algo if cs else 4.0 * elems * (8.0 / 3.0) * 2
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if cs and os.path.exists(tpath) and (B, C, H, W, J, wv) == (32, 2, 512, 512, 4, "db2"):
-        traffic = json.load(open(tpath)).get("wavelet_fused_step_32x2x512x512_db2_J4")
+    traffic, traffic_stale = None, None
+    if cs and (B, C, H, W, J, wv) == (32, 2, 512, 512, 4, "db2"):
+        traffic, traffic_stale, _ = traffic_entry("wavelet_fused_step_32x2x512x512_db2_J4", "wavelet")
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -1149,7 +1155,7 @@ def run_wavelet(args):
         "transform": {"dwt2d_ms": ms_fwd, "idwt2d_ms": ms_inv, "max_abs_reconstruction_error": recon_err,
                       "frac_of_8B_per_element_roofline": [8.0 * B * C * H * W / (t * 1e-3) / 1e9 / (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else FALLBACK_PEAK_GBS) for t in (ms_fwd, ms_inv)]},
         "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "per": "GPU",
-                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": traffic,
+                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": traffic, "traffic_stale": traffic_stale,
                      "moved_estimate_frac": moved / (ms * 1e-3) / 1e9 / peak},
         "loss": float(loss.detach())}))
 

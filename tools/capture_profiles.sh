@@ -2,7 +2,7 @@
 # Run ON THE GPU BOX (gpurun -- 'bash tools/capture_profiles.sh <tag>'): the ncu evidence kept under profiles/.
 #   1. launch list (gpu__time_duration.sum) of the default bench command, 3 steps
 #   2. ncu --set full of one forward + backward of every loss variant (tools/loss_probe.py) and of the Track-W fused plan
-# Each profiled command first runs once WITHOUT ncu and must exit 0.  Reports land in gpurun_out/<tag>_*.ncu-rep; turn them
+# Each profiled command first runs once WITHOUT ncu and must exit 0.  Raw pages of the reports land in gpurun_out/<tag>_full_*.csv; turn them
 # into the tracked text summaries with tools/ncu_summary.py and tools/update_traffic.py in the build container.
 tag=${1:-cap}
 out=gpurun_out
@@ -18,4 +18,7 @@ $WAVE > $out/${tag}_plain_wavelet.log 2>&1 || { echo "wavelet bench failed"; exi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $out/${tag}_launches_wavelet.csv $WAVE > $out/${tag}_ncu_wavelet_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'wavelet_res|db2_' --launch-skip 9 -c 3 -f -o $out/${tag}_full_wavelet \
     $WAVE > $out/${tag}_ncu_wavelet.log 2>&1
+# the reports are large (gpurun merges at most 64 MiB back): keep their raw pages as CSV (what tools/ncu_summary.py and
+# tools/update_traffic.py read) and drop the .ncu-rep files
+for f in $out/${tag}_full_loss $out/${tag}_full_wavelet; do ncu -i $f.ncu-rep --page raw --csv > $f.csv 2>/dev/null && rm -f $f.ncu-rep; done
 echo capture done

@@ -15,7 +15,7 @@ import bench  # noqa: E402
 
 
 def launches(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -60,7 +60,10 @@ def main():
         t["wavelet_per_kernel"] = {k: int(sum(v) / len(v)) for k, v in per.items()}
         t["wavelet_source"] = "ncu --set full of `bench.py --track wavelet` (%s): one launch of each kernel of the fused plan at " \
                               "32x2x512x512, db2, J=4" % os.path.basename(sys.argv[2])
-    t["kernel_source_hash"] = bench.kernel_source_hash()
+    t["kernel_source_hash"] = bench.kernel_source_hash("whitening")
+    if len(sys.argv) > 2:
+        t["wavelet_source_hash"] = bench.kernel_source_hash("wavelet")
+    t["hash_sources"] = {k: list(v) for k, v in bench.TRAFFIC_SOURCES.items()}
     json.dump(t, open(path, "w"), indent=1)
     print(json.dumps(t, indent=1))
 

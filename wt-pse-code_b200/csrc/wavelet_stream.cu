@@ -295,7 +295,9 @@ int wavelet_fused_plan(int H, int W, int taps, int J, int nmaps) {
         const long long px = (long long)H * W;
         // Haar through the two-level passes (wavelet_db2.cu) from J = 2 on large maps: the band kernel reaches 0.69 / 0.59 / 0.52 of the
         // roofline at 1024^2 for J = 2 / 3 / 4 (its deep levels have little parallelism per band)
-        if (g_wavelet_haar_passes && g_wavelet_db2 && split && J >= 2 && px >= (1ll << g_wavelet_haar_min_log2px)) return 2;
+        // (a handful of small maps is launch-bound and keeps the single band kernel: 8 x 2 maps of 256^2, J = 3: 17.1 vs 21.6 us)
+        const bool enough = nmaps == 0 || (long long)nmaps * px >= (1ll << 22);
+        if (g_wavelet_haar_passes && g_wavelet_db2 && split && enough && J >= 2 && px >= (1ll << g_wavelet_haar_min_log2px)) return 2;
         if (J <= 2 || px >= (1ll << 20) || px <= (1ll << 16) || !split) return 1;
     } else if (whole && whole <= 2) {
         // db2 maps that fit a cluster of <= 2 (256^2 and smaller): the pass kernels beat the whole-map-resident kernel by a third
