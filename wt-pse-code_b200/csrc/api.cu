@@ -254,6 +254,7 @@ const Knob* knobs(int* count) {
         {"wavelet_db2_rf", &g_wavelet_db2_rf, 0, 64},
         {"wavelet_db2_ri", &g_wavelet_db2_ri, 0, 128},
         {"wavelet_db2_nw2", &g_wavelet_db2_nw2, 0, 12},
+        {"wavelet_db2_rr", &g_wavelet_db2_rr, 0, 1},
         {"wavelet_peel_max", &g_wavelet_peel_max, 1, 16},
         {"wavelet_split", &g_wavelet_split, -1, 1},
         {"wavelet_cluster_max", &g_wavelet_cluster_max, 1, 8},

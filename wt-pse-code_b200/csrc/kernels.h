@@ -163,7 +163,7 @@ cudaError_t launch_idwt1_tiles(const float* gll, const unsigned char* sg, float*
 extern int g_wavelet_db2;
 extern int g_wavelet_db2_two;
 extern int g_wavelet_db2_deep;
-extern int g_wavelet_db2_rf, g_wavelet_db2_ri, g_wavelet_db2_nw2;
+extern int g_wavelet_db2_rf, g_wavelet_db2_ri, g_wavelet_db2_nw2, g_wavelet_db2_rr;
 extern int g_wavelet_haar_passes;
 bool wavelet_db2_pass(int H, int W, bool two, bool has_ll, int* R_fwd, int* S_fwd, int* NC_fwd, int* R_inv, int* S_inv, bool haar = false);
 cudaError_t launch_db2_analysis(const float* x, float* ll, unsigned char* sg1, unsigned char* sg2, int nmaps, int H, int W, bool two,

@@ -530,7 +530,7 @@ struct Db2InvArgs {
     const unsigned char* sg1;   // [nmaps][H/2][W/2]
     const unsigned char* sg2;   // [nmaps][H/4][W/4] (two levels)
     float* out;                 // [nmaps][H][W]
-    int H, W, nmaps, R, stages, nw2; // R: most level-1 coefficient rows per piece; nw2: warps of the level-2 group
+    int H, W, nmaps, R, stages, nw2, rr; // R: most level-1 coefficient rows per piece; nw2: warps of the level-2 group; rr: pieces dealt round-robin
     float sc1, sc2;
     const float* upstream;      // device scalar multiplied into out (nullptr: 1)
     const double* partial;      // loss partials of the preceding kernels, summed in fixed order by CTA 0 ...
@@ -541,13 +541,28 @@ struct Db2InvArgs {
 
 // contiguous, balanced ranges of the nmaps * h2 coefficient rows, cut into pieces of at most R rows that stay inside a map
 struct Db2Pieces {
-    long long r, e;
-    int h2, R;
-    __device__ Db2Pieces(long long total, int h2_, int R_) : h2(h2_), R(R_) {
+    long long r, e;             // contiguous mode: this CTA's row range
+    long long p, T;             // round-robin mode: next piece, number of pieces
+    int h2, R, ppm;             // rows per map, rows per piece, pieces per map
+    bool rr;
+    // rr: pieces of R rows (the last one of a map shorter) dealt round-robin to the CTAs -- at any moment the grid then writes ONE
+    // contiguous window of the output (148 adjacent pieces) instead of 148 scattered ones; contiguous: balanced row ranges
+    __device__ Db2Pieces(long long total, int h2_, int R_, bool rr_) : h2(h2_), R(R_), rr(rr_) {
         r = total * blockIdx.x / gridDim.x;
         e = total * (blockIdx.x + 1) / gridDim.x;
+        ppm = (h2 + R - 1) / R;
+        p = blockIdx.x;
+        T = (total / h2) * ppm;
     }
     __device__ bool next(long long& m, int& i_first, int& len) {
+        if (rr) {
+            if (p >= T) return false;
+            m = p / ppm;
+            i_first = int(p - m * ppm) * R;
+            len = min(R, h2 - i_first);
+            p += gridDim.x;
+            return true;
+        }
         if (r >= e) return false;
         m = r / h2;
         i_first = int(r - m * h2);
@@ -617,7 +632,7 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) db2_synthesis_kernel(Db2Inv
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    Db2Pieces pieces((long long)a.nmaps * h2, h2, R);
+    Db2Pieces pieces((long long)a.nmaps * h2, h2, R, a.rr != 0);
     long long m;
     int i_first, len;
     if (warp == NW) {
@@ -776,7 +791,7 @@ __global__ void __launch_bounds__(kDb2MaxThreads, 1) haar_synthesis_kernel(Db2In
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    Db2Pieces pieces((long long)a.nmaps * h2, h2, R);
+    Db2Pieces pieces((long long)a.nmaps * h2, h2, R, a.rr != 0);
     long long m;
     int i_first, len;
     if (warp == NW) {
@@ -907,7 +922,8 @@ int g_wavelet_db2_two = 1;      // diagnostics: 0 = one level per pass only
 int g_wavelet_haar_passes = 1;   // Haar: streamed levels through the same passes (1) or the round-1 level kernels / band kernel only (0)
 int g_wavelet_db2_deep = 0;     // 1: keep peeling levels with the factored passes as long as the band's width allows, resident stage only for the rest
 
-int g_wavelet_db2_rf = 0, g_wavelet_db2_ri = 0, g_wavelet_db2_nw2 = 0;     // diagnostics: overrides of the geometry below (0 = automatic)
+int g_wavelet_db2_rf = 0, g_wavelet_db2_ri = 0, g_wavelet_db2_nw2 = 0;
+int g_wavelet_db2_rr = 1;       // synthesis pieces dealt round-robin (1) or one contiguous row range per CTA (0)     // diagnostics: overrides of the geometry below (0 = automatic)
 
 namespace {
 // rows per thread task that minimise rounds * (rows + ~1.5 rows of task prologue) for `rows` rows x `pairs` column groups on `threads` threads
@@ -1015,6 +1031,10 @@ cudaError_t launch_db2_synthesis(const float* g, const unsigned char* sg1, const
     a.magic[0] = code_magic<0>(); a.magic[1] = code_magic<2>(); a.magic[2] = code_magic<4>();
     a.magic[3] = code_magic<8>(); a.magic[4] = code_magic<10>(); a.magic[5] = code_magic<12>();
     a.nw2 = two ? (g_wavelet_db2_nw2 > 0 ? std::min(g_wavelet_db2_nw2, kDb2MaxThreads / 32 - 2) : (W >= 1024 && !haar ? 6 : 4)) : 0;
+    // measured (same box): one-level passes, 1024^2 J = 1: 192.8 -> 187.2 us with round-robin pieces; two-level passes: 512^2 J = 4 52.0 -> 53.6 us,
+    // 1024^2 J = 2 222.7 -> 226.9 us (their pieces carry recomputed overlap rows of level 2, and the hand-over favours long runs)
+    // ... and only with enough pieces for the rounds to come out even (512^2 J = 1: 256 pieces on 148 CTAs, 35.9 -> 37.0 us)
+    a.rr = (g_wavelet_db2_rr && !two && (long long)nmaps * ((H / 2 + Ri - 1) / Ri) >= 6ll * sm_count) ? 1 : 0;
     const long long rows = (long long)nmaps * (H / 2);
     const int grid = int(std::min<long long>(sm_count, std::max<long long>(1, rows / 4)));
     const Db2InvLayout lay = db2_inv_layout(W, Ri, two, has_ll, Si, haar);
