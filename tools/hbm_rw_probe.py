@@ -26,6 +26,6 @@ t_w = timed(lambda: a.zero_())
 t_r = timed(lambda: a.sum())
 t_c = timed(lambda: b.copy_(a))
 gb = n * 4 / 1e9
-print("write (memset)   %.0f GB/s" % (gb / t_w))
+print("write (memset)   %.0f GB/s   (zeros: the memory system may compress them -- an upper bound, not a target)" % (gb / t_w))
 print("read  (sum)      %.0f GB/s" % (gb / t_r))
 print("copy  (D2D)      %.0f GB/s read + write" % (2 * gb / t_c))
