@@ -21,6 +21,15 @@
 //                         lane 0; the row above is carried in registers.
 // Two levels per pass keep LL1 (a quarter of the map, written and read twice by the one-level plan) out of memory: the
 // pass moves 4.6 B per element instead of 5.25 + 1.3, and the resident stage that follows works on 1/16 of the map.
+// The level-1 and level-2 work of a two-level pass run on separate warp groups of the CTA (hand-over buffers + mbarriers),
+// so level 2 of strip n overlaps level 1 of strip n + 1.
+//
+// Haar goes through the same pipelines (kHaar / haar_synthesis_kernel): its filters do not overlap, so there are no halo
+// rows, no carried row and no neighbour exchange -- sums / differences in the analysis, a 2 x 2 Hadamard butterfly per site
+// in the synthesis.
+//
+// Measured (B200, 64 x 2 x 1024^2, J = 2): Haar analysis 84.5 us (the HBM read rate), db2 analysis 123 us (issue-bound: 25 %
+// of the level-1 rows are overlap rows at this width), synthesis 103 us for both (bound by the write stream).
 #include <math.h>
 
 #include <algorithm>
