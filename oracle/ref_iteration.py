@@ -92,7 +92,7 @@ def trainer_iteration(nets, optims, image, target_od, target_oc, hparams, epoch=
             oc_pos_weight = torch.tensor(1.).cuda()
     else:
         oc_pos_weight = torch.where(torch.isfinite(oc_pos_weight), oc_pos_weight, torch.ones_like(oc_pos_weight))
-    loss_seg_oc = F.binary_cross_entropy_with_logits(output_oc * od_pred, target_oc, pos_weight=oc_pos_weight)
+    loss_seg_oc = F.binary_cross_entropy_with_logits(output_oc * od_pred, target_oc, pos_weight=oc_pos_weight.to(output_oc.dtype))   # .to: a no-op in float32 (float64 runs of the tests)
     _item(loss_seg_oc, host_syncs)
     if hparams["whitening"]:
         _item(loss_ins_oc, host_syncs)
