@@ -185,6 +185,10 @@ class ClockSampler:
             self._thread = threading.Thread(target=self._loop, daemon=True)
             self._thread.start()
 
+    def mark(self):
+        """Forget what was sampled so far (warm-up): the report covers the region that starts here."""
+        self.samples, self.reasons = [], set()
+
     def stop(self):
         self._stop.set()
         if self._thread is not None:
@@ -691,23 +695,29 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # NVML is initialised and the sampler thread started BEFORE the warm-up steps (both take tens of milliseconds, during which
+    # an idle GPU drops its clocks): the warm-up then runs right up to the barrier that opens the timed region.
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
-    barrier()
-
-    sampler = ClockSampler(physical_gpu_index(local_rank))
     # Per-kernel CUDA events are recorded inside the timed region on every `stride`-th step only: each
     # bracketed launch costs ~5 us of stream serialisation (measured: 318 us/step with events on every
     # launch vs 302 us/step with none), so sampling keeps the kernel timings "live" without taxing `value`.
+    # The bracketed steps sit in the MIDDLE of each stride (never step 0: the first step after the barrier starts on an idle
+    # GPU and is not what the other K - 1 look like), and a short run (the driver's K = 20) still brackets three of them.
     stride = 0 if args.no_kernel_events else max(1, args.event_stride)
+    if stride and args.steps < 3 * stride:
+        stride = max(1, args.steps // 3)
+    phase = stride // 2
     lib.wtpse_profile_reset()
     lib.wtpse_profile_enable(0)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler.start()
     barrier()
+    sampler.mark()                    # the clocks reported are those sampled from here on (the timed region)
     ev0.record()
     for i in range(args.steps):
-        if stride and i % stride == 0:
+        if stride and i % stride == phase:
             lib.wtpse_profile_enable(1)
             ins, dom = step(i)
             lib.wtpse_profile_enable(0)
