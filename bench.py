@@ -517,34 +517,44 @@ def time_track_r_configs(dev, peak, steps=20):
         entry = {"ms_per_step": ms, "value": pix / (ms * 1e-3) / 1e6, "unit": "Mpix/s", "steps": steps, "n_per_domain": n,
                  "launch_mode": "eager (two C-ABI calls per step from Python)",
                  "step_frac": 192.0 * pix / (ms * 1e-3) / 1e9 / peak if S >= 512 else None,
-                 "note": None if S >= 512 else "100.7 MB per step = 15 us at the HBM peak: bound by launch and forward-tail latency, no roofline claim",
+                 "note": None if S >= 512 else "100.7 MB per step = 15 us at the HBM peak: bound by launch and forward-tail latency (the single-SM tail alone is 10 us), not by HBM",
                  "l2": "%d alternating inputs of %.0f MB" % (nbuf, B * 16 * S * S * 4 / 1e6),
                  "losses": [float(ins.detach()), float(dom.detach())]}
         if S < 512:
             # a step this short is bound by the host's launch path: replay it as a CUDA graph (one graph per input buffer;
             # the C ABI neither allocates nor synchronises, so forward + backward capture as they are)
             try:
+                # the captured step asks autograd for dz directly (torch.autograd.grad): the eager steps above left z's
+                # AccumulateGrad node bound to the default stream, and running THAT node inside a capture on another stream
+                # makes the engine synchronise with the legacy stream, which a capture forbids
+                def gstep(i):
+                    z = zs[i % nbuf]
+                    ins, dom = wb.whitening_folded(z, n, 3, 0.0, 1e-5)
+                    (dz,) = torch.autograd.grad([ins, dom], [z], [one, one])
+                    return ins, dom, dz
+                del ins, dom
                 graphs, outs = [], []
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
                     for i in range(nbuf):
-                        step(i)
+                        gstep(i)
                 torch.cuda.current_stream(dev).wait_stream(side)
                 for i in range(nbuf):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
-                        outs.append(step(i))
+                        outs.append(gstep(i))
                     graphs.append(g)
 
                 def replay(i):
                     graphs[i % nbuf].replay()
-                    return outs[i % nbuf]
+                    return outs[i % nbuf][:2]
                 for i in range(nbuf):
                     replay(i)
                 torch.cuda.synchronize()
                 ms_g, (ins_g, dom_g) = timed(replay)
                 entry.update({"eager_ms_per_step": ms, "ms_per_step": ms_g, "value": pix / (ms_g * 1e-3) / 1e6,
+                              "step_frac": 192.0 * pix / (ms_g * 1e-3) / 1e9 / peak,
                               "launch_mode": "cuda-graph replay of forward + backward (eager: eager_ms_per_step)"})
                 del graphs, outs
             except Exception as exc:
