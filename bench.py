@@ -711,6 +711,12 @@ def run_ours(args):
     sampler.start()
     for i in range(max(args.warmup, 3)):
         step(i)
+    if world > 1:
+        # the first collective of a process group sets up NCCL's channels (hundreds of milliseconds, GPU idle): have it
+        # here, then warm up again, so that the barrier that opens the timed region is a settled one on a busy GPU
+        barrier()
+        for i in range(3):
+            step(i)
     # Per-kernel CUDA events are recorded inside the timed region on every `stride`-th step only: each
     # bracketed launch costs ~5 us of stream serialisation (measured: 318 us/step with events on every
     # launch vs 302 us/step with none), so sampling keeps the kernel timings "live" without taxing `value`.
@@ -749,7 +755,11 @@ def run_ours(args):
             kern[lib.wtpse_profile_kernel_name(kid).decode()] = {"launches": cnt.value, "avg_us": ms.value / cnt.value * 1e3}
 
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    per_rank_ms = [ms_total / args.steps]
     if world > 1:
+        every = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(every, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in every]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
@@ -863,6 +873,7 @@ def run_ours(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(B, H, W, n, K),
+        "ms_per_step_per_rank": per_rank_ms,          # ms_per_step is their maximum (every rank times its own K steps on its device)
         "e2e": e2e, "gpu_launches": launches, "kernels": kern, "roofline": roofline, "cpu_baseline": cpu,
         "gpu_eager_baseline": gpu_eager, "clocks": clocks, "losses": losses, "train_step": train,
         "relu_fusion": relu_fusion, "configs": configs, "wavelet": wavelet,
