@@ -159,7 +159,10 @@ def _check_grads(got, want, noise, truth=None):
             worst = (rel, k)
         if rel > 1e-5 and truth is not None:
             if t64 is None:
-                t64 = truth()
+                try:
+                    t64 = truth()
+                except Exception as exc:              # no float64 evidence: the plain bar decides
+                    raise AssertionError((k, err, scale, floor, "float64 run of the reference failed: %r" % (exc,)))
             ref_err = float((w.double() - t64[k]).abs().max())
             assert rel <= 1e-4 and err <= 0.1 * ref_err, (k, err, scale, floor, ref_err)
             continue
